@@ -1,0 +1,72 @@
+"""Loads tests/golden/*.npz (minted by oracle/make_golden.py from the reference's own code)."""
+import glob
+import json
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+class Fixture:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.name = name
+        self.z = z
+        self.meta = json.loads(str(z["meta"]))
+        self.kind = self.meta["kind"]
+        self.plane = self.meta["plane"]
+        self.dim = 2 if self.kind == "elasticity" else 1
+        self.coords, self.conn = z["coords"], z["conn"]
+        self.mat_id, self.mat = z["mat_id"], z["mat"]
+        self.records = self.meta["records"]
+        self.ndof = len(self.coords) * self.dim
+
+    def rec(self, key):
+        out = []
+        for r in self.records[key]:
+            out.append(tuple(r))
+        return out
+
+    def csr(self, prefix):
+        z = self.z
+        return sp.csr_matrix((z[f"ref_{prefix}_data"], z[f"ref_{prefix}_indices"], z[f"ref_{prefix}_indptr"]),
+                             shape=tuple(z[f"ref_{prefix}_shape"]))
+
+    def ref(self, key):
+        return self.z["ref_" + key]
+
+    @property
+    def oracle_kind(self):
+        from oracle import numpy_oracle as no
+        if self.kind == "magnetic":
+            return no.KIND_MAGNETIC
+        return no.KIND_ELAST_PSTRAIN if self.plane == "strain" else no.KIND_ELAST_PSTRESS
+
+
+def assert_close_rowscaled(a, b, rtol=1e-12):
+    """|a-b| <= rtol * max|row of b| (structurally-present zeros: SURVEY §7 hard part 7)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    scale = np.max(np.abs(b.reshape(b.shape[0], -1)), axis=1)
+    scale = np.where(scale == 0, 1.0, scale).reshape((-1,) + (1,) * (b.ndim - 1))
+    err = np.max(np.abs(a - b) / scale)
+    assert err <= rtol, f"row-scaled error {err:.3e} > {rtol:.1e}"
+
+
+def assert_csr_values_close(a, b, rtol=1e-12):
+    """Same pattern (bit-exact) and values within rtol * max|row|."""
+    assert a.shape == b.shape
+    assert np.array_equal(a.indptr, b.indptr), "indptr differs"
+    assert np.array_equal(a.indices, b.indices), "indices differ"
+    rows = np.repeat(np.arange(b.shape[0]), np.diff(b.indptr))
+    scale = np.zeros(b.shape[0])
+    np.maximum.at(scale, rows, np.abs(b.data))
+    scale[scale == 0] = 1.0
+    err = np.max(np.abs(a.data - b.data) / scale[rows]) if len(rows) else 0.0
+    assert err <= rtol, f"row-scaled value error {err:.3e} > {rtol:.1e}"
