@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- assembled Melem/s + PCG DOF-iters/s on the synthetic 16 M-triangle plane-stress
+mesh (BASELINE.json metric; SURVEY.md §8d defines inputs and algorithmic bytes).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference ...                     # CPU baseline (oracle port)
+
+One "step" = one numeric assembly of the whole mesh (pattern cached, as in a nonlinear /
+time-stepping loop) + in-place Dirichlet elimination + `--pcg-iters` Jacobi-PCG iterations.
+`value` is the assembly throughput (Melem/s = E / t_assembly); the PCG throughput of the same
+step is reported under "pcg".  Both are timed with CUDA events on the launching stream, max
+over ranks.  Inputs (vals 1.9 GB, coords/conn 0.3 GB at S16M) exceed the 126 MB L2, so no
+explicit flush is needed between iterations (config.l2: "inputs_larger_than_l2").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "assembled Melem/s + PCG DOF-iters/s, 16M-tri plane stress"
+MAT = np.array([[210e9, 0.25, 1.0, 7860.0]])  # scripts/Elasticity/beam2d_example_2.py:35
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback"
+
+
+def asm_bytes(n_el, n_nodes, nnz):
+    return 12.0 * n_el + 16.0 * n_nodes + 8.0 * nnz
+
+
+def pcg_bytes_per_iter(n, nnz):
+    return 12.0 * nnz + 108.0 * n
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(nx, ny, pcg_iters):
+    """Oracle port (vectorised numpy/scipy restatement of the reference) on a bounded sample:
+    a (nx x ny)-cell structured mesh of the same family.  Single process; numpy/scipy sparse
+    kernels are single-threaded, so cores = 1."""
+    from oracle import numpy_oracle as no
+    coords, conn = no.structured_mesh(nx, ny)
+    mat_id = np.zeros(len(conn), dtype=np.int32)
+    t0 = time.perf_counter()
+    k = no.assemble_k(no.KIND_ELAST_PSTRESS, coords, conn, mat_id, MAT)
+    t_asm = time.perf_counter() - t0
+    n = k.shape[0]
+    left = np.arange(ny + 1) * (nx + 1)
+    bc = np.stack([2 * left, 2 * left + 1], axis=1).reshape(-1)
+    f = np.zeros(n)
+    f[2 * (left + nx) + 1] = -1000.0 / ny
+    ke, b = no.eliminate_dirichlet(k, f, bc, np.zeros(len(bc)))
+    t0 = time.perf_counter()
+    no.jacobi_pcg(ke, b, rtol=0.0, maxit=pcg_iters)
+    t_pcg = time.perf_counter() - t0
+    return dict(melem_s=len(conn) / t_asm / 1e6, dof_iters_s=n * pcg_iters / t_pcg, t_asm=t_asm, t_pcg=t_pcg,
+                n_el=len(conn), n=n, sample=f"{nx}x{ny}-cell structured plane-stress mesh ({len(conn)} triangles): "
+                f"1 numpy/scipy assembly (COO->CSR) + {pcg_iters} Jacobi-PCG iterations")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, t_asm, t_pcg = max(1, args.steps), [], []
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(args.cpu_nx, args.cpu_ny, 2)
+    for _ in range(steps):
+        r = cpu_baseline(args.cpu_nx, args.cpu_ny, args.cpu_pcg_iters)
+        t_asm.append(r["t_asm"])
+        t_pcg.append(r["t_pcg"])
+    melem = r["n_el"] / np.mean(t_asm) / 1e6
+    dofit = r["n"] * args.cpu_pcg_iters / np.mean(t_pcg)
+    line = {"impl": "reference", "metric": METRIC, "value": melem, "unit": "Melem/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * (np.mean(t_asm) + np.mean(t_pcg)),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"S16M family, bounded sample: {r['sample']}"},
+            "pcg": {"dof_iters_per_s": dofit, "iters": args.cpu_pcg_iters},
+            "cpu_baseline": {"value": melem, "unit": "Melem/s", "cores": 1, "kind": "port", "sample": r["sample"],
+                             "pcg_dof_iters_per_s": dofit},
+            "e2e": {"value": melem, "unit": "Melem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from finite_elements_b200.device import DeviceMesh, Context, KIND_ELAST_PSTRESS
+    from finite_elements_b200.mesh import structured_mesh_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        from finite_elements_b200 import dist as fe_dist
+        dist.init_process_group("nccl", device_id=dev)
+        return fe_dist.bench_distributed(args, METRIC, MAT, measured_peak_hbm, ClockSampler, asm_bytes,
+                                         pcg_bytes_per_iter)
+
+    nx, ny = args.nx, args.ny
+    ctx = Context.get(local_rank)
+    coords, conn = structured_mesh_torch(nx, ny, dev)
+    n_el, n_nodes = conn.shape[0], coords.shape[0]
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    t0 = time.perf_counter()
+    dm = DeviceMesh(coords, conn, None, dim=2, device=local_rank, ctx=ctx)
+    rowptr, colidx = dm.csr_pattern()
+    torch.cuda.synchronize()
+    plan_ms = 1e3 * (time.perf_counter() - t0)
+    n, nnz = dm.n_rows, dm.nnz
+
+    left = torch.arange(ny + 1, device=dev) * (nx + 1)
+    bc = torch.stack([2 * left, 2 * left + 1], dim=1).reshape(-1).int()
+    bc_val = torch.zeros(bc.numel(), dtype=torch.float64, device=dev)
+    f = torch.zeros(n, dtype=torch.float64, device=dev)
+    f[2 * (left + nx) + 1] = -1000.0 / ny
+    vals = torch.empty(nnz, dtype=torch.float64, device=dev)
+    rhs = torch.empty_like(f)
+    x = torch.zeros_like(f)
+    work = dm.pcg_workspace()
+
+    def step(timers=None):
+        a0, a1, p0, p1 = ev(), ev(), ev(), ev()
+        a0.record()
+        dm.assemble(KIND_ELAST_PSTRESS, MAT_DEV, out=vals, variant=args.variant)
+        a1.record()
+        rhs.copy_(f)
+        dm.dirichlet(vals, rhs, bc, bc_val)
+        x.zero_()
+        p0.record()
+        dm.pcg_fixed(vals, rhs, x, args.pcg_iters, work=work)
+        p1.record()
+        if timers is not None:
+            timers.append((a0, a1, p0, p1))
+
+    MAT_DEV = torch.as_tensor(MAT).to(dev)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launches
+    timers = []
+    s0, s1 = ev(), ev()
+    torch.cuda.synchronize()
+    s0.record()
+    for _ in range(args.steps):
+        step(timers)
+    s1.record()
+    torch.cuda.synchronize()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop()
+    t_asm = np.mean([a0.elapsed_time(a1) for a0, a1, _, _ in timers]) * 1e-3
+    t_pcg = np.mean([p0.elapsed_time(p1) for _, _, p0, p1 in timers]) * 1e-3
+    ms_per_step = s0.elapsed_time(s1) / args.steps
+
+    # ---- end to end through the public array API with HOST buffers (pinned) ----------
+    h_coords = coords.cpu().pin_memory()
+    h_vals = torch.empty(nnz, dtype=torch.float64).pin_memory()
+    h_rhs = f.cpu().pin_memory()
+    h_x = torch.empty(n, dtype=torch.float64).pin_memory()
+    e2e_asm, e2e_pcg = [], []
+    for it in range(1 + max(1, min(args.steps, 3))):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dm.coords.copy_(h_coords, non_blocking=True)                 # H2D: geometry of this step
+        dm.assemble(KIND_ELAST_PSTRESS, MAT_DEV, out=vals, variant=args.variant)
+        h_vals.copy_(vals, non_blocking=True)                        # D2H: the assembled matrix values
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        rhs.copy_(h_rhs, non_blocking=True)                          # H2D: right-hand side
+        dm.dirichlet(vals, rhs, bc, bc_val)
+        x.zero_()
+        dm.pcg_fixed(vals, rhs, x, args.pcg_iters, work=work)
+        h_x.copy_(x, non_blocking=True)                              # D2H: the solution vector
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        if it > 0:
+            e2e_asm.append(t1 - t0)
+            e2e_pcg.append(t2 - t1)
+
+    # ---- one full solve to 1e-8 (reported, outside the timed steps) -------------------
+    solve = None
+    if args.full_solve:
+        dm.assemble(KIND_ELAST_PSTRESS, MAT_DEV, out=vals, variant=args.variant)
+        rhs.copy_(f)
+        dm.dirichlet(vals, rhs, bc, bc_val)
+        x.zero_()
+        q0, q1 = ev(), ev()
+        q0.record()
+        _, iters, relres = dm.pcg(vals, rhs, x=x, rtol=1e-8, work=work, raise_on_maxit=False)
+        q1.record()
+        torch.cuda.synchronize()
+        true_res = float(torch.linalg.norm(rhs - dm.spmv(vals, x)) / torch.linalg.norm(rhs))
+        ts = q0.elapsed_time(q1) * 1e-3
+        solve = {"rtol": 1e-8, "iters": iters, "relres": relres, "true_relres": true_res, "seconds": ts,
+                 "dof_iters_per_s": n * iters / ts if ts > 0 else None}
+
+    peak, peak_kind = measured_peak_hbm()
+    a_bytes, p_bytes = asm_bytes(n_el, n_nodes, nnz), pcg_bytes_per_iter(n, nnz)
+    asm_gbs = a_bytes / t_asm / 1e9
+    pcg_gbs = p_bytes * args.pcg_iters / t_pcg / 1e9
+    line = {
+        "metric": METRIC, "value": n_el / t_asm / 1e6, "unit": "Melem/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"S16M-family structured plane-stress mesh {nx}x{ny} cells: {n_el} triangles, "
+                               f"{n_nodes} nodes, {n} DOF, nnz {nnz}; step = numeric assembly + Dirichlet + "
+                               f"{args.pcg_iters} Jacobi-PCG iterations",
+                   "nx": nx, "ny": ny, "pcg_iters_per_step": args.pcg_iters, "l2": "inputs_larger_than_l2",
+                   "assembly_variant": args.variant, "pattern_build_ms": plan_ms},
+        "assembly": {"ms": 1e3 * t_asm, "melem_per_s": n_el / t_asm / 1e6, "algorithmic_bytes": a_bytes},
+        "pcg": {"dof_iters_per_s": n * args.pcg_iters / t_pcg, "ms_per_iter": 1e3 * t_pcg / args.pcg_iters,
+                "iters": args.pcg_iters, "algorithmic_bytes_per_iter": p_bytes,
+                "roofline": {"bound": "hbm", "achieved": pcg_gbs, "peak": peak, "unit": "GB/s",
+                             "frac": pcg_gbs / peak, "traffic": None, "peak_kind": peak_kind}},
+        "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
+                     "traffic": None, "peak_kind": peak_kind, "kernel": "k_assemble_tile<0>"},
+        "e2e": {"value": n_el / np.mean(e2e_asm) / 1e6, "unit": "Melem/s",
+                "h2d_bytes_per_step": int(h_coords.numel() * 8 + h_rhs.numel() * 8),
+                "d2h_bytes_per_step": int(h_vals.numel() * 8 + h_x.numel() * 8),
+                "assembly_ms": 1e3 * float(np.mean(e2e_asm)), "pcg_ms": 1e3 * float(np.mean(e2e_pcg)),
+                "pcg_dof_iters_per_s": n * args.pcg_iters / float(np.mean(e2e_pcg))},
+        "gpu_launches": int(launches), "clocks": clocks, "solve": solve,
+    }
+    if not args.no_cpu_baseline:
+        cb = cpu_baseline(args.cpu_nx, args.cpu_ny, args.cpu_pcg_iters)
+        line["cpu_baseline"] = {"value": cb["melem_s"], "unit": "Melem/s", "cores": 1, "kind": "port",
+                                "sample": cb["sample"], "pcg_dof_iters_per_s": cb["dof_iters_s"]}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=4096)
+    ap.add_argument("--ny", type=int, default=2048)
+    ap.add_argument("--pcg-iters", type=int, default=50)
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--full-solve", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-nx", type=int, default=1024)
+    ap.add_argument("--cpu-ny", type=int, default=512)
+    ap.add_argument("--cpu-pcg-iters", type=int, default=20)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

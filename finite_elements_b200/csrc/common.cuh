@@ -1,0 +1,127 @@
+// Internals shared by every translation unit of libfe_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/fe_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libfe_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace fe {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---- thread-local error text --------------------------------------------------------
+char *last_error_buf();
+int fail(int code, const char *fmt, ...);
+
+#define FE_CUDA(call)                                                                     \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return fe::fail(FE_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,   \
+                      cudaGetErrorString(e__));                                           \
+  } while (0)
+
+#define FE_LAUNCH_CHECK(ctx)                                                              \
+  do {                                                                                    \
+    (ctx)->launches++;                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ != cudaSuccess)                                                               \
+      return fe::fail(FE_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__,         \
+                      __LINE__, cudaGetErrorString(e__));                                 \
+  } while (0)
+
+#define FE_REQUIRE(cond, ...)                                                             \
+  do {                                                                                    \
+    if (!(cond)) return fe::fail(FE_ERR_ARG, __VA_ARGS__);                                \
+  } while (0)
+
+// grow-only device scratch buffer
+struct Scratch {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need) {
+    if (need <= bytes) return FE_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    size_t want = need + need / 8 + 256;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) return fail(FE_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    bytes = want;
+    return FE_OK;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+};
+
+}  // namespace fe
+
+struct fe_ctx {
+  int device = 0;
+  int num_sms = fe::kNumSMs;
+  int64_t launches = 0;
+  fe::Scratch scratch_a;   // material tables, BC flags, scan block sums
+  fe::Scratch scratch_b;   // reduction partials / PCG scalars
+  void *pinned = nullptr;  // small pinned host buffer for scalar read-back
+  // multi-GPU
+  void *nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+  fe::Scratch halo_send, halo_recv;
+};
+
+namespace fe {
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int grid_for(int64_t work, int block) {
+  int64_t g = (work + block - 1) / block;
+  return (int)(g < 1 ? 1 : g);
+}
+
+// Exclusive scan of int32 counts -> int32 offsets (out[n] = total), total also returned as
+// int64 in *total_dev (device).  in/out may alias.  Uses ctx->scratch_a.
+int exclusive_scan_i32(fe_ctx *ctx, cudaStream_t st, const int32_t *in, int32_t *out, int64_t n,
+                       int64_t *total_dev);
+
+// ---- device helpers -----------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum in a fixed order (warp shuffles, then warp 0 over the per-warp partials):
+// the result depends only on blockDim, never on scheduling.  Valid in thread 0.
+template <int BLOCK>
+__device__ __forceinline__ double block_sum(double v, double *smem /* BLOCK/32 doubles */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (lane < BLOCK / 32) ? smem[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ int2 ldg_nc_int2(const int2 *p) {
+  int2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+#endif
+
+}  // namespace fe

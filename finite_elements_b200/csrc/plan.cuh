@@ -1,0 +1,27 @@
+// fe_plan: per-mesh symbolic data built once by fe_plan_create (plan.cu) and consumed by
+// the numeric assembly kernels (assemble.cu).
+#pragma once
+#include "common.cuh"
+
+struct fe_plan {
+  fe_ctx *ctx = nullptr;
+  int32_t n_nodes = 0, n_owned = 0, dim = 0;
+  int64_t n_elems = 0;
+  int64_t n_corners = 0;  // (element, local vertex) pairs whose vertex is an owned node
+  int64_t nnzb = 0;       // node-level adjacency entries (incl. self) over owned rows
+  int64_t nnz = 0;        // nnzb * dim * dim
+  int32_t max_degree = 0;
+  int64_t bytes = 0;
+  // node -> corners, counting-sorted by node, ascending element id within a node
+  int32_t *corner_ptr = nullptr;  // [n_owned + 1]
+  // corner record: .x = (elem << 2) | local_vertex
+  //                .y = k0 | k1 << 8 | k2 << 16 | first0 << 24 | first1 << 25 | first2 << 26
+  //   k_j   = position of the element's j-th vertex in this node's sorted adjacency list
+  //   first_j = this corner is the first (lowest element id) contributor to that block
+  int2 *corner_rec = nullptr;  // [n_corners]
+  // node-level sorted unique adjacency (block-CSR pattern of the owned rows)
+  int32_t *adj_ptr = nullptr;  // [n_owned + 1]
+  int32_t *adj = nullptr;      // [nnzb]
+  // connectivity padded to 16 B with the material id: one LDG.128 per corner visit
+  int4 *conn4 = nullptr;  // [n_elems] {n0, n1, n2, mat_id}
+};

@@ -1,0 +1,438 @@
+// Boundary conditions in place, CSR SpMV and the Jacobi-preconditioned CG.
+//
+// Replaces, on the eliminated SPD system, scipy.sparse.linalg.spsolve at
+// analysis.py:820-822 (SuperLU with NATURAL ordering: O(n * bandwidth^2), infeasible at
+// 16 M triangles) and the Lagrange rows of analysis.py:241-279 / :509-543.
+//
+// PCG iteration = 3 kernels, all scalars stay on the device:
+//   k_spmv<DOT>   q = A p, per-CTA partials of p.q, last CTA sums them in fixed order
+//   k_pcg_update  alpha = rz/pq; x += alpha p; r -= alpha q; partials of r.D^-1 r and r.r
+//   k_pcg_pupdate beta = rz'/rz; p = D^-1 r + beta p; convergence flag for later kernels
+// HBM bytes per iteration: 12 nnz + 108 n.  After convergence the remaining
+// launches of a check interval exit at their first instruction.
+// Multi-GPU (dist.cu) inserts a halo exchange before k_spmv and an all-reduce after the
+// two reducing kernels; the kernels themselves are the same.
+#include <math.h>
+
+#include "common.cuh"
+#include "dist.h"
+
+namespace fe {
+
+// ---------------------------------------------------------------------------------------
+// device-resident solver state
+// ---------------------------------------------------------------------------------------
+struct PcgState {
+  double sums[8];   // [0] pq  [1] rz_new  [2] rr  [3] bnorm2   (all-reduced when nranks > 1)
+  double rz[2];     // r.z, double-buffered by iteration parity
+  double tol2;      // rtol^2
+  int iters;        // completed iterations
+  int converged;
+  int breakdown;
+  unsigned ticket;  // last-CTA election
+};
+
+constexpr int kRedBlock = 256;
+constexpr int kMaxPartials = 148 * 16;  // grids of the reducing kernels are capped to this
+
+// Sum `np` per-CTA partials (stride = number of quantities) in a fixed order.
+template <int NQ>
+__device__ __forceinline__ void final_reduce(const double *__restrict__ partials, int np, double *smem,
+                                             double *__restrict__ out) {
+  double acc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
+  for (int i = threadIdx.x; i < np; i += kRedBlock) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] += __ldcg(partials + (size_t)i * NQ + q);
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const double t = block_sum<kRedBlock>(acc[q], smem);
+    if (threadIdx.x == 0) out[q] = t;
+  }
+}
+
+// Writes this CTA's partials, elects the last CTA, which reduces all of them.
+template <int NQ>
+__device__ __forceinline__ void publish_and_reduce(const double (&local)[NQ], double *__restrict__ partials,
+                                                   PcgState *__restrict__ st, int out_base, double *smem) {
+  __shared__ bool is_last;
+  double tot[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) tot[q] = block_sum<kRedBlock>(local[q], smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) partials[(size_t)blockIdx.x * NQ + q] = tot[q];
+    __threadfence();
+    const unsigned t = atomicAdd(&st->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    final_reduce<NQ>(partials, gridDim.x, smem, st->sums + out_base);
+    if (threadIdx.x == 0) st->ticket = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// SpMV: LPR lanes per row (sub-warp), rows strided over a capped grid
+// ---------------------------------------------------------------------------------------
+template <int LPR, bool DOT>
+__global__ void __launch_bounds__(kRedBlock) k_spmv(int32_t n_rows, const int32_t *__restrict__ rowptr,
+                                                   const int32_t *__restrict__ colidx,
+                                                   const double *__restrict__ vals, const double *__restrict__ x,
+                                                   double *__restrict__ y, double *__restrict__ partials,
+                                                   PcgState *__restrict__ st) {
+  __shared__ double red[kRedBlock / 32];
+  if (DOT && (st->converged | st->breakdown)) return;
+  const int lane = threadIdx.x % LPR;
+  const int64_t rows_per_pass = (int64_t)gridDim.x * (kRedBlock / LPR);
+  double dot = 0.0;
+  for (int64_t row = (int64_t)blockIdx.x * (kRedBlock / LPR) + threadIdx.x / LPR;
+       row < (int64_t)((n_rows + kRedBlock / LPR - 1) / (kRedBlock / LPR)) * (kRedBlock / LPR); row += rows_per_pass) {
+    double acc = 0.0;
+    if (row < n_rows) {
+      const int32_t s = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+      for (int32_t j = s + lane; j < e; j += LPR) acc += vals[j] * __ldg(x + __ldg(colidx + j));
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (row < n_rows && lane == 0) {
+      y[row] = acc;
+      if (DOT) dot += acc * x[row];
+    }
+  }
+  if (DOT) {
+    const double loc[1] = {dot};
+    publish_and_reduce<1>(loc, partials, st, 0, red);
+  }
+}
+
+static int spmv_lpr(int32_t n_rows, int64_t nnz) {
+  const double avg = n_rows > 0 ? (double)nnz / n_rows : 1.0;
+  if (avg <= 6) return 4;
+  if (avg <= 20) return 8;
+  if (avg <= 48) return 16;
+  return 32;
+}
+
+static int reducing_grid(fe_ctx *ctx, int64_t work_items, int items_per_cta) {
+  int64_t g = (work_items + items_per_cta - 1) / items_per_cta;
+  const int64_t cap = (int64_t)ctx->num_sms * 16 < kMaxPartials ? (int64_t)ctx->num_sms * 16 : kMaxPartials;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+template <bool DOT>
+static int launch_spmv(fe_ctx *ctx, cudaStream_t s, int lpr, int32_t n_rows, const int32_t *rowptr,
+                       const int32_t *colidx, const double *vals, const double *x, double *y, double *partials,
+                       PcgState *st) {
+  const int grid = reducing_grid(ctx, n_rows, kRedBlock / lpr);
+  switch (lpr) {
+    case 4: k_spmv<4, DOT><<<grid, kRedBlock, 0, s>>>(n_rows, rowptr, colidx, vals, x, y, partials, st); break;
+    case 8: k_spmv<8, DOT><<<grid, kRedBlock, 0, s>>>(n_rows, rowptr, colidx, vals, x, y, partials, st); break;
+    case 16: k_spmv<16, DOT><<<grid, kRedBlock, 0, s>>>(n_rows, rowptr, colidx, vals, x, y, partials, st); break;
+    default: k_spmv<32, DOT><<<grid, kRedBlock, 0, s>>>(n_rows, rowptr, colidx, vals, x, y, partials, st); break;
+  }
+  FE_LAUNCH_CHECK(ctx);
+  return FE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// PCG vector kernels
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_extract_dinv(int32_t n_rows, const int32_t *__restrict__ rowptr,
+                                                     const int32_t *__restrict__ colidx,
+                                                     const double *__restrict__ vals, double *__restrict__ dinv,
+                                                     PcgState *__restrict__ st) {
+  const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  double d = 0.0;
+  for (int32_t j = rowptr[row]; j < rowptr[row + 1]; ++j)
+    if (colidx[j] == row) d = vals[j];
+  if (!(d > 0.0)) st->breakdown = 1;  // not SPD (e.g. no Dirichlet condition at all)
+  dinv[row] = 1.0 / d;
+}
+
+// r = b - q (q = A x0); p = D^-1 r; sums: rz_new, rr, bnorm2
+__global__ void __launch_bounds__(kRedBlock) k_pcg_init(int32_t n, const double *__restrict__ b,
+                                                       const double *__restrict__ q, const double *__restrict__ dinv,
+                                                       double *__restrict__ r, double *__restrict__ p,
+                                                       double *__restrict__ partials, PcgState *__restrict__ st) {
+  __shared__ double red[kRedBlock / 32];
+  double loc[3] = {0.0, 0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kRedBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kRedBlock) {
+    const double bi = b[i];
+    const double ri = bi - q[i];
+    const double zi = dinv[i] * ri;
+    r[i] = ri;
+    p[i] = zi;
+    loc[0] += ri * zi;
+    loc[1] += ri * ri;
+    loc[2] += bi * bi;
+  }
+  publish_and_reduce<3>(loc, partials, st, 1, red);
+}
+
+// after the (all-reduced) init sums: rz[0] = rz_new, convergence of the initial guess
+__global__ void k_pcg_init_finish(PcgState *st) {
+  st->rz[0] = st->sums[1];
+  if (!(st->sums[3] > 0.0) || st->sums[2] <= st->tol2 * st->sums[3]) st->converged = 1;
+}
+
+__global__ void __launch_bounds__(kRedBlock) k_pcg_update(int32_t n, int parity, const double *__restrict__ p,
+                                                         const double *__restrict__ q,
+                                                         const double *__restrict__ dinv, double *__restrict__ x,
+                                                         double *__restrict__ r, double *__restrict__ partials,
+                                                         PcgState *__restrict__ st) {
+  __shared__ double red[kRedBlock / 32];
+  if (st->converged | st->breakdown) return;
+  const double pq = st->sums[0];
+  if (!(pq > 0.0) || !isfinite(pq)) {  // uniform across the grid
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->breakdown = 1;
+    return;
+  }
+  const double alpha = st->rz[parity] / pq;
+  double loc[2] = {0.0, 0.0};
+  for (int64_t i = (int64_t)blockIdx.x * kRedBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kRedBlock) {
+    const double ri = r[i] - alpha * q[i];
+    x[i] += alpha * p[i];
+    r[i] = ri;
+    loc[0] += ri * (dinv[i] * ri);
+    loc[1] += ri * ri;
+  }
+  publish_and_reduce<2>(loc, partials, st, 1, red);
+}
+
+__global__ void __launch_bounds__(256) k_pcg_pupdate(int32_t n, int parity, const double *__restrict__ r,
+                                                    const double *__restrict__ dinv, double *__restrict__ p,
+                                                    PcgState *__restrict__ st) {
+  if (st->converged | st->breakdown) return;
+  const double rz_new = st->sums[1];
+  const double beta = rz_new / st->rz[parity];
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+    p[i] = dinv[i] * r[i] + beta * p[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->rz[parity ^ 1] = rz_new;
+    st->iters += 1;
+    if (st->sums[2] <= st->tol2 * st->sums[3]) st->converged = 1;
+  }
+}
+
+// NOTE on the flag race in k_pcg_pupdate: CTA 0 sets `converged` while other CTAs of the
+// same launch may still be at their entry test.  A CTA that sees the flag early skips its
+// part of the p update, which is harmless: once converged no later kernel reads p.
+
+__global__ void k_pcg_state_init(PcgState *st, double tol2) {
+  for (int i = 0; i < 8; ++i) st->sums[i] = 0.0;
+  st->rz[0] = st->rz[1] = 0.0;
+  st->tol2 = tol2;
+  st->iters = 0;
+  st->converged = 0;
+  st->breakdown = 0;
+  st->ticket = 0;
+}
+
+__global__ void k_copy(int64_t n, const double *__restrict__ a, double *__restrict__ b) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    b[i] = a[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// Dirichlet elimination in place
+// ---------------------------------------------------------------------------------------
+__global__ void k_bc_scatter(int32_t n_bc, int32_t n_cols, const int32_t *__restrict__ dof,
+                             const double *__restrict__ val, double *__restrict__ g, unsigned char *__restrict__ flag,
+                             int *__restrict__ bad) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_bc) return;
+  const int32_t d = dof[i];
+  if (d < 0 || d >= n_cols) {
+    *bad = 1;
+    return;
+  }
+  g[d] = val[i];
+  flag[d] = 1;
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256) k_bc_apply(int32_t n_rows, const int32_t *__restrict__ rowptr,
+                                                 const int32_t *__restrict__ colidx, double *__restrict__ vals,
+                                                 double *__restrict__ rhs, const double *__restrict__ g,
+                                                 const unsigned char *__restrict__ flag) {
+  const int64_t row = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPR;
+  const int lane = threadIdx.x % LPR;
+  double acc = 0.0;
+  bool row_bc = false;
+  if (row < n_rows) {
+    row_bc = flag[row];
+    const int32_t s = rowptr[row], e = rowptr[row + 1];
+    for (int32_t j = s + lane; j < e; j += LPR) {
+      const int32_t c = colidx[j];
+      if (row_bc) {
+        vals[j] = (c == row) ? 1.0 : 0.0;
+      } else if (flag[c]) {
+        acc += vals[j] * g[c];
+        vals[j] = 0.0;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (row < n_rows && lane == 0) rhs[row] = row_bc ? g[row] : (rhs[row] - acc);
+}
+
+__global__ void k_scatter_add(int32_t n, const int32_t *__restrict__ dof, const double *__restrict__ val,
+                              double *__restrict__ rhs) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rhs[dof[i]] += val[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// host driver shared by fe_pcg / fe_pcg_fixed / fe_dist_pcg
+// ---------------------------------------------------------------------------------------
+int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const int32_t *rowptr,
+              const int32_t *colidx, const double *vals, const double *b, double *x, double *work,
+              const HaloPlan *halo, double rtol, int32_t maxit, bool fixed, int32_t *iters_out, double *relres_out) {
+  FE_REQUIRE(ctx && rowptr && colidx && vals && b && x && work, "pcg: NULL argument");
+  FE_REQUIRE(n_rows >= 0 && n_cols >= n_rows, "pcg: bad sizes %d x %d", n_rows, n_cols);
+  FE_REQUIRE(maxit >= 0, "pcg: negative iteration count");
+  const bool dist = halo != nullptr && ctx->nranks > 1;
+  FE_CUDA(cudaSetDevice(ctx->device));
+  // workspace: r | q | dinv | p (p has the ghost tail)
+  double *r = work, *q = work + n_rows, *dinv = work + 2 * (int64_t)n_rows, *p = work + 3 * (int64_t)n_rows;
+  int rc = ctx->scratch_b.reserve(sizeof(PcgState) + 256 + (size_t)kMaxPartials * 3 * sizeof(double));
+  if (rc) return rc;
+  PcgState *st = (PcgState *)ctx->scratch_b.ptr;
+  double *partials = (double *)((char *)ctx->scratch_b.ptr + 256);
+  static_assert(sizeof(PcgState) <= 256, "PcgState too large");
+
+  int32_t h_rowptr_end = 0;
+  FE_CUDA(cudaMemcpyAsync(&h_rowptr_end, rowptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  k_pcg_state_init<<<1, 1, 0, s>>>(st, fixed ? -1.0 : rtol * rtol);
+  FE_LAUNCH_CHECK(ctx);
+  FE_CUDA(cudaStreamSynchronize(s));
+  const int lpr = spmv_lpr(n_rows, h_rowptr_end);
+  const int vgrid = reducing_grid(ctx, n_rows, kRedBlock * 4);
+
+  if (n_rows > 0) {
+    k_extract_dinv<<<grid_for(n_rows, 256), 256, 0, s>>>(n_rows, rowptr, colidx, vals, dinv, st);
+    FE_LAUNCH_CHECK(ctx);
+  }
+  // q = A x0 (x0 staged in p so that the ghost tail can be exchanged)
+  k_copy<<<reducing_grid(ctx, n_rows, 1024), 256, 0, s>>>(n_rows, x, p);
+  FE_LAUNCH_CHECK(ctx);
+  if (dist && (rc = halo_exchange(ctx, s, halo, p, n_rows))) return rc;
+  if ((rc = launch_spmv<false>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st))) return rc;
+  k_pcg_init<<<vgrid, kRedBlock, 0, s>>>(n_rows, b, q, dinv, r, p, partials, st);
+  FE_LAUNCH_CHECK(ctx);
+  if (dist && (rc = allreduce_sum(ctx, s, st->sums + 1, 3))) return rc;
+  k_pcg_init_finish<<<1, 1, 0, s>>>(st);
+  FE_LAUNCH_CHECK(ctx);
+
+  PcgState *h = (PcgState *)ctx->pinned;
+  const int check_every = fixed ? maxit : 50;
+  int it = 0;
+  bool done = false;
+  while (it < maxit && !done) {
+    const int chunk = (maxit - it < check_every) ? (maxit - it) : check_every;
+    for (int k = 0; k < chunk; ++k, ++it) {
+      const int parity = it & 1;
+      if (dist && (rc = halo_exchange(ctx, s, halo, p, n_rows))) return rc;
+      if ((rc = launch_spmv<true>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st))) return rc;
+      if (dist && (rc = allreduce_sum(ctx, s, st->sums + 0, 1))) return rc;
+      k_pcg_update<<<vgrid, kRedBlock, 0, s>>>(n_rows, parity, p, q, dinv, x, r, partials, st);
+      FE_LAUNCH_CHECK(ctx);
+      if (dist && (rc = allreduce_sum(ctx, s, st->sums + 1, 2))) return rc;
+      k_pcg_pupdate<<<vgrid, 256, 0, s>>>(n_rows, parity, r, dinv, p, st);
+      FE_LAUNCH_CHECK(ctx);
+    }
+    FE_CUDA(cudaMemcpyAsync(h, st, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
+    FE_CUDA(cudaStreamSynchronize(s));
+    done = h->converged || h->breakdown;
+  }
+  if (it == 0) {
+    FE_CUDA(cudaMemcpyAsync(h, st, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
+    FE_CUDA(cudaStreamSynchronize(s));
+  }
+  if (iters_out) *iters_out = h->iters;
+  if (relres_out) *relres_out = (h->sums[3] > 0.0) ? sqrt(h->sums[2] / h->sums[3]) : 0.0;
+  if (h->breakdown)
+    return fail(FE_ERR_BREAKDOWN, "pcg: breakdown after %d iterations (matrix not SPD or singular: p.Ap = %g)",
+                h->iters, h->sums[0]);
+  if (!fixed && !h->converged)
+    return fail(FE_ERR_NOT_CONVERGED, "pcg: not converged after %d iterations (relres %.3e > %.3e)", h->iters,
+                sqrt(h->sums[2] / h->sums[3]), rtol);
+  return FE_OK;
+}
+
+}  // namespace fe
+
+using namespace fe;
+
+extern "C" {
+
+int fe_dirichlet_apply(fe_ctx *ctx, void *stream, int32_t n_rows, int32_t n_cols, const int32_t *rowptr,
+                       const int32_t *colidx, double *vals, double *rhs, int32_t n_bc, const int32_t *bc_dof,
+                       const double *bc_val) {
+  FE_REQUIRE(ctx && rowptr && colidx && vals && rhs, "fe_dirichlet_apply: NULL argument");
+  FE_REQUIRE(n_rows >= 0 && n_cols >= n_rows && n_bc >= 0, "fe_dirichlet_apply: bad sizes");
+  if (n_bc == 0 || n_rows == 0) return FE_OK;
+  FE_REQUIRE(bc_dof && bc_val, "fe_dirichlet_apply: NULL condition arrays");
+  cudaStream_t s = as_stream(stream);
+  const size_t gbytes = ((size_t)n_cols * sizeof(double) + 255) / 256 * 256;
+  int rc = ctx->scratch_a.reserve(gbytes + (size_t)n_cols + 256);
+  if (rc) return rc;
+  double *g = (double *)ctx->scratch_a.ptr;
+  unsigned char *flag = (unsigned char *)ctx->scratch_a.ptr + gbytes;
+  int *bad = (int *)(flag + ((size_t)n_cols + 3) / 4 * 4);
+  FE_CUDA(cudaMemsetAsync(ctx->scratch_a.ptr, 0, gbytes + (size_t)n_cols + 8, s));
+  k_bc_scatter<<<grid_for(n_bc, 256), 256, 0, s>>>(n_bc, n_cols, bc_dof, bc_val, g, flag, bad);
+  FE_LAUNCH_CHECK(ctx);
+  int hbad = 0;
+  FE_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FE_CUDA(cudaStreamSynchronize(s));
+  FE_REQUIRE(!hbad, "fe_dirichlet_apply: a condition DOF is outside [0, %d)", n_cols);
+  k_bc_apply<8><<<grid_for((int64_t)n_rows * 8, 256), 256, 0, s>>>(n_rows, rowptr, colidx, vals, rhs, g, flag);
+  FE_LAUNCH_CHECK(ctx);
+  return FE_OK;
+}
+
+int fe_scatter_add(fe_ctx *ctx, void *stream, int32_t n, const int32_t *dof, const double *val, double *rhs) {
+  FE_REQUIRE(ctx && (n == 0 || (dof && val && rhs)), "fe_scatter_add: NULL argument");
+  if (n <= 0) return FE_OK;
+  k_scatter_add<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(n, dof, val, rhs);
+  FE_LAUNCH_CHECK(ctx);
+  return FE_OK;
+}
+
+int fe_spmv(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr, const int32_t *colidx,
+            const double *vals, const double *x, double *y) {
+  FE_REQUIRE(ctx && rowptr && colidx && vals && x && y, "fe_spmv: NULL argument");
+  if (n_rows <= 0) return FE_OK;
+  cudaStream_t s = as_stream(stream);
+  int32_t nnz = 0;
+  FE_CUDA(cudaMemcpyAsync(&nnz, rowptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  FE_CUDA(cudaStreamSynchronize(s));
+  return launch_spmv<false>(ctx, s, spmv_lpr(n_rows, nnz), n_rows, rowptr, colidx, vals, x, y, nullptr, nullptr);
+}
+
+int64_t fe_pcg_work_len(int32_t n_rows, int32_t n_cols) { return 3 * (int64_t)n_rows + (int64_t)n_cols; }
+
+int fe_pcg(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr, const int32_t *colidx, const double *vals,
+           const double *b, double *x, double *work, double rtol, int32_t maxit, int32_t *iters, double *relres) {
+  return pcg_drive(ctx, as_stream(stream), n, n, rowptr, colidx, vals, b, x, work, nullptr, rtol, maxit, false, iters,
+                   relres);
+}
+
+int fe_pcg_fixed(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr, const int32_t *colidx,
+                 const double *vals, const double *b, double *x, double *work, int32_t iters) {
+  int32_t done = 0;
+  double rel = 0.0;
+  return pcg_drive(ctx, as_stream(stream), n, n, rowptr, colidx, vals, b, x, work, nullptr, 0.0, iters, true, &done,
+                   &rel);
+}
+
+}  // extern "C"

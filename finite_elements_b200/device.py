@@ -1,0 +1,242 @@
+"""Array-level device API: flat mesh arrays in, CSR / solution tensors out.
+
+This is the layer `analysis.FiniteElementAnalysis` (the drop-in class surface) and
+bench.py sit on.  torch tensors are used only as device buffers; every computation is
+a call into libfe_b200.so through ctypes (finite_elements_b200/_lib.py).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, KIND_ELAST_PSTRESS, KIND_ELAST_PSTRAIN, KIND_MAGNETIC, KIND_MASS  # noqa: F401
+
+
+def kind_dim(kind):
+    return 1 if kind == KIND_MAGNETIC else 2
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Context:
+    """One fe_ctx per (thread, device)."""
+
+    _cache = {}
+
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("finite_elements_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device)
+        h = C.c_void_p()
+        check(lib.fe_ctx_create(device, C.byref(h)))
+        self.handle = h
+
+    @classmethod
+    def get(cls, device=0):
+        if device not in cls._cache:
+            cls._cache[device] = cls(device)
+        return cls._cache[device]
+
+    @property
+    def launches(self):
+        return int(lib.fe_ctx_launch_count(self.handle))
+
+
+class DeviceMesh:
+    """Flat mesh on the device + the per-mesh plan (CSR pattern, corner->slot map).
+
+    coords f64[N,2], conn i32[E,3], mat_id i32[E] or None.  `n_owned` < N selects the
+    multi-GPU layout (owned nodes first, ghosts after; rows only for owned nodes)."""
+
+    def __init__(self, coords, conn, mat_id=None, dim=2, device=0, n_owned=None, ctx=None):
+        self.ctx = ctx or Context.get(device)
+        dev = self.ctx.device
+        self.coords = torch.as_tensor(np.ascontiguousarray(coords, dtype=np.float64)).to(dev) \
+            if not torch.is_tensor(coords) else coords.to(dev, torch.float64).contiguous()
+        self.conn = torch.as_tensor(np.ascontiguousarray(conn, dtype=np.int32)).to(dev) \
+            if not torch.is_tensor(conn) else conn.to(dev, torch.int32).contiguous()
+        if mat_id is None:
+            self.mat_id = None
+        else:
+            self.mat_id = torch.as_tensor(np.ascontiguousarray(mat_id, dtype=np.int32)).to(dev) \
+                if not torch.is_tensor(mat_id) else mat_id.to(dev, torch.int32).contiguous()
+        self.n_nodes = int(self.coords.shape[0])
+        self.n_elems = int(self.conn.shape[0])
+        self.n_owned = self.n_nodes if n_owned is None else int(n_owned)
+        self.dim = int(dim)
+        if self.coords.ndim != 2 or self.coords.shape[1] != 2:
+            raise ValueError("coords must have shape (N, 2)")
+        if self.n_elems and (self.conn.ndim != 2 or self.conn.shape[1] != 3):
+            raise ValueError("conn must have shape (E, 3)")
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            check(lib.fe_plan_create(self.ctx.handle, _stream(), self.n_nodes, self.n_owned, self.n_elems, self.dim,
+                                     _ptr(self.conn), _ptr(self.mat_id), C.byref(h)))
+        self.plan = h
+        self.nnz = int(lib.fe_plan_nnz(h))
+        self.n_rows = int(lib.fe_plan_n_rows(h))
+        self.n_cols = self.n_nodes * self.dim
+        self.max_degree = int(lib.fe_plan_max_degree(h))
+        self.plan_bytes = int(lib.fe_plan_bytes(h))
+        self._csr = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                lib.fe_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:  # interpreter shutdown
+            pass
+
+    # ---- pattern ---------------------------------------------------------------------
+    def csr_pattern(self):
+        """(rowptr i32[n_rows+1], colidx i32[nnz]) device tensors; canonical CSR."""
+        if self._csr is None:
+            dev = self.ctx.device
+            rowptr = torch.empty(self.n_rows + 1, dtype=torch.int32, device=dev)
+            colidx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)[:self.nnz]
+            with torch.cuda.device(dev):
+                check(lib.fe_plan_csr(self.plan, _stream(), _ptr(rowptr), _ptr(colidx)))
+            self._csr = (rowptr, colidx)
+        return self._csr
+
+    # ---- numeric ---------------------------------------------------------------------
+    def _mat(self, mat):
+        m = torch.as_tensor(np.ascontiguousarray(mat, dtype=np.float64)) if not torch.is_tensor(mat) else mat
+        m = m.to(self.ctx.device, torch.float64).contiguous()
+        if m.ndim != 2 or m.shape[1] != 4:
+            raise ValueError("mat must have shape (G, 4)")
+        return m
+
+    def assemble(self, kind, mat, out=None, variant=0):
+        """Global matrix values (CSR order of csr_pattern()).  fe_assemble."""
+        m = self._mat(mat)
+        if out is None:
+            out = torch.empty(max(self.nnz, 1), dtype=torch.float64, device=self.ctx.device)[:self.nnz]
+        with torch.cuda.device(self.ctx.device):
+            check(lib.fe_assemble(self.ctx.handle, _stream(), self.plan, int(kind), _ptr(self.coords), _ptr(m),
+                                  int(m.shape[0]), _ptr(out), int(variant)))
+        return out
+
+    def element_matrices(self, kind, mat):
+        """Per-element matrices f64[E, (3 dim)^2] (row-major Ke).  fe_elem_matrices."""
+        m = self._mat(mat)
+        nd = 3 * kind_dim(kind)
+        out = torch.empty((self.n_elems, nd * nd), dtype=torch.float64, device=self.ctx.device)
+        with torch.cuda.device(self.ctx.device):
+            check(lib.fe_elem_matrices(self.ctx.handle, _stream(), int(kind), self.n_elems, _ptr(self.coords),
+                                       _ptr(self.conn), _ptr(self.mat_id), _ptr(m), int(m.shape[0]), _ptr(out)))
+        return out
+
+    def source_factors(self, elem_sel=None):
+        """(factors f64[n,3], area f64[n]) for the selected elements.  fe_source_factors."""
+        dev = self.ctx.device
+        if elem_sel is None:
+            sel, n = None, self.n_elems
+        else:
+            sel = torch.as_tensor(np.ascontiguousarray(elem_sel, dtype=np.int32)).to(dev)
+            n = int(sel.numel())
+        fac = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        area = torch.empty(n, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.fe_source_factors(self.ctx.handle, _stream(), n, _ptr(sel), _ptr(self.coords), _ptr(self.conn),
+                                        _ptr(fac), _ptr(area)))
+        return fac, area
+
+    def dirichlet(self, vals, rhs, bc_dof, bc_val):
+        """In-place symmetric elimination on (vals, rhs).  fe_dirichlet_apply."""
+        dev = self.ctx.device
+        rowptr, colidx = self.csr_pattern()
+        d = torch.as_tensor(np.ascontiguousarray(bc_dof, dtype=np.int32)).to(dev) if not torch.is_tensor(bc_dof) \
+            else bc_dof.to(dev, torch.int32)
+        v = torch.as_tensor(np.ascontiguousarray(bc_val, dtype=np.float64)).to(dev) if not torch.is_tensor(bc_val) \
+            else bc_val.to(dev, torch.float64)
+        with torch.cuda.device(dev):
+            check(lib.fe_dirichlet_apply(self.ctx.handle, _stream(), self.n_rows, self.n_cols, _ptr(rowptr),
+                                         _ptr(colidx), _ptr(vals), _ptr(rhs), int(d.numel()), _ptr(d), _ptr(v)))
+
+    def scatter_add(self, rhs, dof, val):
+        dev = self.ctx.device
+        d = torch.as_tensor(np.ascontiguousarray(dof, dtype=np.int32)).to(dev)
+        v = torch.as_tensor(np.ascontiguousarray(val, dtype=np.float64)).to(dev)
+        with torch.cuda.device(dev):
+            check(lib.fe_scatter_add(self.ctx.handle, _stream(), int(d.numel()), _ptr(d), _ptr(v), _ptr(rhs)))
+
+    def spmv(self, vals, x, y=None):
+        rowptr, colidx = self.csr_pattern()
+        if y is None:
+            y = torch.empty(self.n_rows, dtype=torch.float64, device=self.ctx.device)
+        with torch.cuda.device(self.ctx.device):
+            check(lib.fe_spmv(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals),
+                              _ptr(x), _ptr(y)))
+        return y
+
+    def pcg_workspace(self):
+        n = int(lib.fe_pcg_work_len(self.n_rows, self.n_cols))
+        return torch.empty(n, dtype=torch.float64, device=self.ctx.device)
+
+    def pcg(self, vals, b, x=None, rtol=1e-8, maxit=None, work=None, raise_on_maxit=True):
+        """Jacobi-PCG on the (eliminated, SPD) system.  Returns (x, iters, relres)."""
+        rowptr, colidx = self.csr_pattern()
+        if x is None:
+            x = torch.zeros(self.n_rows, dtype=torch.float64, device=self.ctx.device)
+        if work is None:
+            work = self.pcg_workspace()
+        if maxit is None:
+            maxit = max(1000, 10 * self.n_rows)
+        iters, relres = C.c_int32(0), C.c_double(0.0)
+        with torch.cuda.device(self.ctx.device):
+            rc = lib.fe_pcg(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals), _ptr(b),
+                            _ptr(x), _ptr(work), float(rtol), int(min(maxit, 2 ** 31 - 1)), C.byref(iters),
+                            C.byref(relres))
+        if rc == _lib.FE_ERR_NOT_CONVERGED and not raise_on_maxit:
+            return x, iters.value, relres.value
+        check(rc)
+        return x, iters.value, relres.value
+
+    def pcg_fixed(self, vals, b, x, iters, work=None):
+        """Exactly `iters` PCG iterations, no convergence test (throughput runs)."""
+        rowptr, colidx = self.csr_pattern()
+        if work is None:
+            work = self.pcg_workspace()
+        with torch.cuda.device(self.ctx.device):
+            check(lib.fe_pcg_fixed(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals),
+                                   _ptr(b), _ptr(x), _ptr(work), int(iters)))
+        return x
+
+    # ---- convenience ------------------------------------------------------------------
+    def to_scipy(self, vals):
+        import scipy.sparse as sp
+        rowptr, colidx = self.csr_pattern()
+        return sp.csr_matrix((vals.cpu().numpy(), colidx.cpu().numpy(), rowptr.cpu().numpy()),
+                             shape=(self.n_rows, self.n_cols))
+
+
+def solve_dirichlet_system(dm, kind, mat, load_dof, load_val, bc_dof, bc_val, rtol=1e-12, maxit=None,
+                           variant=0, with_multipliers=True):
+    """assemble -> rhs -> eliminate -> PCG -> (u, lambda, iters, relres) on the device.
+
+    lambda = f_c - (K u)_c reproduces the Lagrange-multiplier tail of the reference's
+    augmented solve (analysis.py:272-277, :539-541)."""
+    dev = dm.ctx.device
+    vals = dm.assemble(kind, mat, variant=variant)
+    f = torch.zeros(dm.n_rows, dtype=torch.float64, device=dev)
+    if len(load_dof):
+        dm.scatter_add(f, load_dof, load_val)
+    rhs = f.clone()
+    dm.dirichlet(vals, rhs, bc_dof, bc_val)
+    u, iters, relres = dm.pcg(vals, rhs, rtol=rtol, maxit=maxit)
+    lam = None
+    if with_multipliers:
+        dm.assemble(kind, mat, out=vals, variant=variant)  # K again (the eliminated copy was overwritten in place)
+        ku = dm.spmv(vals, u)
+        idx = torch.as_tensor(np.asarray(bc_dof, dtype=np.int64)).to(dev)
+        lam = (f - ku)[idx]
+    return u, lam, iters, relres

@@ -1,0 +1,167 @@
+/*
+ * fe_b200.h -- C ABI of libfe_b200.so: the B200 (sm_100a) implementation of the
+ * data-parallel hot path of Dessia-tech/finite_elements v0.2.0.
+ *
+ * The reference is pure Python and has no FFI of its own: the
+ * seam is the Python class surface of finite_elements/analysis.py.  Each entry
+ * point below names the reference code (file:line under
+ * /root/reference/finite_elements/) whose work it replaces; the Python host
+ * layer (finite_elements_b200/analysis.py) keeps the reference's class names and
+ * calls these through ctypes.  INTEGRATION.md shows the binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *  - Every array pointer is a CUDA DEVICE pointer owned by the caller (torch
+ *    tensors' data_ptr()).  The library never frees or keeps caller buffers
+ *    beyond the call.  The library owns only fe_ctx (scratch, NCCL comm) and
+ *    fe_plan (the per-mesh symbolic data built once by fe_plan_create).
+ *  - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream()
+ *    .cuda_stream).  Calls are asynchronous on that stream unless stated.
+ *  - Return value: 0 = FE_OK, negative = error class; text via fe_last_error()
+ *    (thread-local).  No global mutable state; one ctx per (thread, device).
+ *  - Indices are int32 (all sizes on the path fit; fe_plan_create fails with
+ *    FE_ERR_UNSUPPORTED when nnz would overflow int32).  Values are FP64.
+ *  - DOF numbering: dof = node*dim + d  (core.py:89-108).
+ *  - conn is int32[E][3] in the reference's local order points[0..2];
+ *    coords is double[N][2]; mat_id int32[E] (may be NULL = all 0);
+ *    mat is double[G][4]: elasticity rows (E_modulus, poisson, thickness,
+ *    mass_density), magnetic rows (mu_total, -, -, -).
+ */
+#ifndef FE_B200_H
+#define FE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FE_B200_VERSION 100 /* 0.1.0 */
+
+typedef struct fe_ctx fe_ctx;
+typedef struct fe_plan fe_plan;
+
+enum fe_status {
+  FE_OK = 0,
+  FE_ERR_ARG = -1,           /* bad argument (maps to ValueError)                       */
+  FE_ERR_CUDA = -2,          /* CUDA runtime error (RuntimeError)                       */
+  FE_ERR_NCCL = -3,          /* NCCL error (RuntimeError)                               */
+  FE_ERR_NOT_CONVERGED = -4, /* PCG hit maxit (results still written)                   */
+  FE_ERR_BREAKDOWN = -5,     /* PCG: p.Ap <= 0 or non-finite (matrix not SPD / singular;
+                                 the reference raises NotImplementedError from
+                                 MatrixRankWarning, analysis.py:824-826)                */
+  FE_ERR_UNSUPPORTED = -6    /* size/valence outside the implemented range              */
+};
+
+/* elements.py:466-511 (plane stress / plane strain via :251-273), :93-118, :513-536 */
+enum fe_kind {
+  FE_ELAST_PSTRESS = 0, /* ElasticityTriangularElement2D.elementary_matrix(False, True) */
+  FE_ELAST_PSTRAIN = 1, /* ... (True, False)                                            */
+  FE_MAGNETIC = 2,      /* MagneticElement2D.elementary_matrix()                        */
+  FE_MASS = 3           /* ElasticityTriangularElement2D.elementary_mass_matrix()       */
+};
+
+int fe_version(void);
+const char *fe_last_error(void);
+
+int fe_ctx_create(int device, fe_ctx **out);
+int fe_ctx_destroy(fe_ctx *ctx);
+
+/* ---- per-element kernels (parity / debug / host-side element API) -------------------
+ * replaces elements.py:395-416 (_b_matrix), :418-453 (D), :466-511 / :93-118 / :513-536.
+ * out: double[E][(3*dim)^2] row-major, local DOF order [u0,v0,u1,v1,u2,v2] (or [n0,n1,n2]). */
+int fe_elem_matrices(fe_ctx *ctx, void *stream, int kind, int64_t n_elems, const double *coords,
+                     const int32_t *conn, const int32_t *mat_id, const double *mat, int32_t n_mat,
+                     double *out);
+
+/* replaces elements.py:18-53 / :156-191 (element_to_node_factors) for the elements listed
+ * in elem_sel (int32[n_sel], NULL = elements 0..n_sel-1).  out: double[n_sel][3].
+ * out_area (may be NULL): double[n_sel] = volmdlr TriangularElement2D.area (loads.py:31-34). */
+int fe_source_factors(fe_ctx *ctx, void *stream, int64_t n_sel, const int32_t *elem_sel,
+                      const double *coords, const int32_t *conn, double *out, double *out_area);
+
+/* ---- symbolic phase, once per mesh ----------------------------------------------------
+ * replaces analysis.py:714-735 (get_row_col_indices) for all elements plus the
+ * COO->CSR sort/unique scipy does at analysis.py:661 (pattern part).
+ * Builds, for rows of nodes [0, n_owned_nodes): the node->corner incidence (counting sort
+ * keyed by node, corners ordered by element id), the sorted unique node adjacency, and the
+ * corner->CSR-slot map used by fe_assemble.  n_owned_nodes == n_nodes on one GPU; on a
+ * rank of a partition, nodes are numbered owned-first and ghosts after, and `conn` lists
+ * every element incident to an owned node.  SYNCHRONISES the stream. */
+int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned_nodes,
+                   int64_t n_elems, int32_t dim, const int32_t *conn, const int32_t *mat_id,
+                   fe_plan **out);
+int fe_plan_destroy(fe_plan *plan);
+int64_t fe_plan_nnz(const fe_plan *plan);        /* nnz of the (n_owned*dim) x (n_nodes*dim) CSR */
+int32_t fe_plan_n_rows(const fe_plan *plan);     /* n_owned_nodes * dim                         */
+int32_t fe_plan_max_degree(const fe_plan *plan); /* max node valence incl. self                  */
+int64_t fe_plan_bytes(const fe_plan *plan);      /* device bytes held by the plan                */
+/* Canonical CSR pattern (sorted columns, explicit zeros kept): bit-exact with
+ * scipy.sparse.csr_matrix((data,(row,col))) of analysis.py:661 on the K block.
+ * rowptr int32[n_rows+1], colidx int32[nnz]. */
+int fe_plan_csr(const fe_plan *plan, void *stream, int32_t *rowptr, int32_t *colidx);
+
+/* ---- numeric assembly ----------------------------------------------------------------
+ * replaces analysis.py:324-339 (k_matrix_data) / :357-365 (m_matrix_data) and the
+ * duplicate summation of analysis.py:661 / :387-405.  Deterministic: every CSR slot is
+ * summed by one thread in a fixed (element id) order, no atomics.  vals double[nnz] is
+ * fully overwritten.  variant: 0 = default (fastest available), 1 = generic row-owner
+ * kernel (accumulates in global memory), 2 = shared-memory staged tiles. */
+int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *plan, int kind, const double *coords,
+                const double *mat, int32_t n_mat, double *vals, int variant);
+
+/* ---- boundary conditions --------------------------------------------------------------
+ * The reference appends Lagrange rows (analysis.py:241-279, :509-543).  On the solution
+ * block that system is equivalent to symmetric elimination, done here in
+ * place on the caller's CSR: rhs -= K[:,c] g, row/col c zeroed, K[c,c] = 1, rhs[c] = g.
+ * bc_dof int32[n_bc] (unique; local column numbering), bc_val double[n_bc].
+ * n_rows x n_cols CSR (n_cols >= n_rows; columns >= n_rows are ghost columns). */
+int fe_dirichlet_apply(fe_ctx *ctx, void *stream, int32_t n_rows, int32_t n_cols,
+                       const int32_t *rowptr, const int32_t *colidx, double *vals, double *rhs,
+                       int32_t n_bc, const int32_t *bc_dof, const double *bc_val);
+
+/* rhs[dof[i]] += val[i] (analysis.py:698-702); dof unique => deterministic. */
+int fe_scatter_add(fe_ctx *ctx, void *stream, int32_t n, const int32_t *dof, const double *val,
+                   double *rhs);
+
+/* ---- solve ---------------------------------------------------------------------------
+ * y = A x, CSR, sub-warp-per-row vectorised. */
+int fe_spmv(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
+            const int32_t *colidx, const double *vals, const double *x, double *y);
+
+/* Jacobi-preconditioned CG; replaces scipy spsolve at analysis.py:820-822 on the
+ * eliminated SPD system.  x: initial guess in, solution out.  work: double[fe_pcg_work_len(n)].
+ * Stops when ||r||_2 <= rtol * ||b||_2.  SYNCHRONISES the stream; writes iters / relres. */
+int64_t fe_pcg_work_len(int32_t n_rows, int32_t n_cols);
+int fe_pcg(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr, const int32_t *colidx,
+           const double *vals, const double *b, double *x, double *work, double rtol,
+           int32_t maxit, int32_t *iters, double *relres);
+/* Runs exactly `iters` PCG iterations with no convergence test (throughput measurement). */
+int fe_pcg_fixed(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr,
+                 const int32_t *colidx, const double *vals, const double *b, double *x,
+                 double *work, int32_t iters);
+
+/* ---- multi-GPU (one process per GPU) --------------------------------------
+ * nccl_unique_id: 128 bytes from ncclGetUniqueId on rank 0 (fe_dist_unique_id), broadcast
+ * by the host (torch.distributed). */
+int fe_dist_unique_id(void *out128);
+int fe_dist_init(fe_ctx *ctx, const void *nccl_unique_id, int32_t rank, int32_t nranks);
+/* Halo description (device int32 arrays unless noted):
+ *  n_nbr neighbours; nbr_rank (HOST int32[n_nbr]);
+ *  send_ptr (HOST int32[n_nbr+1]) into send_idx (device; owned local DOFs to pack);
+ *  recv_ptr (HOST int32[n_nbr+1]): ghost DOFs received from neighbour k occupy local columns
+ *  n_rows + recv_ptr[k] .. n_rows + recv_ptr[k+1].
+ * work: double[fe_pcg_work_len(n_rows, n_cols)]. */
+int fe_dist_pcg(fe_ctx *ctx, void *stream, int32_t n_rows, int32_t n_cols, const int32_t *rowptr,
+                const int32_t *colidx, const double *vals, const double *b, double *x,
+                double *work, int32_t n_nbr, const int32_t *nbr_rank, const int32_t *send_ptr,
+                const int32_t *send_idx, const int32_t *recv_ptr, double rtol, int32_t maxit,
+                int32_t fixed_iters, int32_t *iters, double *relres);
+
+/* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
+int64_t fe_ctx_launch_count(const fe_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FE_B200_H */

@@ -1,0 +1,285 @@
+"""GPU parity: libfe_b200.so (through ctypes) against fixtures minted from the reference's
+own code (tests/golden) and against the numpy oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): CSR pattern bit-exact; element and global matrix entries
+within 1e-12 (relative to the row maximum, so structurally-present zeros are covered);
+solutions within 1e-8 relative to the reference's spsolve.
+"""
+import numpy as np
+import pytest
+
+from tests.fixtures import Fixture, names, assert_close_rowscaled, assert_csr_values_close
+
+pytestmark = pytest.mark.gpu
+
+ALL = names()
+
+
+def _dm(fx, **kw):
+    from finite_elements_b200.device import DeviceMesh
+    return DeviceMesh(fx.coords, fx.conn, fx.mat_id, dim=fx.dim, **kw)
+
+
+def _kind(fx):
+    return fx.oracle_kind  # numeric values are shared with include/fe_b200.h
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_element_matrices_vs_reference(name):
+    from finite_elements_b200.device import KIND_MASS
+    fx = Fixture(name)
+    dm = _dm(fx)
+    ke = dm.element_matrices(_kind(fx), fx.mat).cpu().numpy()
+    assert_close_rowscaled(ke, fx.ref("ke"), 1e-12)
+    if fx.kind == "elasticity":
+        me = dm.element_matrices(KIND_MASS, fx.mat).cpu().numpy()
+        assert_close_rowscaled(me, fx.ref("me"), 1e-12)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_source_factors_vs_reference(name):
+    fx = Fixture(name)
+    dm = _dm(fx)
+    fac, area = dm.source_factors()
+    fac, area = fac.cpu().numpy(), area.cpu().numpy()
+    ref = fx.ref("factors")
+    tol = 1e-12 * (2 * area) * max(1.0, np.abs(fx.coords).max()) ** 2 / np.minimum(1.0, 2 * area)
+    assert np.all(np.abs(fac - ref) <= tol[:, None] + 1e-12 * np.abs(ref))
+    sel = np.arange(len(fx.conn))[::3].astype(np.int32)
+    fac2, _ = dm.source_factors(sel)
+    assert np.array_equal(fac2.cpu().numpy(), fac[sel])
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_pattern_bit_exact_and_values(name):
+    from finite_elements_b200.device import KIND_MASS
+    fx = Fixture(name)
+    dm = _dm(fx)
+    ref_k = fx.csr("k")
+    rowptr, colidx = dm.csr_pattern()
+    assert dm.nnz == ref_k.nnz
+    assert np.array_equal(rowptr.cpu().numpy(), ref_k.indptr)
+    assert np.array_equal(colidx.cpu().numpy(), ref_k.indices)
+    v1 = dm.assemble(_kind(fx), fx.mat, variant=1)
+    v2 = dm.assemble(_kind(fx), fx.mat, variant=2)
+    v0 = dm.assemble(_kind(fx), fx.mat, variant=0)
+    assert np.array_equal(v1.cpu().numpy(), v2.cpu().numpy()), "kernel variants must agree bit for bit"
+    assert np.array_equal(v0.cpu().numpy(), v2.cpu().numpy())
+    assert_csr_values_close(dm.to_scipy(v2), ref_k, 1e-12)
+    if fx.kind == "elasticity":
+        m = dm.assemble(KIND_MASS, fx.mat)
+        assert_csr_values_close(dm.to_scipy(m), fx.csr("m"), 1e-12)
+
+
+@pytest.mark.parametrize("name", ["struct24x16_jit_pstress", "gmsh_beam_0.1", "semantics_mag"])
+def test_assembly_is_ordered_sum_of_element_matrices(name):
+    """Determinism contract: every slot = sum of its element contributions in ascending
+    element order, bit for bit (the CPU replays the same additions on the GPU's Ke dump)."""
+    fx = Fixture(name)
+    dm = _dm(fx)
+    ke = dm.element_matrices(_kind(fx), fx.mat).cpu().numpy()
+    vals = dm.assemble(_kind(fx), fx.mat).cpu().numpy()
+    again = dm.assemble(_kind(fx), fx.mat).cpu().numpy()
+    assert np.array_equal(vals, again), "two runs must be bit-identical"
+    k = dm.to_scipy(dm.assemble(_kind(fx), fx.mat))
+    from oracle import numpy_oracle as no
+    rows, cols = no.triplet_indices(fx.conn, fx.dim)
+    # slot index of every triplet in the canonical CSR
+    slot = np.empty(rows.size, dtype=np.int64)
+    r, c = rows.reshape(-1), cols.reshape(-1)
+    for t in range(rows.size):
+        s, e = k.indptr[r[t]], k.indptr[r[t] + 1]
+        slot[t] = s + np.searchsorted(k.indices[s:e], c[t])
+    acc = np.zeros(k.nnz)
+    first = np.ones(k.nnz, dtype=bool)
+    flat = ke.reshape(-1)
+    for t in range(rows.size):  # ascending element order, sequential fp64 adds
+        if first[slot[t]]:
+            acc[slot[t]] = flat[t]
+            first[slot[t]] = False
+        else:
+            acc[slot[t]] += flat[t]
+    assert np.array_equal(acc, vals)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_solution_vs_reference_spsolve(name):
+    from finite_elements_b200.device import solve_dirichlet_system
+    from oracle import numpy_oracle as no
+    fx = Fixture(name)
+    dm = _dm(fx)
+    ld, lv = no.loads_to_dof_records(fx.coords, fx.conn, fx.dim, fx.rec("node_loads"), fx.rec("elements_loads"),
+                                     fx.rec("edge_loads"))
+    bc_dofs, bc_vals = fx.ref("bc_dofs"), fx.ref("bc_vals")
+    u, lam, iters, relres = solve_dirichlet_system(dm, _kind(fx), fx.mat, ld, lv, bc_dofs, bc_vals, rtol=1e-13)
+    ref_x = fx.ref("x")
+    un = np.linalg.norm(ref_x[:fx.ndof])
+    err = np.linalg.norm(u.cpu().numpy() - ref_x[:fx.ndof]) / un
+    assert err <= 1e-8, f"solution error {err:.2e} after {iters} iterations (relres {relres:.1e})"
+    ln = np.linalg.norm(ref_x[fx.ndof:])
+    assert np.linalg.norm(lam.cpu().numpy() - ref_x[fx.ndof:]) <= 1e-6 * ln
+
+
+@pytest.mark.parametrize("name", ["gmsh_beam_0.3", "struct24x16_jit_mag"])
+def test_spmv_and_dirichlet_vs_scipy(name):
+    import torch
+    from oracle import numpy_oracle as no
+    fx = Fixture(name)
+    dm = _dm(fx)
+    vals = dm.assemble(_kind(fx), fx.mat)
+    k = dm.to_scipy(vals)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(fx.ndof)
+    y = dm.spmv(vals, torch.as_tensor(x).cuda()).cpu().numpy()
+    yr = k @ x
+    assert np.max(np.abs(y - yr)) <= 1e-13 * np.max(np.abs(yr))
+    f = rng.standard_normal(fx.ndof)
+    bc_dofs, bc_vals = fx.ref("bc_dofs"), rng.standard_normal(len(fx.ref("bc_dofs")))
+    rhs = torch.as_tensor(f.copy()).cuda()
+    dm.dirichlet(vals, rhs, bc_dofs, bc_vals)
+    ke, b = no.eliminate_dirichlet(k, f, bc_dofs, bc_vals)
+    assert_csr_values_close(dm.to_scipy(vals), ke, 1e-15)
+    assert np.max(np.abs(rhs.cpu().numpy() - b)) <= 1e-12 * np.max(np.abs(b))
+
+
+# ------------------------------------------------------------------ seeded mid-size vs oracle
+@pytest.mark.parametrize("kind_name,jitter", [("stress", 0.0), ("strain", 0.2), ("mag", 0.2), ("mass", 0.2)])
+def test_mid_size_vs_oracle(kind_name, jitter):
+    from oracle import numpy_oracle as no
+    from finite_elements_b200.device import DeviceMesh
+    coords, conn = no.structured_mesh(96, 64, jitter=jitter, seed=3)
+    rng = np.random.default_rng(5)
+    mat_id = rng.integers(0, 3, size=len(conn)).astype(np.int32)
+    if kind_name == "mag":
+        kind, mat = no.KIND_MAGNETIC, np.array([[4e-7 * np.pi * s, 0, 0, 0] for s in (1e5, 1, 5e4)])
+    else:
+        kind = {"stress": no.KIND_ELAST_PSTRESS, "strain": no.KIND_ELAST_PSTRAIN, "mass": no.KIND_MASS}[kind_name]
+        mat = np.array([[210e9, 0.25, 1.0, 7860], [70e9, 0.33, 0.5, 2700], [1e9, 0.45, 2.0, 1200]])
+    dm = DeviceMesh(coords, conn, mat_id, dim=no.kind_dim(kind))
+    k_ref = no.assemble_k(kind, coords, conn, mat_id, mat)
+    assert_csr_values_close(dm.to_scipy(dm.assemble(kind, mat)), k_ref, 1e-12)
+    ke = dm.element_matrices(kind, mat).cpu().numpy()
+    assert_close_rowscaled(ke, no.element_matrices(kind, coords, conn, mat_id, mat).reshape(len(conn), -1), 1e-12)
+
+
+def test_unstructured_shuffled_numbering_vs_oracle():
+    """Random node permutation + random element order + flipped orientations: nothing in
+    the plan may depend on the structured numbering."""
+    from oracle import numpy_oracle as no
+    from finite_elements_b200.device import DeviceMesh
+    coords, conn = no.structured_mesh(40, 30, jitter=0.25, seed=11)
+    rng = np.random.default_rng(12)
+    perm = rng.permutation(len(coords))
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    coords2 = coords[perm]
+    conn2 = inv[conn][rng.permutation(len(conn))].astype(np.int32)
+    flip = rng.random(len(conn2)) < 0.5
+    conn2[flip] = conn2[flip][:, [0, 2, 1]]
+    mat = np.array([[210e9, 0.25, 1.0, 7860]])
+    dm = DeviceMesh(coords2, conn2, None, dim=2)
+    k_ref = no.assemble_k(no.KIND_ELAST_PSTRESS, coords2, conn2, np.zeros(len(conn2), np.int32), mat)
+    assert_csr_values_close(dm.to_scipy(dm.assemble(no.KIND_ELAST_PSTRESS, mat)), k_ref, 1e-12)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_empty_single_isolated_and_fan():
+    from oracle import numpy_oracle as no
+    from finite_elements_b200.device import DeviceMesh
+    mat = np.array([[1.0, 0.3, 1.0, 1.0]])
+    dm = DeviceMesh(np.zeros((3, 2)), np.zeros((0, 3), np.int32), None, dim=2)
+    assert dm.nnz == 0 and np.array_equal(dm.csr_pattern()[0].cpu().numpy(), np.zeros(7, np.int32))
+    # one element + an isolated node (empty rows, as scipy gives)
+    coords = np.array([[0, 0], [1, 0], [0, 1], [5, 5]], float)
+    conn = np.array([[0, 1, 2]], np.int32)
+    dm = DeviceMesh(coords, conn, None, dim=2)
+    k_ref = no.assemble_k(no.KIND_ELAST_PSTRESS, coords, conn, np.zeros(1, np.int32), mat)
+    assert_csr_values_close(dm.to_scipy(dm.assemble(no.KIND_ELAST_PSTRESS, mat)), k_ref, 1e-12)
+    # fan: hub of valence 60 -> beyond the shared-memory tile variant, default must still work
+    nf = 60
+    ang = np.linspace(0, 2 * np.pi, nf, endpoint=False)
+    coords = np.vstack([[0.0, 0.0], np.stack([np.cos(ang), np.sin(ang)], axis=1)])
+    conn = np.array([[0, 1 + i, 1 + (i + 1) % nf] for i in range(nf)], np.int32)
+    dm = DeviceMesh(coords, conn, None, dim=2)
+    assert dm.max_degree == nf + 1
+    k_ref = no.assemble_k(no.KIND_ELAST_PSTRESS, coords, conn, np.zeros(nf, np.int32), mat)
+    assert_csr_values_close(dm.to_scipy(dm.assemble(no.KIND_ELAST_PSTRESS, mat)), k_ref, 1e-12)
+    with pytest.raises(NotImplementedError):
+        dm.assemble(no.KIND_ELAST_PSTRESS, mat, variant=2)
+
+
+def test_error_mapping():
+    from finite_elements_b200.device import DeviceMesh, KIND_MAGNETIC, KIND_ELAST_PSTRESS
+    import torch
+    coords = np.array([[0, 0], [1, 0], [0, 1]], float)
+    with pytest.raises(ValueError):
+        DeviceMesh(coords, np.array([[0, 1, 7]], np.int32), None, dim=2)  # node out of range
+    dm = DeviceMesh(coords, np.array([[0, 1, 2]], np.int32), None, dim=2)
+    with pytest.raises(ValueError):
+        dm.assemble(KIND_MAGNETIC, np.array([[1.0, 0, 0, 0]]))  # dim mismatch
+    # no Dirichlet condition + negative modulus -> not SPD -> the reference's NotImplementedError
+    vals = dm.assemble(KIND_ELAST_PSTRESS, np.array([[-1.0, 0.3, 1.0, 1.0]]))
+    with pytest.raises(NotImplementedError):
+        dm.pcg(vals, torch.ones(6, dtype=torch.float64, device="cuda"))
+
+
+# ------------------------------------------------------------------ size-independent properties at scale
+def _device_structured(nx, ny):
+    import torch
+    from finite_elements_b200.mesh import structured_mesh_torch
+    return structured_mesh_torch(nx, ny, device=torch.device("cuda", 0))
+
+
+@pytest.mark.parametrize("nx,ny", [(1024, 512), (4096, 2048)])
+def test_properties_at_baseline_sizes(nx, ny):
+    """S1M / S16M: nnz formula, sorted rows, symmetry, rigid-body null space,
+    mass sum, run-to-run determinism, PCG residual."""
+    import torch
+    from finite_elements_b200.device import DeviceMesh, KIND_ELAST_PSTRESS, KIND_MASS
+    coords, conn = _device_structured(nx, ny)
+    dm = DeviceMesh(coords, conn, None, dim=2)
+    n_nodes = (nx + 1) * (ny + 1)
+    n_el = 2 * nx * ny
+    edges = (3 * n_el + 2 * (nx + ny)) // 2
+    assert dm.nnz == 4 * (n_nodes + 2 * edges)
+    rowptr, colidx = dm.csr_pattern()
+    lens = (rowptr[1:] - rowptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(dm.n_rows, device="cuda"), lens)
+    same_row = rows[1:] == rows[:-1]
+    assert bool(torch.all(colidx[1:][same_row] > colidx[:-1][same_row])), "columns must be strictly increasing"
+    del same_row
+    mat = np.array([[210e9, 0.25, 1.0, 7860.0]])
+    vals = dm.assemble(KIND_ELAST_PSTRESS, mat)
+    assert torch.equal(vals, dm.assemble(KIND_ELAST_PSTRESS, mat))
+    scale = float(vals.abs().max())
+    # rigid modes: K [1,0,1,0..] = K [0,1,0,1..] = K (rotation) = 0
+    xy = coords.reshape(-1)
+    for mode in (torch.tensor([1.0, 0.0]), torch.tensor([0.0, 1.0])):
+        x = mode.double().cuda().repeat(n_nodes)
+        assert float(dm.spmv(vals, x).abs().max()) <= 1e-12 * scale
+    rot = torch.stack([-coords[:, 1], coords[:, 0]], dim=1).reshape(-1).contiguous()
+    assert float(dm.spmv(vals, rot).abs().max()) <= 1e-11 * scale * float(xy.abs().max())
+    # symmetry through x^T K y == y^T K x
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(dm.n_rows, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.rand(dm.n_rows, dtype=torch.float64, device="cuda", generator=g)
+    a, b = float(torch.dot(x, dm.spmv(vals, y))), float(torch.dot(y, dm.spmv(vals, x)))
+    assert abs(a - b) <= 1e-12 * abs(a)
+    # total mass per direction = rho * area * t
+    m = dm.assemble(KIND_MASS, mat)
+    ones_x = torch.tensor([1.0, 0.0]).double().cuda().repeat(n_nodes)
+    total = float(torch.dot(ones_x, dm.spmv(m, ones_x)))
+    assert abs(total - 7860.0 * (nx / ny) * 1.0) <= 1e-10 * total
+    del m
+    # clamp the left edge, load the right edge, solve to 1e-8, check the TRUE residual
+    h = 1.0 / ny
+    left = torch.arange(ny + 1, device="cuda") * (nx + 1)
+    bc = torch.stack([2 * left, 2 * left + 1], dim=1).reshape(-1).int()
+    f = torch.zeros(dm.n_rows, dtype=torch.float64, device="cuda")
+    f[2 * (left + nx) + 1] = -1000.0 * h
+    rhs = f.clone()
+    dm.dirichlet(vals, rhs, bc, torch.zeros(bc.numel(), dtype=torch.float64, device="cuda"))
+    u, iters, relres = dm.pcg(vals, rhs, rtol=1e-8)
+    true = float(torch.linalg.norm(rhs - dm.spmv(vals, u)) / torch.linalg.norm(rhs))
+    assert relres <= 1e-8 and true <= 2e-8, (iters, relres, true)
+    assert float(u[bc.long()].abs().max()) == 0.0
