@@ -41,14 +41,14 @@ SIGNATURES = {
     "fe_assemble": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _i32, _vp, C.c_int]),
     "fe_dirichlet_apply": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "fe_scatter_add": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
-    "fe_spmv": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "fe_spmv": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32]),
     "fe_pcg_work_len": (_i64, [_i32, _i32]),
-    "fe_pcg": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _i32,
+    "fe_pcg": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f64, _i32,
                          C.POINTER(_i32), C.POINTER(_f64)]),
-    "fe_pcg_fixed": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "fe_pcg_fixed": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32]),
     "fe_dist_unique_id": (C.c_int, [_vp]),
     "fe_dist_init": (C.c_int, [_vp, _vp, _i32, _i32]),
-    "fe_dist_pcg": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp,
+    "fe_dist_pcg": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32,
                               _f64, _i32, _i32, C.POINTER(_i32), C.POINTER(_f64)]),
 }
 

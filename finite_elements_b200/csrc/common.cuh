@@ -72,6 +72,8 @@ struct fe_ctx {
   fe::Scratch scratch_a;   // material tables, BC flags, scan block sums
   fe::Scratch scratch_b;   // reduction partials / PCG scalars
   void *pinned = nullptr;  // small pinned host buffer for scalar read-back
+  void *pcg_graph = nullptr;  // cached cudaGraphExec_t of one PCG iteration chunk
+  const void *pcg_graph_key[8] = {nullptr};
   // multi-GPU
   void *nccl_comm = nullptr;
   int rank = 0, nranks = 1;

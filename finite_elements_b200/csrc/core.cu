@@ -266,6 +266,7 @@ int fe_ctx_destroy(fe_ctx *ctx) {
   ctx->halo_send.release();
   ctx->halo_recv.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->pcg_graph) cudaGraphExecDestroy((cudaGraphExec_t)ctx->pcg_graph);
   extern void fe_dist_teardown(fe_ctx *);
   fe_dist_teardown(ctx);
   delete ctx;

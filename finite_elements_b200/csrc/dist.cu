@@ -145,7 +145,7 @@ int fe_dist_init(fe_ctx *ctx, const void *nccl_unique_id, int32_t rank, int32_t 
 int fe_dist_pcg(fe_ctx *ctx, void *stream, int32_t n_rows, int32_t n_cols, const int32_t *rowptr,
                 const int32_t *colidx, const double *vals, const double *b, double *x, double *work, int32_t n_nbr,
                 const int32_t *nbr_rank, const int32_t *send_ptr, const int32_t *send_idx, const int32_t *recv_ptr,
-                double rtol, int32_t maxit, int32_t fixed_iters, int32_t *iters, double *relres) {
+                int32_t block_dim, double rtol, int32_t maxit, int32_t fixed_iters, int32_t *iters, double *relres) {
   FE_REQUIRE(ctx, "fe_dist_pcg: NULL ctx");
   FE_REQUIRE(n_nbr == 0 || (nbr_rank && send_ptr && recv_ptr), "fe_dist_pcg: NULL halo description");
   HaloPlan h;
@@ -160,7 +160,7 @@ int fe_dist_pcg(fe_ctx *ctx, void *stream, int32_t n_rows, int32_t n_cols, const
     FE_REQUIRE(send_ptr[n_nbr] == 0 || send_idx, "fe_dist_pcg: NULL send_idx");
   }
   const bool fixed = fixed_iters > 0;
-  return pcg_drive(ctx, as_stream(stream), n_rows, n_cols, rowptr, colidx, vals, b, x, work, &h, rtol,
+  return pcg_drive(ctx, as_stream(stream), n_rows, n_cols, rowptr, colidx, vals, b, x, work, &h, block_dim, rtol,
                    fixed ? fixed_iters : maxit, fixed, iters, relres);
 }
 

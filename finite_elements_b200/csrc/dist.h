@@ -23,6 +23,7 @@ int allreduce_sum(fe_ctx *ctx, cudaStream_t s, double *dev, int count);
 // host driver in solve.cu
 int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const int32_t *rowptr,
               const int32_t *colidx, const double *vals, const double *b, double *x, double *work,
-              const HaloPlan *halo, double rtol, int32_t maxit, bool fixed, int32_t *iters_out, double *relres_out);
+              const HaloPlan *halo, int block_dim, double rtol, int32_t maxit, bool fixed, int32_t *iters_out,
+              double *relres_out);
 
 }  // namespace fe

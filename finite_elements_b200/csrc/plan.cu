@@ -22,7 +22,115 @@ struct PlanFlags {
   int bad_node;    // connectivity index outside [0, n_nodes)
   int max_degree;  // max node valence incl. self
   int too_dense;   // valence > kMaxDegree
+  int fan_irregular;  // some node's corners do not form simple fans (edge shared by > 2 elements, ...)
 };
+
+// ---------------------------------------------------------------------------------------
+// Fan ordering: walk the corners of a node so that consecutive corners share an edge.  Every
+// off-diagonal block of the node's row then receives its (at most two) contributions from
+// consecutive steps and can be finished in registers by the assembly kernel.
+//   seed record : .x = first neighbour of a chain, .y = k | FAN_SEED << 8 | k_self << 13
+//   step record : .x = the corner's NEW neighbour, .y = k | flags << 8 | mat_id << 13
+// k = position of .x in the node's sorted adjacency row.  A chain is "closed" when the fan
+// wraps around an interior node: its first block is held back (FAN_HOLD_A) and completed by
+// the last step (FAN_ADD_FIRST).
+// ---------------------------------------------------------------------------------------
+constexpr int kFanMaxCorners = 32;
+constexpr int kFanMatBits = 19;
+enum : uint32_t { FAN_SEED = 1, FAN_ADD_CARRY = 2, FAN_HOLD_A = 4, FAN_LAST = 8, FAN_ADD_FIRST = 16 };
+
+__device__ __forceinline__ int row_position(const int32_t *row, int deg, int32_t target) {
+  int lo = 0, hi = deg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (row[mid] < target)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// Returns the number of records of node `self`, or -1 when its corners are not simple fans.
+template <bool EMIT>
+__device__ int fan_walk(int32_t self, int nc, const int32_t *__restrict__ cs, const int32_t *__restrict__ conn,
+                        const int32_t *__restrict__ mat_id, const int32_t *row, int deg, int2 *out) {
+  if (nc > kFanMaxCorners) return -1;
+  int32_t va[kFanMaxCorners], vb[kFanMaxCorners];
+  for (int i = 0; i < nc; ++i) {
+    const int64_t e = cs[i] >> 2;
+    const int v = cs[i] & 3;
+    va[i] = conn[3 * e + (v + 1) % 3];
+    vb[i] = conn[3 * e + (v + 2) % 3];
+    if (va[i] == self || vb[i] == self || va[i] == vb[i]) return -1;  // degenerate element
+    if (mat_id && (uint32_t)mat_id[e] >= (1u << kFanMatBits)) return -1;
+  }
+  auto occurrences = [&](int32_t m) {
+    int c = 0;
+    for (int j = 0; j < nc; ++j) c += (va[j] == m) + (vb[j] == m);
+    return c;
+  };
+  for (int i = 0; i < nc; ++i)
+    if (occurrences(va[i]) > 2 || occurrences(vb[i]) > 2) return -1;
+  const uint32_t full = (nc == 32) ? 0xffffffffu : ((1u << nc) - 1u);
+  uint32_t used = 0;
+  int nrec = 0;
+  const int k_self = EMIT ? row_position(row, deg, self) : 0;
+  while (used != full) {
+    int start = -1;
+    int32_t sv = 0;
+    for (int i = 0; i < nc && start < 0; ++i) {
+      if (used & (1u << i)) continue;
+      if (occurrences(va[i]) == 1) {
+        start = i;
+        sv = va[i];
+      } else if (occurrences(vb[i]) == 1) {
+        start = i;
+        sv = vb[i];
+      }
+    }
+    bool closed = false;
+    if (start < 0) {
+      for (int i = 0; i < nc; ++i)
+        if (!(used & (1u << i))) {
+          start = i;
+          break;
+        }
+      sv = va[start];
+      closed = true;
+    }
+    if (EMIT)
+      out[nrec] = make_int2(sv, (int)((uint32_t)row_position(row, deg, sv) | (FAN_SEED << 8) | ((uint32_t)k_self << 13)));
+    ++nrec;
+    int32_t cur = sv;
+    int j = start;
+    bool first = true;
+    while (true) {
+      const int32_t next = (va[j] == cur) ? vb[j] : va[j];
+      used |= 1u << j;
+      int jn = -1;
+      for (int i = 0; i < nc; ++i)
+        if (!(used & (1u << i)) && (va[i] == next || vb[i] == next)) {
+          jn = i;
+          break;
+        }
+      const bool last = jn < 0;
+      if (last && closed && next != sv) return -1;
+      if (EMIT) {
+        const uint32_t fl = (first ? 0u : FAN_ADD_CARRY) | ((first && closed) ? FAN_HOLD_A : 0u) |
+                            (last ? FAN_LAST : 0u) | ((last && closed) ? FAN_ADD_FIRST : 0u);
+        const uint32_t mid = mat_id ? (uint32_t)mat_id[cs[j] >> 2] : 0u;
+        out[nrec] = make_int2(next, (int)((uint32_t)row_position(row, deg, next) | (fl << 8) | (mid << 13)));
+      }
+      ++nrec;
+      if (last) break;
+      first = false;
+      cur = next;
+      j = jn;
+    }
+  }
+  return nrec;
+}
 
 __global__ void k_count_corners(int64_t n3, const int32_t *__restrict__ conn, int32_t n_nodes, int32_t n_owned,
                                 int32_t *__restrict__ cnt, PlanFlags *__restrict__ flags) {
@@ -64,7 +172,8 @@ __device__ __forceinline__ void insertion_sort(int32_t *a, int n) {
 __global__ void __launch_bounds__(128) k_node_adjacency(int32_t n_owned, const int32_t *__restrict__ conn,
                                                        const int32_t *__restrict__ corner_ptr,
                                                        int32_t *__restrict__ corner_tmp, int32_t *__restrict__ cand,
-                                                       int32_t *__restrict__ ndeg, PlanFlags *__restrict__ flags) {
+                                                       int32_t *__restrict__ ndeg, const int32_t *__restrict__ mat_id,
+                                                       int32_t *__restrict__ nfan, PlanFlags *__restrict__ flags) {
   const int32_t n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_owned) return;
   const int32_t c0 = corner_ptr[n], c1 = corner_ptr[n + 1];
@@ -85,6 +194,9 @@ __global__ void __launch_bounds__(128) k_node_adjacency(int32_t n_owned, const i
   ndeg[n] = m;
   atomicMax(&flags->max_degree, m);
   if (m > kMaxDegree) flags->too_dense = 1;
+  const int nf = fan_walk<false>(n, nc, cs, conn, mat_id, nullptr, 0, nullptr);
+  nfan[n] = nf < 0 ? 0 : nf;
+  if (nf < 0) flags->fan_irregular = 1;
 }
 
 // One thread per owned node: publish the adjacency row and the corner records.
@@ -93,7 +205,9 @@ __global__ void __launch_bounds__(128) k_node_records(int32_t n_owned, const int
                                                      const int32_t *__restrict__ corner_tmp,
                                                      const int32_t *__restrict__ cand,
                                                      const int32_t *__restrict__ adj_ptr, int32_t *__restrict__ adj,
-                                                     int2 *__restrict__ corner_rec) {
+                                                     int2 *__restrict__ corner_rec,
+                                                     const int32_t *__restrict__ mat_id,
+                                                     const int32_t *__restrict__ fan_ptr, int2 *__restrict__ fan_rec) {
   const int32_t n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_owned) return;
   const int32_t c0 = corner_ptr[n], c1 = corner_ptr[n + 1];
@@ -128,6 +242,7 @@ __global__ void __launch_bounds__(128) k_node_records(int32_t n_owned, const int
     }
     corner_rec[c] = make_int2(ev, (int)packed);
   }
+  if (fan_rec) fan_walk<true>(n, c1 - c0, corner_tmp + c0, conn, mat_id, cd, deg, fan_rec + fan_ptr[n]);
 }
 
 __global__ void k_conn4(int64_t n_elems, const int32_t *__restrict__ conn, const int32_t *__restrict__ mat_id,
@@ -180,6 +295,8 @@ int fe_plan_destroy(fe_plan *p) {
   cudaFree(p->adj_ptr);
   cudaFree(p->adj);
   cudaFree(p->conn4);
+  cudaFree(p->fan_ptr);
+  cudaFree(p->fan_rec);
   delete p;
   return FE_OK;
 }
@@ -204,12 +321,12 @@ int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, 
   p->dim = dim;
   p->n_elems = n_elems;
   int rc = FE_OK;
-  int32_t *cursor = nullptr, *corner_tmp = nullptr, *cand = nullptr, *ndeg = nullptr;
+  int32_t *cursor = nullptr, *corner_tmp = nullptr, *cand = nullptr, *ndeg = nullptr, *nfan = nullptr;
   PlanFlags *flags = nullptr;
   int64_t *totals = nullptr;
   const int64_t n3 = 3 * n_elems;
-  PlanFlags hflags = {0, 0, 0};
-  int64_t htot[2] = {0, 0};
+  PlanFlags hflags = {0, 0, 0, 0};
+  int64_t htot[3] = {0, 0, 0};
 
 #define PLAN_TRY(expr)            \
   do {                            \
@@ -240,11 +357,14 @@ int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, 
   PLAN_TRY(dev_alloc(&cursor, (int64_t)n_owned + 1, nullptr));
   PLAN_TRY(dev_alloc(&ndeg, (int64_t)n_owned + 1, nullptr));
   PLAN_TRY(dev_alloc(&flags, 1, nullptr));
-  PLAN_TRY(dev_alloc(&totals, 2, nullptr));
+  PLAN_TRY(dev_alloc(&totals, 3, nullptr));
+  PLAN_TRY(dev_alloc(&nfan, (int64_t)n_owned + 1, nullptr));
+  PLAN_TRY(dev_alloc(&p->fan_ptr, (int64_t)n_owned + 1, &p->bytes));
   PLAN_CUDA(cudaMemsetAsync(cursor, 0, ((size_t)n_owned + 1) * sizeof(int32_t), st));
   PLAN_CUDA(cudaMemsetAsync(ndeg, 0, ((size_t)n_owned + 1) * sizeof(int32_t), st));
   PLAN_CUDA(cudaMemsetAsync(flags, 0, sizeof(PlanFlags), st));
-  PLAN_CUDA(cudaMemsetAsync(totals, 0, 2 * sizeof(int64_t), st));
+  PLAN_CUDA(cudaMemsetAsync(totals, 0, 3 * sizeof(int64_t), st));
+  PLAN_CUDA(cudaMemsetAsync(nfan, 0, ((size_t)n_owned + 1) * sizeof(int32_t), st));
 
   if (n_elems > 0 && n_owned > 0) {
     // 1. histogram of corners per owned node (cursor doubles as the count array)
@@ -271,12 +391,13 @@ int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, 
     k_fill_corners<<<grid_for(n3, 256), 256, 0, st>>>(n3, conn, n_nodes, n_owned, p->corner_ptr, cursor, corner_tmp);
     PLAN_LAUNCHED();
     k_node_adjacency<<<grid_for(n_owned, 128), 128, 0, st>>>(n_owned, conn, p->corner_ptr, corner_tmp, cand, ndeg,
-                                                            flags);
+                                                            mat_id, nfan, flags);
     PLAN_LAUNCHED();
   }
   // 3. row lengths -> block row pointer
   PLAN_TRY(exclusive_scan_i32(ctx, st, ndeg, p->adj_ptr, n_owned, totals + 1));
-  PLAN_CUDA(cudaMemcpyAsync(htot, totals, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  PLAN_TRY(exclusive_scan_i32(ctx, st, nfan, p->fan_ptr, n_owned, totals + 2));
+  PLAN_CUDA(cudaMemcpyAsync(htot, totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   PLAN_CUDA(cudaMemcpyAsync(&hflags, flags, sizeof(PlanFlags), cudaMemcpyDeviceToHost, st));
   PLAN_CUDA(cudaStreamSynchronize(st));
   p->nnzb = htot[1];
@@ -292,9 +413,13 @@ int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, 
     goto done;
   }
   PLAN_TRY(dev_alloc(&p->adj, p->nnzb, &p->bytes));
+  p->fan_ok = !hflags.fan_irregular;
+  p->n_fan = p->fan_ok ? htot[2] : 0;
+  if (p->fan_ok) PLAN_TRY(dev_alloc(&p->fan_rec, p->n_fan, &p->bytes));
   if (p->n_corners > 0) {
     k_node_records<<<grid_for(n_owned, 128), 128, 0, st>>>(n_owned, conn, p->corner_ptr, corner_tmp, cand, p->adj_ptr,
-                                                          p->adj, p->corner_rec);
+                                                          p->adj, p->corner_rec, mat_id, p->fan_ptr,
+                                                          p->fan_ok ? p->fan_rec : nullptr);
     PLAN_LAUNCHED();
   }
   PLAN_CUDA(cudaStreamSynchronize(st));
@@ -304,6 +429,7 @@ done:
   cudaFree(corner_tmp);
   cudaFree(cand);
   cudaFree(ndeg);
+  cudaFree(nfan);
   cudaFree(flags);
   cudaFree(totals);
   if (rc != FE_OK) {

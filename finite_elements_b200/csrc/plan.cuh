@@ -24,4 +24,9 @@ struct fe_plan {
   int32_t *adj = nullptr;      // [nnzb]
   // connectivity padded to 16 B with the material id: one LDG.128 per corner visit
   int4 *conn4 = nullptr;  // [n_elems] {n0, n1, n2, mat_id}
+  // fan-ordered corner records (plan.cu: fan_walk); valid when fan_ok
+  bool fan_ok = false;
+  int64_t n_fan = 0;
+  int32_t *fan_ptr = nullptr;  // [n_owned + 1]
+  int2 *fan_rec = nullptr;     // [n_fan]
 };

@@ -13,6 +13,7 @@
 // Multi-GPU (dist.cu) inserts a halo exchange before k_spmv and an all-reduce after the
 // two reducing kernels; the kernels themselves are the same.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "dist.h"
@@ -110,7 +111,63 @@ __global__ void __launch_bounds__(kRedBlock) k_spmv(int32_t n_rows, const int32_
   }
 }
 
-static int spmv_lpr(int32_t n_rows, int64_t nnz) {
+// ---------------------------------------------------------------------------------------
+// SpMV for node-blocked matrices (block_dim = 2): rows 2i and 2i+1 share one column list made
+// of (2m, 2m+1) pairs -- exactly what fe_plan emits for 2 DOF per node, and what
+// fe_dirichlet_apply preserves.  8 lanes per node; a lane owns one 2x2 block: ONE column
+// index, one 128-bit load of x, two 128-bit loads of vals, four FMAs.  Only the even entries
+// of the first row's colidx are read (half of the index bytes never leave HBM).
+// ---------------------------------------------------------------------------------------
+template <bool DOT>
+__global__ void __launch_bounds__(kRedBlock) k_spmv_b2(int32_t n_nodes, const int32_t *__restrict__ rowptr,
+                                                      const int32_t *__restrict__ colidx,
+                                                      const double *__restrict__ vals, const double *__restrict__ x,
+                                                      double *__restrict__ y, double *__restrict__ partials,
+                                                      PcgState *__restrict__ st) {
+  __shared__ double red[kRedBlock / 32];
+  if (DOT && (st->converged | st->breakdown)) return;
+  constexpr int LPN = 8, NPB = kRedBlock / LPN;
+  const int lane = threadIdx.x % LPN;
+  const int64_t n_pad = (int64_t)((n_nodes + NPB - 1) / NPB) * NPB;
+  double dot = 0.0;
+  for (int64_t node = (int64_t)blockIdx.x * NPB + threadIdx.x / LPN; node < n_pad; node += (int64_t)gridDim.x * NPB) {
+    double a0 = 0.0, a1 = 0.0;
+    if (node < n_nodes) {
+      const int32_t s0 = __ldg(rowptr + 2 * node), s2 = __ldg(rowptr + 2 * node + 2);
+      const int32_t len = (s2 - s0) >> 1;  // entries per row = 2 * valence
+      const double *r0 = vals + s0, *r1 = vals + s0 + len;
+      for (int32_t k = 2 * lane; k < len; k += 2 * LPN) {
+        const int32_t c = __ldg(colidx + s0 + k);
+        const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + c));
+        const double2 v0 = __ldcs(reinterpret_cast<const double2 *>(r0 + k));
+        const double2 v1 = __ldcs(reinterpret_cast<const double2 *>(r1 + k));
+        a0 += v0.x * xv.x + v0.y * xv.y;
+        a1 += v1.x * xv.x + v1.y * xv.y;
+      }
+    }
+#pragma unroll
+    for (int o = LPN / 2; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (node < n_nodes && lane == 0) {
+      *reinterpret_cast<double2 *>(y + 2 * node) = make_double2(a0, a1);
+      if (DOT) {
+        const double2 xs = *reinterpret_cast<const double2 *>(x + 2 * node);
+        dot += a0 * xs.x + a1 * xs.y;
+      }
+    }
+  }
+  if (DOT) {
+    const double loc[1] = {dot};
+    publish_and_reduce<1>(loc, partials, st, 0, red);
+  }
+}
+
+constexpr int kBlock2 = -2;  // pseudo "lanes per row" selecting k_spmv_b2
+
+static int spmv_lpr(int32_t n_rows, int64_t nnz, int block_dim) {
+  if (block_dim == 2 && n_rows % 2 == 0) return kBlock2;
   const double avg = n_rows > 0 ? (double)nnz / n_rows : 1.0;
   if (avg <= 6) return 4;
   if (avg <= 20) return 8;
@@ -129,6 +186,12 @@ template <bool DOT>
 static int launch_spmv(fe_ctx *ctx, cudaStream_t s, int lpr, int32_t n_rows, const int32_t *rowptr,
                        const int32_t *colidx, const double *vals, const double *x, double *y, double *partials,
                        PcgState *st) {
+  if (lpr == kBlock2) {  // node-blocked fast path
+    const int grid = reducing_grid(ctx, n_rows / 2, kRedBlock / 8);
+    k_spmv_b2<DOT><<<grid, kRedBlock, 0, s>>>(n_rows / 2, rowptr, colidx, vals, x, y, partials, st);
+    FE_LAUNCH_CHECK(ctx);
+    return FE_OK;
+  }
   const int grid = reducing_grid(ctx, n_rows, kRedBlock / lpr);
   switch (lpr) {
     case 4: k_spmv<4, DOT><<<grid, kRedBlock, 0, s>>>(n_rows, rowptr, colidx, vals, x, y, partials, st); break;
@@ -293,69 +356,171 @@ __global__ void k_scatter_add(int32_t n, const int32_t *__restrict__ dof, const 
 // ---------------------------------------------------------------------------------------
 // host driver shared by fe_pcg / fe_pcg_fixed / fe_dist_pcg
 // ---------------------------------------------------------------------------------------
+__global__ void k_pcg_clear_converged(PcgState *st) { st->converged = 0; }
+
+struct PcgLaunch {
+  fe_ctx *ctx;
+  cudaStream_t s;
+  int32_t n_rows;
+  const int32_t *rowptr, *colidx;
+  const double *vals, *b;
+  double *x, *r, *q, *dinv, *p, *partials;
+  PcgState *st;
+  const HaloPlan *halo;
+  bool dist;
+  int lpr, vgrid;
+
+  // r = b - A x, p = D^-1 r, sums[1..3] = (r.z, r.r, b.b); converged flag from the TRUE residual
+  int true_residual_start() {
+    int rc;
+    k_copy<<<reducing_grid(ctx, n_rows, 1024), 256, 0, s>>>(n_rows, x, p);
+    FE_LAUNCH_CHECK(ctx);
+    if (dist && (rc = halo_exchange(ctx, s, halo, p, n_rows))) return rc;
+    if ((rc = launch_spmv<false>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st))) return rc;
+    k_pcg_init<<<vgrid, kRedBlock, 0, s>>>(n_rows, b, q, dinv, r, p, partials, st);
+    FE_LAUNCH_CHECK(ctx);
+    if (dist && (rc = allreduce_sum(ctx, s, st->sums + 1, 3))) return rc;
+    k_pcg_init_finish<<<1, 1, 0, s>>>(st);
+    FE_LAUNCH_CHECK(ctx);
+    return FE_OK;
+  }
+
+  int iteration(int parity) {
+    int rc;
+    if (dist && (rc = halo_exchange(ctx, s, halo, p, n_rows))) return rc;
+    if ((rc = launch_spmv<true>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st))) return rc;
+    if (dist && (rc = allreduce_sum(ctx, s, st->sums + 0, 1))) return rc;
+    k_pcg_update<<<vgrid, kRedBlock, 0, s>>>(n_rows, parity, p, q, dinv, x, r, partials, st);
+    FE_LAUNCH_CHECK(ctx);
+    if (dist && (rc = allreduce_sum(ctx, s, st->sums + 1, 2))) return rc;
+    k_pcg_pupdate<<<vgrid, 256, 0, s>>>(n_rows, parity, r, dinv, p, st);
+    FE_LAUNCH_CHECK(ctx);
+    return FE_OK;
+  }
+};
+
+// One CUDA graph holding `len` (even) iterations; single-GPU only.  Cached in the ctx as long
+// as the same buffers are used (bench / time-stepping loops call the solver repeatedly).
+static int get_chunk_graph(PcgLaunch &L, int len, cudaGraphExec_t *out) {
+  fe_ctx *ctx = L.ctx;
+  const void *key[8] = {L.rowptr, L.colidx, L.vals, L.x, L.r, L.st, (void *)(intptr_t)L.n_rows,
+                        (void *)(intptr_t)(len * 64 + (L.lpr & 63))};
+  if (ctx->pcg_graph && memcmp(key, ctx->pcg_graph_key, sizeof(key)) == 0) {
+    *out = (cudaGraphExec_t)ctx->pcg_graph;
+    return FE_OK;
+  }
+  if (ctx->pcg_graph) {
+    cudaGraphExecDestroy((cudaGraphExec_t)ctx->pcg_graph);
+    ctx->pcg_graph = nullptr;
+  }
+  const int64_t launches_before = ctx->launches;
+  FE_CUDA(cudaStreamBeginCapture(L.s, cudaStreamCaptureModeRelaxed));
+  int rc = FE_OK;
+  for (int k = 0; k < len && rc == FE_OK; ++k) rc = L.iteration(k & 1);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(L.s, &graph);
+  ctx->launches = launches_before;  // captured, not launched
+  if (rc != FE_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(FE_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(FE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  ctx->pcg_graph = exec;
+  memcpy(ctx->pcg_graph_key, key, sizeof(key));
+  *out = exec;
+  return FE_OK;
+}
+
 int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const int32_t *rowptr,
               const int32_t *colidx, const double *vals, const double *b, double *x, double *work,
-              const HaloPlan *halo, double rtol, int32_t maxit, bool fixed, int32_t *iters_out, double *relres_out) {
+              const HaloPlan *halo, int block_dim, double rtol, int32_t maxit, bool fixed, int32_t *iters_out,
+              double *relres_out) {
   FE_REQUIRE(ctx && rowptr && colidx && vals && b && x && work, "pcg: NULL argument");
   FE_REQUIRE(n_rows >= 0 && n_cols >= n_rows, "pcg: bad sizes %d x %d", n_rows, n_cols);
   FE_REQUIRE(maxit >= 0, "pcg: negative iteration count");
-  const bool dist = halo != nullptr && ctx->nranks > 1;
+  FE_REQUIRE(block_dim == 1 || block_dim == 2, "pcg: block_dim must be 1 or 2");
   FE_CUDA(cudaSetDevice(ctx->device));
-  // workspace: r | q | dinv | p (p has the ghost tail)
-  double *r = work, *q = work + n_rows, *dinv = work + 2 * (int64_t)n_rows, *p = work + 3 * (int64_t)n_rows;
   int rc = ctx->scratch_b.reserve(sizeof(PcgState) + 256 + (size_t)kMaxPartials * 3 * sizeof(double));
   if (rc) return rc;
-  PcgState *st = (PcgState *)ctx->scratch_b.ptr;
-  double *partials = (double *)((char *)ctx->scratch_b.ptr + 256);
   static_assert(sizeof(PcgState) <= 256, "PcgState too large");
+
+  PcgLaunch L;
+  L.ctx = ctx;
+  L.s = s;
+  L.n_rows = n_rows;
+  L.rowptr = rowptr;
+  L.colidx = colidx;
+  L.vals = vals;
+  L.b = b;
+  L.x = x;
+  // workspace: r | q | dinv | p (p has the ghost tail)
+  L.r = work;
+  L.q = work + n_rows;
+  L.dinv = work + 2 * (int64_t)n_rows;
+  L.p = work + 3 * (int64_t)n_rows;
+  L.st = (PcgState *)ctx->scratch_b.ptr;
+  L.partials = (double *)((char *)ctx->scratch_b.ptr + 256);
+  L.halo = halo;
+  L.dist = halo != nullptr && ctx->nranks > 1;
+  PcgState *st = L.st;
 
   int32_t h_rowptr_end = 0;
   FE_CUDA(cudaMemcpyAsync(&h_rowptr_end, rowptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   k_pcg_state_init<<<1, 1, 0, s>>>(st, fixed ? -1.0 : rtol * rtol);
   FE_LAUNCH_CHECK(ctx);
   FE_CUDA(cudaStreamSynchronize(s));
-  const int lpr = spmv_lpr(n_rows, h_rowptr_end);
-  const int vgrid = reducing_grid(ctx, n_rows, kRedBlock * 4);
+  L.lpr = spmv_lpr(n_rows, h_rowptr_end, block_dim);
+  L.vgrid = reducing_grid(ctx, n_rows, kRedBlock * 4);
 
   if (n_rows > 0) {
-    k_extract_dinv<<<grid_for(n_rows, 256), 256, 0, s>>>(n_rows, rowptr, colidx, vals, dinv, st);
+    k_extract_dinv<<<grid_for(n_rows, 256), 256, 0, s>>>(n_rows, rowptr, colidx, vals, L.dinv, st);
     FE_LAUNCH_CHECK(ctx);
   }
-  // q = A x0 (x0 staged in p so that the ghost tail can be exchanged)
-  k_copy<<<reducing_grid(ctx, n_rows, 1024), 256, 0, s>>>(n_rows, x, p);
-  FE_LAUNCH_CHECK(ctx);
-  if (dist && (rc = halo_exchange(ctx, s, halo, p, n_rows))) return rc;
-  if ((rc = launch_spmv<false>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st))) return rc;
-  k_pcg_init<<<vgrid, kRedBlock, 0, s>>>(n_rows, b, q, dinv, r, p, partials, st);
-  FE_LAUNCH_CHECK(ctx);
-  if (dist && (rc = allreduce_sum(ctx, s, st->sums + 1, 3))) return rc;
-  k_pcg_init_finish<<<1, 1, 0, s>>>(st);
-  FE_LAUNCH_CHECK(ctx);
+  if ((rc = L.true_residual_start())) return rc;
 
   PcgState *h = (PcgState *)ctx->pinned;
-  const int check_every = fixed ? maxit : 50;
-  int it = 0;
-  bool done = false;
-  while (it < maxit && !done) {
-    const int chunk = (maxit - it < check_every) ? (maxit - it) : check_every;
-    for (int k = 0; k < chunk; ++k, ++it) {
-      const int parity = it & 1;
-      if (dist && (rc = halo_exchange(ctx, s, halo, p, n_rows))) return rc;
-      if ((rc = launch_spmv<true>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st))) return rc;
-      if (dist && (rc = allreduce_sum(ctx, s, st->sums + 0, 1))) return rc;
-      k_pcg_update<<<vgrid, kRedBlock, 0, s>>>(n_rows, parity, p, q, dinv, x, r, partials, st);
-      FE_LAUNCH_CHECK(ctx);
-      if (dist && (rc = allreduce_sum(ctx, s, st->sums + 1, 2))) return rc;
-      k_pcg_pupdate<<<vgrid, 256, 0, s>>>(n_rows, parity, r, dinv, p, st);
-      FE_LAUNCH_CHECK(ctx);
+  constexpr int kChunk = 50;   // iterations between convergence polls (even: graph parity)
+  constexpr int kMaxRestarts = 12;
+  const bool use_graph = !L.dist && getenv("FE_B200_NO_GRAPH") == nullptr;
+  int it = 0, local = 0, restarts = 0;
+  bool done = (maxit == 0);
+  FE_CUDA(cudaMemcpyAsync(h, st, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
+  FE_CUDA(cudaStreamSynchronize(s));
+  if (h->converged || h->breakdown) done = true;
+  while (!done) {
+    // ---- run until the recurrence says converged (or maxit / breakdown)
+    while (it < maxit) {
+      const int chunk = (maxit - it < kChunk) ? (maxit - it) : kChunk;
+      if (use_graph && chunk == kChunk && (local & 1) == 0) {
+        cudaGraphExec_t exec;
+        if ((rc = get_chunk_graph(L, kChunk, &exec))) return rc;
+        FE_CUDA(cudaGraphLaunch(exec, s));
+        ctx->launches += 3 * kChunk;
+        it += kChunk;
+        local += kChunk;
+      } else {
+        for (int k = 0; k < chunk; ++k, ++it, ++local)
+          if ((rc = L.iteration(local & 1))) return rc;
+      }
+      if (fixed && it < maxit) continue;  // no polling in throughput mode
+      FE_CUDA(cudaMemcpyAsync(h, st, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
+      FE_CUDA(cudaStreamSynchronize(s));
+      if (h->converged || h->breakdown) break;
     }
+    if (fixed || h->breakdown || !h->converged) break;
+    // ---- the recurrence residual drifts from b - A x over tens of thousands of iterations:
+    //      recompute the true residual and, if it is not below the tolerance, restart from x.
+    k_pcg_clear_converged<<<1, 1, 0, s>>>(st);
+    FE_LAUNCH_CHECK(ctx);
+    if ((rc = L.true_residual_start())) return rc;
+    local = 0;
     FE_CUDA(cudaMemcpyAsync(h, st, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
     FE_CUDA(cudaStreamSynchronize(s));
-    done = h->converged || h->breakdown;
-  }
-  if (it == 0) {
-    FE_CUDA(cudaMemcpyAsync(h, st, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
-    FE_CUDA(cudaStreamSynchronize(s));
+    if (h->converged || ++restarts > kMaxRestarts || it >= maxit) done = true;
   }
   if (iters_out) *iters_out = h->iters;
   if (relres_out) *relres_out = (h->sums[3] > 0.0) ? sqrt(h->sums[2] / h->sums[3]) : 0.0;
@@ -409,30 +574,31 @@ int fe_scatter_add(fe_ctx *ctx, void *stream, int32_t n, const int32_t *dof, con
 }
 
 int fe_spmv(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr, const int32_t *colidx,
-            const double *vals, const double *x, double *y) {
+            const double *vals, const double *x, double *y, int32_t block_dim) {
   FE_REQUIRE(ctx && rowptr && colidx && vals && x && y, "fe_spmv: NULL argument");
   if (n_rows <= 0) return FE_OK;
   cudaStream_t s = as_stream(stream);
   int32_t nnz = 0;
   FE_CUDA(cudaMemcpyAsync(&nnz, rowptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   FE_CUDA(cudaStreamSynchronize(s));
-  return launch_spmv<false>(ctx, s, spmv_lpr(n_rows, nnz), n_rows, rowptr, colidx, vals, x, y, nullptr, nullptr);
+  return launch_spmv<false>(ctx, s, spmv_lpr(n_rows, nnz, block_dim), n_rows, rowptr, colidx, vals, x, y, nullptr, nullptr);
 }
 
 int64_t fe_pcg_work_len(int32_t n_rows, int32_t n_cols) { return 3 * (int64_t)n_rows + (int64_t)n_cols; }
 
 int fe_pcg(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr, const int32_t *colidx, const double *vals,
-           const double *b, double *x, double *work, double rtol, int32_t maxit, int32_t *iters, double *relres) {
-  return pcg_drive(ctx, as_stream(stream), n, n, rowptr, colidx, vals, b, x, work, nullptr, rtol, maxit, false, iters,
-                   relres);
+           const double *b, double *x, double *work, int32_t block_dim, double rtol, int32_t maxit, int32_t *iters,
+           double *relres) {
+  return pcg_drive(ctx, as_stream(stream), n, n, rowptr, colidx, vals, b, x, work, nullptr, block_dim, rtol, maxit,
+                   false, iters, relres);
 }
 
 int fe_pcg_fixed(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr, const int32_t *colidx,
-                 const double *vals, const double *b, double *x, double *work, int32_t iters) {
+                 const double *vals, const double *b, double *x, double *work, int32_t block_dim, int32_t iters) {
   int32_t done = 0;
   double rel = 0.0;
-  return pcg_drive(ctx, as_stream(stream), n, n, rowptr, colidx, vals, b, x, work, nullptr, 0.0, iters, true, &done,
-                   &rel);
+  return pcg_drive(ctx, as_stream(stream), n, n, rowptr, colidx, vals, b, x, work, nullptr, block_dim, 0.0, iters,
+                   true, &done, &rel);
 }
 
 }  // extern "C"

@@ -175,7 +175,7 @@ class DeviceMesh:
             y = torch.empty(self.n_rows, dtype=torch.float64, device=self.ctx.device)
         with torch.cuda.device(self.ctx.device):
             check(lib.fe_spmv(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals),
-                              _ptr(x), _ptr(y)))
+                              _ptr(x), _ptr(y), self.dim))
         return y
 
     def pcg_workspace(self):
@@ -194,7 +194,7 @@ class DeviceMesh:
         iters, relres = C.c_int32(0), C.c_double(0.0)
         with torch.cuda.device(self.ctx.device):
             rc = lib.fe_pcg(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals), _ptr(b),
-                            _ptr(x), _ptr(work), float(rtol), int(min(maxit, 2 ** 31 - 1)), C.byref(iters),
+                            _ptr(x), _ptr(work), self.dim, float(rtol), int(min(maxit, 2 ** 31 - 1)), C.byref(iters),
                             C.byref(relres))
         if rc == _lib.FE_ERR_NOT_CONVERGED and not raise_on_maxit:
             return x, iters.value, relres.value
@@ -208,7 +208,7 @@ class DeviceMesh:
             work = self.pcg_workspace()
         with torch.cuda.device(self.ctx.device):
             check(lib.fe_pcg_fixed(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals),
-                                   _ptr(b), _ptr(x), _ptr(work), int(iters)))
+                                   _ptr(b), _ptr(x), _ptr(work), self.dim, int(iters)))
         return x
 
     # ---- convenience ------------------------------------------------------------------

@@ -172,7 +172,7 @@ class DistributedMesh:
             rc = lib.fe_dist_pcg(self.ctx.handle, C.c_void_p(torch.cuda.current_stream().cuda_stream), dm.n_rows,
                                  dm.n_cols, _ptr(rowptr), _ptr(colidx), _ptr(vals), _ptr(b), _ptr(x), _ptr(work),
                                  len(self._nbr), ip(self._nbr), ip(self._sp), _ptr(self.send_idx), ip(self._rp),
-                                 float(rtol), int(maxit), int(fixed_iters), C.byref(iters), C.byref(relres))
+                                 dm.dim, float(rtol), int(maxit), int(fixed_iters), C.byref(iters), C.byref(relres))
         if rc != _lib.FE_ERR_NOT_CONVERGED:
             check(rc)
         return x, iters.value, relres.value

@@ -106,7 +106,9 @@ int fe_plan_csr(const fe_plan *plan, void *stream, int32_t *rowptr, int32_t *col
  * duplicate summation of analysis.py:661 / :387-405.  Deterministic: every CSR slot is
  * summed by one thread in a fixed (element id) order, no atomics.  vals double[nnz] is
  * fully overwritten.  variant: 0 = default (fastest available), 1 = generic row-owner
- * kernel (accumulates in global memory), 2 = shared-memory staged tiles. */
+ * kernel (accumulates in global memory), 2 = shared-memory staged tiles, 3 = fan-ordered
+ * traversal + staged tiles (needs node stars that are simple fans, i.e. no edge shared by
+ * more than two elements; FE_ERR_UNSUPPORTED otherwise -- variant 0 then picks 2). */
 int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *plan, int kind, const double *coords,
                 const double *mat, int32_t n_mat, double *vals, int variant);
 
@@ -125,21 +127,30 @@ int fe_scatter_add(fe_ctx *ctx, void *stream, int32_t n, const int32_t *dof, con
                    double *rhs);
 
 /* ---- solve ---------------------------------------------------------------------------
- * y = A x, CSR, sub-warp-per-row vectorised. */
+ * block_dim (all solve entry points): 1 = arbitrary CSR; 2 = the CSR was produced by an
+ * fe_plan with dim == 2 (rows 2i and 2i+1 share one column list made of (2m, 2m+1) pairs;
+ * fe_dirichlet_apply keeps that structure), which lets the SpMV read ONE column index per
+ * 2x2 block and use 128-bit loads.  Passing 2 for a matrix without that structure is an error
+ * the library cannot detect.
+ *
+ * y = A x, CSR, sub-warp-per-row (block_dim 1) or 8-lanes-per-node (block_dim 2). */
 int fe_spmv(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
-            const int32_t *colidx, const double *vals, const double *x, double *y);
+            const int32_t *colidx, const double *vals, const double *x, double *y,
+            int32_t block_dim);
 
 /* Jacobi-preconditioned CG; replaces scipy spsolve at analysis.py:820-822 on the
  * eliminated SPD system.  x: initial guess in, solution out.  work: double[fe_pcg_work_len(n)].
- * Stops when ||r||_2 <= rtol * ||b||_2.  SYNCHRONISES the stream; writes iters / relres. */
+ * Stops when ||r||_2 <= rtol * ||b||_2, where r is re-computed as b - A x once the recurrence
+ * signals convergence (restart from x if the recurrence had drifted).  SYNCHRONISES the
+ * stream; writes iters / relres (the true relative residual). */
 int64_t fe_pcg_work_len(int32_t n_rows, int32_t n_cols);
 int fe_pcg(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr, const int32_t *colidx,
-           const double *vals, const double *b, double *x, double *work, double rtol,
-           int32_t maxit, int32_t *iters, double *relres);
+           const double *vals, const double *b, double *x, double *work, int32_t block_dim,
+           double rtol, int32_t maxit, int32_t *iters, double *relres);
 /* Runs exactly `iters` PCG iterations with no convergence test (throughput measurement). */
 int fe_pcg_fixed(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr,
                  const int32_t *colidx, const double *vals, const double *b, double *x,
-                 double *work, int32_t iters);
+                 double *work, int32_t block_dim, int32_t iters);
 
 /* ---- multi-GPU (one process per GPU) --------------------------------------
  * nccl_unique_id: 128 bytes from ncclGetUniqueId on rank 0 (fe_dist_unique_id), broadcast
@@ -155,8 +166,8 @@ int fe_dist_init(fe_ctx *ctx, const void *nccl_unique_id, int32_t rank, int32_t 
 int fe_dist_pcg(fe_ctx *ctx, void *stream, int32_t n_rows, int32_t n_cols, const int32_t *rowptr,
                 const int32_t *colidx, const double *vals, const double *b, double *x,
                 double *work, int32_t n_nbr, const int32_t *nbr_rank, const int32_t *send_ptr,
-                const int32_t *send_idx, const int32_t *recv_ptr, double rtol, int32_t maxit,
-                int32_t fixed_iters, int32_t *iters, double *relres);
+                const int32_t *send_idx, const int32_t *recv_ptr, int32_t block_dim, double rtol,
+                int32_t maxit, int32_t fixed_iters, int32_t *iters, double *relres);
 
 /* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 int64_t fe_ctx_launch_count(const fe_ctx *ctx);

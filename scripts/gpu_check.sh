@@ -13,7 +13,7 @@ fi
 if [[ $what == all || $what == bench ]]; then
   timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" | tee -a gpurun_out/summary.txt
   tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
-  for v in 1 2; do
+  for v in 2 3; do
     timeout 300 python bench.py --steps 3 --warmup 3 --variant $v --full-solve 0 --no-cpu-baseline --pcg-iters 5 > gpurun_out/bench_v$v.json 2>> gpurun_out/bench.err
   done
   timeout 300 python bench.py --steps 3 --warmup 3 --nx 1024 --ny 512 --no-cpu-baseline > gpurun_out/bench_s1m.json 2>> gpurun_out/bench.err

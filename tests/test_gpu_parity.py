@@ -62,10 +62,13 @@ def test_pattern_bit_exact_and_values(name):
     assert np.array_equal(colidx.cpu().numpy(), ref_k.indices)
     v1 = dm.assemble(_kind(fx), fx.mat, variant=1)
     v2 = dm.assemble(_kind(fx), fx.mat, variant=2)
+    v3 = dm.assemble(_kind(fx), fx.mat, variant=3)   # fan-ordered (all fixtures are manifold)
     v0 = dm.assemble(_kind(fx), fx.mat, variant=0)
-    assert np.array_equal(v1.cpu().numpy(), v2.cpu().numpy()), "kernel variants must agree bit for bit"
-    assert np.array_equal(v0.cpu().numpy(), v2.cpu().numpy())
+    assert np.array_equal(v1.cpu().numpy(), v2.cpu().numpy()), "element-order variants must agree bit for bit"
+    assert np.array_equal(v0.cpu().numpy(), v3.cpu().numpy()), "default = fan variant on a manifold mesh"
+    assert_csr_values_close(dm.to_scipy(v3), dm.to_scipy(v2), 1e-14)  # vertex relabelling: last-ulp only
     assert_csr_values_close(dm.to_scipy(v2), ref_k, 1e-12)
+    assert_csr_values_close(dm.to_scipy(v3), ref_k, 1e-12)
     if fx.kind == "elasticity":
         m = dm.assemble(KIND_MASS, fx.mat)
         assert_csr_values_close(dm.to_scipy(m), fx.csr("m"), 1e-12)
@@ -78,10 +81,13 @@ def test_assembly_is_ordered_sum_of_element_matrices(name):
     fx = Fixture(name)
     dm = _dm(fx)
     ke = dm.element_matrices(_kind(fx), fx.mat).cpu().numpy()
-    vals = dm.assemble(_kind(fx), fx.mat).cpu().numpy()
-    again = dm.assemble(_kind(fx), fx.mat).cpu().numpy()
+    vals = dm.assemble(_kind(fx), fx.mat, variant=2).cpu().numpy()   # element-order kernel
+    again = dm.assemble(_kind(fx), fx.mat, variant=2).cpu().numpy()
     assert np.array_equal(vals, again), "two runs must be bit-identical"
-    k = dm.to_scipy(dm.assemble(_kind(fx), fx.mat))
+    for v in (0, 1, 3):
+        a = dm.assemble(_kind(fx), fx.mat, variant=v).cpu().numpy()
+        assert np.array_equal(a, dm.assemble(_kind(fx), fx.mat, variant=v).cpu().numpy()), f"variant {v} not reproducible"
+    k = dm.to_scipy(dm.assemble(_kind(fx), fx.mat, variant=2))
     from oracle import numpy_oracle as no
     rows, cols = no.triplet_indices(fx.conn, fx.dim)
     # slot index of every triplet in the canonical CSR
@@ -208,6 +214,30 @@ def test_empty_single_isolated_and_fan():
         dm.assemble(no.KIND_ELAST_PSTRESS, mat, variant=2)
 
 
+def test_non_manifold_and_bowtie_fall_back_from_fan_variant():
+    """Edge shared by three elements: not a simple fan -> variant 3 refuses, default still exact.
+    Bow-tie (two fans meeting at one node) and open boundary fans stay on the fan path."""
+    from oracle import numpy_oracle as no
+    from finite_elements_b200.device import DeviceMesh
+    mat = np.array([[3.0, 0.3, 1.0, 1.0]])
+    coords = np.array([[0, 0], [1, 0], [0.5, 1], [0.5, -1], [0.4, 0.6]], float)
+    conn = np.array([[0, 1, 2], [1, 0, 3], [0, 1, 4]], np.int32)       # edge (0,1) in three triangles
+    dm = DeviceMesh(coords, conn, None, dim=2)
+    k_ref = no.assemble_k(no.KIND_ELAST_PSTRESS, coords, conn, np.zeros(3, np.int32), mat)
+    assert_csr_values_close(dm.to_scipy(dm.assemble(no.KIND_ELAST_PSTRESS, mat)), k_ref, 1e-12)
+    with pytest.raises(NotImplementedError):
+        dm.assemble(no.KIND_ELAST_PSTRESS, mat, variant=3)
+    coords = np.array([[0, 0], [1, 0], [1, 1], [-1, 0], [-1, -1], [0.2, 1.0]], float)
+    conn = np.array([[0, 1, 2], [0, 3, 4], [2, 5, 0]], np.int32)       # node 0: a 2-corner fan + a 1-corner fan
+    dm = DeviceMesh(coords, conn, None, dim=2)
+    k_ref = no.assemble_k(no.KIND_ELAST_PSTRESS, coords, conn, np.zeros(3, np.int32), mat)
+    assert_csr_values_close(dm.to_scipy(dm.assemble(no.KIND_ELAST_PSTRESS, mat, variant=3)), k_ref, 1e-12)
+    dm1 = DeviceMesh(coords, conn, None, dim=1)
+    k_ref = no.assemble_k(no.KIND_MAGNETIC, coords, conn, np.zeros(3, np.int32), np.array([[2.0, 0, 0, 0]]))
+    assert_csr_values_close(dm1.to_scipy(dm1.assemble(no.KIND_MAGNETIC, np.array([[2.0, 0, 0, 0]]), variant=3)),
+                            k_ref, 1e-12)
+
+
 def test_error_mapping():
     from finite_elements_b200.device import DeviceMesh, KIND_MAGNETIC, KIND_ELAST_PSTRESS
     import torch
@@ -281,5 +311,5 @@ def test_properties_at_baseline_sizes(nx, ny):
     dm.dirichlet(vals, rhs, bc, torch.zeros(bc.numel(), dtype=torch.float64, device="cuda"))
     u, iters, relres = dm.pcg(vals, rhs, rtol=1e-8)
     true = float(torch.linalg.norm(rhs - dm.spmv(vals, u)) / torch.linalg.norm(rhs))
-    assert relres <= 1e-8 and true <= 2e-8, (iters, relres, true)
+    assert relres <= 1e-8 and true <= 1.0001e-8, (iters, relres, true)   # relres is the TRUE residual
     assert float(u[bc.long()].abs().max()) == 0.0
