@@ -147,6 +147,9 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # an explicit (non-default) stream: kernels, CUDA-graph launches and the timing events all
+    # live on it (the legacy default stream cannot be captured)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     if world > 1:
         from finite_elements_b200 import dist as fe_dist
         dist.init_process_group("nccl", device_id=dev)

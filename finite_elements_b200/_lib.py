@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfe_b200.so")
+LIB_PATH = os.environ.get("FE_B200_LIB") or os.path.join(_HERE, "libfe_b200.so")  # env: tuning builds only
 
 FE_OK = 0
 FE_ERR_ARG, FE_ERR_CUDA, FE_ERR_NCCL = -1, -2, -3

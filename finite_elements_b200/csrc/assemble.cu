@@ -23,7 +23,6 @@
 
 namespace fe {
 
-constexpr int kTile = 128;  // nodes (= threads) per CTA
 
 struct CornerCtx {
   int v;        // local vertex of this node in the element
@@ -188,163 +187,209 @@ __global__ void __launch_bounds__(kTile) k_assemble_tile(int32_t n_owned, const 
 // variant 3: fan-ordered traversal + shared-memory staged tile (the default)
 // ---------------------------------------------------------------------------------------
 // The plan orders each node's corners around the node (plan.cu: fan_walk), so a step shares
-// its "previous" neighbour with the step before it.  Per step: ONE 8-byte record and ONE
-// 16-byte coordinate load (the other two vertices are already in registers), no connectivity
-// read; the block towards the previous neighbour is completed in registers (carry + this
-// element) and stored once; the diagonal block never leaves registers until the end.  Shared
-// memory therefore sees every value exactly once, as a 128-bit store, and the tile is then
-// streamed to HBM as full contiguous rows.  Element geometry is evaluated in (self, prev,
-// next) vertex order -- Ke is invariant under relabelling, rounding differs in the last ulp
-// from the element-order kernels (tests: 1e-14 between variants).
+// its "previous" neighbour with the step before it.
+//  * The tile's fan records are one contiguous range of fan_rec: the CTA copies it to shared
+//    memory with coalesced 128-bit streaming loads (each record leaves HBM exactly once).
+//  * Per step: one LDS.64 record and ONE 16-byte coordinate gather, issued two steps ahead
+//    (software pipeline) -- the other two vertices are already in registers, no connectivity.
+//  * The block towards the previous neighbour is completed in registers (carry + this
+//    element) and stored once; the diagonal block stays in registers until the end.  Shared
+//    memory sees every value exactly once, as a 128-bit store ([slot][thread] layout), and the
+//    tile is then streamed to HBM as full contiguous rows.
+// Element geometry is evaluated in (self, prev, next) vertex order -- Ke is invariant under
+// relabelling, rounding differs in the last ulp from the element-order kernels (tests: 1e-14
+// between variants).
+#ifndef FE_FAN_MINB
+#define FE_FAN_MINB 6  // resident CTAs per SM the register allocation targets
+#endif
+
 struct FanFlags {
   static constexpr uint32_t SEED = 1, ADD_CARRY = 2, HOLD_A = 4, LAST = 8, ADD_FIRST = 16;
 };
 
 template <int KC>
-__global__ void __launch_bounds__(kTile) k_assemble_fan(int32_t n_owned, const int32_t *__restrict__ fan_ptr,
+struct FanOps;  // per-kind value type of one (node, neighbour) block
+
+template <>
+struct FanOps<2> {  // magnetic: scalar entries
+  using Val = double;
+  using Slot = double;
+  static __device__ __forceinline__ Val zero() { return 0.0; }
+  static __device__ __forceinline__ void rows(const TriGeom &g, const MatRow &m, Val r[3]) { mag_row(g, m, 0, r); }
+  static __device__ __forceinline__ void add(Val &a, const Val &b) { a += b; }
+  static __device__ __forceinline__ void store(Slot *my, int /*deg*/, int k, int ld, const Val &v) { my[k * ld] = v; }
+};
+
+template <int KC>
+struct FanOps {  // elasticity (0) / mass (1): 2x2 blocks, stored as two double2 (one per row)
+  using Val = Blk2;
+  using Slot = double2;
+  static __device__ __forceinline__ Val zero() { return Blk2{0.0, 0.0, 0.0, 0.0}; }
+  static __device__ __forceinline__ void rows(const TriGeom &g, const MatRow &m, Val r[3]) {
+    if (KC == 0)
+      elast_row_blocks(g, m, 0, r);
+    else
+      mass_row_blocks(g, m, 0, r);
+  }
+  static __device__ __forceinline__ void add(Val &a, const Val &b) {
+    a.k00 += b.k00;
+    a.k01 += b.k01;
+    a.k10 += b.k10;
+    a.k11 += b.k11;
+  }
+  static __device__ __forceinline__ void store(Slot *my, int deg, int k, int ld, const Val &v) {
+    my[k * ld] = make_double2(v.k00, v.k01);
+    my[(deg + k) * ld] = make_double2(v.k10, v.k11);
+  }
+};
+
+__device__ __forceinline__ int4 ld_stream_int4(const int4 *p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// smem: a_tile[kTile+1] | f_tile[kTile+1] | recs int2[rec_cap] | acc Slot[dim*maxdeg][kTile+1]
+template <int KC>
+__global__ void __launch_bounds__(kTile, FE_FAN_MINB) k_assemble_fan(int32_t n_owned, const int32_t *__restrict__ fan_ptr,
                                                        const int2 *__restrict__ fan_rec,
                                                        const int32_t *__restrict__ adj_ptr,
                                                        const double2 *__restrict__ coords,
-                                                       const MatRow *__restrict__ tab, double *__restrict__ vals) {
-  constexpr int DIM = (KC == 2) ? 1 : 2;
+                                                       const MatRow *__restrict__ tab, double *__restrict__ vals,
+                                                       int rec_cap) {
+  using Ops = FanOps<KC>;
+  using Val = typename Ops::Val;
+  using Slot = typename Ops::Slot;
   constexpr int LD = kTile + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t *a_tile = reinterpret_cast<int32_t *>(smem_raw);
-  unsigned char *acc_raw = smem_raw + ((kTile + 1) * sizeof(int32_t) + 15) / 16 * 16;
+  int32_t *f_tile = a_tile + (kTile + 1);
+  constexpr size_t kHdr = (2 * (kTile + 1) * sizeof(int32_t) + 15) / 16 * 16;
+  int2 *recs = reinterpret_cast<int2 *>(smem_raw + kHdr);
+  Slot *acc = reinterpret_cast<Slot *>(smem_raw + kHdr + (size_t)rec_cap * sizeof(int2));
 
   const int tid = threadIdx.x;
   const int32_t n0 = blockIdx.x * kTile;
   const int32_t n = n0 + tid;
   const int n_in_tile = min(kTile, n_owned - n0);
-  if (tid <= n_in_tile) a_tile[tid] = adj_ptr[n0 + tid];
-  if (tid == 0 && n_in_tile == kTile) a_tile[kTile] = adj_ptr[n0 + kTile];
+  if (tid <= n_in_tile) {
+    a_tile[tid] = adj_ptr[n0 + tid];
+    f_tile[tid] = fan_ptr[n0 + tid];
+  }
+  if (tid == 0 && n_in_tile == kTile) {
+    a_tile[kTile] = adj_ptr[n0 + kTile];
+    f_tile[kTile] = fan_ptr[n0 + kTile];
+  }
+  __syncthreads();
+  // stage the tile's records: [base, r1) with base rounded down to a 16-byte boundary
+  const int32_t base = f_tile[0] & ~1;
+  {
+    const int n16 = (f_tile[n_in_tile] - base + 1) >> 1;
+    const int4 *src = reinterpret_cast<const int4 *>(fan_rec + base);
+    int4 *dst = reinterpret_cast<int4 *>(recs);
+    for (int i = tid; i < n16; i += kTile) dst[i] = ld_stream_int4(src + i);
+  }
   __syncthreads();
 
   if (n < n_owned) {
-    const int32_t f0 = fan_ptr[n], f1 = fan_ptr[n + 1];
+    int f = f_tile[tid] - base;
+    const int fe = f_tile[tid + 1] - base;
     const int deg = a_tile[tid + 1] - a_tile[tid];
+    const bool any = f < fe;
     const double2 ps = __ldg(coords + n);
+    Slot *my = acc + tid;
+    // two-deep software pipeline over (record, neighbour coordinates)
+    int2 r0 = make_int2(n, 0), r1 = r0, r2 = r0;
+    double2 p0 = ps, p1 = ps, p2 = ps;
+    if (f < fe) {
+      r0 = recs[f];
+      p0 = __ldg(coords + r0.x);
+    }
+    if (f + 1 < fe) {
+      r1 = recs[f + 1];
+      p1 = __ldg(coords + r1.x);
+    }
+    if (f + 2 < fe) {
+      r2 = recs[f + 2];
+      p2 = __ldg(coords + r2.x);
+    }
     double2 pprev = ps;
     int kprev = 0, kself = 0, cur_mat = -1;
     MatRow m = {0.0, 0.0, 0.0, 0.0};
-    if (KC == 2) {
-      double *my = reinterpret_cast<double *>(acc_raw) + tid;
-      double diag = 0.0, carry = 0.0, first = 0.0;
-      for (int32_t f = f0; f < f1; ++f) {
-        const int2 rec = ldg_nc_int2(fan_rec + f);
-        const uint32_t y = (uint32_t)rec.y;
-        const int k = y & 255;
-        const uint32_t fl = (y >> 8) & 31;
-        const double2 pc = __ldg(coords + rec.x);
-        if (fl & FanFlags::SEED) {
-          kself = y >> 13;
-        } else {
-          const int mid = y >> 13;
-          if (mid != cur_mat) {
-            m = tab[mid];
-            cur_mat = mid;
-          }
-          const TriGeom g = tri_geom(ps, pprev, pc);
-          double r[3];
-          mag_row(g, m, 0, r);
-          diag += r[0];
-          double a = r[1];
-          if (fl & FanFlags::ADD_CARRY) a += carry;
-          if (fl & FanFlags::HOLD_A)
-            first = a;
-          else
-            my[kprev * LD] = a;
-          carry = r[2];
-          if (fl & FanFlags::LAST) my[k * LD] = (fl & FanFlags::ADD_FIRST) ? carry + first : carry;
+    Val diag = Ops::zero(), carry = Ops::zero(), first = Ops::zero();
+    for (; f < fe; ++f) {
+      const uint32_t y = (uint32_t)r0.y;
+      const int k = y & 255;
+      const uint32_t fl = (y >> 8) & 31;
+      const double2 pc = p0;
+      // shift the pipeline and issue the gather for step f + 3
+      r0 = r1;
+      p0 = p1;
+      r1 = r2;
+      p1 = p2;
+      if (f + 3 < fe) {
+        r2 = recs[f + 3];
+        p2 = __ldg(coords + r2.x);
+      }
+      if (fl & FanFlags::SEED) {
+        kself = y >> 13;
+      } else {
+        const int mid = y >> 13;
+        if (mid != cur_mat) {
+          m = tab[mid];
+          cur_mat = mid;
         }
-        pprev = pc;
-        kprev = k;
-      }
-      if (f1 > f0) my[kself * LD] = diag;
-    } else {
-      double2 *my = reinterpret_cast<double2 *>(acc_raw) + tid;
-      Blk2 diag = {0.0, 0.0, 0.0, 0.0}, carry = diag, first = diag;
-      for (int32_t f = f0; f < f1; ++f) {
-        const int2 rec = ldg_nc_int2(fan_rec + f);
-        const uint32_t y = (uint32_t)rec.y;
-        const int k = y & 255;
-        const uint32_t fl = (y >> 8) & 31;
-        const double2 pc = __ldg(coords + rec.x);
-        if (fl & FanFlags::SEED) {
-          kself = y >> 13;
-        } else {
-          const int mid = y >> 13;
-          if (mid != cur_mat) {
-            m = tab[mid];
-            cur_mat = mid;
-          }
-          const TriGeom g = tri_geom(ps, pprev, pc);
-          Blk2 r[3];
-          if (KC == 0)
-            elast_row_blocks(g, m, 0, r);
-          else
-            mass_row_blocks(g, m, 0, r);
-          diag.k00 += r[0].k00;
-          diag.k01 += r[0].k01;
-          diag.k10 += r[0].k10;
-          diag.k11 += r[0].k11;
-          Blk2 a = r[1];
-          if (fl & FanFlags::ADD_CARRY) {
-            a.k00 += carry.k00;
-            a.k01 += carry.k01;
-            a.k10 += carry.k10;
-            a.k11 += carry.k11;
-          }
-          if (fl & FanFlags::HOLD_A) {
-            first = a;
-          } else {
-            my[kprev * LD] = make_double2(a.k00, a.k01);
-            my[(deg + kprev) * LD] = make_double2(a.k10, a.k11);
-          }
-          carry = r[2];
-          if (fl & FanFlags::LAST) {
-            Blk2 b = carry;
-            if (fl & FanFlags::ADD_FIRST) {
-              b.k00 += first.k00;
-              b.k01 += first.k01;
-              b.k10 += first.k10;
-              b.k11 += first.k11;
-            }
-            my[k * LD] = make_double2(b.k00, b.k01);
-            my[(deg + k) * LD] = make_double2(b.k10, b.k11);
-          }
+        const TriGeom g = tri_geom(ps, pprev, pc);
+        Val r[3];
+        Ops::rows(g, m, r);
+        Ops::add(diag, r[0]);
+        Val a = r[1];
+        if (fl & FanFlags::ADD_CARRY) Ops::add(a, carry);
+        if (fl & FanFlags::HOLD_A)
+          first = a;
+        else
+          Ops::store(my, deg, kprev, LD, a);
+        carry = r[2];
+        if (fl & FanFlags::LAST) {
+          Val b = carry;
+          if (fl & FanFlags::ADD_FIRST) Ops::add(b, first);
+          Ops::store(my, deg, k, LD, b);
         }
-        pprev = pc;
-        kprev = k;
       }
-      if (f1 > f0) {
-        my[kself * LD] = make_double2(diag.k00, diag.k01);
-        my[(deg + kself) * LD] = make_double2(diag.k10, diag.k11);
-      }
+      pprev = pc;
+      kprev = k;
     }
+    if (any) Ops::store(my, deg, kself, LD, diag);
   }
   __syncthreads();
 
   const int lane = tid & 31, w = tid >> 5;
   if (KC == 2) {
-    const double *acc = reinterpret_cast<const double *>(acc_raw);
     for (int i = w; i < n_in_tile; i += kTile / 32) {
       const int32_t a0 = a_tile[i];
       const int len = a_tile[i + 1] - a0;
       double *dst = vals + a0;
-      for (int q = lane; q < len; q += 32) dst[q] = acc[q * LD + i];
+      const double *src = reinterpret_cast<const double *>(acc);
+      for (int q = lane; q < len; q += 32) dst[q] = src[q * LD + i];
     }
   } else {
     // half a warp per node: its 2 * valence double2 entries are contiguous in vals
-    const double2 *acc = reinterpret_cast<const double2 *>(acc_raw);
+    const double2 *src = reinterpret_cast<const double2 *>(acc);
     const int hl = lane & 15;
     for (int i = 2 * w + (lane >> 4); i < n_in_tile; i += 2 * (kTile / 32)) {
       const int32_t a0 = a_tile[i];
       const int len2 = 2 * (a_tile[i + 1] - a0);
       double2 *dst = reinterpret_cast<double2 *>(vals + 4 * (int64_t)a0);
-      for (int q = hl; q < len2; q += 16) dst[q] = acc[q * LD + i];
+      for (int q = hl; q < len2; q += 16) dst[q] = src[q * LD + i];
     }
   }
+}
+
+static size_t fan_smem_bytes(int dim, int max_degree, int rec_cap) {
+  return (2 * (kTile + 1) * sizeof(int32_t) + 15) / 16 * 16 + (size_t)rec_cap * sizeof(int2) +
+         (size_t)dim * dim * max_degree * (kTile + 1) * sizeof(double);
 }
 
 static size_t tile_smem_bytes(int dim, int max_degree) {
@@ -368,9 +413,12 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
   if (rc) return rc;
   const double2 *xy = reinterpret_cast<const double2 *>(coords);
   const int grid = grid_for(p->n_owned, kTile);
-  const size_t smem = tile_smem_bytes(dim, p->max_degree);
+  const int rec_cap = (p->fan_tile_max + 3) & ~1;  // +1 alignment slack, +1 over-read, even
+  size_t smem = tile_smem_bytes(dim, p->max_degree);
+  const size_t smem_fan = fan_smem_bytes(dim, p->max_degree, rec_cap);
   const size_t smem_limit = 200 * 1024;
-  if (variant == 0) variant = (smem <= smem_limit) ? (p->fan_ok ? 3 : 2) : 1;
+  if (variant == 0) variant = (p->fan_ok && smem_fan <= smem_limit) ? 3 : ((smem <= smem_limit) ? 2 : 1);
+  if (variant == 3) smem = smem_fan;
   if (variant == 3 && !p->fan_ok)
     return fail(FE_ERR_UNSUPPORTED, "fe_assemble: the fan variant needs a mesh whose node stars are simple fans");
   if (variant >= 2 && smem > smem_limit)
@@ -386,7 +434,7 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
     } else if (variant == 3) {                                                                                  \
       FE_CUDA(cudaFuncSetAttribute(k_assemble_fan<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_assemble_fan<KC><<<grid, kTile, smem, st>>>(p->n_owned, p->fan_ptr, p->fan_rec, p->adj_ptr, xy, tab,     \
-                                                    vals);                                                      \
+                                                    vals, rec_cap);                                             \
     } else {                                                                                                    \
       FE_CUDA(cudaFuncSetAttribute(k_assemble_tile<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_assemble_tile<KC><<<grid, kTile, smem, st>>>(p->n_owned, p->corner_ptr, p->corner_rec, p->adj_ptr,       \

@@ -74,6 +74,8 @@ struct fe_ctx {
   void *pinned = nullptr;  // small pinned host buffer for scalar read-back
   void *pcg_graph = nullptr;  // cached cudaGraphExec_t of one PCG iteration chunk
   const void *pcg_graph_key[8] = {nullptr};
+  void *work_stream = nullptr;  // cudaStream_t used when the caller passes a default stream
+  void *work_event = nullptr;   // cudaEvent_t ordering work_stream after the caller's stream
   // multi-GPU
   void *nccl_comm = nullptr;
   int rank = 0, nranks = 1;

@@ -254,6 +254,12 @@ int fe_ctx_create(int device, fe_ctx **out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   FE_CUDA(cudaMallocHost(&c->pinned, 4096));
+  cudaStream_t ws;
+  cudaEvent_t we;
+  FE_CUDA(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
+  FE_CUDA(cudaEventCreateWithFlags(&we, cudaEventDisableTiming));
+  c->work_stream = ws;
+  c->work_event = we;
   *out = c;
   return FE_OK;
 }
@@ -267,6 +273,8 @@ int fe_ctx_destroy(fe_ctx *ctx) {
   ctx->halo_recv.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->pcg_graph) cudaGraphExecDestroy((cudaGraphExec_t)ctx->pcg_graph);
+  if (ctx->work_stream) cudaStreamDestroy((cudaStream_t)ctx->work_stream);
+  if (ctx->work_event) cudaEventDestroy((cudaEvent_t)ctx->work_event);
   extern void fe_dist_teardown(fe_ctx *);
   fe_dist_teardown(ctx);
   delete ctx;

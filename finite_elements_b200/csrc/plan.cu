@@ -272,6 +272,14 @@ __global__ void __launch_bounds__(128) k_export_csr(int32_t n_owned, int32_t dim
   if (n == n_owned - 1 && lane == 0) rowptr[n_owned * dim] = (int32_t)(base + (int64_t)dim * rowlen);
 }
 
+__global__ void k_fan_tile_max(int32_t n_owned, const int32_t *__restrict__ fan_ptr, int *__restrict__ out) {
+  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t n0 = t * kTile;
+  if (n0 >= n_owned) return;
+  const int32_t n1 = min(n0 + kTile, n_owned);
+  atomicMax(out, fan_ptr[n1] - fan_ptr[n0]);
+}
+
 template <typename T>
 static int dev_alloc(T **p, int64_t count, int64_t *bytes_acc) {
   size_t b = (size_t)(count > 0 ? count : 1) * sizeof(T);
@@ -415,14 +423,22 @@ int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, 
   PLAN_TRY(dev_alloc(&p->adj, p->nnzb, &p->bytes));
   p->fan_ok = !hflags.fan_irregular;
   p->n_fan = p->fan_ok ? htot[2] : 0;
-  if (p->fan_ok) PLAN_TRY(dev_alloc(&p->fan_rec, p->n_fan, &p->bytes));
+  if (p->fan_ok) PLAN_TRY(dev_alloc(&p->fan_rec, p->n_fan + 2, &p->bytes));  // +2: 16-byte staging over-read
   if (p->n_corners > 0) {
     k_node_records<<<grid_for(n_owned, 128), 128, 0, st>>>(n_owned, conn, p->corner_ptr, corner_tmp, cand, p->adj_ptr,
                                                           p->adj, p->corner_rec, mat_id, p->fan_ptr,
                                                           p->fan_ok ? p->fan_rec : nullptr);
     PLAN_LAUNCHED();
   }
+  if (p->fan_ok && n_owned > 0) {
+    PLAN_CUDA(cudaMemsetAsync(&flags->max_degree, 0, sizeof(int), st));  // reuse as the tile maximum
+    k_fan_tile_max<<<grid_for((n_owned + kTile - 1) / kTile, 128), 128, 0, st>>>(n_owned, p->fan_ptr,
+                                                                                 &flags->max_degree);
+    PLAN_LAUNCHED();
+    PLAN_CUDA(cudaMemcpyAsync(&hflags, flags, sizeof(PlanFlags), cudaMemcpyDeviceToHost, st));
+  }
   PLAN_CUDA(cudaStreamSynchronize(st));
+  if (p->fan_ok) p->fan_tile_max = hflags.max_degree;
 
 done:
   cudaFree(cursor);

@@ -3,6 +3,10 @@
 #pragma once
 #include "common.cuh"
 
+namespace fe {
+constexpr int kTile = 128;  // nodes (= threads) per CTA of the tiled assembly kernels
+}
+
 struct fe_plan {
   fe_ctx *ctx = nullptr;
   int32_t n_nodes = 0, n_owned = 0, dim = 0;
@@ -27,6 +31,7 @@ struct fe_plan {
   // fan-ordered corner records (plan.cu: fan_walk); valid when fan_ok
   bool fan_ok = false;
   int64_t n_fan = 0;
+  int32_t fan_tile_max = 0;    // max records of one kTile-node tile
   int32_t *fan_ptr = nullptr;  // [n_owned + 1]
   int2 *fan_rec = nullptr;     // [n_fan]
 };

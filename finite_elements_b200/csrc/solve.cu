@@ -444,6 +444,14 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
   FE_REQUIRE(maxit >= 0, "pcg: negative iteration count");
   FE_REQUIRE(block_dim == 1 || block_dim == 2, "pcg: block_dim must be 1 or 2");
   FE_CUDA(cudaSetDevice(ctx->device));
+  // The legacy / per-thread default streams cannot be captured into a CUDA graph: run the
+  // solve on the ctx's own stream, ordered after the caller's stream.  The driver ends with a
+  // host synchronisation, so work the caller submits afterwards is ordered behind the solve.
+  if (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread) {
+    FE_CUDA(cudaEventRecord((cudaEvent_t)ctx->work_event, s));
+    FE_CUDA(cudaStreamWaitEvent((cudaStream_t)ctx->work_stream, (cudaEvent_t)ctx->work_event, 0));
+    s = (cudaStream_t)ctx->work_stream;
+  }
   int rc = ctx->scratch_b.reserve(sizeof(PcgState) + 256 + (size_t)kMaxPartials * 3 * sizeof(double));
   if (rc) return rc;
   static_assert(sizeof(PcgState) <= 256, "PcgState too large");
