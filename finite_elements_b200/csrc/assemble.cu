@@ -194,13 +194,14 @@ __global__ void __launch_bounds__(kTile) k_assemble_tile(int32_t n_owned, const 
 //    (software pipeline) -- the other two vertices are already in registers, no connectivity.
 //  * The block towards the previous neighbour is completed in registers (carry + this
 //    element) and stored once; the diagonal block stays in registers until the end.  Shared
-//    memory sees every value exactly once, as a 128-bit store ([slot][thread] layout), and the
-//    tile is then streamed to HBM as full contiguous rows.
+//    memory sees every value exactly once, as a 128-bit store into the exact image of the
+//    tile's slice of `vals`, which one thread then hands to the TMA engine as a single bulk
+//    store (cp.async.bulk.global.shared::cta) -- no per-lane write-out loop at all.
 // Element geometry is evaluated in (self, prev, next) vertex order -- Ke is invariant under
 // relabelling, rounding differs in the last ulp from the element-order kernels (tests: 1e-14
 // between variants).
 #ifndef FE_FAN_MINB
-#define FE_FAN_MINB 6  // resident CTAs per SM the register allocation targets
+#define FE_FAN_MINB 5  // resident CTAs per SM the register allocation targets (96 registers, no spills)
 #endif
 
 struct FanFlags {
@@ -218,6 +219,7 @@ struct FanOps<2> {  // magnetic: scalar entries
   static __device__ __forceinline__ void rows(const TriGeom &g, const MatRow &m, Val r[3]) { mag_row(g, m, 0, r); }
   static __device__ __forceinline__ void add(Val &a, const Val &b) { a += b; }
   static __device__ __forceinline__ void store(Slot *my, int /*deg*/, int k, int ld, const Val &v) { my[k * ld] = v; }
+  static __device__ __forceinline__ Val load(const Slot *my, int /*deg*/, int k) { return my[k]; }
 };
 
 template <int KC>
@@ -241,6 +243,10 @@ struct FanOps {  // elasticity (0) / mass (1): 2x2 blocks, stored as two double2
     my[k * ld] = make_double2(v.k00, v.k01);
     my[(deg + k) * ld] = make_double2(v.k10, v.k11);
   }
+  static __device__ __forceinline__ Val load(const Slot *my, int deg, int k) {
+    const double2 u = my[k], w = my[deg + k];
+    return Blk2{u.x, u.y, w.x, w.y};
+  }
 };
 
 __device__ __forceinline__ int4 ld_stream_int4(const int4 *p) {
@@ -251,7 +257,7 @@ __device__ __forceinline__ int4 ld_stream_int4(const int4 *p) {
   return r;
 }
 
-// smem: a_tile[kTile+1] | f_tile[kTile+1] | recs int2[rec_cap] | acc Slot[dim*maxdeg][kTile+1]
+// smem: a_tile[kTile+1] | f_tile[kTile+1] | recs int2[rec_cap] | acc double[dim^2 * blocks in tile]
 template <int KC>
 __global__ void __launch_bounds__(kTile, FE_FAN_MINB) k_assemble_fan(int32_t n_owned, const int32_t *__restrict__ fan_ptr,
                                                        const int2 *__restrict__ fan_rec,
@@ -262,8 +268,7 @@ __global__ void __launch_bounds__(kTile, FE_FAN_MINB) k_assemble_fan(int32_t n_o
   using Ops = FanOps<KC>;
   using Val = typename Ops::Val;
   using Slot = typename Ops::Slot;
-  constexpr int LD = kTile + 1;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t *a_tile = reinterpret_cast<int32_t *>(smem_raw);
   int32_t *f_tile = a_tile + (kTile + 1);
   constexpr size_t kHdr = (2 * (kTile + 1) * sizeof(int32_t) + 15) / 16 * 16;
@@ -299,97 +304,98 @@ __global__ void __launch_bounds__(kTile, FE_FAN_MINB) k_assemble_fan(int32_t n_o
     const int deg = a_tile[tid + 1] - a_tile[tid];
     const bool any = f < fe;
     const double2 ps = __ldg(coords + n);
-    Slot *my = acc + tid;
-    // two-deep software pipeline over (record, neighbour coordinates)
-    int2 r0 = make_int2(n, 0), r1 = r0, r2 = r0;
-    double2 p0 = ps, p1 = ps, p2 = ps;
-    if (f < fe) {
-      r0 = recs[f];
-      p0 = __ldg(coords + r0.x);
-    }
-    if (f + 1 < fe) {
-      r1 = recs[f + 1];
-      p1 = __ldg(coords + r1.x);
-    }
-    if (f + 2 < fe) {
-      r2 = recs[f + 2];
-      p2 = __ldg(coords + r2.x);
-    }
-    double2 pprev = ps;
-    int kprev = 0, kself = 0, cur_mat = -1;
-    MatRow m = {0.0, 0.0, 0.0, 0.0};
-    Val diag = Ops::zero(), carry = Ops::zero(), first = Ops::zero();
-    for (; f < fe; ++f) {
-      const uint32_t y = (uint32_t)r0.y;
-      const int k = y & 255;
-      const uint32_t fl = (y >> 8) & 31;
-      const double2 pc = p0;
-      // shift the pipeline and issue the gather for step f + 3
-      r0 = r1;
-      p0 = p1;
-      r1 = r2;
-      p1 = p2;
-      if (f + 3 < fe) {
-        r2 = recs[f + 3];
-        p2 = __ldg(coords + r2.x);
+    Slot *my = acc + (KC == 2 ? 1 : 2) * (a_tile[tid] - a_tile[0]);  // natural (output-image) layout
+    // Software pipeline over (record, neighbour coordinates): four rotating register sets, the
+    // gather for step f+3 is issued while step f computes, and the set of step f-1 doubles as
+    // "previous neighbour" of step f -- no register shifting.
+    struct Item {
+      int2 rec;
+      double2 p;
+    };
+    Item ia = {make_int2(n, 0), ps}, ib = ia, ic = ia, id = ia;
+    auto fetch = [&](int i, Item &it) {
+      if (i < fe) {
+        it.rec = recs[i];
+        it.p = __ldg(coords + it.rec.x);
       }
+    };
+    int kself = 0, cur_mat = -1;
+    MatRow m = {0.0, 0.0, 0.0, 0.0};
+    Val diag = Ops::zero(), carry = Ops::zero();
+    auto process = [&](const Item &cur, const Item &prev) {
+      const uint32_t y = (uint32_t)cur.rec.y;
+      const uint32_t fl = (y >> 8) & 31;
       if (fl & FanFlags::SEED) {
         kself = y >> 13;
-      } else {
-        const int mid = y >> 13;
-        if (mid != cur_mat) {
-          m = tab[mid];
-          cur_mat = mid;
-        }
-        const TriGeom g = tri_geom(ps, pprev, pc);
-        Val r[3];
-        Ops::rows(g, m, r);
-        Ops::add(diag, r[0]);
-        Val a = r[1];
-        if (fl & FanFlags::ADD_CARRY) Ops::add(a, carry);
-        if (fl & FanFlags::HOLD_A)
-          first = a;
-        else
-          Ops::store(my, deg, kprev, LD, a);
-        carry = r[2];
-        if (fl & FanFlags::LAST) {
-          Val b = carry;
-          if (fl & FanFlags::ADD_FIRST) Ops::add(b, first);
-          Ops::store(my, deg, k, LD, b);
-        }
+        return;
       }
-      pprev = pc;
-      kprev = k;
+      const int mid = y >> 13;
+      if (mid != cur_mat) {
+        m = tab[mid];
+        cur_mat = mid;
+      }
+      const TriGeom g = tri_geom(ps, prev.p, cur.p);
+      Val r[3];
+      Ops::rows(g, m, r);
+      Ops::add(diag, r[0]);
+      if (fl & FanFlags::ADD_CARRY) Ops::add(r[1], carry);
+      // (a closed fan's first block waits in its slot; the last step completes it there)
+      Ops::store(my, deg, (uint32_t)prev.rec.y & 255, 1, r[1]);
+      carry = r[2];
+      if (fl & FanFlags::LAST) {
+        if (fl & FanFlags::ADD_FIRST) Ops::add(r[2], Ops::load(my, deg, y & 255));
+        Ops::store(my, deg, y & 255, 1, r[2]);
+      }
+    };
+    fetch(f, ia);
+    fetch(f + 1, ib);
+    fetch(f + 2, ic);
+    while (true) {
+      if (f >= fe) break;
+      process(ia, id);
+      fetch(f + 3, id);
+      ++f;
+      if (f >= fe) break;
+      process(ib, ia);
+      fetch(f + 3, ia);
+      ++f;
+      if (f >= fe) break;
+      process(ic, ib);
+      fetch(f + 3, ib);
+      ++f;
+      if (f >= fe) break;
+      process(id, ic);
+      fetch(f + 3, ic);
+      ++f;
     }
-    if (any) Ops::store(my, deg, kself, LD, diag);
+    if (any) Ops::store(my, deg, kself, 1, diag);
   }
+  if (KC != 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy
   __syncthreads();
 
-  const int lane = tid & 31, w = tid >> 5;
+  // The staged tile is the exact image of vals[dim^2 * a_tile[0] .. dim^2 * a_tile[n_in_tile]).
+  const int32_t tile_lo = a_tile[0];
+  const int tile_len = a_tile[n_in_tile] - tile_lo;  // node-level blocks in the tile
   if (KC == 2) {
-    for (int i = w; i < n_in_tile; i += kTile / 32) {
-      const int32_t a0 = a_tile[i];
-      const int len = a_tile[i + 1] - a0;
-      double *dst = vals + a0;
-      const double *src = reinterpret_cast<const double *>(acc);
-      for (int q = lane; q < len; q += 32) dst[q] = src[q * LD + i];
-    }
-  } else {
-    // half a warp per node: its 2 * valence double2 entries are contiguous in vals
-    const double2 *src = reinterpret_cast<const double2 *>(acc);
-    const int hl = lane & 15;
-    for (int i = 2 * w + (lane >> 4); i < n_in_tile; i += 2 * (kTile / 32)) {
-      const int32_t a0 = a_tile[i];
-      const int len2 = 2 * (a_tile[i + 1] - a0);
-      double2 *dst = reinterpret_cast<double2 *>(vals + 4 * (int64_t)a0);
-      for (int q = hl; q < len2; q += 16) dst[q] = src[q * LD + i];
-    }
+    // 1 DOF per node: the destination is only 8-byte aligned -> plain coalesced copy
+    const double *src = reinterpret_cast<const double *>(acc);
+    double *dst = vals + tile_lo;
+    for (int q = tid; q < tile_len; q += kTile) dst[q] = src[q];
+  } else if (tid == 0 && tile_len > 0) {
+    // 2 DOF per node: one TMA bulk store of the whole tile (32 * tile_len bytes, 32-byte aligned)
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(acc);
+    double *dst = vals + 4 * (int64_t)tile_lo;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                 "r"((uint32_t)tile_len * 32u)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the copy
   }
 }
 
 static size_t fan_smem_bytes(int dim, int max_degree, int rec_cap) {
   return (2 * (kTile + 1) * sizeof(int32_t) + 15) / 16 * 16 + (size_t)rec_cap * sizeof(int2) +
-         (size_t)dim * dim * max_degree * (kTile + 1) * sizeof(double);
+         (size_t)dim * dim * max_degree * kTile * sizeof(double);
 }
 
 static size_t tile_smem_bytes(int dim, int max_degree) {

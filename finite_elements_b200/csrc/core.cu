@@ -136,10 +136,10 @@ __global__ void k_material_table(int kind, int n_mat, const double *__restrict__
     // elements.py:426-429 (strain) / :444-447 (stress)
     const double a = (kind == FE_ELAST_PSTRAIN) ? (p0 * p1) / ((1 + p1) * (1 - 2 * p1)) : (p0 * p1) / (1 - p1 * p1);
     const double b = p0 / (2 * (1 + p1));
-    r.p0 = a + 2 * b;
-    r.p1 = a;
-    r.p2 = b;
-    r.p3 = p2;  // thickness
+    r.p0 = (a + 2 * b) * p2;  // c * thickness
+    r.p1 = a * p2;
+    r.p2 = b * p2;
+    r.p3 = p2;
   } else if (kind == FE_MAGNETIC) {
     r.p0 = 1.0 / p0;  // elements.py:108
     r.p1 = r.p2 = r.p3 = 0.0;

@@ -15,7 +15,7 @@
 namespace fe {
 
 // Per-material constants precomputed once per call (k_material_table).
-//   elasticity: (c, a, b, thickness) with D = [[c,a,0],[a,c,0],[0,0,b]]
+//   elasticity: (c t, a t, b t, t) with D = [[c,a,0],[a,c,0],[0,0,b]] and t = thickness
 //   magnetic  : (1/mu, 0, 0, 0)
 //   mass      : (rho * thickness / 12, 0, 0, 0)
 struct MatRow {
@@ -55,28 +55,24 @@ struct Blk2 {
 };
 
 __device__ __forceinline__ void elast_row_blocks(const TriGeom &g, const MatRow &m, int v, Blk2 out[3]) {
+  // Ke(v, j) = t A B_v^T D B_j with B_i = (1/det) [[beta_i, 0], [0, gamma_i], [gamma_i, beta_i]].
+  // The two 1/det factors and t*A are folded into the row-v multipliers so that the column
+  // side uses the raw beta_j / gamma_j (saves the six per-vertex scalings).
   const double inv = 1.0 / g.det;
-  const double area = 0.5 * fabs(g.cross);
-  const double t = m.p3 * area;
-  double bb[3], bg[3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    bb[j] = g.beta[j] * inv;
-    bg[j] = g.gamma[j] * inv;
-  }
+  const double s = (0.5 * fabs(g.cross)) * inv * inv;  // area / det^2   (thickness is inside m)
   // select row v without dynamic register indexing
-  const double bbv = (v == 0) ? bb[0] : ((v == 1) ? bb[1] : bb[2]);
-  const double bgv = (v == 0) ? bg[0] : ((v == 1) ? bg[1] : bg[2]);
-  const double tb = t * bbv, tg = t * bgv;
-  const double cb = m.p0 * tb, cg = m.p0 * tg;  // c
-  const double ab = m.p1 * tb, ag = m.p1 * tg;  // a
-  const double sb = m.p2 * tb, sg = m.p2 * tg;  // b (shear)
+  const double bv = (v == 0) ? g.beta[0] : ((v == 1) ? g.beta[1] : g.beta[2]);
+  const double gv = (v == 0) ? g.gamma[0] : ((v == 1) ? g.gamma[1] : g.gamma[2]);
+  const double tb = s * bv, tg = s * gv;
+  const double cb = m.p0 * tb, cg = m.p0 * tg;  // c t
+  const double ab = m.p1 * tb, ag = m.p1 * tg;  // a t
+  const double sb = m.p2 * tb, sg = m.p2 * tg;  // b t (shear)
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    out[j].k00 = cb * bb[j] + sg * bg[j];
-    out[j].k01 = ab * bg[j] + sg * bb[j];
-    out[j].k10 = ag * bb[j] + sb * bg[j];
-    out[j].k11 = cg * bg[j] + sb * bb[j];
+    out[j].k00 = cb * g.beta[j] + sg * g.gamma[j];
+    out[j].k01 = ab * g.gamma[j] + sg * g.beta[j];
+    out[j].k10 = ag * g.beta[j] + sb * g.gamma[j];
+    out[j].k11 = cg * g.gamma[j] + sb * g.beta[j];
   }
 }
 

@@ -126,35 +126,64 @@ __global__ void __launch_bounds__(kRedBlock) k_spmv_b2(int32_t n_nodes, const in
                                                       PcgState *__restrict__ st) {
   __shared__ double red[kRedBlock / 32];
   if (DOT && (st->converged | st->breakdown)) return;
-  constexpr int LPN = 8, NPB = kRedBlock / LPN;
+  constexpr int LPN = 8, NPB = kRedBlock / LPN, U = 2;  // U nodes in flight per lane group
   const int lane = threadIdx.x % LPN;
+  const int64_t stride = (int64_t)gridDim.x * NPB;
   const int64_t n_pad = (int64_t)((n_nodes + NPB - 1) / NPB) * NPB;
   double dot = 0.0;
-  for (int64_t node = (int64_t)blockIdx.x * NPB + threadIdx.x / LPN; node < n_pad; node += (int64_t)gridDim.x * NPB) {
-    double a0 = 0.0, a1 = 0.0;
-    if (node < n_nodes) {
-      const int32_t s0 = __ldg(rowptr + 2 * node), s2 = __ldg(rowptr + 2 * node + 2);
-      const int32_t len = (s2 - s0) >> 1;  // entries per row = 2 * valence
-      const double *r0 = vals + s0, *r1 = vals + s0 + len;
-      for (int32_t k = 2 * lane; k < len; k += 2 * LPN) {
-        const int32_t c = __ldg(colidx + s0 + k);
-        const double2 xv = __ldg(reinterpret_cast<const double2 *>(x + c));
-        const double2 v0 = __ldcs(reinterpret_cast<const double2 *>(r0 + k));
-        const double2 v1 = __ldcs(reinterpret_cast<const double2 *>(r1 + k));
-        a0 += v0.x * xv.x + v0.y * xv.y;
-        a1 += v1.x * xv.x + v1.y * xv.y;
+  for (int64_t node0 = (int64_t)blockIdx.x * NPB + threadIdx.x / LPN; node0 < n_pad; node0 += U * stride) {
+    int32_t s0[U], len[U];
+    double a0[U], a1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t node = node0 + u * stride;
+      a0[u] = a1[u] = 0.0;
+      s0[u] = 0;
+      len[u] = 0;
+      if (node < n_nodes) {
+        s0[u] = __ldg(rowptr + 2 * node);
+        len[u] = (__ldg(rowptr + 2 * node + 2) - s0[u]) >> 1;  // entries per row = 2 * valence
+      }
+    }
+    // first (usually only) block of every node in flight: all loads are issued before any FMA
+    int32_t c[U];
+    double2 xv[U], v0[U], v1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool on = 2 * lane < len[u];
+      c[u] = on ? __ldg(colidx + s0[u] + 2 * lane) : 0;
+      v0[u] = on ? __ldg(reinterpret_cast<const double2 *>(vals + s0[u] + 2 * lane)) : make_double2(0.0, 0.0);
+      v1[u] = on ? __ldg(reinterpret_cast<const double2 *>(vals + s0[u] + len[u] + 2 * lane)) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) xv[u] = __ldg(reinterpret_cast<const double2 *>(x + c[u]));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      a0[u] = v0[u].x * xv[u].x + v0[u].y * xv[u].y;
+      a1[u] = v1[u].x * xv[u].x + v1[u].y * xv[u].y;
+      for (int32_t k = 2 * (lane + LPN); k < len[u]; k += 2 * LPN) {  // valence > 8
+        const int32_t cc = __ldg(colidx + s0[u] + k);
+        const double2 xx = __ldg(reinterpret_cast<const double2 *>(x + cc));
+        const double2 w0 = __ldg(reinterpret_cast<const double2 *>(vals + s0[u] + k));
+        const double2 w1 = __ldg(reinterpret_cast<const double2 *>(vals + s0[u] + len[u] + k));
+        a0[u] += w0.x * xx.x + w0.y * xx.y;
+        a1[u] += w1.x * xx.x + w1.y * xx.y;
       }
     }
 #pragma unroll
-    for (int o = LPN / 2; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    }
-    if (node < n_nodes && lane == 0) {
-      *reinterpret_cast<double2 *>(y + 2 * node) = make_double2(a0, a1);
-      if (DOT) {
-        const double2 xs = *reinterpret_cast<const double2 *>(x + 2 * node);
-        dot += a0 * xs.x + a1 * xs.y;
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int o = LPN / 2; o > 0; o >>= 1) {
+        a0[u] += __shfl_xor_sync(0xffffffffu, a0[u], o);
+        a1[u] += __shfl_xor_sync(0xffffffffu, a1[u], o);
+      }
+      const int64_t node = node0 + u * stride;
+      if (node < n_nodes && lane == 0) {
+        *reinterpret_cast<double2 *>(y + 2 * node) = make_double2(a0[u], a1[u]);
+        if (DOT) {
+          const double2 xs = *reinterpret_cast<const double2 *>(x + 2 * node);
+          dot += a0[u] * xs.x + a1[u] * xs.y;
+        }
       }
     }
   }
@@ -495,7 +524,8 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
   constexpr int kMaxRestarts = 12;
   const bool use_graph = !L.dist && getenv("FE_B200_NO_GRAPH") == nullptr;
   int it = 0, local = 0, restarts = 0;
-  bool done = (maxit == 0);
+  bool done = (maxit == 0), stagnated = false;
+  double prev_true_rr = -1.0;
   FE_CUDA(cudaMemcpyAsync(h, st, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
   FE_CUDA(cudaStreamSynchronize(s));
   if (h->converged || h->breakdown) done = true;
@@ -528,14 +558,21 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
     local = 0;
     FE_CUDA(cudaMemcpyAsync(h, st, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
     FE_CUDA(cudaStreamSynchronize(s));
-    if (h->converged || ++restarts > kMaxRestarts || it >= maxit) done = true;
+    if (h->converged || it >= maxit) {
+      done = true;
+    } else {
+      // attainable accuracy: a restart that no longer reduces the true residual cannot help
+      if (prev_true_rr >= 0.0 && h->sums[2] > 0.25 * prev_true_rr) stagnated = true;
+      prev_true_rr = h->sums[2];
+      if (stagnated || ++restarts > kMaxRestarts) done = true;
+    }
   }
   if (iters_out) *iters_out = h->iters;
   if (relres_out) *relres_out = (h->sums[3] > 0.0) ? sqrt(h->sums[2] / h->sums[3]) : 0.0;
   if (h->breakdown)
     return fail(FE_ERR_BREAKDOWN, "pcg: breakdown after %d iterations (matrix not SPD or singular: p.Ap = %g)",
                 h->iters, h->sums[0]);
-  if (!fixed && !h->converged)
+  if (!fixed && !h->converged && !stagnated)
     return fail(FE_ERR_NOT_CONVERGED, "pcg: not converged after %d iterations (relres %.3e > %.3e)", h->iters,
                 sqrt(h->sums[2] / h->sums[3]), rtol);
   return FE_OK;

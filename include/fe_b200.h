@@ -141,8 +141,10 @@ int fe_spmv(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
 /* Jacobi-preconditioned CG; replaces scipy spsolve at analysis.py:820-822 on the
  * eliminated SPD system.  x: initial guess in, solution out.  work: double[fe_pcg_work_len(n)].
  * Stops when ||r||_2 <= rtol * ||b||_2, where r is re-computed as b - A x once the recurrence
- * signals convergence (restart from x if the recurrence had drifted).  SYNCHRONISES the
- * stream; writes iters / relres (the true relative residual). */
+ * signals convergence (restart from x if the recurrence had drifted).  If restarts stop
+ * reducing the true residual (attainable FP64 accuracy reached) the call returns FE_OK with
+ * relres > rtol -- callers that need a hard bound compare *relres themselves.  SYNCHRONISES
+ * the stream; writes iters / relres (the true relative residual). */
 int64_t fe_pcg_work_len(int32_t n_rows, int32_t n_cols);
 int fe_pcg(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr, const int32_t *colidx,
            const double *vals, const double *b, double *x, double *work, int32_t block_dim,
