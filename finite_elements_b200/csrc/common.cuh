@@ -71,6 +71,7 @@ struct fe_ctx {
   int64_t launches = 0;
   fe::Scratch scratch_a;   // material tables, BC flags, scan block sums
   fe::Scratch scratch_b;   // reduction partials / PCG scalars
+  fe::Scratch scratch_c;   // node-level block pattern of the streamed SpMV
   void *pinned = nullptr;  // small pinned host buffer for scalar read-back
   void *pcg_graph = nullptr;  // cached cudaGraphExec_t of one PCG iteration chunk
   const void *pcg_graph_key[8] = {nullptr};

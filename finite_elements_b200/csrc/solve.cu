@@ -193,6 +193,8 @@ __global__ void __launch_bounds__(kRedBlock) k_spmv_b2(int32_t n_nodes, const in
   }
 }
 
+#include "spmv_stream.cuh"
+
 constexpr int kBlock2 = -2;  // pseudo "lanes per row" selecting k_spmv_b2
 
 static int spmv_lpr(int32_t n_rows, int64_t nnz, int block_dim) {
@@ -214,7 +216,13 @@ static int reducing_grid(fe_ctx *ctx, int64_t work_items, int items_per_cta) {
 template <bool DOT>
 static int launch_spmv(fe_ctx *ctx, cudaStream_t s, int lpr, int32_t n_rows, const int32_t *rowptr,
                        const int32_t *colidx, const double *vals, const double *x, double *y, double *partials,
-                       PcgState *st) {
+                       PcgState *st, const StreamPlan *sp = nullptr) {
+  if (sp && sp->on) {  // persistent TMA-streamed kernel (PCG)
+    k_spmv_stream<DOT><<<sp->grid, kStreamThreads, sp->smem, s>>>(n_rows / 2, sp->T, sp->cap, sp->bptr, sp->bidx,
+                                                                   vals, x, y, partials, st);
+    FE_LAUNCH_CHECK(ctx);
+    return FE_OK;
+  }
   if (lpr == kBlock2) {  // node-blocked fast path
     const int grid = reducing_grid(ctx, n_rows / 2, kRedBlock / 8);
     k_spmv_b2<DOT><<<grid, kRedBlock, 0, s>>>(n_rows / 2, rowptr, colidx, vals, x, y, partials, st);
@@ -398,6 +406,7 @@ struct PcgLaunch {
   const HaloPlan *halo;
   bool dist;
   int lpr, vgrid;
+  StreamPlan sp;
 
   // r = b - A x, p = D^-1 r, sums[1..3] = (r.z, r.r, b.b); converged flag from the TRUE residual
   int true_residual_start() {
@@ -405,7 +414,7 @@ struct PcgLaunch {
     k_copy<<<reducing_grid(ctx, n_rows, 1024), 256, 0, s>>>(n_rows, x, p);
     FE_LAUNCH_CHECK(ctx);
     if (dist && (rc = halo_exchange(ctx, s, halo, p, n_rows))) return rc;
-    if ((rc = launch_spmv<false>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st))) return rc;
+    if ((rc = launch_spmv<false>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st, &sp))) return rc;
     k_pcg_init<<<vgrid, kRedBlock, 0, s>>>(n_rows, b, q, dinv, r, p, partials, st);
     FE_LAUNCH_CHECK(ctx);
     if (dist && (rc = allreduce_sum(ctx, s, st->sums + 1, 3))) return rc;
@@ -417,7 +426,7 @@ struct PcgLaunch {
   int iteration(int parity) {
     int rc;
     if (dist && (rc = halo_exchange(ctx, s, halo, p, n_rows))) return rc;
-    if ((rc = launch_spmv<true>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st))) return rc;
+    if ((rc = launch_spmv<true>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st, &sp))) return rc;
     if (dist && (rc = allreduce_sum(ctx, s, st->sums + 0, 1))) return rc;
     k_pcg_update<<<vgrid, kRedBlock, 0, s>>>(n_rows, parity, p, q, dinv, x, r, partials, st);
     FE_LAUNCH_CHECK(ctx);
@@ -433,7 +442,7 @@ struct PcgLaunch {
 static int get_chunk_graph(PcgLaunch &L, int len, cudaGraphExec_t *out) {
   fe_ctx *ctx = L.ctx;
   const void *key[8] = {L.rowptr, L.colidx, L.vals, L.x, L.r, L.st, (void *)(intptr_t)L.n_rows,
-                        (void *)(intptr_t)(len * 64 + (L.lpr & 63))};
+                        (void *)(intptr_t)(len * 64 + (L.lpr & 31) + (L.sp.on ? 32 : 0))};
   if (ctx->pcg_graph && memcmp(key, ctx->pcg_graph_key, sizeof(key)) == 0) {
     *out = (cudaGraphExec_t)ctx->pcg_graph;
     return FE_OK;
@@ -512,6 +521,38 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
   FE_CUDA(cudaStreamSynchronize(s));
   L.lpr = spmv_lpr(n_rows, h_rowptr_end, block_dim);
   L.vgrid = reducing_grid(ctx, n_rows, kRedBlock * 4);
+  if (L.lpr == kBlock2 && n_rows > 0 && getenv("FE_B200_NO_STREAM") == nullptr) {
+    // node-level pattern for the TMA-streamed SpMV (rebuilt per solve: one pass over colidx)
+    const int32_t n_nodes = n_rows / 2;
+    const int64_t nnzb = h_rowptr_end / 4;
+    const size_t bptr_bytes = ((size_t)(n_nodes + 1) * 4 + 255) / 256 * 256;
+    const size_t bidx_bytes = ((size_t)(nnzb + 8) * 4 + 255) / 256 * 256;
+    if ((rc = ctx->scratch_c.reserve(bptr_bytes + bidx_bytes + 256))) return rc;
+    L.sp.bptr = (int32_t *)ctx->scratch_c.ptr;
+    L.sp.bidx = (int32_t *)((char *)ctx->scratch_c.ptr + bptr_bytes);
+    int *max_deg = (int *)((char *)ctx->scratch_c.ptr + bptr_bytes + bidx_bytes);
+    FE_CUDA(cudaMemsetAsync(max_deg, 0, sizeof(int), s));
+    k_block_pattern<<<grid_for(((int64_t)n_nodes + 1) * 8, 256), 256, 0, s>>>(n_nodes, rowptr, colidx, L.sp.bptr,
+                                                                              L.sp.bidx, max_deg);
+    FE_LAUNCH_CHECK(ctx);
+    int h_max_deg = 0;
+    FE_CUDA(cudaMemcpyAsync(&h_max_deg, max_deg, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FE_CUDA(cudaStreamSynchronize(s));
+    int T = 128;
+    while (T > 8 && stream_smem_bytes(T, (T * h_max_deg + 3) & ~3) > 100 * 1024) T >>= 1;
+    const int cap = (T * (h_max_deg > 0 ? h_max_deg : 1) + 3) & ~3;
+    const size_t smem = stream_smem_bytes(T, cap);
+    if (smem <= 100 * 1024) {
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      L.sp.on = true;
+      L.sp.T = T;
+      L.sp.cap = cap;
+      L.sp.smem = smem;
+      const int n_tiles = (n_nodes + T - 1) / T;
+      L.sp.grid = n_tiles < 2 * ctx->num_sms ? n_tiles : 2 * ctx->num_sms;
+    }
+  }
 
   if (n_rows > 0) {
     k_extract_dinv<<<grid_for(n_rows, 256), 256, 0, s>>>(n_rows, rowptr, colidx, vals, L.dinv, st);

@@ -1,0 +1,205 @@
+// Streaming SpMV for node-blocked (2 DOF per node) matrices -- the PCG hot kernel.
+//
+// Included by solve.cu after PcgState / publish_and_reduce.
+//
+// The CSR of an fe_plan with dim == 2 is a block-CSR in disguise: node i owns rows 2i, 2i+1,
+// whose values are ONE contiguous run of 4*valence doubles, and whose columns are the
+// (2m, 2m+1) pairs of its neighbour nodes m.  k_block_pattern extracts the node-level pattern
+// once per solve:  bptr[i] = rowptr[2i] / 4,  bidx[b] = colidx[rowptr[2i] + 2j] / 2  -- 4 bytes
+// per 2x2 block instead of 16.
+//
+// k_spmv_stream then runs persistent CTAs (2 per SM).  A tile = T consecutive nodes = one
+// contiguous slice of vals (32 B per block) and one of bidx (4 B per block).  Thread 0 hands both
+// slices of tile t+1 to the TMA engine (cp.async.bulk global -> shared, completion counted on an
+// mbarrier) while all threads compute tile t out of shared memory, so HBM streaming never waits
+// for the per-row dependent work (pointer look-up -> column -> gather of x).  The tile's bptr
+// slice travels with cp.async (LDGSTS).  8 lanes per node, one 2x2 block per lane:
+// LDS.128 x2 (vals), LDS.32 (column), LDG.128 (x, L1/L2 resident), 4 FMAs; fused p.q partials.
+//
+// HBM bytes per call:  8 nnz (vals) + nnz (bidx) + 2 n (bptr) + 8 n (x) + 8 n (y).
+#pragma once
+// (included from inside namespace fe)
+
+__global__ void __launch_bounds__(256) k_block_pattern(int32_t n_nodes, const int32_t *__restrict__ rowptr,
+                                                      const int32_t *__restrict__ colidx,
+                                                      int32_t *__restrict__ bptr, int32_t *__restrict__ bidx,
+                                                      int *__restrict__ max_deg) {
+  // 8 lanes per node
+  const int64_t node = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
+  const int lane = threadIdx.x & 7;
+  if (node > n_nodes) return;
+  if (node == n_nodes) {
+    if (lane == 0) bptr[n_nodes] = rowptr[2 * n_nodes] >> 2;
+    return;
+  }
+  const int32_t s0 = rowptr[2 * node], s2 = rowptr[2 * node + 2];
+  const int deg = (s2 - s0) >> 2;
+  if (lane == 0) {
+    bptr[node] = s0 >> 2;
+    atomicMax(max_deg, deg);
+  }
+  for (int j = lane; j < deg; j += 8) bidx[(s0 >> 2) + j] = colidx[s0 + 2 * j] >> 1;
+}
+
+namespace ptx {
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+}  // namespace ptx
+
+constexpr int kStreamThreads = 256;
+
+// smem: [2 mbarriers][2 x (T+1) bptr ints][2 x cap blocks x 32 B vals][2 x cap blocks x 4 B bidx]
+template <bool DOT>
+__global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream(
+    int32_t n_nodes, int T, int cap /* blocks per stage */, const int32_t *__restrict__ bptr,
+    const int32_t *__restrict__ bidx, const double *__restrict__ vals, const double *__restrict__ x,
+    double *__restrict__ y, double *__restrict__ partials, PcgState *__restrict__ st) {
+  __shared__ double red[kStreamThreads / 32];
+  if (DOT && (st->converged | st->breakdown)) return;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+  int32_t *ptr_s = reinterpret_cast<int32_t *>(smem + 16);
+  const size_t ptr_bytes = ((size_t)2 * (T + 1) * sizeof(int32_t) + 16 + 127) / 128 * 128;
+  double *vals_s = reinterpret_cast<double *>(smem + ptr_bytes);
+  int32_t *idx_s = reinterpret_cast<int32_t *>(smem + ptr_bytes + (size_t)2 * cap * 32);
+
+  const int tid = threadIdx.x;
+  const int n_tiles = (n_nodes + T - 1) / T;
+  if (tid == 0) {
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::mbar_init_fence();
+  }
+  __syncthreads();
+
+  double dot = 0.0;
+  int it = 0;
+  // prologue: stage 0 <- first tile
+  int tile = blockIdx.x;
+  auto load_tile = [&](int tl, int stage) {
+    // bptr slice via LDGSTS (all threads), vals + bidx via TMA (thread 0)
+    const int32_t n0 = tl * T, n1 = min(n0 + T, n_nodes);
+    int32_t *ps = ptr_s + stage * (T + 1);
+    for (int i = tid; i <= n1 - n0; i += kStreamThreads) ptx::cp_async4(ps + i, bptr + n0 + i);
+    ptx::cp_async_commit();
+    if (tid == 0) {
+      const int32_t b0 = __ldg(bptr + n0), b1 = __ldg(bptr + n1);
+      // bidx copy must be 16-byte aligned on both sides: start at b0 & ~3, length rounded up to 4 ints
+      const int32_t a0 = b0 & ~3;
+      const uint32_t nb = (uint32_t)(b1 - b0);
+      const uint32_t ni = ((uint32_t)(b1 - a0) + 3u) & ~3u;
+      ptx::mbar_expect_tx(&bars[stage], nb * 32u + (nb ? ni * 4u : 0u));
+      if (nb) {
+        ptx::bulk_load(vals_s + (size_t)stage * cap * 4, vals + 4 * (int64_t)b0, nb * 32u, &bars[stage]);
+        ptx::bulk_load(idx_s + (size_t)stage * (cap + 8), bidx + a0, ni * 4u, &bars[stage]);
+      }
+    }
+  };
+  if (tile < n_tiles) load_tile(tile, 0);
+
+  for (; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const int next = tile + gridDim.x;
+    if (next < n_tiles) load_tile(next, stage ^ 1);  // overlaps with the compute below
+    // wait for this tile: bptr slice (own cp.async groups: all but the one just committed) + TMA bytes
+    if (next < n_tiles)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else
+      ptx::cp_async_wait_all();
+    ptx::mbar_wait(&bars[stage], (uint32_t)((it >> 1) & 1));
+    __syncthreads();
+
+    const int32_t n0 = tile * T, n1 = min(n0 + T, n_nodes);
+    const int32_t *ps = ptr_s + stage * (T + 1);
+    const int32_t b0 = ps[0];
+    const double *vs = vals_s + (size_t)stage * cap * 4;
+    const int32_t *is = idx_s + (size_t)stage * (cap + 8) + (b0 - (b0 & ~3));
+    const int lane = tid & 7;
+    for (int i = tid >> 3; i < n1 - n0; i += kStreamThreads / 8) {
+      const int32_t s = ps[i] - b0;
+      const int deg = ps[i + 1] - ps[i];
+      const double *r0 = vs + 4 * (int64_t)s, *r1 = r0 + 2 * deg;
+      double a0 = 0.0, a1 = 0.0;
+      for (int k = lane; k < deg; k += 8) {
+        const int32_t c = is[s + k];
+        const double2 xv = __ldg(reinterpret_cast<const double2 *>(x) + c);
+        const double2 v0 = *reinterpret_cast<const double2 *>(r0 + 2 * k);
+        const double2 v1 = *reinterpret_cast<const double2 *>(r1 + 2 * k);
+        a0 += v0.x * xv.x + v0.y * xv.y;
+        a1 += v1.x * xv.x + v1.y * xv.y;
+      }
+      // the 8 lanes of a node are the same quarter-warp; a partial last pass leaves some groups idle,
+      // so shuffle under the group's own mask
+      const unsigned gmask = 0xffu << ((tid & 31) & ~7);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(gmask, a0, o);
+        a1 += __shfl_xor_sync(gmask, a1, o);
+      }
+      if (lane == 0) {
+        const int32_t node = n0 + i;
+        reinterpret_cast<double2 *>(y)[node] = make_double2(a0, a1);
+        if (DOT) {
+          const double2 xs = reinterpret_cast<const double2 *>(x)[node];
+          dot += a0 * xs.x + a1 * xs.y;
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with `stage` before the next TMA load overwrites it
+  }
+  if (DOT) {
+    const double loc[1] = {dot};
+    publish_and_reduce<1>(loc, partials, st, 0, red);
+  }
+}
+
+struct StreamPlan {
+  bool on = false;
+  int T = 0, cap = 0, grid = 0;
+  size_t smem = 0;
+  int32_t *bptr = nullptr, *bidx = nullptr;
+};
+
+static size_t stream_smem_bytes(int T, int cap) {
+  const size_t ptr_bytes = ((size_t)2 * (T + 1) * sizeof(int32_t) + 16 + 127) / 128 * 128;
+  return ptr_bytes + (size_t)2 * cap * 32 + (size_t)2 * (cap + 8) * 4;
+}
+

