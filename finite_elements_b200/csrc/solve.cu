@@ -37,31 +37,31 @@ constexpr int kRedBlock = 256;
 constexpr int kMaxPartials = 148 * 16;  // grids of the reducing kernels are capped to this
 
 // Sum `np` per-CTA partials (stride = number of quantities) in a fixed order.
-template <int NQ>
+template <int NQ, int BLOCK = kRedBlock>
 __device__ __forceinline__ void final_reduce(const double *__restrict__ partials, int np, double *smem,
                                              double *__restrict__ out) {
   double acc[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
-  for (int i = threadIdx.x; i < np; i += kRedBlock) {
+  for (int i = threadIdx.x; i < np; i += BLOCK) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] += __ldcg(partials + (size_t)i * NQ + q);
   }
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
-    const double t = block_sum<kRedBlock>(acc[q], smem);
+    const double t = block_sum<BLOCK>(acc[q], smem);
     if (threadIdx.x == 0) out[q] = t;
   }
 }
 
 // Writes this CTA's partials, elects the last CTA, which reduces all of them.
-template <int NQ>
+template <int NQ, int BLOCK = kRedBlock>
 __device__ __forceinline__ void publish_and_reduce(const double (&local)[NQ], double *__restrict__ partials,
                                                    PcgState *__restrict__ st, int out_base, double *smem) {
   __shared__ bool is_last;
   double tot[NQ];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) tot[q] = block_sum<kRedBlock>(local[q], smem);
+  for (int q = 0; q < NQ; ++q) tot[q] = block_sum<BLOCK>(local[q], smem);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) partials[(size_t)blockIdx.x * NQ + q] = tot[q];
@@ -72,7 +72,7 @@ __device__ __forceinline__ void publish_and_reduce(const double (&local)[NQ], do
   __syncthreads();
   if (is_last) {
     __threadfence();
-    final_reduce<NQ>(partials, gridDim.x, smem, st->sums + out_base);
+    final_reduce<NQ, BLOCK>(partials, gridDim.x, smem, st->sums + out_base);
     if (threadIdx.x == 0) st->ticket = 0;
   }
 }
@@ -538,8 +538,7 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
     int h_max_deg = 0;
     FE_CUDA(cudaMemcpyAsync(&h_max_deg, max_deg, sizeof(int), cudaMemcpyDeviceToHost, s));
     FE_CUDA(cudaStreamSynchronize(s));
-    int T = 128;
-    while (T > 8 && stream_smem_bytes(T, (T * h_max_deg + 3) & ~3) > 100 * 1024) T >>= 1;
+    const int T = kStreamTile;  // fixed tile; meshes whose valence makes it too large use k_spmv_b2
     const int cap = (T * (h_max_deg > 0 ? h_max_deg : 1) + 3) & ~3;
     const size_t smem = stream_smem_bytes(T, cap);
     if (smem <= 100 * 1024) {

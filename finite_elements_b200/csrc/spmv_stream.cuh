@@ -84,20 +84,22 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 }  // namespace ptx
 
-constexpr int kStreamThreads = 256;
+constexpr int kStreamThreads = 512;  // 16 warps per CTA, 2 CTAs per SM
+constexpr int kStreamTile = 128;     // nodes per tile (T); 64 lane groups -> 2 passes per tile
 
-// smem: [2 mbarriers][2 x (T+1) bptr ints][2 x cap blocks x 32 B vals][2 x cap blocks x 4 B bidx]
+// smem: [2 mbarriers][2 x (T+1) bptr ints][2 x cap blocks x 32 B vals][2 x (cap+8) x 4 B bidx]
 template <bool DOT>
 __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream(
-    int32_t n_nodes, int T, int cap /* blocks per stage */, const int32_t *__restrict__ bptr,
+    int32_t n_nodes, int /*T == kStreamTile*/, int cap /* blocks per stage */, const int32_t *__restrict__ bptr,
     const int32_t *__restrict__ bidx, const double *__restrict__ vals, const double *__restrict__ x,
     double *__restrict__ y, double *__restrict__ partials, PcgState *__restrict__ st) {
+  constexpr int T = kStreamTile, GROUPS = kStreamThreads / 8, PASSES = T / GROUPS;
   __shared__ double red[kStreamThreads / 32];
   if (DOT && (st->converged | st->breakdown)) return;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
   int32_t *ptr_s = reinterpret_cast<int32_t *>(smem + 16);
-  const size_t ptr_bytes = ((size_t)2 * (T + 1) * sizeof(int32_t) + 16 + 127) / 128 * 128;
+  constexpr size_t ptr_bytes = ((size_t)2 * (T + 1) * sizeof(int32_t) + 16 + 127) / 128 * 128;
   double *vals_s = reinterpret_cast<double *>(smem + ptr_bytes);
   int32_t *idx_s = reinterpret_cast<int32_t *>(smem + ptr_bytes + (size_t)2 * cap * 32);
 
@@ -110,15 +112,10 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream(
   }
   __syncthreads();
 
-  double dot = 0.0;
-  int it = 0;
-  // prologue: stage 0 <- first tile
-  int tile = blockIdx.x;
   auto load_tile = [&](int tl, int stage) {
-    // bptr slice via LDGSTS (all threads), vals + bidx via TMA (thread 0)
+    // bptr slice via LDGSTS (first T+1 threads), vals + bidx via TMA (thread 0)
     const int32_t n0 = tl * T, n1 = min(n0 + T, n_nodes);
-    int32_t *ps = ptr_s + stage * (T + 1);
-    for (int i = tid; i <= n1 - n0; i += kStreamThreads) ptx::cp_async4(ps + i, bptr + n0 + i);
+    if (tid <= n1 - n0) ptx::cp_async4(ptr_s + stage * (T + 1) + tid, bptr + n0 + tid);
     ptx::cp_async_commit();
     if (tid == 0) {
       const int32_t b0 = __ldg(bptr + n0), b1 = __ldg(bptr + n1);
@@ -133,52 +130,72 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream(
       }
     }
   };
+
+  double dot = 0.0;
+  int it = 0;
+  int tile = blockIdx.x;
   if (tile < n_tiles) load_tile(tile, 0);
+  const int grp = tid >> 3, lane = tid & 7;
+  const double2 *x2 = reinterpret_cast<const double2 *>(x);
+  double2 *y2 = reinterpret_cast<double2 *>(y);
 
   for (; tile < n_tiles; tile += gridDim.x, ++it) {
     const int stage = it & 1;
     const int next = tile + gridDim.x;
-    if (next < n_tiles) load_tile(next, stage ^ 1);  // overlaps with the compute below
-    // wait for this tile: bptr slice (own cp.async groups: all but the one just committed) + TMA bytes
-    if (next < n_tiles)
+    if (next < n_tiles) {
+      load_tile(next, stage ^ 1);  // overlaps with the compute below
       asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else
+    } else {
       ptx::cp_async_wait_all();
+    }
     ptx::mbar_wait(&bars[stage], (uint32_t)((it >> 1) & 1));
     __syncthreads();
 
-    const int32_t n0 = tile * T, n1 = min(n0 + T, n_nodes);
+    const int32_t n0 = tile * T;
+    const int nn = min(T, n_nodes - n0);
     const int32_t *ps = ptr_s + stage * (T + 1);
     const int32_t b0 = ps[0];
-    const double *vs = vals_s + (size_t)stage * cap * 4;
+    const double2 *vs = reinterpret_cast<const double2 *>(vals_s + (size_t)stage * cap * 4);
     const int32_t *is = idx_s + (size_t)stage * (cap + 8) + (b0 - (b0 & ~3));
-    const int lane = tid & 7;
-    for (int i = tid >> 3; i < n1 - n0; i += kStreamThreads / 8) {
-      const int32_t s = ps[i] - b0;
-      const int deg = ps[i + 1] - ps[i];
-      const double *r0 = vs + 4 * (int64_t)s, *r1 = r0 + 2 * deg;
-      double a0 = 0.0, a1 = 0.0;
-      for (int k = lane; k < deg; k += 8) {
-        const int32_t c = is[s + k];
-        const double2 xv = __ldg(reinterpret_cast<const double2 *>(x) + c);
-        const double2 v0 = *reinterpret_cast<const double2 *>(r0 + 2 * k);
-        const double2 v1 = *reinterpret_cast<const double2 *>(r1 + 2 * k);
-        a0 += v0.x * xv.x + v0.y * xv.y;
-        a1 += v1.x * xv.x + v1.y * xv.y;
+
+    int32_t s[PASSES], deg[PASSES], c[PASSES];
+    double2 v0[PASSES], v1[PASSES], xv[PASSES];
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {  // all shared-memory reads of the tile first ...
+      const int i = grp + p * GROUPS;
+      s[p] = 0;
+      deg[p] = 0;
+      if (i < nn) {
+        s[p] = ps[i] - b0;
+        deg[p] = ps[i + 1] - ps[i];
       }
-      // the 8 lanes of a node are the same quarter-warp; a partial last pass leaves some groups idle,
-      // so shuffle under the group's own mask
-      const unsigned gmask = 0xffu << ((tid & 31) & ~7);
+      const bool act = lane < deg[p];
+      c[p] = act ? is[s[p] + lane] : 0;
+      v0[p] = act ? vs[2 * s[p] + lane] : make_double2(0.0, 0.0);
+      v1[p] = act ? vs[2 * s[p] + deg[p] + lane] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) xv[p] = __ldg(x2 + c[p]);  // ... then every gather of x in flight
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+      double a0 = v0[p].x * xv[p].x + v0[p].y * xv[p].y;
+      double a1 = v1[p].x * xv[p].x + v1[p].y * xv[p].y;
+      for (int k = lane + 8; k < deg[p]; k += 8) {  // valence > 8
+        const double2 xx = __ldg(x2 + is[s[p] + k]);
+        const double2 w0 = vs[2 * s[p] + k], w1 = vs[2 * s[p] + deg[p] + k];
+        a0 += w0.x * xx.x + w0.y * xx.y;
+        a1 += w1.x * xx.x + w1.y * xx.y;
+      }
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(gmask, a0, o);
-        a1 += __shfl_xor_sync(gmask, a1, o);
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
       }
-      if (lane == 0) {
-        const int32_t node = n0 + i;
-        reinterpret_cast<double2 *>(y)[node] = make_double2(a0, a1);
+      const int i = grp + p * GROUPS;
+      if (lane == 0 && i < nn) {
+        y2[n0 + i] = make_double2(a0, a1);
         if (DOT) {
-          const double2 xs = reinterpret_cast<const double2 *>(x)[node];
+          const double2 xs = x2[n0 + i];
           dot += a0 * xs.x + a1 * xs.y;
         }
       }
@@ -187,7 +204,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream(
   }
   if (DOT) {
     const double loc[1] = {dot};
-    publish_and_reduce<1>(loc, partials, st, 0, red);
+    publish_and_reduce<1, kStreamThreads>(loc, partials, st, 0, red);
   }
 }
 
