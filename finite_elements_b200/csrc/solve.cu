@@ -525,7 +525,7 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
     // node-level pattern for the TMA-streamed SpMV (rebuilt per solve: one pass over colidx)
     const int32_t n_nodes = n_rows / 2;
     const int64_t nnzb = h_rowptr_end / 4;
-    const size_t bptr_bytes = ((size_t)(n_nodes + 1) * 4 + 255) / 256 * 256;
+    const size_t bptr_bytes = ((size_t)(n_nodes + 1 + 128) * 4 + 255) / 256 * 256;  // +128: tile slice over-read
     const size_t bidx_bytes = ((size_t)(nnzb + 8) * 4 + 255) / 256 * 256;
     if ((rc = ctx->scratch_c.reserve(bptr_bytes + bidx_bytes + 256))) return rc;
     L.sp.bptr = (int32_t *)ctx->scratch_c.ptr;
@@ -541,7 +541,7 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
     const int T = kStreamTile;  // fixed tile; meshes whose valence makes it too large use k_spmv_b2
     const int cap = (T * (h_max_deg > 0 ? h_max_deg : 1) + 3) & ~3;
     const size_t smem = stream_smem_bytes(T, cap);
-    if (smem <= 100 * 1024) {
+    if (smem <= 110 * 1024) {
       FE_CUDA(cudaFuncSetAttribute(k_spmv_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       FE_CUDA(cudaFuncSetAttribute(k_spmv_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       L.sp.on = true;

@@ -56,6 +56,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
   uint32_t done = 0;
@@ -84,123 +87,129 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 }  // namespace ptx
 
-constexpr int kStreamThreads = 512;  // 16 warps per CTA, 2 CTAs per SM
-constexpr int kStreamTile = 128;     // nodes per tile (T); 64 lane groups -> 2 passes per tile
+constexpr int kStreamConsumerWarps = 15;                        // + 1 producer warp
+constexpr int kStreamThreads = (kStreamConsumerWarps + 1) * 32;  // 512
+constexpr int kStreamGroups = kStreamConsumerWarps * 4;          // 8-lane groups = nodes per pass
+constexpr int kStreamTile = 2 * kStreamGroups;                   // 120 nodes per tile, 2 passes
+constexpr int kStreamStages = 3;
+constexpr int kStreamPtrInts = (kStreamTile + 1 + 3) & ~3;       // bptr slice copied per tile (16 B units)
 
-// smem: [2 mbarriers][2 x (T+1) bptr ints][2 x cap blocks x 32 B vals][2 x (cap+8) x 4 B bidx]
+// smem: [full[S], empty[S] mbarriers][S x kStreamPtrInts ints][S x cap x 32 B vals][S x (cap+8) x 4 B bidx]
 template <bool DOT>
 __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream(
     int32_t n_nodes, int /*T == kStreamTile*/, int cap /* blocks per stage */, const int32_t *__restrict__ bptr,
     const int32_t *__restrict__ bidx, const double *__restrict__ vals, const double *__restrict__ x,
     double *__restrict__ y, double *__restrict__ partials, PcgState *__restrict__ st) {
-  constexpr int T = kStreamTile, GROUPS = kStreamThreads / 8, PASSES = T / GROUPS;
+  constexpr int T = kStreamTile, S = kStreamStages, GROUPS = kStreamGroups, PASSES = 2;
   __shared__ double red[kStreamThreads / 32];
   if (DOT && (st->converged | st->breakdown)) return;
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-  int32_t *ptr_s = reinterpret_cast<int32_t *>(smem + 16);
-  constexpr size_t ptr_bytes = ((size_t)2 * (T + 1) * sizeof(int32_t) + 16 + 127) / 128 * 128;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *empty = full + S;
+  constexpr size_t kHdr = 128;
+  int32_t *ptr_s = reinterpret_cast<int32_t *>(smem + kHdr);
+  constexpr size_t ptr_bytes = (kHdr + (size_t)S * kStreamPtrInts * sizeof(int32_t) + 127) / 128 * 128;
   double *vals_s = reinterpret_cast<double *>(smem + ptr_bytes);
-  int32_t *idx_s = reinterpret_cast<int32_t *>(smem + ptr_bytes + (size_t)2 * cap * 32);
+  int32_t *idx_s = reinterpret_cast<int32_t *>(smem + ptr_bytes + (size_t)S * cap * 32);
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int n_tiles = (n_nodes + T - 1) / T;
   if (tid == 0) {
-    ptx::mbar_init(&bars[0], 1);
-    ptx::mbar_init(&bars[1], 1);
+    for (int i = 0; i < S; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], kStreamConsumerWarps);
+    }
     ptx::mbar_init_fence();
   }
   __syncthreads();
 
-  auto load_tile = [&](int tl, int stage) {
-    // bptr slice via LDGSTS (first T+1 threads), vals + bidx via TMA (thread 0)
-    const int32_t n0 = tl * T, n1 = min(n0 + T, n_nodes);
-    if (tid <= n1 - n0) ptx::cp_async4(ptr_s + stage * (T + 1) + tid, bptr + n0 + tid);
-    ptx::cp_async_commit();
-    if (tid == 0) {
-      const int32_t b0 = __ldg(bptr + n0), b1 = __ldg(bptr + n1);
-      // bidx copy must be 16-byte aligned on both sides: start at b0 & ~3, length rounded up to 4 ints
-      const int32_t a0 = b0 & ~3;
-      const uint32_t nb = (uint32_t)(b1 - b0);
-      const uint32_t ni = ((uint32_t)(b1 - a0) + 3u) & ~3u;
-      ptx::mbar_expect_tx(&bars[stage], nb * 32u + (nb ? ni * 4u : 0u));
-      if (nb) {
-        ptx::bulk_load(vals_s + (size_t)stage * cap * 4, vals + 4 * (int64_t)b0, nb * 32u, &bars[stage]);
-        ptx::bulk_load(idx_s + (size_t)stage * (cap + 8), bidx + a0, ni * 4u, &bars[stage]);
-      }
-    }
-  };
-
   double dot = 0.0;
-  int it = 0;
-  int tile = blockIdx.x;
-  if (tile < n_tiles) load_tile(tile, 0);
-  const int grp = tid >> 3, lane = tid & 7;
-  const double2 *x2 = reinterpret_cast<const double2 *>(x);
-  double2 *y2 = reinterpret_cast<double2 *>(y);
-
-  for (; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int stage = it & 1;
-    const int next = tile + gridDim.x;
-    if (next < n_tiles) {
-      load_tile(next, stage ^ 1);  // overlaps with the compute below
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      ptx::cp_async_wait_all();
-    }
-    ptx::mbar_wait(&bars[stage], (uint32_t)((it >> 1) & 1));
-    __syncthreads();
-
-    const int32_t n0 = tile * T;
-    const int nn = min(T, n_nodes - n0);
-    const int32_t *ps = ptr_s + stage * (T + 1);
-    const int32_t b0 = ps[0];
-    const double2 *vs = reinterpret_cast<const double2 *>(vals_s + (size_t)stage * cap * 4);
-    const int32_t *is = idx_s + (size_t)stage * (cap + 8) + (b0 - (b0 & ~3));
-
-    int32_t s[PASSES], deg[PASSES], c[PASSES];
-    double2 v0[PASSES], v1[PASSES], xv[PASSES];
-#pragma unroll
-    for (int p = 0; p < PASSES; ++p) {  // all shared-memory reads of the tile first ...
-      const int i = grp + p * GROUPS;
-      s[p] = 0;
-      deg[p] = 0;
-      if (i < nn) {
-        s[p] = ps[i] - b0;
-        deg[p] = ps[i + 1] - ps[i];
-      }
-      const bool act = lane < deg[p];
-      c[p] = act ? is[s[p] + lane] : 0;
-      v0[p] = act ? vs[2 * s[p] + lane] : make_double2(0.0, 0.0);
-      v1[p] = act ? vs[2 * s[p] + deg[p] + lane] : make_double2(0.0, 0.0);
-    }
-#pragma unroll
-    for (int p = 0; p < PASSES; ++p) xv[p] = __ldg(x2 + c[p]);  // ... then every gather of x in flight
-#pragma unroll
-    for (int p = 0; p < PASSES; ++p) {
-      double a0 = v0[p].x * xv[p].x + v0[p].y * xv[p].y;
-      double a1 = v1[p].x * xv[p].x + v1[p].y * xv[p].y;
-      for (int k = lane + 8; k < deg[p]; k += 8) {  // valence > 8
-        const double2 xx = __ldg(x2 + is[s[p] + k]);
-        const double2 w0 = vs[2 * s[p] + k], w1 = vs[2 * s[p] + deg[p] + k];
-        a0 += w0.x * xx.x + w0.y * xx.y;
-        a1 += w1.x * xx.x + w1.y * xx.y;
-      }
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      }
-      const int i = grp + p * GROUPS;
-      if (lane == 0 && i < nn) {
-        y2[n0 + i] = make_double2(a0, a1);
-        if (DOT) {
-          const double2 xs = x2[n0 + i];
-          dot += a0 * xs.x + a1 * xs.y;
+  if (warp == kStreamConsumerWarps) {
+    // ===== producer warp: one lane feeds the ring with TMA bulk loads =====
+    if ((tid & 31) == 0) {
+      int j = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+        const int stage = j % S, use = j / S;
+        if (use > 0) ptx::mbar_wait(&empty[stage], (uint32_t)((use - 1) & 1));  // consumers released it
+        const int32_t n0 = tile * T, n1 = min(n0 + T, n_nodes);
+        const int32_t b0 = __ldg(bptr + n0), b1 = __ldg(bptr + n1);
+        const int32_t a0 = b0 & ~3;  // bidx copy is 16-byte aligned on both sides
+        const uint32_t nb = (uint32_t)(b1 - b0);
+        const uint32_t ni = ((uint32_t)(b1 - a0) + 3u) & ~3u;
+        ptx::mbar_expect_tx(&full[stage], kStreamPtrInts * 4u + nb * 32u + (nb ? ni * 4u : 0u));
+        ptx::bulk_load(ptr_s + stage * kStreamPtrInts, bptr + n0, kStreamPtrInts * 4u, &full[stage]);
+        if (nb) {
+          ptx::bulk_load(vals_s + (size_t)stage * cap * 4, vals + 4 * (int64_t)b0, nb * 32u, &full[stage]);
+          ptx::bulk_load(idx_s + (size_t)stage * (cap + 8), bidx + a0, ni * 4u, &full[stage]);
         }
       }
     }
-    __syncthreads();  // everyone is done with `stage` before the next TMA load overwrites it
+  } else {
+    // ===== consumer warps: 8 lanes per node, one 2x2 block per lane =====
+    const int grp = tid >> 3, lane = tid & 7;
+    const double2 *x2 = reinterpret_cast<const double2 *>(x);
+    double2 *y2 = reinterpret_cast<double2 *>(y);
+    int j = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+      const int stage = j % S, use = j / S;
+      ptx::mbar_wait(&full[stage], (uint32_t)(use & 1));
+      const int32_t n0 = tile * T;
+      const int nn = min(T, n_nodes - n0);
+      const int32_t *ps = ptr_s + stage * kStreamPtrInts;
+      const int32_t b0 = ps[0];
+      const double2 *vs = reinterpret_cast<const double2 *>(vals_s + (size_t)stage * cap * 4);
+      const int32_t *is = idx_s + (size_t)stage * (cap + 8) + (b0 - (b0 & ~3));
+
+      int32_t s[PASSES], deg[PASSES], c[PASSES];
+      double2 v0[PASSES], v1[PASSES], xv[PASSES];
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {  // all shared-memory reads of the tile first ...
+        const int i = grp + p * GROUPS;
+        s[p] = 0;
+        deg[p] = 0;
+        if (i < nn) {
+          s[p] = ps[i] - b0;
+          deg[p] = ps[i + 1] - ps[i];
+        }
+        const bool act = lane < deg[p];
+        c[p] = act ? is[s[p] + lane] : 0;
+        v0[p] = act ? vs[2 * s[p] + lane] : make_double2(0.0, 0.0);
+        v1[p] = act ? vs[2 * s[p] + deg[p] + lane] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) xv[p] = __ldg(x2 + c[p]);  // ... then every gather of x in flight
+      double a0[PASSES], a1[PASSES];
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {
+        a0[p] = v0[p].x * xv[p].x + v0[p].y * xv[p].y;
+        a1[p] = v1[p].x * xv[p].x + v1[p].y * xv[p].y;
+        for (int k = lane + 8; k < deg[p]; k += 8) {  // valence > 8
+          const double2 xx = __ldg(x2 + is[s[p] + k]);
+          const double2 w0 = vs[2 * s[p] + k], w1 = vs[2 * s[p] + deg[p] + k];
+          a0[p] += w0.x * xx.x + w0.y * xx.y;
+          a1[p] += w1.x * xx.x + w1.y * xx.y;
+        }
+      }
+      // this warp is done reading the stage: hand it back to the producer
+      __syncwarp();
+      if ((tid & 31) == 0) ptx::mbar_arrive(&empty[stage]);
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          a0[p] += __shfl_xor_sync(0xffffffffu, a0[p], o);
+          a1[p] += __shfl_xor_sync(0xffffffffu, a1[p], o);
+        }
+        const int i = grp + p * GROUPS;
+        if (lane == 0 && i < nn) {
+          y2[n0 + i] = make_double2(a0[p], a1[p]);
+          if (DOT) {
+            const double2 xs = x2[n0 + i];
+            dot += a0[p] * xs.x + a1[p] * xs.y;
+          }
+        }
+      }
+    }
   }
   if (DOT) {
     const double loc[1] = {dot};
@@ -215,8 +224,7 @@ struct StreamPlan {
   int32_t *bptr = nullptr, *bidx = nullptr;
 };
 
-static size_t stream_smem_bytes(int T, int cap) {
-  const size_t ptr_bytes = ((size_t)2 * (T + 1) * sizeof(int32_t) + 16 + 127) / 128 * 128;
-  return ptr_bytes + (size_t)2 * cap * 32 + (size_t)2 * (cap + 8) * 4;
+static size_t stream_smem_bytes(int /*T*/, int cap) {
+  const size_t ptr_bytes = (128 + (size_t)kStreamStages * kStreamPtrInts * sizeof(int32_t) + 127) / 128 * 128;
+  return ptr_bytes + (size_t)kStreamStages * cap * 32 + (size_t)kStreamStages * (cap + 8) * 4;
 }
-
