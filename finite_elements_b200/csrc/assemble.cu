@@ -20,6 +20,7 @@
 //                          tile out with fully coalesced 128-bit-per-lane row writes.
 #include "elem.cuh"
 #include "plan.cuh"
+#include "ptx.cuh"
 
 namespace fe {
 
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kTile) k_assemble_tile(int32_t n_owned, const 
                                                         const MatRow *__restrict__ tab, double *__restrict__ vals) {
   constexpr int DIM = (KC == 2) ? 1 : 2;
   constexpr int LD = kTile + 1;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   int32_t *a_tile = reinterpret_cast<int32_t *>(smem_raw);
   double *acc = reinterpret_cast<double *>(smem_raw + ((kTile + 1) * sizeof(int32_t) + 15) / 16 * 16);
 
@@ -249,153 +250,185 @@ struct FanOps {  // elasticity (0) / mass (1): 2x2 blocks, stored as two double2
   }
 };
 
-__device__ __forceinline__ int4 ld_stream_int4(const int4 *p) {
-  int4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
+// Persistent, software-pipelined kernel.  CTA = 128 threads, one per node of a 128-node tile;
+// every CTA walks the tiles blockIdx.x, +gridDim.x, ...  While tile j is being computed, thread 0
+// has already handed tile j+1 to the TMA engine: the two pointer slices (adj_ptr, fan_ptr: 132
+// ints each) and the tile's contiguous record range are bulk-loaded into the other half of a
+// 2-stage shared-memory ring (completion on an mbarrier), and the record-range end points of
+// tile j+2 are already travelling towards thread 0's registers.  The dependent pointer ->
+// record round trips that used to idle the whole CTA at the start of every tile are hidden.
+// Consumers build the tile's slice of `vals` in shared memory and thread 0 hands it to the TMA
+// engine as a single bulk store.
+// smem: [full[2]] | 2 x { a_tile[132], f_tile[132], recs int2[rec_cap] } | out tile
+constexpr int kFanConsumers = kTile;               // 128 threads
+constexpr int kFanThreads = kFanConsumers;
+constexpr int kFanPtrInts = (kTile + 1 + 3) & ~3;  // 132
+
+__host__ __device__ inline size_t fan_stage_bytes(int rec_cap) {
+  return ((size_t)2 * kFanPtrInts * sizeof(int32_t) + (size_t)rec_cap * sizeof(int2) + 127) / 128 * 128;
 }
 
-// smem: a_tile[kTile+1] | f_tile[kTile+1] | recs int2[rec_cap] | acc double[dim^2 * blocks in tile]
 template <int KC>
-__global__ void __launch_bounds__(kTile, FE_FAN_MINB) k_assemble_fan(int32_t n_owned, const int32_t *__restrict__ fan_ptr,
-                                                       const int2 *__restrict__ fan_rec,
-                                                       const int32_t *__restrict__ adj_ptr,
-                                                       const double2 *__restrict__ coords,
-                                                       const MatRow *__restrict__ tab, double *__restrict__ vals,
-                                                       int rec_cap) {
+__global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
+    int32_t n_owned, const int32_t *__restrict__ fan_ptr, const int2 *__restrict__ fan_rec,
+    const int32_t *__restrict__ adj_ptr, const double2 *__restrict__ coords, const MatRow *__restrict__ tab,
+    double *__restrict__ vals, int rec_cap) {
   using Ops = FanOps<KC>;
   using Val = typename Ops::Val;
   using Slot = typename Ops::Slot;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t *a_tile = reinterpret_cast<int32_t *>(smem_raw);
-  int32_t *f_tile = a_tile + (kTile + 1);
-  constexpr size_t kHdr = (2 * (kTile + 1) * sizeof(int32_t) + 15) / 16 * 16;
-  int2 *recs = reinterpret_cast<int2 *>(smem_raw + kHdr);
-  Slot *acc = reinterpret_cast<Slot *>(smem_raw + kHdr + (size_t)rec_cap * sizeof(int2));
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+  const size_t stage_bytes = fan_stage_bytes(rec_cap);
+  unsigned char *stage0 = smem_raw + 128;
+  Slot *acc = reinterpret_cast<Slot *>(stage0 + 2 * stage_bytes);
 
   const int tid = threadIdx.x;
-  const int32_t n0 = blockIdx.x * kTile;
-  const int32_t n = n0 + tid;
-  const int n_in_tile = min(kTile, n_owned - n0);
-  if (tid <= n_in_tile) {
-    a_tile[tid] = adj_ptr[n0 + tid];
-    f_tile[tid] = fan_ptr[n0 + tid];
-  }
-  if (tid == 0 && n_in_tile == kTile) {
-    a_tile[kTile] = adj_ptr[n0 + kTile];
-    f_tile[kTile] = fan_ptr[n0 + kTile];
-  }
-  __syncthreads();
-  // stage the tile's records: [base, r1) with base rounded down to a 16-byte boundary
-  const int32_t base = f_tile[0] & ~1;
-  {
-    const int n16 = (f_tile[n_in_tile] - base + 1) >> 1;
-    const int4 *src = reinterpret_cast<const int4 *>(fan_rec + base);
-    int4 *dst = reinterpret_cast<int4 *>(recs);
-    for (int i = tid; i < n16; i += kTile) dst[i] = ld_stream_int4(src + i);
+  const int n_tiles = (n_owned + kTile - 1) / kTile;
+  if (tid == 0) {
+    ptx::mbar_init(&full[0], 1);
+    ptx::mbar_init(&full[1], 1);
+    ptx::mbar_init_fence();
   }
   __syncthreads();
 
-  if (n < n_owned) {
-    int f = f_tile[tid] - base;
-    const int fe = f_tile[tid + 1] - base;
-    const int deg = a_tile[tid + 1] - a_tile[tid];
-    const bool any = f < fe;
-    const double2 ps = __ldg(coords + n);
-    Slot *my = acc + (KC == 2 ? 1 : 2) * (a_tile[tid] - a_tile[0]);  // natural (output-image) layout
-    // Software pipeline over (record, neighbour coordinates): four rotating register sets, the
-    // gather for step f+3 is issued while step f computes, and the set of step f-1 doubles as
-    // "previous neighbour" of step f -- no register shifting.
-    struct Item {
-      int2 rec;
-      double2 p;
-    };
-    Item ia = {make_int2(n, 0), ps}, ib = ia, ic = ia, id = ia;
-    auto fetch = [&](int i, Item &it) {
-      if (i < fe) {
-        it.rec = recs[i];
-        it.p = __ldg(coords + it.rec.x);
-      }
-    };
-    int kself = 0, cur_mat = -1;
-    MatRow m = {0.0, 0.0, 0.0, 0.0};
-    Val diag = Ops::zero(), carry = Ops::zero();
-    auto process = [&](const Item &cur, const Item &prev) {
-      const uint32_t y = (uint32_t)cur.rec.y;
-      const uint32_t fl = (y >> 8) & 31;
-      if (fl & FanFlags::SEED) {
-        kself = y >> 13;
-        return;
-      }
-      const int mid = y >> 13;
-      if (mid != cur_mat) {
-        m = tab[mid];
-        cur_mat = mid;
-      }
-      const TriGeom g = tri_geom(ps, prev.p, cur.p);
-      Val r[3];
-      Ops::rows(g, m, r);
-      Ops::add(diag, r[0]);
-      if (fl & FanFlags::ADD_CARRY) Ops::add(r[1], carry);
-      // (a closed fan's first block waits in its slot; the last step completes it there)
-      Ops::store(my, deg, (uint32_t)prev.rec.y & 255, 1, r[1]);
-      carry = r[2];
-      if (fl & FanFlags::LAST) {
-        if (fl & FanFlags::ADD_FIRST) Ops::add(r[2], Ops::load(my, deg, y & 255));
-        Ops::store(my, deg, y & 255, 1, r[2]);
-      }
-    };
-    fetch(f, ia);
-    fetch(f + 1, ib);
-    fetch(f + 2, ic);
-    while (true) {
-      if (f >= fe) break;
-      process(ia, id);
-      fetch(f + 3, id);
-      ++f;
-      if (f >= fe) break;
-      process(ib, ia);
-      fetch(f + 3, ia);
-      ++f;
-      if (f >= fe) break;
-      process(ic, ib);
-      fetch(f + 3, ib);
-      ++f;
-      if (f >= fe) break;
-      process(id, ic);
-      fetch(f + 3, ic);
-      ++f;
+  // thread 0 only: end points of a tile's record range, and the TMA loads of a tile
+  auto endpoints = [&](int tile, int32_t &r0, int32_t &r1) {
+    if (tile < n_tiles) {
+      const int32_t n0 = tile * kTile;
+      r0 = __ldg(fan_ptr + n0);
+      r1 = __ldg(fan_ptr + min(n0 + kTile, n_owned));
     }
-    if (any) Ops::store(my, deg, kself, 1, diag);
+  };
+  auto issue = [&](int tile, int stage, int32_t r0, int32_t r1) {
+    const int32_t n0 = tile * kTile;
+    const int32_t base = r0 & ~1;  // 16-byte aligned start of the record copy
+    const uint32_t rec_bytes = (uint32_t)((r1 - base + 1) >> 1) * 16u;
+    unsigned char *st = stage0 + stage * stage_bytes;
+    ptx::mbar_expect_tx(&full[stage], 2u * kFanPtrInts * 4u + rec_bytes);
+    ptx::bulk_load(st, adj_ptr + n0, kFanPtrInts * 4u, &full[stage]);
+    ptx::bulk_load(st + kFanPtrInts * 4, fan_ptr + n0, kFanPtrInts * 4u, &full[stage]);
+    if (rec_bytes) ptx::bulk_load(st + 2 * kFanPtrInts * 4, fan_rec + base, rec_bytes, &full[stage]);
+  };
+  int32_t nr0 = 0, nr1 = 0;  // end points of the NEXT tile to issue (thread 0)
+  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+    int32_t r0 = 0, r1 = 0;
+    endpoints(blockIdx.x, r0, r1);
+    issue(blockIdx.x, 0, r0, r1);
+    endpoints(blockIdx.x + gridDim.x, nr0, nr1);
   }
-  if (KC != 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy
-  __syncthreads();
 
-  // The staged tile is the exact image of vals[dim^2 * a_tile[0] .. dim^2 * a_tile[n_in_tile]).
-  const int32_t tile_lo = a_tile[0];
-  const int tile_len = a_tile[n_in_tile] - tile_lo;  // node-level blocks in the tile
-  if (KC == 2) {
-    // 1 DOF per node: the destination is only 8-byte aligned -> plain coalesced copy
-    const double *src = reinterpret_cast<const double *>(acc);
-    double *dst = vals + tile_lo;
-    for (int q = tid; q < tile_len; q += kTile) dst[q] = src[q];
-  } else if (tid == 0 && tile_len > 0) {
-    // 2 DOF per node: one TMA bulk store of the whole tile (32 * tile_len bytes, 32-byte aligned)
-    const uint32_t src = (uint32_t)__cvta_generic_to_shared(acc);
-    double *dst = vals + 4 * (int64_t)tile_lo;
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
-                 "r"((uint32_t)tile_len * 32u)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the copy
+  int j = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+    const int stage = j & 1, use = j >> 1;
+    if (tid == 0) {
+      // the other ring slot was released by the barrier that ended the previous tile
+      const int next = tile + gridDim.x;
+      if (next < n_tiles) issue(next, stage ^ 1, nr0, nr1);
+      endpoints(next + gridDim.x, nr0, nr1);  // lands while this tile computes
+    }
+    const int32_t n0 = tile * kTile;
+    const int32_t n = n0 + tid;
+    const int n_in_tile = min(kTile, n_owned - n0);
+    const unsigned char *st = stage0 + stage * stage_bytes;
+    const int32_t *a_tile = reinterpret_cast<const int32_t *>(st);
+    const int32_t *f_tile = a_tile + kFanPtrInts;
+    const int2 *recs = reinterpret_cast<const int2 *>(st + 2 * kFanPtrInts * 4);
+    const double2 ps = (n < n_owned) ? __ldg(coords + n) : make_double2(0.0, 0.0);  // before the wait: overlaps
+    ptx::mbar_wait(&full[stage], (uint32_t)(use & 1));
+    const int32_t base = f_tile[0] & ~1;
+    const int32_t tile_lo = a_tile[0];
+    const int tile_len = a_tile[n_in_tile] - tile_lo;  // node-level blocks in the tile
+
+    if (n < n_owned) {
+      int f = f_tile[tid] - base;
+      const int fe = f_tile[tid + 1] - base;
+      const int deg = a_tile[tid + 1] - a_tile[tid];
+      const bool any = f < fe;
+      Slot *my = acc + (KC == 2 ? 1 : 2) * (a_tile[tid] - tile_lo);  // natural (output-image) layout
+      // Software pipeline over (record, neighbour coordinates): four rotating register sets, the
+      // gather for step f+3 is issued while step f computes, and the set of step f-1 doubles as
+      // "previous neighbour" of step f -- no register shifting.
+      struct Item {
+        int2 rec;
+        double2 p;
+      };
+      Item ia = {make_int2(n, 0), ps}, ib = ia, ic = ia, id = ia;
+      auto fetch = [&](int i, Item &it) {
+        if (i < fe) {
+          it.rec = recs[i];
+          it.p = __ldg(coords + it.rec.x);
+        }
+      };
+      int kself = 0, cur_mat = -1;
+      MatRow m = {0.0, 0.0, 0.0, 0.0};
+      Val diag = Ops::zero(), carry = Ops::zero();
+      auto process = [&](const Item &cur, const Item &prev) {
+        const uint32_t y = (uint32_t)cur.rec.y;
+        const uint32_t fl = (y >> 8) & 31;
+        if (fl & FanFlags::SEED) {
+          kself = y >> 13;
+          return;
+        }
+        const int mid = y >> 13;
+        if (mid != cur_mat) {
+          m = tab[mid];
+          cur_mat = mid;
+        }
+        const TriGeom g = tri_geom(ps, prev.p, cur.p);
+        Val r[3];
+        Ops::rows(g, m, r);
+        Ops::add(diag, r[0]);
+        if (fl & FanFlags::ADD_CARRY) Ops::add(r[1], carry);
+        // (a closed fan's first block waits in its slot; the last step completes it there)
+        Ops::store(my, deg, (uint32_t)prev.rec.y & 255, 1, r[1]);
+        carry = r[2];
+        if (fl & FanFlags::LAST) {
+          if (fl & FanFlags::ADD_FIRST) Ops::add(r[2], Ops::load(my, deg, y & 255));
+          Ops::store(my, deg, y & 255, 1, r[2]);
+        }
+      };
+      fetch(f, ia);
+      fetch(f + 1, ib);
+      fetch(f + 2, ic);
+      while (true) {
+        if (f >= fe) break;
+        process(ia, id);
+        fetch(f + 3, id);
+        ++f;
+        if (f >= fe) break;
+        process(ib, ia);
+        fetch(f + 3, ia);
+        ++f;
+        if (f >= fe) break;
+        process(ic, ib);
+        fetch(f + 3, ib);
+        ++f;
+        if (f >= fe) break;
+        process(id, ic);
+        fetch(f + 3, ic);
+        ++f;
+      }
+      if (any) Ops::store(my, deg, kself, 1, diag);
+    }
+    if (KC != 2) ptx::fence_async_smem();  // generic writes -> visible to the async proxy
+    __syncthreads();
+    // The staged tile is the exact image of vals[dim^2 * tile_lo .. dim^2 * (tile_lo + tile_len)).
+    if (KC == 2) {
+      // 1 DOF per node: the destination is only 8-byte aligned -> plain coalesced copy
+      const double *src = reinterpret_cast<const double *>(acc);
+      double *dst = vals + tile_lo;
+      for (int q = tid; q < tile_len; q += kFanConsumers) dst[q] = src[q];
+    } else if (tid == 0 && tile_len > 0) {
+      // 2 DOF per node: one TMA bulk store of the whole tile (32 * tile_len bytes, 32-byte aligned)
+      ptx::bulk_store(vals + 4 * (int64_t)tile_lo, acc, (uint32_t)tile_len * 32u);
+      ptx::bulk_store_wait_read();  // the tile buffer is reused by the next tile
+    }
+    __syncthreads();
   }
 }
 
 static size_t fan_smem_bytes(int dim, int max_degree, int rec_cap) {
-  return (2 * (kTile + 1) * sizeof(int32_t) + 15) / 16 * 16 + (size_t)rec_cap * sizeof(int2) +
-         (size_t)dim * dim * max_degree * kTile * sizeof(double);
+  return 128 + 2 * fan_stage_bytes(rec_cap) + (size_t)dim * dim * max_degree * kTile * sizeof(double);
 }
 
 static size_t tile_smem_bytes(int dim, int max_degree) {
@@ -439,8 +472,9 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
                                                     p->conn4, xy, tab, vals);                                   \
     } else if (variant == 3) {                                                                                  \
       FE_CUDA(cudaFuncSetAttribute(k_assemble_fan<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      k_assemble_fan<KC><<<grid, kTile, smem, st>>>(p->n_owned, p->fan_ptr, p->fan_rec, p->adj_ptr, xy, tab,     \
-                                                    vals, rec_cap);                                             \
+      const int fgrid = grid < FE_FAN_MINB * ctx->num_sms ? grid : FE_FAN_MINB * ctx->num_sms;                  \
+      k_assemble_fan<KC><<<fgrid, kFanThreads, smem, st>>>(p->n_owned, p->fan_ptr, p->fan_rec, p->adj_ptr, xy,  \
+                                                           tab, vals, rec_cap);                                 \
     } else {                                                                                                    \
       FE_CUDA(cudaFuncSetAttribute(k_assemble_tile<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_assemble_tile<KC><<<grid, kTile, smem, st>>>(p->n_owned, p->corner_ptr, p->corner_rec, p->adj_ptr,       \

@@ -360,14 +360,14 @@ int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, 
   } while (0)
 
   PLAN_TRY(dev_alloc(&p->corner_ptr, (int64_t)n_owned + 1, &p->bytes));
-  PLAN_TRY(dev_alloc(&p->adj_ptr, (int64_t)n_owned + 1, &p->bytes));
+  PLAN_TRY(dev_alloc(&p->adj_ptr, (int64_t)n_owned + 1 + 136, &p->bytes));  // +136: TMA tile-slice over-read
   PLAN_TRY(dev_alloc(&p->conn4, n_elems, &p->bytes));
   PLAN_TRY(dev_alloc(&cursor, (int64_t)n_owned + 1, nullptr));
   PLAN_TRY(dev_alloc(&ndeg, (int64_t)n_owned + 1, nullptr));
   PLAN_TRY(dev_alloc(&flags, 1, nullptr));
   PLAN_TRY(dev_alloc(&totals, 3, nullptr));
   PLAN_TRY(dev_alloc(&nfan, (int64_t)n_owned + 1, nullptr));
-  PLAN_TRY(dev_alloc(&p->fan_ptr, (int64_t)n_owned + 1, &p->bytes));
+  PLAN_TRY(dev_alloc(&p->fan_ptr, (int64_t)n_owned + 1 + 136, &p->bytes));
   PLAN_CUDA(cudaMemsetAsync(cursor, 0, ((size_t)n_owned + 1) * sizeof(int32_t), st));
   PLAN_CUDA(cudaMemsetAsync(ndeg, 0, ((size_t)n_owned + 1) * sizeof(int32_t), st));
   PLAN_CUDA(cudaMemsetAsync(flags, 0, sizeof(PlanFlags), st));

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "dist.h"
+#include "ptx.cuh"
 
 namespace fe {
 
