@@ -250,18 +250,20 @@ struct FanOps {  // elasticity (0) / mass (1): 2x2 blocks, stored as two double2
   }
 };
 
-// Persistent, software-pipelined kernel.  CTA = 128 threads, one per node of a 128-node tile;
-// every CTA walks the tiles blockIdx.x, +gridDim.x, ...  While tile j is being computed, thread 0
-// has already handed tile j+1 to the TMA engine: the two pointer slices (adj_ptr, fan_ptr: 132
-// ints each) and the tile's contiguous record range are bulk-loaded into the other half of a
-// 2-stage shared-memory ring (completion on an mbarrier), and the record-range end points of
-// tile j+2 are already travelling towards thread 0's registers.  The dependent pointer ->
-// record round trips that used to idle the whole CTA at the start of every tile are hidden.
-// Consumers build the tile's slice of `vals` in shared memory and thread 0 hands it to the TMA
-// engine as a single bulk store.
-// smem: [full[2]] | 2 x { a_tile[132], f_tile[132], recs int2[rec_cap] } | out tile
-constexpr int kFanConsumers = kTile;               // 128 threads
-constexpr int kFanThreads = kFanConsumers;
+// Persistent, software-pipelined kernel.  CTA = 128 threads = 4 warps, one thread per node of a
+// 128-node tile; every CTA walks the tiles blockIdx.x, +gridDim.x, ...
+//  * Input ring (2 stages, full/empty mbarriers): while tile j is computed, thread 0 has already
+//    handed tile j+1 to the TMA engine -- the two pointer slices (adj_ptr, fan_ptr: 132 ints
+//    each) and the tile's contiguous record range -- and the record-range end points of tile
+//    j+2 are travelling towards its registers.  The dependent pointer -> record round trips
+//    that used to idle the CTA at the start of every tile are hidden.
+//  * The warps never meet at a block barrier.  Each warp owns a private output sub-tile (the
+//    exact image of its 32 nodes' slice of `vals`), hands it to the TMA engine with its own
+//    bulk store, releases the ring slot, and issues the first coordinate gathers of its nodes of
+//    tile j+1 BEFORE waiting for that store to finish reading shared memory.
+// smem: [full[2], empty[2]] | 2 x { a_tile[132], f_tile[132], recs int2[rec_cap] } | 4 warp sub-tiles
+constexpr int kFanThreads = kTile;                 // 128
+constexpr int kFanWarps = kFanThreads / 32;
 constexpr int kFanPtrInts = (kTile + 1 + 3) & ~3;  // 132
 
 __host__ __device__ inline size_t fan_stage_bytes(int rec_cap) {
@@ -272,26 +274,30 @@ template <int KC>
 __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     int32_t n_owned, const int32_t *__restrict__ fan_ptr, const int2 *__restrict__ fan_rec,
     const int32_t *__restrict__ adj_ptr, const double2 *__restrict__ coords, const MatRow *__restrict__ tab,
-    double *__restrict__ vals, int rec_cap) {
+    double *__restrict__ vals, int rec_cap, int warp_slots /* Slot capacity of one warp sub-tile */) {
   using Ops = FanOps<KC>;
   using Val = typename Ops::Val;
   using Slot = typename Ops::Slot;
+  constexpr int SPB = (KC == 2) ? 1 : 2;  // Slots per node-level block
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+  uint64_t *empty = full + 2;
   const size_t stage_bytes = fan_stage_bytes(rec_cap);
   unsigned char *stage0 = smem_raw + 128;
-  Slot *acc = reinterpret_cast<Slot *>(stage0 + 2 * stage_bytes);
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Slot *acc = reinterpret_cast<Slot *>(stage0 + 2 * stage_bytes) + (size_t)warp * warp_slots;
   const int n_tiles = (n_owned + kTile - 1) / kTile;
   if (tid == 0) {
     ptx::mbar_init(&full[0], 1);
     ptx::mbar_init(&full[1], 1);
+    ptx::mbar_init(&empty[0], kFanWarps);
+    ptx::mbar_init(&empty[1], kFanWarps);
     ptx::mbar_init_fence();
   }
   __syncthreads();
 
-  // thread 0 only: end points of a tile's record range, and the TMA loads of a tile
+  // ---- thread 0: end points of a tile's record range, and the TMA loads of a tile
   auto endpoints = [&](int tile, int32_t &r0, int32_t &r1) {
     if (tile < n_tiles) {
       const int32_t n0 = tile * kTile;
@@ -317,119 +323,142 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     endpoints(blockIdx.x + gridDim.x, nr0, nr1);
   }
 
-  int j = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
-    const int stage = j & 1, use = j >> 1;
-    if (tid == 0) {
-      // the other ring slot was released by the barrier that ended the previous tile
-      const int next = tile + gridDim.x;
-      if (next < n_tiles) issue(next, stage ^ 1, nr0, nr1);
-      endpoints(next + gridDim.x, nr0, nr1);  // lands while this tile computes
+  // ---- per-thread state of the tile about to be computed (filled by begin_tile)
+  struct Item {
+    int2 rec;
+    double2 p;
+  };
+  Item ia, ib, ic, id;
+  double2 ps = make_double2(0.0, 0.0);
+  const int2 *recs = nullptr;
+  Slot *my = acc;
+  int f = 0, fe = 0, deg = 0;
+  int32_t warp_lo = 0, warp_len = 0;  // node-level block range of this warp's sub-tile
+  auto fetch = [&](int i, Item &it) {
+    if (i < fe) {
+      it.rec = recs[i];
+      it.p = __ldg(coords + it.rec.x);
     }
+  };
+  // Waits for the tile's ring slot and puts the first gathers in flight.
+  auto begin_tile = [&](int tile, int jj) {
+    const int stage = jj & 1;
+    ptx::mbar_wait(&full[stage], (uint32_t)((jj >> 1) & 1));
     const int32_t n0 = tile * kTile;
-    const int32_t n = n0 + tid;
     const int n_in_tile = min(kTile, n_owned - n0);
     const unsigned char *st = stage0 + stage * stage_bytes;
     const int32_t *a_tile = reinterpret_cast<const int32_t *>(st);
     const int32_t *f_tile = a_tile + kFanPtrInts;
-    const int2 *recs = reinterpret_cast<const int2 *>(st + 2 * kFanPtrInts * 4);
-    const double2 ps = (n < n_owned) ? __ldg(coords + n) : make_double2(0.0, 0.0);  // before the wait: overlaps
-    ptx::mbar_wait(&full[stage], (uint32_t)(use & 1));
+    recs = reinterpret_cast<const int2 *>(st + 2 * kFanPtrInts * 4);
     const int32_t base = f_tile[0] & ~1;
-    const int32_t tile_lo = a_tile[0];
-    const int tile_len = a_tile[n_in_tile] - tile_lo;  // node-level blocks in the tile
-
-    if (n < n_owned) {
-      int f = f_tile[tid] - base;
-      const int fe = f_tile[tid + 1] - base;
-      const int deg = a_tile[tid + 1] - a_tile[tid];
-      const bool any = f < fe;
-      Slot *my = acc + (KC == 2 ? 1 : 2) * (a_tile[tid] - tile_lo);  // natural (output-image) layout
-      // Software pipeline over (record, neighbour coordinates): four rotating register sets, the
-      // gather for step f+3 is issued while step f computes, and the set of step f-1 doubles as
-      // "previous neighbour" of step f -- no register shifting.
-      struct Item {
-        int2 rec;
-        double2 p;
-      };
-      Item ia = {make_int2(n, 0), ps}, ib = ia, ic = ia, id = ia;
-      auto fetch = [&](int i, Item &it) {
-        if (i < fe) {
-          it.rec = recs[i];
-          it.p = __ldg(coords + it.rec.x);
-        }
-      };
-      int kself = 0, cur_mat = -1;
-      MatRow m = {0.0, 0.0, 0.0, 0.0};
-      Val diag = Ops::zero(), carry = Ops::zero();
-      auto process = [&](const Item &cur, const Item &prev) {
-        const uint32_t y = (uint32_t)cur.rec.y;
-        const uint32_t fl = (y >> 8) & 31;
-        if (fl & FanFlags::SEED) {
-          kself = y >> 13;
-          return;
-        }
-        const int mid = y >> 13;
-        if (mid != cur_mat) {
-          m = tab[mid];
-          cur_mat = mid;
-        }
-        const TriGeom g = tri_geom(ps, prev.p, cur.p);
-        Val r[3];
-        Ops::rows(g, m, r);
-        Ops::add(diag, r[0]);
-        if (fl & FanFlags::ADD_CARRY) Ops::add(r[1], carry);
-        // (a closed fan's first block waits in its slot; the last step completes it there)
-        Ops::store(my, deg, (uint32_t)prev.rec.y & 255, 1, r[1]);
-        carry = r[2];
-        if (fl & FanFlags::LAST) {
-          if (fl & FanFlags::ADD_FIRST) Ops::add(r[2], Ops::load(my, deg, y & 255));
-          Ops::store(my, deg, y & 255, 1, r[2]);
-        }
-      };
-      fetch(f, ia);
-      fetch(f + 1, ib);
-      fetch(f + 2, ic);
-      while (true) {
-        if (f >= fe) break;
-        process(ia, id);
-        fetch(f + 3, id);
-        ++f;
-        if (f >= fe) break;
-        process(ib, ia);
-        fetch(f + 3, ia);
-        ++f;
-        if (f >= fe) break;
-        process(ic, ib);
-        fetch(f + 3, ib);
-        ++f;
-        if (f >= fe) break;
-        process(id, ic);
-        fetch(f + 3, ic);
-        ++f;
-      }
-      if (any) Ops::store(my, deg, kself, 1, diag);
+    const int w0 = min(32 * warp, n_in_tile), w1 = min(32 * warp + 32, n_in_tile);
+    warp_lo = a_tile[w0];
+    warp_len = a_tile[w1] - warp_lo;
+    f = fe = deg = 0;
+    if (tid < n_in_tile) {
+      ps = __ldg(coords + n0 + tid);
+      f = f_tile[tid] - base;
+      fe = f_tile[tid + 1] - base;
+      deg = a_tile[tid + 1] - a_tile[tid];
+      my = acc + SPB * (a_tile[tid] - warp_lo);
     }
+    ia.rec = ib.rec = ic.rec = id.rec = make_int2(0, 0);
+    ia.p = ib.p = ic.p = id.p = ps;
+    fetch(f, ia);
+    fetch(f + 1, ib);
+    fetch(f + 2, ic);
+  };
+
+  int j = 0;
+  int tile = blockIdx.x;
+  if (tile < n_tiles) begin_tile(tile, 0);
+  for (; tile < n_tiles; tile += gridDim.x, ++j) {
+    const int stage = j & 1;
+    const int next = tile + gridDim.x;
+    if (tid == 0) {
+      // ring slot stage^1 held tile j-1: wait until all four warps have released it
+      if (next < n_tiles) {
+        if (j >= 1) ptx::mbar_wait(&empty[stage ^ 1], (uint32_t)(((j - 1) >> 1) & 1));
+        issue(next, stage ^ 1, nr0, nr1);
+      }
+      endpoints(next + gridDim.x, nr0, nr1);  // lands while this tile computes
+    }
+    __syncwarp();
+
+    // ---- the fan walk of this thread's node (records + neighbour coordinates, 4 rotating sets)
+    const bool any = f < fe;
+    int kself = 0, cur_mat = -1;
+    MatRow m = {0.0, 0.0, 0.0, 0.0};
+    Val diag = Ops::zero(), carry = Ops::zero();
+    auto process = [&](const Item &cur, const Item &prev) {
+      const uint32_t y = (uint32_t)cur.rec.y;
+      const uint32_t fl = (y >> 8) & 31;
+      if (fl & FanFlags::SEED) {
+        kself = y >> 13;
+        return;
+      }
+      const int mid = y >> 13;
+      if (mid != cur_mat) {
+        m = tab[mid];
+        cur_mat = mid;
+      }
+      const TriGeom g = tri_geom(ps, prev.p, cur.p);
+      Val r[3];
+      Ops::rows(g, m, r);
+      Ops::add(diag, r[0]);
+      if (fl & FanFlags::ADD_CARRY) Ops::add(r[1], carry);
+      // (a closed fan's first block waits in its slot; the last step completes it there)
+      Ops::store(my, deg, (uint32_t)prev.rec.y & 255, 1, r[1]);
+      carry = r[2];
+      if (fl & FanFlags::LAST) {
+        if (fl & FanFlags::ADD_FIRST) Ops::add(r[2], Ops::load(my, deg, y & 255));
+        Ops::store(my, deg, y & 255, 1, r[2]);
+      }
+    };
+    while (true) {
+      if (f >= fe) break;
+      process(ia, id);
+      fetch(f + 3, id);
+      ++f;
+      if (f >= fe) break;
+      process(ib, ia);
+      fetch(f + 3, ia);
+      ++f;
+      if (f >= fe) break;
+      process(ic, ib);
+      fetch(f + 3, ib);
+      ++f;
+      if (f >= fe) break;
+      process(id, ic);
+      fetch(f + 3, ic);
+      ++f;
+    }
+    if (any) Ops::store(my, deg, kself, 1, diag);
+
+    // ---- this warp's sub-tile is complete: the exact image of vals[dim^2 * warp_lo ...)
     if (KC != 2) ptx::fence_async_smem();  // generic writes -> visible to the async proxy
-    __syncthreads();
-    // The staged tile is the exact image of vals[dim^2 * tile_lo .. dim^2 * (tile_lo + tile_len)).
+    __syncwarp();
+    const int32_t out_lo = warp_lo, out_len = warp_len;
     if (KC == 2) {
       // 1 DOF per node: the destination is only 8-byte aligned -> plain coalesced copy
       const double *src = reinterpret_cast<const double *>(acc);
-      double *dst = vals + tile_lo;
-      for (int q = tid; q < tile_len; q += kFanConsumers) dst[q] = src[q];
-    } else if (tid == 0 && tile_len > 0) {
-      // 2 DOF per node: one TMA bulk store of the whole tile (32 * tile_len bytes, 32-byte aligned)
-      ptx::bulk_store(vals + 4 * (int64_t)tile_lo, acc, (uint32_t)tile_len * 32u);
-      ptx::bulk_store_wait_read();  // the tile buffer is reused by the next tile
+      double *dst = vals + out_lo;
+      for (int q = lane; q < out_len; q += 32) dst[q] = src[q];
+    } else if (lane == 0 && out_len > 0) {
+      ptx::bulk_store(vals + 4 * (int64_t)out_lo, acc, (uint32_t)out_len * 32u);  // one TMA bulk store
     }
-    __syncthreads();
+    if (lane == 0) ptx::mbar_arrive(&empty[stage]);  // ring slot released by this warp
+    // first gathers of the next tile go out before we wait for the store to drain the sub-tile
+    if (next < n_tiles) begin_tile(next, j + 1);
+    if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
+    __syncwarp();
   }
 }
 
 static size_t fan_smem_bytes(int dim, int max_degree, int rec_cap) {
   return 128 + 2 * fan_stage_bytes(rec_cap) + (size_t)dim * dim * max_degree * kTile * sizeof(double);
 }
+static int fan_warp_slots(int dim, int max_degree) { return (dim == 2 ? 2 : 1) * max_degree * 32; }
 
 static size_t tile_smem_bytes(int dim, int max_degree) {
   return ((kTile + 1) * sizeof(int32_t) + 15) / 16 * 16 + (size_t)dim * dim * max_degree * (kTile + 1) * sizeof(double);
@@ -474,7 +503,7 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
       FE_CUDA(cudaFuncSetAttribute(k_assemble_fan<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       const int fgrid = grid < FE_FAN_MINB * ctx->num_sms ? grid : FE_FAN_MINB * ctx->num_sms;                  \
       k_assemble_fan<KC><<<fgrid, kFanThreads, smem, st>>>(p->n_owned, p->fan_ptr, p->fan_rec, p->adj_ptr, xy,  \
-                                                           tab, vals, rec_cap);                                 \
+                                                           tab, vals, rec_cap, fan_warp_slots(dim, p->max_degree)); \
     } else {                                                                                                    \
       FE_CUDA(cudaFuncSetAttribute(k_assemble_tile<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_assemble_tile<KC><<<grid, kTile, smem, st>>>(p->n_owned, p->corner_ptr, p->corner_rec, p->adj_ptr,       \
