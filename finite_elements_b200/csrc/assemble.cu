@@ -250,63 +250,65 @@ struct FanOps {  // elasticity (0) / mass (1): 2x2 blocks, stored as two double2
   }
 };
 
-// Persistent, software-pipelined kernel.  CTA = 128 threads = 4 warps, one thread per node of a
-// 128-node tile; every CTA walks the tiles blockIdx.x, +gridDim.x, ...
-//  * Input ring (2 stages, full/empty mbarriers): while tile j is computed, thread 0 has already
-//    handed tile j+1 to the TMA engine -- the two pointer slices (adj_ptr, fan_ptr: 132 ints
-//    each) and the tile's contiguous record range -- and the record-range end points of tile
-//    j+2 are travelling towards its registers.  The dependent pointer -> record round trips
-//    that used to idle the CTA at the start of every tile are hidden.
-//  * The warps never meet at a block barrier.  Each warp owns a private output sub-tile (the
-//    exact image of its 32 nodes' slice of `vals`), hands it to the TMA engine with its own
-//    bulk store, releases the ring slot, and issues the first coordinate gathers of its nodes of
-//    tile j+1 BEFORE waiting for that store to finish reading shared memory.
-// smem: [full[2], empty[2]] | 2 x { a_tile[132], f_tile[132], recs int2[rec_cap] } | 4 warp sub-tiles
-constexpr int kFanThreads = kTile;                 // 128
+// Persistent kernel in which every WARP is an independent software pipeline over 32-node
+// chunks (chunk = global warp id, + total warps, ...); warps never synchronise with each other.
+//  * Input ring per warp (2 stages, one mbarrier each): while chunk c is computed, lane 0 has
+//    already handed chunk c+1 to the TMA engine -- the two pointer slices (adj_ptr, fan_ptr: 36
+//    ints each) and the chunk's contiguous record range -- and the record-range end points of
+//    chunk c+2 are travelling towards its registers.  The dependent pointer -> record round
+//    trips are off the critical path.
+//  * Output: each warp owns a private sub-tile, the exact image of its 32 nodes' slice of
+//    `vals`, and hands it to the TMA engine with one bulk store; the first coordinate gathers of
+//    chunk c+1 are issued BEFORE the warp waits for that store to finish reading shared memory.
+// smem per warp: full[2] | 2 x { a_slice[36], f_slice[36], recs int2[rec_cap] } | sub-tile
+constexpr int kFanThreads = kTile;  // 128 = 4 independent warps
 constexpr int kFanWarps = kFanThreads / 32;
-constexpr int kFanPtrInts = (kTile + 1 + 3) & ~3;  // 132
+constexpr int kFanChunk = 32;
+constexpr int kFanPtrInts = (kFanChunk + 1 + 3) & ~3;  // 36
 
 __host__ __device__ inline size_t fan_stage_bytes(int rec_cap) {
-  return ((size_t)2 * kFanPtrInts * sizeof(int32_t) + (size_t)rec_cap * sizeof(int2) + 127) / 128 * 128;
+  return ((size_t)2 * kFanPtrInts * sizeof(int32_t) + (size_t)rec_cap * sizeof(int2) + 15) / 16 * 16;
+}
+__host__ __device__ inline size_t fan_warp_bytes(int rec_cap, int warp_slot_bytes) {
+  return (16 + 2 * fan_stage_bytes(rec_cap) + (size_t)warp_slot_bytes + 127) / 128 * 128;
 }
 
 template <int KC>
 __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     int32_t n_owned, const int32_t *__restrict__ fan_ptr, const int2 *__restrict__ fan_rec,
     const int32_t *__restrict__ adj_ptr, const double2 *__restrict__ coords, const MatRow *__restrict__ tab,
-    double *__restrict__ vals, int rec_cap, int warp_slots /* Slot capacity of one warp sub-tile */) {
+    double *__restrict__ vals, int rec_cap, int warp_slot_bytes) {
   using Ops = FanOps<KC>;
   using Val = typename Ops::Val;
   using Slot = typename Ops::Slot;
   constexpr int SPB = (KC == 2) ? 1 : 2;  // Slots per node-level block
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
-  uint64_t *empty = full + 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wbase = smem_raw + (size_t)warp * fan_warp_bytes(rec_cap, warp_slot_bytes);
+  uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
   const size_t stage_bytes = fan_stage_bytes(rec_cap);
-  unsigned char *stage0 = smem_raw + 128;
+  unsigned char *stage0 = wbase + 16;
+  Slot *acc = reinterpret_cast<Slot *>(stage0 + 2 * stage_bytes);
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  Slot *acc = reinterpret_cast<Slot *>(stage0 + 2 * stage_bytes) + (size_t)warp * warp_slots;
-  const int n_tiles = (n_owned + kTile - 1) / kTile;
-  if (tid == 0) {
+  const int n_chunks = (n_owned + kFanChunk - 1) / kFanChunk;
+  const int chunk_stride = gridDim.x * kFanWarps;
+  if (lane == 0) {
     ptx::mbar_init(&full[0], 1);
     ptx::mbar_init(&full[1], 1);
-    ptx::mbar_init(&empty[0], kFanWarps);
-    ptx::mbar_init(&empty[1], kFanWarps);
     ptx::mbar_init_fence();
   }
-  __syncthreads();
+  __syncwarp();
 
-  // ---- thread 0: end points of a tile's record range, and the TMA loads of a tile
-  auto endpoints = [&](int tile, int32_t &r0, int32_t &r1) {
-    if (tile < n_tiles) {
-      const int32_t n0 = tile * kTile;
+  // ---- lane 0: end points of a chunk's record range, and the TMA loads of a chunk
+  auto endpoints = [&](int chunk, int32_t &r0, int32_t &r1) {
+    if (chunk < n_chunks) {
+      const int32_t n0 = chunk * kFanChunk;
       r0 = __ldg(fan_ptr + n0);
-      r1 = __ldg(fan_ptr + min(n0 + kTile, n_owned));
+      r1 = __ldg(fan_ptr + min(n0 + kFanChunk, n_owned));
     }
   };
-  auto issue = [&](int tile, int stage, int32_t r0, int32_t r1) {
-    const int32_t n0 = tile * kTile;
+  auto issue = [&](int chunk, int stage, int32_t r0, int32_t r1) {
+    const int32_t n0 = chunk * kFanChunk;
     const int32_t base = r0 & ~1;  // 16-byte aligned start of the record copy
     const uint32_t rec_bytes = (uint32_t)((r1 - base + 1) >> 1) * 16u;
     unsigned char *st = stage0 + stage * stage_bytes;
@@ -315,75 +317,69 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     ptx::bulk_load(st + kFanPtrInts * 4, fan_ptr + n0, kFanPtrInts * 4u, &full[stage]);
     if (rec_bytes) ptx::bulk_load(st + 2 * kFanPtrInts * 4, fan_rec + base, rec_bytes, &full[stage]);
   };
-  int32_t nr0 = 0, nr1 = 0;  // end points of the NEXT tile to issue (thread 0)
-  if (tid == 0 && (int)blockIdx.x < n_tiles) {
+  int chunk = blockIdx.x * kFanWarps + warp;
+  int32_t nr0 = 0, nr1 = 0;  // end points of the chunk after the next one (lane 0)
+  if (lane == 0 && chunk < n_chunks) {
     int32_t r0 = 0, r1 = 0;
-    endpoints(blockIdx.x, r0, r1);
-    issue(blockIdx.x, 0, r0, r1);
-    endpoints(blockIdx.x + gridDim.x, nr0, nr1);
+    endpoints(chunk, r0, r1);
+    issue(chunk, 0, r0, r1);
+    if (chunk + chunk_stride < n_chunks) {
+      endpoints(chunk + chunk_stride, r0, r1);
+      issue(chunk + chunk_stride, 1, r0, r1);
+    }
+    endpoints(chunk + 2 * chunk_stride, nr0, nr1);
   }
 
-  // ---- per-thread state of the tile about to be computed (filled by begin_tile)
+  // ---- per-thread state of the chunk about to be computed (filled by begin_chunk)
   struct Item {
     int2 rec;
     double2 p;
   };
   Item ia, ib, ic, id;
+  ia.rec = ib.rec = ic.rec = id.rec = make_int2(0, 0);
+  ia.p = ib.p = ic.p = id.p = make_double2(0.0, 0.0);
   double2 ps = make_double2(0.0, 0.0);
   const int2 *recs = nullptr;
   Slot *my = acc;
   int f = 0, fe = 0, deg = 0;
-  int32_t warp_lo = 0, warp_len = 0;  // node-level block range of this warp's sub-tile
+  int32_t out_lo = 0, out_len = 0;  // node-level block range of this chunk
   auto fetch = [&](int i, Item &it) {
     if (i < fe) {
       it.rec = recs[i];
       it.p = __ldg(coords + it.rec.x);
     }
   };
-  // Waits for the tile's ring slot and puts the first gathers in flight.
-  auto begin_tile = [&](int tile, int jj) {
+  // Waits for the chunk's ring slot and puts the first gathers in flight.
+  auto begin_chunk = [&](int c, int jj) {
     const int stage = jj & 1;
     ptx::mbar_wait(&full[stage], (uint32_t)((jj >> 1) & 1));
-    const int32_t n0 = tile * kTile;
-    const int n_in_tile = min(kTile, n_owned - n0);
+    const int32_t n0 = c * kFanChunk;
+    const int n_in = min(kFanChunk, n_owned - n0);
     const unsigned char *st = stage0 + stage * stage_bytes;
-    const int32_t *a_tile = reinterpret_cast<const int32_t *>(st);
-    const int32_t *f_tile = a_tile + kFanPtrInts;
+    const int32_t *a_sl = reinterpret_cast<const int32_t *>(st);
+    const int32_t *f_sl = a_sl + kFanPtrInts;
     recs = reinterpret_cast<const int2 *>(st + 2 * kFanPtrInts * 4);
-    const int32_t base = f_tile[0] & ~1;
-    const int w0 = min(32 * warp, n_in_tile), w1 = min(32 * warp + 32, n_in_tile);
-    warp_lo = a_tile[w0];
-    warp_len = a_tile[w1] - warp_lo;
+    const int32_t base = f_sl[0] & ~1;
+    out_lo = a_sl[0];
+    out_len = a_sl[n_in] - out_lo;
     f = fe = deg = 0;
-    if (tid < n_in_tile) {
-      ps = __ldg(coords + n0 + tid);
-      f = f_tile[tid] - base;
-      fe = f_tile[tid + 1] - base;
-      deg = a_tile[tid + 1] - a_tile[tid];
-      my = acc + SPB * (a_tile[tid] - warp_lo);
+    if (lane < n_in) {
+      ps = __ldg(coords + n0 + lane);
+      f = f_sl[lane] - base;
+      fe = f_sl[lane + 1] - base;
+      deg = a_sl[lane + 1] - a_sl[lane];
+      my = acc + SPB * (a_sl[lane] - out_lo);
     }
-    ia.rec = ib.rec = ic.rec = id.rec = make_int2(0, 0);
-    ia.p = ib.p = ic.p = id.p = ps;
     fetch(f, ia);
     fetch(f + 1, ib);
     fetch(f + 2, ic);
   };
 
   int j = 0;
-  int tile = blockIdx.x;
-  if (tile < n_tiles) begin_tile(tile, 0);
-  for (; tile < n_tiles; tile += gridDim.x, ++j) {
+  if (chunk < n_chunks) begin_chunk(chunk, 0);
+  for (; chunk < n_chunks; chunk += chunk_stride, ++j) {
     const int stage = j & 1;
-    const int next = tile + gridDim.x;
-    if (tid == 0) {
-      // ring slot stage^1 held tile j-1: wait until all four warps have released it
-      if (next < n_tiles) {
-        if (j >= 1) ptx::mbar_wait(&empty[stage ^ 1], (uint32_t)(((j - 1) >> 1) & 1));
-        issue(next, stage ^ 1, nr0, nr1);
-      }
-      endpoints(next + gridDim.x, nr0, nr1);  // lands while this tile computes
-    }
-    __syncwarp();
+    const int next = chunk + chunk_stride;
 
     // ---- the fan walk of this thread's node (records + neighbour coordinates, 4 rotating sets)
     const bool any = f < fe;
@@ -435,10 +431,9 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     }
     if (any) Ops::store(my, deg, kself, 1, diag);
 
-    // ---- this warp's sub-tile is complete: the exact image of vals[dim^2 * warp_lo ...)
-    if (KC != 2) ptx::fence_async_smem();  // generic writes -> visible to the async proxy
+    // ---- the sub-tile is complete: the exact image of vals[dim^2 * out_lo ...)
+    ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy
     __syncwarp();
-    const int32_t out_lo = warp_lo, out_len = warp_len;
     if (KC == 2) {
       // 1 DOF per node: the destination is only 8-byte aligned -> plain coalesced copy
       const double *src = reinterpret_cast<const double *>(acc);
@@ -447,18 +442,23 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     } else if (lane == 0 && out_len > 0) {
       ptx::bulk_store(vals + 4 * (int64_t)out_lo, acc, (uint32_t)out_len * 32u);  // one TMA bulk store
     }
-    if (lane == 0) ptx::mbar_arrive(&empty[stage]);  // ring slot released by this warp
-    // first gathers of the next tile go out before we wait for the store to drain the sub-tile
-    if (next < n_tiles) begin_tile(next, j + 1);
+    if (lane == 0) {
+      // this warp is done with ring slot `stage`: refill it with the chunk after the next one
+      const int nn = next + chunk_stride;
+      if (nn < n_chunks) issue(nn, stage, nr0, nr1);
+      endpoints(nn + chunk_stride, nr0, nr1);
+    }
+    // first gathers of the next chunk go out before we wait for the store to drain the sub-tile
+    if (next < n_chunks) begin_chunk(next, j + 1);
     if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
     __syncwarp();
   }
 }
 
+static int fan_warp_slot_bytes(int dim, int max_degree) { return dim * dim * max_degree * kFanChunk * 8; }
 static size_t fan_smem_bytes(int dim, int max_degree, int rec_cap) {
-  return 128 + 2 * fan_stage_bytes(rec_cap) + (size_t)dim * dim * max_degree * kTile * sizeof(double);
+  return kFanWarps * fan_warp_bytes(rec_cap, fan_warp_slot_bytes(dim, max_degree));
 }
-static int fan_warp_slots(int dim, int max_degree) { return (dim == 2 ? 2 : 1) * max_degree * 32; }
 
 static size_t tile_smem_bytes(int dim, int max_degree) {
   return ((kTile + 1) * sizeof(int32_t) + 15) / 16 * 16 + (size_t)dim * dim * max_degree * (kTile + 1) * sizeof(double);
@@ -503,7 +503,7 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
       FE_CUDA(cudaFuncSetAttribute(k_assemble_fan<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       const int fgrid = grid < FE_FAN_MINB * ctx->num_sms ? grid : FE_FAN_MINB * ctx->num_sms;                  \
       k_assemble_fan<KC><<<fgrid, kFanThreads, smem, st>>>(p->n_owned, p->fan_ptr, p->fan_rec, p->adj_ptr, xy,  \
-                                                           tab, vals, rec_cap, fan_warp_slots(dim, p->max_degree)); \
+                                                           tab, vals, rec_cap, fan_warp_slot_bytes(dim, p->max_degree)); \
     } else {                                                                                                    \
       FE_CUDA(cudaFuncSetAttribute(k_assemble_tile<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_assemble_tile<KC><<<grid, kTile, smem, st>>>(p->n_owned, p->corner_ptr, p->corner_rec, p->adj_ptr,       \

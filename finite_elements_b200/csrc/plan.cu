@@ -274,9 +274,9 @@ __global__ void __launch_bounds__(128) k_export_csr(int32_t n_owned, int32_t dim
 
 __global__ void k_fan_tile_max(int32_t n_owned, const int32_t *__restrict__ fan_ptr, int *__restrict__ out) {
   const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int32_t n0 = t * kTile;
+  const int32_t n0 = t * 32;  // assemble.cu: kFanChunk (one warp's 32-node chunk)
   if (n0 >= n_owned) return;
-  const int32_t n1 = min(n0 + kTile, n_owned);
+  const int32_t n1 = min(n0 + 32, n_owned);
   atomicMax(out, fan_ptr[n1] - fan_ptr[n0]);
 }
 
@@ -432,7 +432,7 @@ int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, 
   }
   if (p->fan_ok && n_owned > 0) {
     PLAN_CUDA(cudaMemsetAsync(&flags->max_degree, 0, sizeof(int), st));  // reuse as the tile maximum
-    k_fan_tile_max<<<grid_for((n_owned + kTile - 1) / kTile, 128), 128, 0, st>>>(n_owned, p->fan_ptr,
+    k_fan_tile_max<<<grid_for((n_owned + 31) / 32, 128), 128, 0, st>>>(n_owned, p->fan_ptr,
                                                                                  &flags->max_degree);
     PLAN_LAUNCHED();
     PLAN_CUDA(cudaMemcpyAsync(&hflags, flags, sizeof(PlanFlags), cudaMemcpyDeviceToHost, st));

@@ -31,7 +31,7 @@ struct fe_plan {
   // fan-ordered corner records (plan.cu: fan_walk); valid when fan_ok
   bool fan_ok = false;
   int64_t n_fan = 0;
-  int32_t fan_tile_max = 0;    // max records of one kTile-node tile
+  int32_t fan_tile_max = 0;    // max records of one 32-node chunk (one warp of k_assemble_fan)
   int32_t *fan_ptr = nullptr;  // [n_owned + 1]
   int2 *fan_rec = nullptr;     // [n_fan]
 };
