@@ -260,7 +260,7 @@ struct FanOps {  // elasticity (0) / mass (1): 2x2 blocks, stored as two double2
 //  * Output: each warp owns a private sub-tile, the exact image of its 32 nodes' slice of
 //    `vals`, and hands it to the TMA engine with one bulk store; the first coordinate gathers of
 //    chunk c+1 are issued BEFORE the warp waits for that store to finish reading shared memory.
-// smem per warp: full[2] | 2 x { a_slice[36], f_slice[36], recs int2[rec_cap] } | sub-tile
+// smem per warp: full[2] | end points int[2][2] | 2 x { a_slice[36], f_slice[36], recs[rec_cap] } | sub-tile
 constexpr int kFanThreads = kTile;  // 128 = 4 independent warps
 constexpr int kFanWarps = kFanThreads / 32;
 constexpr int kFanChunk = 32;
@@ -270,7 +270,7 @@ __host__ __device__ inline size_t fan_stage_bytes(int rec_cap) {
   return ((size_t)2 * kFanPtrInts * sizeof(int32_t) + (size_t)rec_cap * sizeof(int2) + 15) / 16 * 16;
 }
 __host__ __device__ inline size_t fan_warp_bytes(int rec_cap, int warp_slot_bytes) {
-  return (16 + 2 * fan_stage_bytes(rec_cap) + (size_t)warp_slot_bytes + 127) / 128 * 128;
+  return (32 + 2 * fan_stage_bytes(rec_cap) + (size_t)warp_slot_bytes + 127) / 128 * 128;
 }
 
 template <int KC>
@@ -287,7 +287,8 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
   unsigned char *wbase = smem_raw + (size_t)warp * fan_warp_bytes(rec_cap, warp_slot_bytes);
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
   const size_t stage_bytes = fan_stage_bytes(rec_cap);
-  unsigned char *stage0 = wbase + 16;
+  int32_t *ep = reinterpret_cast<int32_t *>(wbase + 16);  // [2][2] record-range end points (LDGSTS)
+  unsigned char *stage0 = wbase + 32;
   Slot *acc = reinterpret_cast<Slot *>(stage0 + 2 * stage_bytes);
 
   const int n_chunks = (n_owned + kFanChunk - 1) / kFanChunk;
@@ -299,13 +300,15 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
   }
   __syncwarp();
 
-  // ---- lane 0: end points of a chunk's record range, and the TMA loads of a chunk
-  auto endpoints = [&](int chunk, int32_t &r0, int32_t &r1) {
+  // ---- lane 0: the TMA loads of a chunk.  The end points of its record range are fetched one
+  //      chunk ahead with cp.async (global -> shared, no registers held across the compute loop).
+  auto request_endpoints = [&](int chunk, int slot) {
     if (chunk < n_chunks) {
       const int32_t n0 = chunk * kFanChunk;
-      r0 = __ldg(fan_ptr + n0);
-      r1 = __ldg(fan_ptr + min(n0 + kFanChunk, n_owned));
+      ptx::cp_async4(ep + 2 * slot, fan_ptr + n0);
+      ptx::cp_async4(ep + 2 * slot + 1, fan_ptr + min(n0 + kFanChunk, n_owned));
     }
+    ptx::cp_async_commit();
   };
   auto issue = [&](int chunk, int stage, int32_t r0, int32_t r1) {
     const int32_t n0 = chunk * kFanChunk;
@@ -318,16 +321,16 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     if (rec_bytes) ptx::bulk_load(st + 2 * kFanPtrInts * 4, fan_rec + base, rec_bytes, &full[stage]);
   };
   int chunk = blockIdx.x * kFanWarps + warp;
-  int32_t nr0 = 0, nr1 = 0;  // end points of the chunk after the next one (lane 0)
   if (lane == 0 && chunk < n_chunks) {
-    int32_t r0 = 0, r1 = 0;
-    endpoints(chunk, r0, r1);
-    issue(chunk, 0, r0, r1);
-    if (chunk + chunk_stride < n_chunks) {
-      endpoints(chunk + chunk_stride, r0, r1);
-      issue(chunk + chunk_stride, 1, r0, r1);
+    // chunks 0 and 1 of this warp: direct loads (start-up only); chunk 2's end points requested
+    for (int q = 0; q < 2; ++q) {
+      const int c = chunk + q * chunk_stride;
+      if (c < n_chunks) {
+        const int32_t n0 = c * kFanChunk;
+        issue(c, q, __ldg(fan_ptr + n0), __ldg(fan_ptr + min(n0 + kFanChunk, n_owned)));
+      }
     }
-    endpoints(chunk + 2 * chunk_stride, nr0, nr1);
+    request_endpoints(chunk + 2 * chunk_stride, 0);
   }
 
   // ---- per-thread state of the chunk about to be computed (filled by begin_chunk)
@@ -444,9 +447,11 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     }
     if (lane == 0) {
       // this warp is done with ring slot `stage`: refill it with the chunk after the next one
+      // (its end points were requested a whole chunk ago and sit in ep[stage])
       const int nn = next + chunk_stride;
-      if (nn < n_chunks) issue(nn, stage, nr0, nr1);
-      endpoints(nn + chunk_stride, nr0, nr1);
+      ptx::cp_async_wait_all();
+      if (nn < n_chunks) issue(nn, stage, ep[2 * stage], ep[2 * stage + 1]);
+      request_endpoints(nn + chunk_stride, stage ^ 1);
     }
     // first gathers of the next chunk go out before we wait for the store to drain the sub-tile
     if (next < n_chunks) begin_chunk(next, j + 1);
