@@ -338,14 +338,13 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     int2 rec;
     double2 p;
   };
-  Item ia, ib, ic, id;
-  ia.rec = ib.rec = ic.rec = id.rec = make_int2(0, 0);
-  ia.p = ib.p = ic.p = id.p = make_double2(0.0, 0.0);
+  Item ia, ib, ic;  // three rotating sets: current, previous, and the gather two steps ahead
+  ia.rec = ib.rec = ic.rec = make_int2(0, 0);
+  ia.p = ib.p = ic.p = make_double2(0.0, 0.0);
   double2 ps = make_double2(0.0, 0.0);
   const int2 *recs = nullptr;
   Slot *my = acc;
   int f = 0, fe = 0, deg = 0;
-  int32_t out_lo = 0, out_len = 0;  // node-level block range of this chunk
   auto fetch = [&](int i, Item &it) {
     if (i < fe) {
       it.rec = recs[i];
@@ -363,8 +362,7 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     const int32_t *f_sl = a_sl + kFanPtrInts;
     recs = reinterpret_cast<const int2 *>(st + 2 * kFanPtrInts * 4);
     const int32_t base = f_sl[0] & ~1;
-    out_lo = a_sl[0];
-    out_len = a_sl[n_in] - out_lo;
+    const int32_t out_lo = a_sl[0];
     f = fe = deg = 0;
     if (lane < n_in) {
       ps = __ldg(coords + n0 + lane);
@@ -375,16 +373,15 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     }
     fetch(f, ia);
     fetch(f + 1, ib);
-    fetch(f + 2, ic);
   };
 
-  int j = 0;
+  int j = 0;  // ring position mod 4: stage = j & 1, barrier parity = (j >> 1) & 1
   if (chunk < n_chunks) begin_chunk(chunk, 0);
-  for (; chunk < n_chunks; chunk += chunk_stride, ++j) {
+  for (; chunk < n_chunks; chunk += chunk_stride, j = (j + 1) & 3) {
     const int stage = j & 1;
     const int next = chunk + chunk_stride;
 
-    // ---- the fan walk of this thread's node (records + neighbour coordinates, 4 rotating sets)
+    // ---- the fan walk of this thread's node (records + neighbour coordinates, 3 rotating sets)
     const bool any = f < fe;
     int kself = 0, cur_mat = -1;
     MatRow m = {0.0, 0.0, 0.0, 0.0};
@@ -416,20 +413,16 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     };
     while (true) {
       if (f >= fe) break;
-      process(ia, id);
-      fetch(f + 3, id);
+      process(ia, ic);
+      fetch(f + 2, ic);
       ++f;
       if (f >= fe) break;
       process(ib, ia);
-      fetch(f + 3, ia);
+      fetch(f + 2, ia);
       ++f;
       if (f >= fe) break;
       process(ic, ib);
-      fetch(f + 3, ib);
-      ++f;
-      if (f >= fe) break;
-      process(id, ic);
-      fetch(f + 3, ic);
+      fetch(f + 2, ib);
       ++f;
     }
     if (any) Ops::store(my, deg, kself, 1, diag);
@@ -437,6 +430,12 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     // ---- the sub-tile is complete: the exact image of vals[dim^2 * out_lo ...)
     ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy
     __syncwarp();
+    int32_t out_lo, out_len;  // node-level block range of this chunk (slice still in the ring slot)
+    {
+      const int32_t *a_sl = reinterpret_cast<const int32_t *>(stage0 + stage * stage_bytes);
+      out_lo = a_sl[0];
+      out_len = a_sl[min(kFanChunk, n_owned - chunk * kFanChunk)] - out_lo;
+    }
     if (KC == 2) {
       // 1 DOF per node: the destination is only 8-byte aligned -> plain coalesced copy
       const double *src = reinterpret_cast<const double *>(acc);
@@ -454,7 +453,7 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
       request_endpoints(nn + chunk_stride, stage ^ 1);
     }
     // first gathers of the next chunk go out before we wait for the store to drain the sub-tile
-    if (next < n_chunks) begin_chunk(next, j + 1);
+    if (next < n_chunks) begin_chunk(next, (j + 1) & 3);
     if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
     __syncwarp();
   }
