@@ -27,6 +27,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "assembled Melem/s + PCG DOF-iters/s, 16M-tri plane stress"
 MAT = np.array([[210e9, 0.25, 1.0, 7860.0]])  # scripts/Elasticity/beam2d_example_2.py:35
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at S16M from the committed ncu captures
+# (profiles/r01_d_*.md): only meaningful for the default 4096x2048 workload on one GPU.
+ASM_TRAFFIC_NCU = 2.495e9    # k_assemble_fan<0>: 0.673 GB read + 1.822 GB written
+SPMV_TRAFFIC_NCU = 2.467e9   # k_spmv_stream<1>: 2.334 GB read + 0.134 GB written
 
 
 def measured_peak_hbm():
@@ -46,7 +50,10 @@ def pcg_bytes_per_iter(n, nnz):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler is started
+    early (nvidia-smi needs a few hundred ms to come up) and rows are time-stamped on arrival;
+    summary() keeps the rows that fall inside [t0, t1] (or the closest ones if the region is shorter
+    than the sampling period)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -57,22 +64,32 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:  # noqa: BLE001
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
+            self.rows.append((time.perf_counter(), [t.strip() for t in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
+        rows = list(self.rows)
+        inside = [r for t, r in rows if t0 is not None and t0 <= t <= t1]
+        where = "inside timed region"
+        if not inside and rows and t0 is not None:
+            mid = 0.5 * (t0 + t1)
+            inside = [r for _, r in sorted(rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+            where = "nearest to timed region"
+        elif t0 is None:
+            inside = [r for _, r in rows]
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -82,7 +99,7 @@ class ClockSampler:
             except Exception:  # noqa: BLE001
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "where": where}
 
 
 # ------------------------------------------------------------------------------ CPU baseline
@@ -194,22 +211,24 @@ def run_gpu(args):
             timers.append((a0, a1, p0, p1))
 
     MAT_DEV = torch.as_tensor(MAT).to(dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.launches
     timers = []
     s0, s1 = ev(), ev()
     torch.cuda.synchronize()
+    tw0 = time.perf_counter()
     s0.record()
     for _ in range(args.steps):
         step(timers)
     s1.record()
     torch.cuda.synchronize()
+    tw1 = time.perf_counter()
     launches = ctx.launches - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(tw0, tw1)
     t_asm = np.mean([a0.elapsed_time(a1) for a0, a1, _, _ in timers]) * 1e-3
     t_pcg = np.mean([p0.elapsed_time(p1) for _, _, p0, p1 in timers]) * 1e-3
     ms_per_step = s0.elapsed_time(s1) / args.steps
@@ -273,9 +292,10 @@ def run_gpu(args):
         "pcg": {"dof_iters_per_s": n * args.pcg_iters / t_pcg, "ms_per_iter": 1e3 * t_pcg / args.pcg_iters,
                 "iters": args.pcg_iters, "algorithmic_bytes_per_iter": p_bytes,
                 "roofline": {"bound": "hbm", "achieved": pcg_gbs, "peak": peak, "unit": "GB/s",
-                             "frac": pcg_gbs / peak, "traffic": None, "peak_kind": peak_kind}},
+                             "frac": pcg_gbs / peak, "traffic": SPMV_TRAFFIC_NCU, "peak_kind": peak_kind,
+                             "kernel": "k_spmv_stream<1> (+ k_pcg_update, k_pcg_pupdate)"}},
         "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
-                     "traffic": None, "peak_kind": peak_kind, "kernel": "k_assemble_tile<0>"},
+                     "traffic": ASM_TRAFFIC_NCU, "peak_kind": peak_kind, "kernel": "k_assemble_fan<0>"},
         "e2e": {"value": n_el / np.mean(e2e_asm) / 1e6, "unit": "Melem/s",
                 "h2d_bytes_per_step": int(h_coords.numel() * 8 + h_rhs.numel() * 8),
                 "d2h_bytes_per_step": int(h_vals.numel() * 8 + h_x.numel() * 8),

@@ -30,6 +30,7 @@ SIGNATURES = {
     "fe_ctx_destroy": (C.c_int, [_vp]),
     "fe_ctx_launch_count": (_i64, [_vp]),
     "fe_elem_matrices": (C.c_int, [_vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fe_elem_post": (C.c_int, [_vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "fe_source_factors": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "fe_plan_create": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, C.POINTER(_vp)]),
     "fe_plan_destroy": (C.c_int, [_vp]),

@@ -22,7 +22,7 @@ from . import core
 from . import elements as fe_elements
 from .core import DessiaObject
 from .loads import NodeLoad
-from .mesh import ArrayMesh
+from .mesh import ArrayMesh, flatten_mesh
 from .results import Result
 
 
@@ -101,40 +101,9 @@ class FiniteElements(DessiaObject):
 
     def _flatten(self):
         """coords f64[N,2], conn i32[E,3], mat_id i32[E], mat f64[G,4], element -> flat index."""
-        if self._flat is not None:
-            return self._flat
-        mesh = self.mesh
-        if isinstance(mesh, ArrayMesh):
-            flat = dict(coords=mesh.coords, conn=mesh.conn, mat_id=mesh.mat_id, mat=mesh.group_params,
-                        element_index=None, magnetic=mesh.kind != 'elasticity')
-        else:
-            nodes = mesh.nodes
-            coords = np.array([[node[0], node[1]] for node in nodes], dtype=np.float64).reshape(-1, 2)
-            conn, mat_id, rows, row_of, element_index = [], [], [], {}, {}
-            magnetic = None
-            for group in mesh.elements_groups:
-                for element in group.elements:
-                    is_mag = hasattr(element, 'mu_total')
-                    if magnetic is None:
-                        magnetic = is_mag
-                    elif magnetic != is_mag:
-                        raise NotImplementedError('a mesh mixing magnetic and elasticity elements is not supported')
-                    if is_mag:
-                        row = (float(element.mu_total), 0.0, 0.0, 0.0)
-                    else:
-                        row = (float(element.elasticity_modulus), float(element.poisson_ratio),
-                               float(element.thickness), float(element.mass_density))
-                    if row not in row_of:
-                        row_of[row] = len(rows)
-                        rows.append(row)
-                    element_index[id(element)] = len(conn)
-                    conn.append([mesh.node_to_index[point] for point in element.points])
-                    mat_id.append(row_of[row])
-            flat = dict(coords=coords, conn=np.array(conn, dtype=np.int32).reshape(-1, 3),
-                        mat_id=np.array(mat_id, dtype=np.int32), mat=np.array(rows, dtype=np.float64).reshape(-1, 4),
-                        element_index=element_index, magnetic=bool(magnetic))
-        self._flat = flat
-        return flat
+        if self._flat is None:
+            self._flat = flatten_mesh(self.mesh)
+        return self._flat
 
     def _kind(self):
         from ._lib import KIND_ELAST_PSTRESS, KIND_ELAST_PSTRAIN, KIND_MAGNETIC

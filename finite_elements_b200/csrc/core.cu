@@ -229,6 +229,63 @@ __global__ void __launch_bounds__(128) k_source_factors(int64_t n_sel, const int
   if (out_area) out_area[i] = 0.5 * det;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// element post-processing: one thread per element, gathers the element's
+// nodal solution and evaluates
+//   elasticity: strain = B u_e, stress = D strain (results.py:809-830), energy = 1/2 u_e^T Ke u_e
+//               = 1/2 t A strain . stress (results.py:769-781, elements.py:275-292)  -> out[e][7]
+//   magnetic  : B = (sum c_i A_i, -sum b_i A_i) (results.py:121-152)                    -> out[e][2]
+// ---------------------------------------------------------------------------------------
+template <bool MAGNETIC>
+__global__ void __launch_bounds__(128) k_elem_post(int64_t n_elems, const double2 *__restrict__ coords,
+                                                  const int32_t *__restrict__ conn,
+                                                  const int32_t *__restrict__ mat_id,
+                                                  const MatRow *__restrict__ tab, const double *__restrict__ u,
+                                                  double *__restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elems) return;
+  const int n0 = conn[3 * e + 0], n1 = conn[3 * e + 1], n2 = conn[3 * e + 2];
+  const TriGeom g = tri_geom(__ldg(coords + n0), __ldg(coords + n1), __ldg(coords + n2));
+  if (MAGNETIC) {
+    const double a[3] = {u[n0], u[n1], u[n2]};
+    double bx = 0.0, by = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      bx += (g.gamma[i] / g.cross) * a[i];  // c_i A_i
+      by -= (g.beta[i] / g.cross) * a[i];   // -b_i A_i
+    }
+    out[2 * e + 0] = bx;
+    out[2 * e + 1] = by;
+  } else {
+    const MatRow m = tab[mat_id ? mat_id[e] : 0];  // (c t, a t, b t, t)
+    const double2 *u2 = reinterpret_cast<const double2 *>(u);
+    const double2 d[3] = {u2[n0], u2[n1], u2[n2]};
+    const double inv = 1.0 / g.det;
+    double exx = 0.0, eyy = 0.0, gxy = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      exx += g.beta[i] * d[i].x;
+      eyy += g.gamma[i] * d[i].y;
+      gxy += g.gamma[i] * d[i].x + g.beta[i] * d[i].y;
+    }
+    exx *= inv;
+    eyy *= inv;
+    gxy *= inv;
+    const double it = 1.0 / m.p3;  // D = (c, a, b) = m.p0..2 / thickness
+    const double c = m.p0 * it, a = m.p1 * it, b = m.p2 * it;
+    const double sxx = c * exx + a * eyy, syy = a * exx + c * eyy, sxy = b * gxy;
+    double *o = out + 7 * e;
+    o[0] = exx;
+    o[1] = eyy;
+    o[2] = gxy;
+    o[3] = sxx;
+    o[4] = syy;
+    o[5] = sxy;
+    o[6] = 0.5 * m.p3 * (0.5 * fabs(g.cross)) * (exx * sxx + eyy * syy + gxy * sxy);
+  }
+}
+
 }  // namespace fe
 
 using namespace fe;
@@ -311,6 +368,25 @@ int fe_source_factors(fe_ctx *ctx, void *stream, int64_t n_sel, const int32_t *e
   if (n_sel <= 0) return FE_OK;
   k_source_factors<<<grid_for(n_sel, 128), 128, 0, as_stream(stream)>>>(
       n_sel, elem_sel, reinterpret_cast<const double2 *>(coords), conn, out, out_area);
+  FE_LAUNCH_CHECK(ctx);
+  return FE_OK;
+}
+
+int fe_elem_post(fe_ctx *ctx, void *stream, int kind, int64_t n_elems, const double *coords, const int32_t *conn,
+                 const int32_t *mat_id, const double *mat, int32_t n_mat, const double *u, double *out) {
+  FE_REQUIRE(ctx && coords && conn && u && out, "fe_elem_post: NULL argument");
+  FE_REQUIRE(kind == FE_ELAST_PSTRESS || kind == FE_ELAST_PSTRAIN || kind == FE_MAGNETIC,
+             "fe_elem_post: kind %d has no post-processing", kind);
+  if (n_elems <= 0) return FE_OK;
+  cudaStream_t st = as_stream(stream);
+  MatRow *tab = nullptr;
+  int rc = build_material_table(ctx, st, kind, mat, n_mat, &tab, &ctx->scratch_b);
+  if (rc) return rc;
+  const double2 *xy = reinterpret_cast<const double2 *>(coords);
+  if (kind == FE_MAGNETIC)
+    k_elem_post<true><<<grid_for(n_elems, 128), 128, 0, st>>>(n_elems, xy, conn, mat_id, tab, u, out);
+  else
+    k_elem_post<false><<<grid_for(n_elems, 128), 128, 0, st>>>(n_elems, xy, conn, mat_id, tab, u, out);
   FE_LAUNCH_CHECK(ctx);
   return FE_OK;
 }

@@ -135,6 +135,22 @@ class DeviceMesh:
                                        _ptr(self.conn), _ptr(self.mat_id), _ptr(m), int(m.shape[0]), _ptr(out)))
         return out
 
+    def element_post(self, kind, mat, u):
+        """Per-element post-processing of the solution u.  fe_elem_post.
+        elasticity: f64[E,7] = (eps_xx, eps_yy, gamma_xy, sig_xx, sig_yy, tau_xy, energy);
+        magnetic: f64[E,2] = (B_x, B_y)."""
+        m = self._mat(mat)
+        u = (torch.as_tensor(np.ascontiguousarray(u, dtype=np.float64)) if not torch.is_tensor(u) else u)
+        u = u.to(self.ctx.device, torch.float64).contiguous()
+        if u.numel() < self.n_nodes * self.dim:
+            raise ValueError("solution vector is shorter than n_nodes * dim")
+        out = torch.empty((self.n_elems, 2 if kind == KIND_MAGNETIC else 7), dtype=torch.float64,
+                          device=self.ctx.device)
+        with torch.cuda.device(self.ctx.device):
+            check(lib.fe_elem_post(self.ctx.handle, _stream(), int(kind), self.n_elems, _ptr(self.coords),
+                                   _ptr(self.conn), _ptr(self.mat_id), _ptr(m), int(m.shape[0]), _ptr(u), _ptr(out)))
+        return out
+
     def source_factors(self, elem_sel=None):
         """(factors f64[n,3], area f64[n]) for the selected elements.  fe_source_factors."""
         dev = self.ctx.device

@@ -243,25 +243,27 @@ def bench_distributed(args, metric, mat, measured_peak_hbm, ClockSampler, asm_by
             timers.append((a0, a1, p0, p1))
 
     warm = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(warm):
         step()
     torch.cuda.synchronize()
     dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = ctx.launches
     timers = []
     s0, s1 = ev(), ev()
     torch.cuda.synchronize()
+    tw0 = time.perf_counter()
     s0.record()
     for _ in range(args.steps):
         step(timers)
     s1.record()
     torch.cuda.synchronize()
+    tw1 = time.perf_counter()
     dist.barrier()
     launches = ctx.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     loc = torch.tensor([np.mean([a0.elapsed_time(a1) for a0, a1, _, _ in timers]),
                         np.mean([p0.elapsed_time(p1) for _, _, p0, p1 in timers]),
                         s0.elapsed_time(s1) / args.steps, float(dm.nnz), float(launches)],

@@ -280,6 +280,41 @@ class ArrayMesh:
         return self._groups
 
 
+def flatten_mesh(mesh):
+    """Mesh object -> flat arrays, once: coords f64[N,2], conn i32[E,3], mat_id i32[E], mat f64[G,4]
+    ((E, nu, thickness, rho) or (mu, 0, 0, 0) rows, de-duplicated), `elements` (the element objects
+    in flat order, None for an ArrayMesh), `element_index` ({id(element): flat index}) and
+    `magnetic`.  Duck-typed on what the reference reads from volmdlr meshes."""
+    if isinstance(mesh, ArrayMesh):
+        return dict(coords=mesh.coords, conn=mesh.conn, mat_id=mesh.mat_id, mat=mesh.group_params,
+                    elements=None, element_index=None, magnetic=mesh.kind != 'elasticity')
+    coords = np.array([[node[0], node[1]] for node in mesh.nodes], dtype=np.float64).reshape(-1, 2)
+    conn, mat_id, rows, row_of, element_index, elements = [], [], [], {}, {}, []
+    magnetic = None
+    for group in mesh.elements_groups:
+        for element in group.elements:
+            is_mag = hasattr(element, 'mu_total')
+            if magnetic is None:
+                magnetic = is_mag
+            elif magnetic != is_mag:
+                raise NotImplementedError('a mesh mixing magnetic and elasticity elements is not supported')
+            if is_mag:
+                row = (float(element.mu_total), 0.0, 0.0, 0.0)
+            else:
+                row = (float(element.elasticity_modulus), float(element.poisson_ratio),
+                       float(element.thickness), float(element.mass_density))
+            if row not in row_of:
+                row_of[row] = len(rows)
+                rows.append(row)
+            element_index[id(element)] = len(conn)
+            elements.append(element)
+            conn.append([mesh.node_to_index[point] for point in element.points])
+            mat_id.append(row_of[row])
+    return dict(coords=coords, conn=np.array(conn, dtype=np.int32).reshape(-1, 3),
+                mat_id=np.array(mat_id, dtype=np.int32), mat=np.array(rows, dtype=np.float64).reshape(-1, 4),
+                elements=elements, element_index=element_index, magnetic=bool(magnetic))
+
+
 # ---------------------------------------------------------------------------------------
 # synthetic meshes and gmsh input
 # ---------------------------------------------------------------------------------------

@@ -80,6 +80,15 @@ int fe_elem_matrices(fe_ctx *ctx, void *stream, int kind, int64_t n_elems, const
 int fe_source_factors(fe_ctx *ctx, void *stream, int64_t n_sel, const int32_t *elem_sel,
                       const double *coords, const int32_t *conn, double *out, double *out_area);
 
+/* Element post-processing of a solution vector u (double[n_nodes*dim], device):
+ *   elasticity kinds: out double[E][7] = (eps_xx, eps_yy, gamma_xy, sig_xx, sig_yy, tau_xy, energy)
+ *     replaces results.py:809-830 (strain = B u_e, stress = D B u_e) and results.py:769-781 /
+ *     elements.py:275-292 (energy = 1/2 u_e^T Ke u_e);
+ *   FE_MAGNETIC: out double[E][2] = (B_x, B_y) = (sum c_i A_i, -sum b_i A_i), results.py:121-152. */
+int fe_elem_post(fe_ctx *ctx, void *stream, int kind, int64_t n_elems, const double *coords,
+                 const int32_t *conn, const int32_t *mat_id, const double *mat, int32_t n_mat,
+                 const double *u, double *out);
+
 /* ---- symbolic phase, once per mesh ----------------------------------------------------
  * replaces analysis.py:714-735 (get_row_col_indices) for all elements plus the
  * COO->CSR sort/unique scipy does at analysis.py:661 (pattern part).

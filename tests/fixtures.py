@@ -70,3 +70,45 @@ def assert_csr_values_close(a, b, rtol=1e-12):
     scale[scale == 0] = 1.0
     err = np.max(np.abs(a.data - b.data) / scale[rows]) if len(rows) else 0.0
     assert err <= rtol, f"row-scaled value error {err:.3e} > {rtol:.1e}"
+
+
+def build_object_analysis(fx, with_element_records=False, **kw):
+    """The fixture as the reference's scripts would build it: one Python object per node /
+    element, load and condition records on those objects (finite_elements_b200 classes)."""
+    import finite_elements_b200 as fe
+    m = fe.mesh
+    nodes = [m.Node2D(float(x), float(y)) for x, y in fx.coords]
+    groups, elems = [], []
+    bounds = fx.meta["group_bounds"]
+    for g in range(len(bounds) - 1):
+        ge = []
+        for e in range(bounds[g], bounds[g + 1]):
+            tri = m.TriangularElement2D([nodes[i] for i in fx.conn[e]])
+            p = fx.mat[g]
+            if fx.kind == "elasticity":
+                ge.append(fe.elements.ElasticityTriangularElement2D(tri, p[0], p[1], p[3], p[2]))
+            else:
+                ge.append(fe.elements.MagneticElement2D(tri, p[0]))
+        elems.extend(ge)
+        groups.append(m.ElementsGroup(ge, ''))
+    mesh = m.Mesh(groups)
+    mesh.nodes = nodes  # keep the fixture numbering, as beam2d_example_3.py:72-73 does
+    mesh.node_to_index = {nodes[i]: i for i in range(len(nodes))}
+
+    class Edge:
+        def __init__(self, a, b):
+            self.start, self.end = a, b
+
+    nl = [fe.loads.NodeLoad(nodes[n], v, d) for n, v, d in fx.rec("node_loads")]
+    edl = [fe.loads.EdgeLoad(Edge(nodes[a], nodes[b]), v, d) for a, b, v, d in fx.rec("edge_loads")]
+    nb = [fe.conditions.NodeBoundaryCondition(nodes[n], v, d) for n, v, d in fx.rec("node_bcs")]
+    edb = [fe.conditions.EdgeBoundaryCondition(Edge(nodes[a], nodes[b]), v, d) for a, b, v, d in fx.rec("edge_bcs")]
+    el, elb = [], []
+    if with_element_records:
+        el = [fe.loads.ElementsLoad([elems[j] for j in idx], v, d) for idx, v, d in fx.rec("elements_loads")]
+        elb = [fe.conditions.ElementBoundaryCondition(elems[j], v, d) for j, v, d in fx.rec("element_bcs")]
+    ps = fx.plane
+    an = fe.analysis.FiniteElementAnalysis(mesh, el, edl, nl, [], [], nb, edb, elb,
+                                           None if ps is None else ps == "strain",
+                                           None if ps is None else ps == "stress", **kw)
+    return an, mesh, elems

@@ -135,40 +135,7 @@ def test_mesh_lookalike_first_seen_order_and_approx_equality():
 
 
 # ------------------------------------------------------------------ host logic of the analysis
-def _object_analysis(fx, **kw):
-    import finite_elements_b200 as fe
-    m = fe.mesh
-    nodes = [m.Node2D(float(x), float(y)) for x, y in fx.coords]
-    groups, elems = [], []
-    bounds = fx.meta["group_bounds"]
-    for g in range(len(bounds) - 1):
-        ge = []
-        for e in range(bounds[g], bounds[g + 1]):
-            tri = m.TriangularElement2D([nodes[i] for i in fx.conn[e]])
-            p = fx.mat[g]
-            if fx.kind == "elasticity":
-                ge.append(fe.elements.ElasticityTriangularElement2D(tri, p[0], p[1], p[3], p[2]))
-            else:
-                ge.append(fe.elements.MagneticElement2D(tri, p[0]))
-        elems.extend(ge)
-        groups.append(m.ElementsGroup(ge, ''))
-    mesh = m.Mesh(groups)
-    mesh.nodes = nodes  # keep the fixture numbering, as beam2d_example_3.py:72-73 does
-    mesh.node_to_index = {nodes[i]: i for i in range(len(nodes))}
-
-    class Edge:
-        def __init__(self, a, b):
-            self.start, self.end = a, b
-
-    nl = [fe.loads.NodeLoad(nodes[n], v, d) for n, v, d in fx.rec("node_loads")]
-    edl = [fe.loads.EdgeLoad(Edge(nodes[a], nodes[b]), v, d) for a, b, v, d in fx.rec("edge_loads")]
-    nb = [fe.conditions.NodeBoundaryCondition(nodes[n], v, d) for n, v, d in fx.rec("node_bcs")]
-    edb = [fe.conditions.EdgeBoundaryCondition(Edge(nodes[a], nodes[b]), v, d) for a, b, v, d in fx.rec("edge_bcs")]
-    ps = fx.plane
-    an = fe.analysis.FiniteElementAnalysis(mesh, [], edl, nl, [], [], nb, edb, [],
-                                           None if ps is None else ps == "strain",
-                                           None if ps is None else ps == "stress", **kw)
-    return an, mesh, elems
+from tests.fixtures import build_object_analysis as _object_analysis  # noqa: E402
 
 
 def test_flatten_positions_and_triplet_indices():
