@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(128) k_node_adjacency(int32_t n_owned, const i
   for (int k = 0; k < 3 * nc; ++k)
     if (m == 0 || cd[k] != cd[m - 1]) cd[m++] = cd[k];
   ndeg[n] = m;
-  atomicMax(&flags->max_degree, m);
+  if (m > *reinterpret_cast<volatile int *>(&flags->max_degree)) atomicMax(&flags->max_degree, m);  // rarely taken
   if (m > kMaxDegree) flags->too_dense = 1;
   const int nf = fan_walk<false>(n, nc, cs, conn, mat_id, nullptr, 0, nullptr);
   nfan[n] = nf < 0 ? 0 : nf;
@@ -277,7 +277,8 @@ __global__ void k_fan_tile_max(int32_t n_owned, const int32_t *__restrict__ fan_
   const int32_t n0 = t * 32;  // assemble.cu: kFanChunk (one warp's 32-node chunk)
   if (n0 >= n_owned) return;
   const int32_t n1 = min(n0 + 32, n_owned);
-  atomicMax(out, fan_ptr[n1] - fan_ptr[n0]);
+  const int cnt = fan_ptr[n1] - fan_ptr[n0];
+  if (cnt > *reinterpret_cast<volatile int *>(out)) atomicMax(out, cnt);
 }
 
 template <typename T>

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_block_pattern(int32_t n_nodes, const in
   const int deg = (s2 - s0) >> 2;
   if (lane == 0) {
     bptr[node] = s0 >> 2;
-    atomicMax(max_deg, deg);
+    if (deg > *reinterpret_cast<volatile int *>(max_deg)) atomicMax(max_deg, deg);  // rarely taken
   }
   for (int j = lane; j < deg; j += 8) bidx[(s0 >> 2) + j] = colidx[s0 + 2 * j] >> 1;
 }
