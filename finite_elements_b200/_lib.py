@@ -49,7 +49,9 @@ SIGNATURES = {
     "fe_pcg_fixed": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32]),
     "fe_dist_unique_id": (C.c_int, [_vp]),
     "fe_dist_init": (C.c_int, [_vp, _vp, _i32, _i32]),
-    "fe_dist_pcg": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32,
+    "fe_dist_p2p_export": (C.c_int, [_vp, _i32, _vp]),
+    "fe_dist_p2p_import": (C.c_int, [_vp, _vp]),
+    "fe_dist_pcg": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32,
                               _f64, _i32, _i32, C.POINTER(_i32), C.POINTER(_f64)]),
 }
 

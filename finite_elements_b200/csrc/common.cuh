@@ -65,6 +65,25 @@ struct Scratch {
 
 }  // namespace fe
 
+namespace fe {
+// Peer-memory communication block (dist.cu).  Every rank owns one cudaMalloc'ed buffer, exported
+// with CUDA IPC and mapped by all peers of the node (NVLink / NVSwitch):
+//   slots  double[2][nranks][4]   per-source partial sums of the current all-reduce (parity-buffered)
+//   rflags u64   [2][nranks]      sequence number of the all-reduce whose partial the slot holds
+//   hflags u64   [nranks]         sequence number of the last halo a source rank delivered
+//   ghost  double[n_ghost]        ghost values, written by the owning neighbours
+constexpr int kMaxRanks = 16;
+struct P2PDev {
+  int nranks, rank, n_ghost, pad;
+  unsigned long long red_seq;   // all-reduces pushed by this rank so far
+  unsigned long long halo_seq;  // halo exchanges pushed by this rank so far
+  double *slots[kMaxRanks];
+  unsigned long long *rflags[kMaxRanks];
+  unsigned long long *hflags[kMaxRanks];
+  double *ghost[kMaxRanks];
+};
+}  // namespace fe
+
 struct fe_ctx {
   int device = 0;
   int num_sms = fe::kNumSMs;
@@ -81,6 +100,13 @@ struct fe_ctx {
   void *nccl_comm = nullptr;
   int rank = 0, nranks = 1;
   fe::Scratch halo_send, halo_recv;
+  // NCCL-free peer-memory path (fe_dist_p2p_export / _import)
+  void *p2p_buf = nullptr;          // this rank's communication block
+  size_t p2p_bytes = 0;
+  void *p2p_peer[fe::kMaxRanks] = {nullptr};  // mapped peer blocks (self = p2p_buf)
+  fe::P2PDev *p2p_dev = nullptr;    // device copy of the pointer table + sequence counters
+  int p2p_n_ghost = 0;
+  fe::Scratch p2p_halo;             // device copies of send_ptr / dst_off / neighbour ranks
 };
 
 namespace fe {

@@ -96,6 +96,104 @@ int halo_exchange(fe_ctx *ctx, cudaStream_t s, const HaloPlan *h, double *vec, i
   return FE_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// peer-memory transport (no NCCL inside the PCG loop)
+// ---------------------------------------------------------------------------------------
+struct HaloDev {  // device copy of the halo description, in ctx->p2p_halo
+  int n_nbr, n_send, n_ghost, ticket;
+  int nbr_rank[kMaxRanks];
+  int send_ptr[kMaxRanks + 1];
+  int dst_off[kMaxRanks];
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Interface values -> the neighbours' ghost blocks (peer stores over NVLink), then their flags.
+__global__ void __launch_bounds__(256) k_halo_push(P2PDev *pp, HaloDev *hd, const int32_t *__restrict__ send_idx,
+                                                  const double *__restrict__ vec) {
+  __shared__ bool is_last;
+  const int n_send = hd->n_send;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_send; i += gridDim.x * blockDim.x) {
+    int k = 0;
+    while (i >= hd->send_ptr[k + 1]) ++k;
+    pp->ghost[hd->nbr_rank[k]][hd->dst_off[k] + (i - hd->send_ptr[k])] = vec[send_idx[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(&hd->ticket, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned long long seq = pp->halo_seq + 1;
+    for (int k = 0; k < hd->n_nbr; ++k) st_release_sys_u64(pp->hflags[hd->nbr_rank[k]] + pp->rank, seq);
+    pp->halo_seq = seq;
+    hd->ticket = 0;
+  }
+}
+
+// Wait for every neighbour's delivery of the current exchange, then ghost block -> vec tail.
+__global__ void __launch_bounds__(256) k_halo_wait_copy(const P2PDev *pp, const HaloDev *hd,
+                                                       double *__restrict__ vec_tail) {
+  const unsigned long long seq = pp->halo_seq;
+  if (threadIdx.x < hd->n_nbr) {
+    const unsigned long long *f = pp->hflags[pp->rank] + hd->nbr_rank[threadIdx.x];
+    while (ld_acquire_sys_u64(f) < seq) {
+    }
+  }
+  __syncthreads();
+  const volatile double *g = pp->ghost[pp->rank];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hd->n_ghost; i += gridDim.x * blockDim.x) vec_tail[i] = g[i];
+}
+
+int halo_exchange_p2p(fe_ctx *ctx, cudaStream_t s, const HaloPlan *h, double *vec, int32_t n_rows) {
+  if (!h || h->n_nbr == 0) return FE_OK;
+  FE_REQUIRE(ctx->p2p_dev && ctx->p2p_halo.ptr, "halo_exchange_p2p: peer memory is not set up");
+  HaloDev *hd = (HaloDev *)ctx->p2p_halo.ptr;
+  const int32_t n_send = h->send_ptr[h->n_nbr], n_ghost = h->recv_ptr[h->n_nbr];
+  if (n_send > 0) {
+    int grid = grid_for(n_send, 256);
+    if (grid > 64) grid = 64;
+    k_halo_push<<<grid, 256, 0, s>>>(ctx->p2p_dev, hd, h->send_idx, vec);
+    FE_LAUNCH_CHECK(ctx);
+  }
+  if (n_ghost > 0) {
+    int grid = grid_for(n_ghost, 256);
+    if (grid > 64) grid = 64;
+    k_halo_wait_copy<<<grid, 256, 0, s>>>(ctx->p2p_dev, hd, vec + n_rows);
+    FE_LAUNCH_CHECK(ctx);
+  }
+  return FE_OK;
+}
+
+static int upload_p2p_halo(fe_ctx *ctx, cudaStream_t s, const HaloPlan *h) {
+  FE_REQUIRE(h->n_nbr <= kMaxRanks, "p2p: more than %d neighbours", kMaxRanks);
+  FE_REQUIRE(h->recv_ptr[h->n_nbr] <= ctx->p2p_n_ghost, "p2p: ghost block too small (%d > %d): call fe_dist_p2p_export again",
+             h->recv_ptr[h->n_nbr], ctx->p2p_n_ghost);
+  HaloDev hd;
+  memset(&hd, 0, sizeof(hd));
+  hd.n_nbr = h->n_nbr;
+  hd.n_send = h->send_ptr[h->n_nbr];
+  hd.n_ghost = h->recv_ptr[h->n_nbr];
+  for (int k = 0; k < h->n_nbr; ++k) {
+    hd.nbr_rank[k] = h->nbr_rank[k];
+    hd.send_ptr[k] = h->send_ptr[k];
+    hd.dst_off[k] = h->peer_dst_off[k];
+  }
+  hd.send_ptr[h->n_nbr] = h->send_ptr[h->n_nbr];
+  int rc = ctx->p2p_halo.reserve(sizeof(HaloDev));
+  if (rc) return rc;
+  FE_CUDA(cudaMemcpyAsync(ctx->p2p_halo.ptr, &hd, sizeof(hd), cudaMemcpyHostToDevice, s));
+  FE_CUDA(cudaStreamSynchronize(s));  // hd lives on this stack frame
+  return FE_OK;
+}
+
 int allreduce_sum(fe_ctx *ctx, cudaStream_t s, double *dev, int count) {
   if (ctx->nranks <= 1) return FE_OK;
   FE_REQUIRE(ctx->nccl_comm, "allreduce_sum: fe_dist_init was not called");
@@ -109,7 +207,77 @@ using namespace fe;
 
 extern "C" {
 
+static size_t p2p_block_bytes(int nranks, int n_ghost, size_t *off_rflags, size_t *off_hflags, size_t *off_ghost) {
+  size_t o = (size_t)2 * nranks * 4 * sizeof(double);
+  *off_rflags = o;
+  o += (size_t)2 * nranks * sizeof(unsigned long long);
+  *off_hflags = o;
+  o += (size_t)nranks * sizeof(unsigned long long);
+  o = (o + 255) / 256 * 256;
+  *off_ghost = o;
+  return o + (size_t)(n_ghost > 0 ? n_ghost : 1) * sizeof(double);
+}
+
+int fe_dist_p2p_export(fe_ctx *ctx, int32_t n_ghost_dofs, void *handle64) {
+  FE_REQUIRE(ctx && handle64 && n_ghost_dofs >= 0, "fe_dist_p2p_export: bad argument");
+  FE_REQUIRE(ctx->nranks > 1 && ctx->nranks <= kMaxRanks, "fe_dist_p2p_export: needs fe_dist_init with 2..%d ranks",
+             kMaxRanks);
+  FE_CUDA(cudaSetDevice(ctx->device));
+  FE_CUDA(cudaDeviceSynchronize());
+  for (int r = 0; r < kMaxRanks; ++r) {
+    if (ctx->p2p_peer[r] && ctx->p2p_peer[r] != ctx->p2p_buf) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+    ctx->p2p_peer[r] = nullptr;
+  }
+  if (ctx->p2p_buf) cudaFree(ctx->p2p_buf);
+  ctx->p2p_buf = nullptr;
+  size_t o1, o2, o3;
+  ctx->p2p_bytes = p2p_block_bytes(ctx->nranks, n_ghost_dofs, &o1, &o2, &o3);
+  FE_CUDA(cudaMalloc(&ctx->p2p_buf, ctx->p2p_bytes));
+  FE_CUDA(cudaMemset(ctx->p2p_buf, 0, ctx->p2p_bytes));
+  ctx->p2p_n_ghost = n_ghost_dofs;
+  cudaIpcMemHandle_t h;
+  FE_CUDA(cudaIpcGetMemHandle(&h, ctx->p2p_buf));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return FE_OK;
+}
+
+int fe_dist_p2p_import(fe_ctx *ctx, const void *handles) {
+  FE_REQUIRE(ctx && handles && ctx->p2p_buf, "fe_dist_p2p_import: call fe_dist_p2p_export first");
+  FE_CUDA(cudaSetDevice(ctx->device));
+  P2PDev host;
+  memset(&host, 0, sizeof(host));
+  host.nranks = ctx->nranks;
+  host.rank = ctx->rank;
+  host.n_ghost = ctx->p2p_n_ghost;
+  size_t o1, o2, o3;
+  p2p_block_bytes(ctx->nranks, 0, &o1, &o2, &o3);
+  for (int r = 0; r < ctx->nranks; ++r) {
+    void *base = ctx->p2p_buf;
+    if (r != ctx->rank) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char *)handles + 64 * r, 64);
+      FE_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    ctx->p2p_peer[r] = base;
+    host.slots[r] = (double *)base;
+    host.rflags[r] = (unsigned long long *)((char *)base + o1);
+    host.hflags[r] = (unsigned long long *)((char *)base + o2);
+    host.ghost[r] = (double *)((char *)base + o3);
+  }
+  if (!ctx->p2p_dev) FE_CUDA(cudaMalloc((void **)&ctx->p2p_dev, sizeof(P2PDev)));
+  FE_CUDA(cudaMemcpy(ctx->p2p_dev, &host, sizeof(host), cudaMemcpyHostToDevice));
+  return FE_OK;
+}
+
 void fe_dist_teardown(fe_ctx *ctx) {
+  if (ctx) {
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (ctx->p2p_peer[r] && ctx->p2p_peer[r] != ctx->p2p_buf) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+    if (ctx->p2p_buf) cudaFree(ctx->p2p_buf);
+    if (ctx->p2p_dev) cudaFree(ctx->p2p_dev);
+    ctx->p2p_halo.release();
+  }
   if (ctx && ctx->nccl_comm && g_nccl.CommDestroy) {
     g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
@@ -145,7 +313,7 @@ int fe_dist_init(fe_ctx *ctx, const void *nccl_unique_id, int32_t rank, int32_t 
 int fe_dist_pcg(fe_ctx *ctx, void *stream, int32_t n_rows, int32_t n_cols, const int32_t *rowptr,
                 const int32_t *colidx, const double *vals, const double *b, double *x, double *work, int32_t n_nbr,
                 const int32_t *nbr_rank, const int32_t *send_ptr, const int32_t *send_idx, const int32_t *recv_ptr,
-                int32_t block_dim, double rtol, int32_t maxit, int32_t fixed_iters, int32_t *iters, double *relres) {
+                const int32_t *peer_dst_off, int32_t block_dim, double rtol, int32_t maxit, int32_t fixed_iters, int32_t *iters, double *relres) {
   FE_REQUIRE(ctx, "fe_dist_pcg: NULL ctx");
   FE_REQUIRE(n_nbr == 0 || (nbr_rank && send_ptr && recv_ptr), "fe_dist_pcg: NULL halo description");
   HaloPlan h;
@@ -154,10 +322,15 @@ int fe_dist_pcg(fe_ctx *ctx, void *stream, int32_t n_rows, int32_t n_cols, const
   h.send_ptr = send_ptr;
   h.send_idx = send_idx;
   h.recv_ptr = recv_ptr;
+  h.peer_dst_off = ctx->p2p_dev ? peer_dst_off : nullptr;  // non-NULL selects the peer-memory transport
   if (n_nbr > 0) {
     FE_REQUIRE(n_rows + recv_ptr[n_nbr] == n_cols, "fe_dist_pcg: ghost count %d does not match n_cols - n_rows = %d",
                recv_ptr[n_nbr], n_cols - n_rows);
     FE_REQUIRE(send_ptr[n_nbr] == 0 || send_idx, "fe_dist_pcg: NULL send_idx");
+  }
+  if (h.peer_dst_off) {
+    int rc = upload_p2p_halo(ctx, as_stream(stream), &h);
+    if (rc) return rc;
   }
   const bool fixed = fixed_iters > 0;
   return pcg_drive(ctx, as_stream(stream), n_rows, n_cols, rowptr, colidx, vals, b, x, work, &h, block_dim, rtol,

@@ -11,11 +11,18 @@ struct HaloPlan {
   const int32_t *send_idx = nullptr;  // device [send_ptr[n_nbr]]  owned local DOFs to pack
   const int32_t *recv_ptr = nullptr;  // host [n_nbr + 1]  ghost DOFs of neighbour k land at
                                       // vec[n_rows + recv_ptr[k] .. n_rows + recv_ptr[k+1])
+  const int32_t *peer_dst_off = nullptr;  // host [n_nbr]  offset of MY values in neighbour k's ghost block
+                                          // (= its recv_ptr entry for me); NULL -> NCCL transport
 };
 
 // Pack the interface values of `vec`, exchange them with the neighbours (grouped
 // ncclSend/ncclRecv on `s`) and receive straight into the ghost tail of `vec`.
 int halo_exchange(fe_ctx *ctx, cudaStream_t s, const HaloPlan *h, double *vec, int32_t n_rows);
+
+// Same exchange without NCCL: k_halo_push stores the interface values straight into the
+// neighbours' ghost blocks over the NVLink peer mappings and raises their flags; k_halo_wait_copy
+// waits for this rank's neighbours and moves its ghost block behind `vec`.
+int halo_exchange_p2p(fe_ctx *ctx, cudaStream_t s, const HaloPlan *h, double *vec, int32_t n_rows);
 
 // In-place sum over all ranks of `count` doubles in device memory (ncclAllReduce on `s`).
 int allreduce_sum(fe_ctx *ctx, cudaStream_t s, double *dev, int count);

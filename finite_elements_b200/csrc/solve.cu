@@ -32,7 +32,74 @@ struct PcgState {
   int converged;
   int breakdown;
   unsigned ticket;  // last-CTA election
+  P2PDev *pp;       // peer-memory all-reduce (NULL: single GPU, or NCCL between the kernels)
 };
+
+// ---- peer-memory all-reduce, fused into the reducing kernels ------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// Producer side (one thread of the last CTA): store this rank's NQ totals into every rank's slot
+// for sequence number red_seq + 1, then raise the flags.
+template <int NQ>
+__device__ __forceinline__ void p2p_push(P2PDev *pp, const double *tot) {
+  const unsigned long long seq = pp->red_seq + 1;
+  const int par = (int)(seq & 1), R = pp->nranks, me = pp->rank;
+  for (int r = 0; r < R; ++r) {
+    double *dst = pp->slots[r] + ((size_t)par * R + me) * 4;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) dst[q] = tot[q];
+  }
+  __threadfence_system();
+  for (int r = 0; r < R; ++r) st_release_sys(pp->rflags[r] + (size_t)par * R + me, seq);
+  pp->red_seq = seq;
+}
+// Consumer side (any thread, typically thread 0 of every CTA): wait for all ranks' partials of the
+// most recent all-reduce and add them in rank order -- every rank gets bit-identical sums.
+template <int NQ>
+__device__ __forceinline__ void p2p_gather(const P2PDev *pp, double *out) {
+  const unsigned long long seq = pp->red_seq;
+  const int par = (int)(seq & 1), R = pp->nranks, me = pp->rank;
+  const unsigned long long *flags = pp->rflags[me] + (size_t)par * R;
+  const double *slots = pp->slots[me] + (size_t)par * R * 4;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) out[q] = 0.0;
+  for (int r = 0; r < R; ++r) {
+    while (ld_acquire_sys(flags + r) < seq) {
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) out[q] += *reinterpret_cast<const volatile double *>(slots + r * 4 + q);
+  }
+}
+// Block-wide: the all-reduced values of sums[base .. base+NQ), whichever transport is active.
+template <int NQ>
+__device__ __forceinline__ void reduced_sums(PcgState *st, int base, double *out /* NQ */) {
+  __shared__ double bc[4];
+  if (st->pp) {
+    if (threadIdx.x == 0) {
+      double t[NQ];
+      p2p_gather<NQ>(st->pp, t);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) bc[q] = t[q];
+      if (blockIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) st->sums[base + q] = t[q];  // for the host read-back
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) out[q] = bc[q];
+    __syncthreads();
+  } else {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) out[q] = st->sums[base + q];
+  }
+}
 
 constexpr int kRedBlock = 256;
 constexpr int kMaxPartials = 148 * 16;  // grids of the reducing kernels are capped to this
@@ -40,7 +107,7 @@ constexpr int kMaxPartials = 148 * 16;  // grids of the reducing kernels are cap
 // Sum `np` per-CTA partials (stride = number of quantities) in a fixed order.
 template <int NQ, int BLOCK = kRedBlock>
 __device__ __forceinline__ void final_reduce(const double *__restrict__ partials, int np, double *smem,
-                                             double *__restrict__ out) {
+                                             double *__restrict__ out, P2PDev *pp) {
   double acc[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
@@ -48,10 +115,16 @@ __device__ __forceinline__ void final_reduce(const double *__restrict__ partials
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] += __ldcg(partials + (size_t)i * NQ + q);
   }
+  double tot[NQ];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    const double t = block_sum<BLOCK>(acc[q], smem);
-    if (threadIdx.x == 0) out[q] = t;
+  for (int q = 0; q < NQ; ++q) tot[q] = block_sum<BLOCK>(acc[q], smem);
+  if (threadIdx.x == 0) {
+    if (pp)
+      p2p_push<NQ>(pp, tot);  // all-reduce over peer memory: consumers gather (reduced_sums)
+    else {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) out[q] = tot[q];
+    }
   }
 }
 
@@ -73,7 +146,7 @@ __device__ __forceinline__ void publish_and_reduce(const double (&local)[NQ], do
   __syncthreads();
   if (is_last) {
     __threadfence();
-    final_reduce<NQ, BLOCK>(partials, gridDim.x, smem, st->sums + out_base);
+    final_reduce<NQ, BLOCK>(partials, gridDim.x, smem, st->sums + out_base, st->pp);
     if (threadIdx.x == 0) st->ticket = 0;
   }
 }
@@ -279,8 +352,15 @@ __global__ void __launch_bounds__(kRedBlock) k_pcg_init(int32_t n, const double 
 
 // after the (all-reduced) init sums: rz[0] = rz_new, convergence of the initial guess
 __global__ void k_pcg_init_finish(PcgState *st) {
-  st->rz[0] = st->sums[1];
-  if (!(st->sums[3] > 0.0) || st->sums[2] <= st->tol2 * st->sums[3]) st->converged = 1;
+  double t[3];
+  reduced_sums<3>(st, 1, t);  // (r.z, r.r, b.b)
+  if (threadIdx.x == 0) {
+    st->sums[1] = t[0];
+    st->sums[2] = t[1];
+    st->sums[3] = t[2];
+    st->rz[0] = t[0];
+    if (!(t[2] > 0.0) || t[1] <= st->tol2 * t[2]) st->converged = 1;
+  }
 }
 
 __global__ void __launch_bounds__(kRedBlock) k_pcg_update(int32_t n, int parity, const double *__restrict__ p,
@@ -290,7 +370,9 @@ __global__ void __launch_bounds__(kRedBlock) k_pcg_update(int32_t n, int parity,
                                                          PcgState *__restrict__ st) {
   __shared__ double red[kRedBlock / 32];
   if (st->converged | st->breakdown) return;
-  const double pq = st->sums[0];
+  double pq_[1];
+  reduced_sums<1>(st, 0, pq_);
+  const double pq = pq_[0];
   if (!(pq > 0.0) || !isfinite(pq)) {  // uniform across the grid
     if (blockIdx.x == 0 && threadIdx.x == 0) st->breakdown = 1;
     return;
@@ -311,14 +393,16 @@ __global__ void __launch_bounds__(256) k_pcg_pupdate(int32_t n, int parity, cons
                                                     const double *__restrict__ dinv, double *__restrict__ p,
                                                     PcgState *__restrict__ st) {
   if (st->converged | st->breakdown) return;
-  const double rz_new = st->sums[1];
+  double t2[2];
+  reduced_sums<2>(st, 1, t2);  // (r.z, r.r)
+  const double rz_new = t2[0];
   const double beta = rz_new / st->rz[parity];
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
     p[i] = dinv[i] * r[i] + beta * p[i];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->rz[parity ^ 1] = rz_new;
     st->iters += 1;
-    if (st->sums[2] <= st->tol2 * st->sums[3]) st->converged = 1;
+    if (t2[1] <= st->tol2 * st->sums[3]) st->converged = 1;
   }
 }
 
@@ -326,7 +410,8 @@ __global__ void __launch_bounds__(256) k_pcg_pupdate(int32_t n, int parity, cons
 // same launch may still be at their entry test.  A CTA that sees the flag early skips its
 // part of the p update, which is harmless: once converged no later kernel reads p.
 
-__global__ void k_pcg_state_init(PcgState *st, double tol2) {
+__global__ void k_pcg_state_init(PcgState *st, double tol2, P2PDev *pp) {
+  st->pp = pp;
   for (int i = 0; i < 8; ++i) st->sums[i] = 0.0;
   st->rz[0] = st->rz[1] = 0.0;
   st->tol2 = tol2;
@@ -405,7 +490,7 @@ struct PcgLaunch {
   double *x, *r, *q, *dinv, *p, *partials;
   PcgState *st;
   const HaloPlan *halo;
-  bool dist;
+  bool dist, p2p = false;
   int lpr, vgrid;
   StreamPlan sp;
 
@@ -414,24 +499,26 @@ struct PcgLaunch {
     int rc;
     k_copy<<<reducing_grid(ctx, n_rows, 1024), 256, 0, s>>>(n_rows, x, p);
     FE_LAUNCH_CHECK(ctx);
-    if (dist && (rc = halo_exchange(ctx, s, halo, p, n_rows))) return rc;
+    if (dist && (rc = (p2p ? halo_exchange_p2p(ctx, s, halo, p, n_rows) : halo_exchange(ctx, s, halo, p, n_rows))))
+      return rc;
     if ((rc = launch_spmv<false>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st, &sp))) return rc;
     k_pcg_init<<<vgrid, kRedBlock, 0, s>>>(n_rows, b, q, dinv, r, p, partials, st);
     FE_LAUNCH_CHECK(ctx);
-    if (dist && (rc = allreduce_sum(ctx, s, st->sums + 1, 3))) return rc;
-    k_pcg_init_finish<<<1, 1, 0, s>>>(st);
+    if (dist && !p2p && (rc = allreduce_sum(ctx, s, st->sums + 1, 3))) return rc;
+    k_pcg_init_finish<<<1, 32, 0, s>>>(st);
     FE_LAUNCH_CHECK(ctx);
     return FE_OK;
   }
 
   int iteration(int parity) {
     int rc;
-    if (dist && (rc = halo_exchange(ctx, s, halo, p, n_rows))) return rc;
+    if (dist && (rc = (p2p ? halo_exchange_p2p(ctx, s, halo, p, n_rows) : halo_exchange(ctx, s, halo, p, n_rows))))
+      return rc;
     if ((rc = launch_spmv<true>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st, &sp))) return rc;
-    if (dist && (rc = allreduce_sum(ctx, s, st->sums + 0, 1))) return rc;
+    if (dist && !p2p && (rc = allreduce_sum(ctx, s, st->sums + 0, 1))) return rc;
     k_pcg_update<<<vgrid, kRedBlock, 0, s>>>(n_rows, parity, p, q, dinv, x, r, partials, st);
     FE_LAUNCH_CHECK(ctx);
-    if (dist && (rc = allreduce_sum(ctx, s, st->sums + 1, 2))) return rc;
+    if (dist && !p2p && (rc = allreduce_sum(ctx, s, st->sums + 1, 2))) return rc;
     k_pcg_pupdate<<<vgrid, 256, 0, s>>>(n_rows, parity, r, dinv, p, st);
     FE_LAUNCH_CHECK(ctx);
     return FE_OK;
@@ -513,11 +600,15 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
   L.partials = (double *)((char *)ctx->scratch_b.ptr + 256);
   L.halo = halo;
   L.dist = halo != nullptr && ctx->nranks > 1;
+  // NCCL-free transport: peer-memory halo stores + all-reduce fused into the kernels
+  const bool p2p = L.dist && ctx->p2p_dev != nullptr && halo->peer_dst_off != nullptr &&
+                   getenv("FE_B200_NO_P2P") == nullptr;
+  L.p2p = p2p;
   PcgState *st = L.st;
 
   int32_t h_rowptr_end = 0;
   FE_CUDA(cudaMemcpyAsync(&h_rowptr_end, rowptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  k_pcg_state_init<<<1, 1, 0, s>>>(st, fixed ? -1.0 : rtol * rtol);
+  k_pcg_state_init<<<1, 1, 0, s>>>(st, fixed ? -1.0 : rtol * rtol, p2p ? ctx->p2p_dev : nullptr);
   FE_LAUNCH_CHECK(ctx);
   FE_CUDA(cudaStreamSynchronize(s));
   L.lpr = spmv_lpr(n_rows, h_rowptr_end, block_dim);

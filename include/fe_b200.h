@@ -177,8 +177,20 @@ int fe_dist_init(fe_ctx *ctx, const void *nccl_unique_id, int32_t rank, int32_t 
 int fe_dist_pcg(fe_ctx *ctx, void *stream, int32_t n_rows, int32_t n_cols, const int32_t *rowptr,
                 const int32_t *colidx, const double *vals, const double *b, double *x,
                 double *work, int32_t n_nbr, const int32_t *nbr_rank, const int32_t *send_ptr,
-                const int32_t *send_idx, const int32_t *recv_ptr, int32_t block_dim, double rtol,
-                int32_t maxit, int32_t fixed_iters, int32_t *iters, double *relres);
+                const int32_t *send_idx, const int32_t *recv_ptr, const int32_t *peer_dst_off,
+                int32_t block_dim, double rtol, int32_t maxit, int32_t fixed_iters, int32_t *iters,
+                double *relres);
+
+/* Peer-memory transport for fe_dist_pcg (one node, NVLink / NVSwitch): every rank exports one
+ * communication block (all-reduce slots + flags, ghost values) with CUDA IPC, the host gathers the
+ * 64-byte handles of all ranks (rank order) and every rank imports them.  Afterwards fe_dist_pcg
+ * -- given peer_dst_off (HOST int32[n_nbr]: where this rank's interface values start inside
+ * neighbour k's ghost block, i.e. that neighbour's recv_ptr entry for this rank) -- runs without
+ * any NCCL call in the iteration: halo values are stored straight into the neighbours' memory and
+ * the dot products are all-reduced through peer-written slots inside the PCG kernels themselves.
+ * n_ghost_dofs = this rank's ghost count (n_cols - n_rows).  Both calls are collective. */
+int fe_dist_p2p_export(fe_ctx *ctx, int32_t n_ghost_dofs, void *handle64_out);
+int fe_dist_p2p_import(fe_ctx *ctx, const void *handles /* nranks * 64 bytes */);
 
 /* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 int64_t fe_ctx_launch_count(const fe_ctx *ctx);
