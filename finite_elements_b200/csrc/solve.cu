@@ -530,7 +530,7 @@ struct PcgLaunch {
 static int get_chunk_graph(PcgLaunch &L, int len, cudaGraphExec_t *out) {
   fe_ctx *ctx = L.ctx;
   const void *key[8] = {L.rowptr, L.colidx, L.vals, L.x, L.r, L.st, (void *)(intptr_t)L.n_rows,
-                        (void *)(intptr_t)(len * 64 + (L.lpr & 31) + (L.sp.on ? 32 : 0))};
+                        (void *)(intptr_t)(len * 128 + (L.lpr & 31) + (L.sp.on ? 32 : 0) + (L.p2p ? 64 : 0))};
   if (ctx->pcg_graph && memcmp(key, ctx->pcg_graph_key, sizeof(key)) == 0) {
     *out = (cudaGraphExec_t)ctx->pcg_graph;
     return FE_OK;
@@ -654,7 +654,8 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
   PcgState *h = (PcgState *)ctx->pinned;
   constexpr int kChunk = 50;   // iterations between convergence polls (even: graph parity)
   constexpr int kMaxRestarts = 12;
-  const bool use_graph = !L.dist && getenv("FE_B200_NO_GRAPH") == nullptr;
+  // (the peer-memory transport keeps its sequence numbers on the device, so it can be captured too)
+  const bool use_graph = (!L.dist || L.p2p) && getenv("FE_B200_NO_GRAPH") == nullptr;
   int it = 0, local = 0, restarts = 0;
   bool done = (maxit == 0), stagnated = false;
   double prev_true_rr = -1.0;
@@ -669,7 +670,7 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
         cudaGraphExec_t exec;
         if ((rc = get_chunk_graph(L, kChunk, &exec))) return rc;
         FE_CUDA(cudaGraphLaunch(exec, s));
-        ctx->launches += 3 * kChunk;
+        ctx->launches += (3 + (L.p2p ? 2 : 0)) * kChunk;
         it += kChunk;
         local += kChunk;
       } else {

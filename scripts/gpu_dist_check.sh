@@ -5,7 +5,7 @@ set -u
 N=${1:-2}
 mkdir -p gpurun_out
 run() { timeout ${T:-600} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 "$@"; }
-for mode in p2p nccl; do
+for mode in ${MODES:-p2p nccl}; do
   if [[ $mode == nccl ]]; then export FE_B200_NO_P2P=1; else unset FE_B200_NO_P2P; fi
   run tests/dist_gpu_worker.py 96 64 > gpurun_out/dist_worker_${N}_$mode.log 2>&1; echo "[$mode] dist worker rc=$?"; grep -E "DIST-OK|Error|error" gpurun_out/dist_worker_${N}_$mode.log | head -3
   run tests/dist_gpu_worker.py 301 77 >> gpurun_out/dist_worker_${N}_$mode.log 2>&1; echo "[$mode] dist worker(301x77) rc=$?"; grep -E "DIST-OK" gpurun_out/dist_worker_${N}_$mode.log | tail -1
