@@ -198,6 +198,10 @@ def run_gpu(args):
 
     def step(timers=None):
         a0, a1, p0, p1 = ev(), ev(), ev(), ev()
+        # the previous step ended with a host synchronisation: keep the GPU busy for ~0.1 ms so the
+        # launches below are queued before it gets to them (the events then bracket device time,
+        # not the CPU's launch latency)
+        torch.cuda._sleep(200_000)
         a0.record()
         dm.assemble(KIND_ELAST_PSTRESS, MAT_DEV, out=vals, variant=args.variant)
         a1.record()

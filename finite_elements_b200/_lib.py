@@ -44,6 +44,7 @@ SIGNATURES = {
     "fe_scatter_add": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "fe_spmv": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32]),
     "fe_pcg_work_len": (_i64, [_i32, _i32]),
+    "fe_pcg_cache_pattern": (C.c_int, [_vp, _vp, _vp, _i64]),
     "fe_pcg": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f64, _i32,
                          C.POINTER(_i32), C.POINTER(_f64)]),
     "fe_pcg_fixed": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32]),

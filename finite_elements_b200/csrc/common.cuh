@@ -67,20 +67,22 @@ struct Scratch {
 
 namespace fe {
 // Peer-memory communication block (dist.cu).  Every rank owns one cudaMalloc'ed buffer, exported
-// with CUDA IPC and mapped by all peers of the node (NVLink / NVSwitch):
-//   slots  double[2][nranks][4]   per-source partial sums of the current all-reduce (parity-buffered)
-//   rflags u64   [2][nranks]      sequence number of the all-reduce whose partial the slot holds
-//   hflags u64   [nranks]         sequence number of the last halo a source rank delivered
-//   ghost  double[n_ghost]        ghost values, written by the owning neighbours
+// with CUDA IPC and mapped by all peers of the node (NVLink / NVSwitch).  Everything in it is made
+// of 16-byte "LL" cells {lo32(value), seq, hi32(value), seq}: a double travels together with the
+// sequence number of the exchange it belongs to, so the receiver needs no separate flag and the
+// sender needs no fence -- each 8-byte half is self-validating (8-byte stores are atomic on
+// NVLink; the protocol NCCL calls LL).  Cells are double-buffered by the parity of the sequence
+// number, which is enough because two exchanges of the same parity are always separated by a
+// full round trip between the two ranks involved.
+//   red    cell[2][nranks][4]   per-source partial sums of an all-reduce
+//   ghost  cell[2][n_ghost]     ghost values, written by the owning neighbours
 constexpr int kMaxRanks = 16;
 struct P2PDev {
   int nranks, rank, n_ghost, pad;
-  unsigned long long red_seq;   // all-reduces pushed by this rank so far
-  unsigned long long halo_seq;  // halo exchanges pushed by this rank so far
-  double *slots[kMaxRanks];
-  unsigned long long *rflags[kMaxRanks];
-  unsigned long long *hflags[kMaxRanks];
-  double *ghost[kMaxRanks];
+  unsigned red_seq;   // all-reduces pushed by this rank so far
+  unsigned halo_seq;  // halo exchanges pushed by this rank so far
+  uint4 *red[kMaxRanks];
+  uint4 *ghost[kMaxRanks];
 };
 }  // namespace fe
 
@@ -91,6 +93,12 @@ struct fe_ctx {
   fe::Scratch scratch_a;   // material tables, BC flags, scan block sums
   fe::Scratch scratch_b;   // reduction partials / PCG scalars
   fe::Scratch scratch_c;   // node-level block pattern of the streamed SpMV
+  // fe_pcg_cache_pattern: the caller vouches that the CSR pattern at (rowptr, colidx) is immutable
+  // while `token` stays the same, so the block pattern in scratch_c is reused across solves
+  const void *bp_rowptr = nullptr, *bp_colidx = nullptr;
+  int64_t bp_token = 0, bp_built_token = 0;
+  int32_t bp_built_rows = -1;
+  int bp_max_deg = 0;
   void *pinned = nullptr;  // small pinned host buffer for scalar read-back
   void *pcg_graph = nullptr;  // cached cudaGraphExec_t of one PCG iteration chunk
   const void *pcg_graph_key[8] = {nullptr};
@@ -152,6 +160,26 @@ __device__ __forceinline__ int2 ldg_nc_int2(const int2 *p) {
   int2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
+}
+
+// ---- LL cells (see P2PDev) -------------------------------------------------------------------
+__device__ __forceinline__ void ll_store(uint4 *cell, double v, unsigned seq) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"((unsigned)b), "r"(seq),
+               "r"((unsigned)(b >> 32)), "r"(seq)
+               : "memory");
+}
+__device__ __forceinline__ bool ll_try(const uint4 *cell, unsigned seq, double *out) {
+  unsigned a, fa, b, fb;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(cell) : "memory");
+  *out = __longlong_as_double((long long)(((unsigned long long)b << 32) | a));
+  return fa == seq && fb == seq;
+}
+__device__ __forceinline__ double ll_wait(const uint4 *cell, unsigned seq) {
+  double v;
+  while (!ll_try(cell, seq, &v)) {
+  }
+  return v;
 }
 #endif
 

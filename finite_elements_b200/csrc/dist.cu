@@ -100,56 +100,35 @@ int halo_exchange(fe_ctx *ctx, cudaStream_t s, const HaloPlan *h, double *vec, i
 // peer-memory transport (no NCCL inside the PCG loop)
 // ---------------------------------------------------------------------------------------
 struct HaloDev {  // device copy of the halo description, in ctx->p2p_halo
-  int n_nbr, n_send, n_ghost, ticket;
+  int n_nbr, n_send, n_ghost;
+  unsigned ticket;
   int nbr_rank[kMaxRanks];
   int send_ptr[kMaxRanks + 1];
   int dst_off[kMaxRanks];
 };
 
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// Interface values -> the neighbours' ghost blocks (peer stores over NVLink), then their flags.
-__global__ void __launch_bounds__(256) k_halo_push(P2PDev *pp, HaloDev *hd, const int32_t *__restrict__ send_idx,
-                                                  const double *__restrict__ vec) {
-  __shared__ bool is_last;
-  const int n_send = hd->n_send;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_send; i += gridDim.x * blockDim.x) {
+// One launch per exchange.  Every thread first stores its share of the interface values straight
+// into the neighbours' ghost cells (peer stores over NVLink, LL cells: no fence, no flag), then
+// waits for its share of this rank's own ghost cells and moves them behind `vec`.  The wait is per
+// cell, so no grid-wide synchronisation is needed; the last CTA to finish bumps halo_seq.
+__global__ void __launch_bounds__(256) k_halo_ll(P2PDev *pp, HaloDev *hd, const int32_t *__restrict__ send_idx,
+                                                const double *__restrict__ vec, double *__restrict__ vec_tail) {
+  const unsigned seq = pp->halo_seq + 1, par = seq & 1;  // cell of ghost j and parity: 2 j + par
+  const int n_send = hd->n_send, n_ghost = hd->n_ghost;
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = t0; i < n_send; i += stride) {
     int k = 0;
     while (i >= hd->send_ptr[k + 1]) ++k;
-    pp->ghost[hd->nbr_rank[k]][hd->dst_off[k] + (i - hd->send_ptr[k])] = vec[send_idx[i]];
+    ll_store(pp->ghost[hd->nbr_rank[k]] + 2 * (size_t)(hd->dst_off[k] + (i - hd->send_ptr[k])) + par,
+             vec[send_idx[i]], seq);
   }
-  __threadfence_system();
+  const uint4 *mine = pp->ghost[pp->rank] + par;
+  for (int i = t0; i < n_ghost; i += stride) vec_tail[i] = ll_wait(mine + 2 * (size_t)i, seq);
   __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(&hd->ticket, 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    __threadfence_system();
-    const unsigned long long seq = pp->halo_seq + 1;
-    for (int k = 0; k < hd->n_nbr; ++k) st_release_sys_u64(pp->hflags[hd->nbr_rank[k]] + pp->rank, seq);
-    pp->halo_seq = seq;
+  if (threadIdx.x == 0 && atomicAdd(&hd->ticket, 1u) == gridDim.x - 1) {
     hd->ticket = 0;
+    pp->halo_seq = seq;
   }
-}
-
-// Wait for every neighbour's delivery of the current exchange, then ghost block -> vec tail.
-__global__ void __launch_bounds__(256) k_halo_wait_copy(const P2PDev *pp, const HaloDev *hd,
-                                                       double *__restrict__ vec_tail) {
-  const unsigned long long seq = pp->halo_seq;
-  if (threadIdx.x < hd->n_nbr) {
-    const unsigned long long *f = pp->hflags[pp->rank] + hd->nbr_rank[threadIdx.x];
-    while (ld_acquire_sys_u64(f) < seq) {
-    }
-  }
-  __syncthreads();
-  const volatile double *g = pp->ghost[pp->rank];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hd->n_ghost; i += gridDim.x * blockDim.x) vec_tail[i] = g[i];
 }
 
 int halo_exchange_p2p(fe_ctx *ctx, cudaStream_t s, const HaloPlan *h, double *vec, int32_t n_rows) {
@@ -157,16 +136,13 @@ int halo_exchange_p2p(fe_ctx *ctx, cudaStream_t s, const HaloPlan *h, double *ve
   FE_REQUIRE(ctx->p2p_dev && ctx->p2p_halo.ptr, "halo_exchange_p2p: peer memory is not set up");
   HaloDev *hd = (HaloDev *)ctx->p2p_halo.ptr;
   const int32_t n_send = h->send_ptr[h->n_nbr], n_ghost = h->recv_ptr[h->n_nbr];
-  if (n_send > 0) {
-    int grid = grid_for(n_send, 256);
-    if (grid > 64) grid = 64;
-    k_halo_push<<<grid, 256, 0, s>>>(ctx->p2p_dev, hd, h->send_idx, vec);
-    FE_LAUNCH_CHECK(ctx);
-  }
-  if (n_ghost > 0) {
-    int grid = grid_for(n_ghost, 256);
-    if (grid > 64) grid = 64;
-    k_halo_wait_copy<<<grid, 256, 0, s>>>(ctx->p2p_dev, hd, vec + n_rows);
+  const int32_t n_max = n_send > n_ghost ? n_send : n_ghost;
+  if (n_max > 0) {
+    // every CTA spins on cells a peer fills: the grid must be co-resident (<= 1 CTA per SM is plenty
+    // for an interface; a 2-D stripe at S16M is 16 K values)
+    int grid = grid_for(n_max, 256);
+    if (grid > ctx->num_sms) grid = ctx->num_sms;
+    k_halo_ll<<<grid, 256, 0, s>>>(ctx->p2p_dev, hd, h->send_idx, vec, vec + n_rows);
     FE_LAUNCH_CHECK(ctx);
   }
   return FE_OK;
@@ -207,15 +183,12 @@ using namespace fe;
 
 extern "C" {
 
-static size_t p2p_block_bytes(int nranks, int n_ghost, size_t *off_rflags, size_t *off_hflags, size_t *off_ghost) {
-  size_t o = (size_t)2 * nranks * 4 * sizeof(double);
-  *off_rflags = o;
-  o += (size_t)2 * nranks * sizeof(unsigned long long);
-  *off_hflags = o;
-  o += (size_t)nranks * sizeof(unsigned long long);
+// communication block: red cell[2][nranks][4] | ghost cell[n_ghost][2]
+static size_t p2p_block_bytes(int nranks, int n_ghost, size_t *off_ghost) {
+  size_t o = (size_t)2 * nranks * 4 * sizeof(uint4);
   o = (o + 255) / 256 * 256;
   *off_ghost = o;
-  return o + (size_t)(n_ghost > 0 ? n_ghost : 1) * sizeof(double);
+  return o + (size_t)2 * (n_ghost > 0 ? n_ghost : 1) * sizeof(uint4);
 }
 
 int fe_dist_p2p_export(fe_ctx *ctx, int32_t n_ghost_dofs, void *handle64) {
@@ -230,8 +203,8 @@ int fe_dist_p2p_export(fe_ctx *ctx, int32_t n_ghost_dofs, void *handle64) {
   }
   if (ctx->p2p_buf) cudaFree(ctx->p2p_buf);
   ctx->p2p_buf = nullptr;
-  size_t o1, o2, o3;
-  ctx->p2p_bytes = p2p_block_bytes(ctx->nranks, n_ghost_dofs, &o1, &o2, &o3);
+  size_t off_ghost;
+  ctx->p2p_bytes = p2p_block_bytes(ctx->nranks, n_ghost_dofs, &off_ghost);
   FE_CUDA(cudaMalloc(&ctx->p2p_buf, ctx->p2p_bytes));
   FE_CUDA(cudaMemset(ctx->p2p_buf, 0, ctx->p2p_bytes));
   ctx->p2p_n_ghost = n_ghost_dofs;
@@ -250,8 +223,8 @@ int fe_dist_p2p_import(fe_ctx *ctx, const void *handles) {
   host.nranks = ctx->nranks;
   host.rank = ctx->rank;
   host.n_ghost = ctx->p2p_n_ghost;
-  size_t o1, o2, o3;
-  p2p_block_bytes(ctx->nranks, 0, &o1, &o2, &o3);
+  size_t off_ghost;
+  p2p_block_bytes(ctx->nranks, 0, &off_ghost);
   for (int r = 0; r < ctx->nranks; ++r) {
     void *base = ctx->p2p_buf;
     if (r != ctx->rank) {
@@ -260,10 +233,8 @@ int fe_dist_p2p_import(fe_ctx *ctx, const void *handles) {
       FE_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
     }
     ctx->p2p_peer[r] = base;
-    host.slots[r] = (double *)base;
-    host.rflags[r] = (unsigned long long *)((char *)base + o1);
-    host.hflags[r] = (unsigned long long *)((char *)base + o2);
-    host.ghost[r] = (double *)((char *)base + o3);
+    host.red[r] = (uint4 *)base;
+    host.ghost[r] = (uint4 *)((char *)base + off_ghost);
   }
   if (!ctx->p2p_dev) FE_CUDA(cudaMalloc((void **)&ctx->p2p_dev, sizeof(P2PDev)));
   FE_CUDA(cudaMemcpy(ctx->p2p_dev, &host, sizeof(host), cudaMemcpyHostToDevice));

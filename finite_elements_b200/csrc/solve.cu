@@ -36,59 +36,45 @@ struct PcgState {
 };
 
 // ---- peer-memory all-reduce, fused into the reducing kernels ------------------------------
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-// Producer side (one thread of the last CTA): store this rank's NQ totals into every rank's slot
-// for sequence number red_seq + 1, then raise the flags.
+// Producer side (threads 0 .. nranks-1 of the last CTA, `tot` in shared memory): thread r stores
+// this rank's NQ totals into rank r's cells for all-reduce number red_seq + 1.  No fence, no flag:
+// the cells carry the sequence number (LL protocol, common.cuh).
 template <int NQ>
-__device__ __forceinline__ void p2p_push(P2PDev *pp, const double *tot) {
-  const unsigned long long seq = pp->red_seq + 1;
+__device__ __forceinline__ void p2p_push(P2PDev *pp, const double *tot /* shared, NQ */) {
+  const unsigned seq = pp->red_seq + 1;
   const int par = (int)(seq & 1), R = pp->nranks, me = pp->rank;
-  for (int r = 0; r < R; ++r) {
-    double *dst = pp->slots[r] + ((size_t)par * R + me) * 4;
+  if ((int)threadIdx.x < R) {
+    uint4 *dst = pp->red[threadIdx.x] + ((size_t)par * R + me) * 4;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) dst[q] = tot[q];
+    for (int q = 0; q < NQ; ++q) ll_store(dst + q, tot[q], seq);
   }
-  __threadfence_system();
-  for (int r = 0; r < R; ++r) st_release_sys(pp->rflags[r] + (size_t)par * R + me, seq);
-  pp->red_seq = seq;
-}
-// Consumer side (any thread, typically thread 0 of every CTA): wait for all ranks' partials of the
-// most recent all-reduce and add them in rank order -- every rank gets bit-identical sums.
-template <int NQ>
-__device__ __forceinline__ void p2p_gather(const P2PDev *pp, double *out) {
-  const unsigned long long seq = pp->red_seq;
-  const int par = (int)(seq & 1), R = pp->nranks, me = pp->rank;
-  const unsigned long long *flags = pp->rflags[me] + (size_t)par * R;
-  const double *slots = pp->slots[me] + (size_t)par * R * 4;
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) out[q] = 0.0;
-  for (int r = 0; r < R; ++r) {
-    while (ld_acquire_sys(flags + r) < seq) {
-    }
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) out[q] += *reinterpret_cast<const volatile double *>(slots + r * 4 + q);
-  }
+  __syncthreads();
+  if (threadIdx.x == 0) pp->red_seq = seq;
 }
 // Block-wide: the all-reduced values of sums[base .. base+NQ), whichever transport is active.
+// Peer memory: thread r waits for rank r's cells of the most recent all-reduce; thread 0 adds them
+// in rank order -- every CTA of every rank gets bit-identical sums.
 template <int NQ>
 __device__ __forceinline__ void reduced_sums(PcgState *st, int base, double *out /* NQ */) {
-  __shared__ double bc[4];
+  __shared__ double part[kMaxRanks][NQ];
+  __shared__ double bc[NQ];
   if (st->pp) {
+    const P2PDev *pp = st->pp;
+    const unsigned seq = pp->red_seq;
+    const int par = (int)(seq & 1), R = pp->nranks, me = pp->rank;
+    if ((int)threadIdx.x < R) {
+      const uint4 *src = pp->red[me] + ((size_t)par * R + threadIdx.x) * 4;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) part[threadIdx.x][q] = ll_wait(src + q, seq);
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-      double t[NQ];
-      p2p_gather<NQ>(st->pp, t);
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) bc[q] = t[q];
-      if (blockIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) st->sums[base + q] = t[q];  // for the host read-back
+      for (int q = 0; q < NQ; ++q) {
+        double t = 0.0;
+        for (int r = 0; r < R; ++r) t += part[r][q];
+        bc[q] = t;
+        if (blockIdx.x == 0) st->sums[base + q] = t;  // for the host read-back
       }
     }
     __syncthreads();
@@ -115,16 +101,20 @@ __device__ __forceinline__ void final_reduce(const double *__restrict__ partials
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] += __ldcg(partials + (size_t)i * NQ + q);
   }
+  __shared__ double tot_s[NQ];
   double tot[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) tot[q] = block_sum<BLOCK>(acc[q], smem);
-  if (threadIdx.x == 0) {
-    if (pp)
-      p2p_push<NQ>(pp, tot);  // all-reduce over peer memory: consumers gather (reduced_sums)
-    else {
+  if (pp) {  // all-reduce over peer memory: consumers gather (reduced_sums)
+    if (threadIdx.x == 0) {
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) out[q] = tot[q];
+      for (int q = 0; q < NQ; ++q) tot_s[q] = tot[q];
     }
+    __syncthreads();
+    p2p_push<NQ>(pp, tot_s);
+  } else if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) out[q] = tot[q];
   }
 }
 
@@ -623,13 +613,23 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
     L.sp.bptr = (int32_t *)ctx->scratch_c.ptr;
     L.sp.bidx = (int32_t *)((char *)ctx->scratch_c.ptr + bptr_bytes);
     int *max_deg = (int *)((char *)ctx->scratch_c.ptr + bptr_bytes + bidx_bytes);
-    FE_CUDA(cudaMemsetAsync(max_deg, 0, sizeof(int), s));
-    k_block_pattern<<<grid_for(((int64_t)n_nodes + 1) * 8, 256), 256, 0, s>>>(n_nodes, rowptr, colidx, L.sp.bptr,
-                                                                              L.sp.bidx, max_deg);
-    FE_LAUNCH_CHECK(ctx);
-    int h_max_deg = 0;
-    FE_CUDA(cudaMemcpyAsync(&h_max_deg, max_deg, sizeof(int), cudaMemcpyDeviceToHost, s));
-    FE_CUDA(cudaStreamSynchronize(s));
+    const bool cached = ctx->bp_token != 0 && ctx->bp_rowptr == rowptr && ctx->bp_colidx == colidx &&
+                        ctx->bp_built_token == ctx->bp_token && ctx->bp_built_rows == n_rows;
+    int h_max_deg = ctx->bp_max_deg;
+    if (!cached) {
+      ctx->bp_built_token = 0;
+      FE_CUDA(cudaMemsetAsync(max_deg, 0, sizeof(int), s));
+      k_block_pattern<<<grid_for(((int64_t)n_nodes + 1) * 8, 256), 256, 0, s>>>(n_nodes, rowptr, colidx, L.sp.bptr,
+                                                                                L.sp.bidx, max_deg);
+      FE_LAUNCH_CHECK(ctx);
+      FE_CUDA(cudaMemcpyAsync(&h_max_deg, max_deg, sizeof(int), cudaMemcpyDeviceToHost, s));
+      FE_CUDA(cudaStreamSynchronize(s));
+      if (ctx->bp_token != 0 && ctx->bp_rowptr == rowptr && ctx->bp_colidx == colidx) {
+        ctx->bp_built_token = ctx->bp_token;
+        ctx->bp_built_rows = n_rows;
+        ctx->bp_max_deg = h_max_deg;
+      }
+    }
     const int T = kStreamTile;  // fixed tile; meshes whose valence makes it too large use k_spmv_b2
     const int cap = (T * (h_max_deg > 0 ? h_max_deg : 1) + 3) & ~3;
     const size_t smem = stream_smem_bytes(T, cap);
@@ -670,7 +670,7 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
         cudaGraphExec_t exec;
         if ((rc = get_chunk_graph(L, kChunk, &exec))) return rc;
         FE_CUDA(cudaGraphLaunch(exec, s));
-        ctx->launches += (3 + (L.p2p ? 2 : 0)) * kChunk;
+        ctx->launches += (3 + (L.p2p ? 1 : 0)) * kChunk;
         it += kChunk;
         local += kChunk;
       } else {
@@ -760,6 +760,14 @@ int fe_spmv(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr, co
   FE_CUDA(cudaMemcpyAsync(&nnz, rowptr + n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   FE_CUDA(cudaStreamSynchronize(s));
   return launch_spmv<false>(ctx, s, spmv_lpr(n_rows, nnz, block_dim), n_rows, rowptr, colidx, vals, x, y, nullptr, nullptr);
+}
+
+int fe_pcg_cache_pattern(fe_ctx *ctx, const int32_t *rowptr, const int32_t *colidx, int64_t token) {
+  FE_REQUIRE(ctx, "fe_pcg_cache_pattern: NULL ctx");
+  ctx->bp_rowptr = rowptr;
+  ctx->bp_colidx = colidx;
+  ctx->bp_token = (rowptr && colidx) ? token : 0;
+  return FE_OK;
 }
 
 int64_t fe_pcg_work_len(int32_t n_rows, int32_t n_cols) { return 3 * (int64_t)n_rows + (int64_t)n_cols; }

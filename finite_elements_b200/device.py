@@ -86,6 +86,17 @@ class DeviceMesh:
         self.max_degree = int(lib.fe_plan_max_degree(h))
         self.plan_bytes = int(lib.fe_plan_bytes(h))
         self._csr = None
+        DeviceMesh._tokens += 1
+        self._token = DeviceMesh._tokens   # identifies this mesh's immutable CSR pattern to the solver
+
+    _tokens = 0
+
+    def _vouch_pattern(self):
+        """fe_pcg_cache_pattern: the CSR tensors of csr_pattern() live as long as this object and
+        are never written again, so the solver may keep what it derives from them."""
+        rowptr, colidx = self.csr_pattern()
+        check(lib.fe_pcg_cache_pattern(self.ctx.handle, _ptr(rowptr), _ptr(colidx), self._token))
+        return rowptr, colidx
 
     def __del__(self):
         try:
@@ -200,7 +211,7 @@ class DeviceMesh:
 
     def pcg(self, vals, b, x=None, rtol=1e-8, maxit=None, work=None, raise_on_maxit=True):
         """Jacobi-PCG on the (eliminated, SPD) system.  Returns (x, iters, relres)."""
-        rowptr, colidx = self.csr_pattern()
+        rowptr, colidx = self._vouch_pattern()
         if x is None:
             x = torch.zeros(self.n_rows, dtype=torch.float64, device=self.ctx.device)
         if work is None:
@@ -219,7 +230,7 @@ class DeviceMesh:
 
     def pcg_fixed(self, vals, b, x, iters, work=None):
         """Exactly `iters` PCG iterations, no convergence test (throughput runs)."""
-        rowptr, colidx = self.csr_pattern()
+        rowptr, colidx = self._vouch_pattern()
         if work is None:
             work = self.pcg_workspace()
         with torch.cuda.device(self.ctx.device):

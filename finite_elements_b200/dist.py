@@ -192,7 +192,7 @@ class DistributedMesh:
 
     def pcg(self, vals, b, x=None, rtol=1e-8, maxit=None, fixed_iters=0, work=None):
         dm = self.dm
-        rowptr, colidx = dm.csr_pattern()
+        rowptr, colidx = dm._vouch_pattern()
         if x is None:
             x = torch.zeros(dm.n_rows, dtype=torch.float64, device=self.ctx.device)
         if work is None:
@@ -264,6 +264,10 @@ def bench_distributed(args, metric, mat, measured_peak_hbm, ClockSampler, asm_by
 
     def step(timers=None):
         a0, a1, p0, p1 = ev(), ev(), ev(), ev()
+        # the previous step ended with a host synchronisation: keep the GPU busy for ~0.1 ms so the
+        # launches below are queued before it gets to them (the events then bracket device time,
+        # not the CPU's launch latency)
+        torch.cuda._sleep(200_000)
         a0.record()
         dm.assemble(KIND_ELAST_PSTRESS, mat_dev, out=vals, variant=args.variant)
         a1.record()

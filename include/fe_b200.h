@@ -162,6 +162,12 @@ int fe_pcg(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr, const in
 int fe_pcg_fixed(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr,
                  const int32_t *colidx, const double *vals, const double *b, double *x,
                  double *work, int32_t block_dim, int32_t iters);
+/* Optional: the caller vouches that the CSR pattern stored at (rowptr, colidx) does not change
+ * while it keeps passing the same non-zero `token` (the host layer uses one token per mesh).  The
+ * solver then builds its node-level block pattern once instead of once per solve -- the analogue
+ * of the reference caching `_boundary_conditions` / `_positions` on the analysis object
+ * (analysis.py:169-171).  (NULL, NULL, 0) clears the hint. */
+int fe_pcg_cache_pattern(fe_ctx *ctx, const int32_t *rowptr, const int32_t *colidx, int64_t token);
 
 /* ---- multi-GPU (one process per GPU) --------------------------------------
  * nccl_unique_id: 128 bytes from ncclGetUniqueId on rank 0 (fe_dist_unique_id), broadcast

@@ -1,0 +1,8 @@
+#!/bin/bash
+# Development call on a 2-GPU box: GPU tests, 1-GPU quick bench, 2-GPU parity worker + bench (p2p / nccl).
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python bench.py --steps 5 --warmup 3 --full-solve 0 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; tail -2 gpurun_out/bench_quick.err
+python scripts/show_bench.py gpurun_out/bench_quick.json
+MODES="${MODES:-p2p}" FULL=${FULL:-1} bash scripts/gpu_dist_check.sh 2
