@@ -279,6 +279,11 @@ def run_gpu(args):
         solve = {"rtol": 1e-8, "iters": iters, "relres": relres, "true_relres": true_res, "seconds": ts,
                  "dof_iters_per_s": n * iters / ts if ts > 0 else None}
 
+    # ---- BASELINE configs[4]: lowest modes of K x = lambda M x on the 1 M-triangle mesh (LOBPCG) ----
+    modal = None
+    if args.modal > 0:
+        modal = run_modal(args.modal, 1024, 512, local_rank)
+
     peak, peak_kind = measured_peak_hbm()
     a_bytes, p_bytes = asm_bytes(n_el, n_nodes, nnz), pcg_bytes_per_iter(n, nnz)
     asm_gbs = a_bytes / t_asm / 1e9
@@ -307,11 +312,40 @@ def run_gpu(args):
                 "pcg_dof_iters_per_s": n * args.pcg_iters / float(np.mean(e2e_pcg))},
         "gpu_launches": int(launches), "clocks": clocks, "solve": solve,
     }
+    if modal is not None:
+        line["modal"] = modal
     if not args.no_cpu_baseline:
         cb = cpu_baseline(args.cpu_nx, args.cpu_ny, args.cpu_pcg_iters)
         line["cpu_baseline"] = {"value": cb["melem_s"], "unit": "Melem/s", "cores": 1, "kind": "port",
                                 "sample": cb["sample"], "pcg_dof_iters_per_s": cb["dof_iters_s"]}
     print(json.dumps(line))
+
+
+def run_modal(k, nx, ny, device):
+    """Lowest k modes of the unconstrained plane-stress pencil on an nx x ny-cell mesh: assembly of K
+    and M + LOBPCG (Chebyshev-Jacobi preconditioner), wall time with a device synchronise."""
+    import torch
+    from finite_elements_b200.device import DeviceMesh, KIND_ELAST_PSTRESS, KIND_MASS
+    from finite_elements_b200.mesh import structured_mesh_torch
+    from finite_elements_b200.modal import modal_solve
+    dev = torch.device("cuda", device)
+    coords, conn = structured_mesh_torch(nx, ny, dev)
+    dm = DeviceMesh(coords, conn, None, dim=2, device=device)
+    mat_dev = torch.as_tensor(MAT).to(dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kv = dm.assemble(KIND_ELAST_PSTRESS, mat_dev)
+    mv = dm.assemble(KIND_MASS, mat_dev)
+    lam, vec, info = modal_solve(dm, kv, mv, k, "smallest", tol=1e-8)
+    torch.cuda.synchronize()
+    t = time.perf_counter() - t0
+    kx, mx = dm.spmm_pair(kv, mv, vec.contiguous())
+    res = torch.linalg.norm(kx - mx * lam[None, :], dim=0) / (torch.linalg.norm(kx, dim=0) + 1e-300)
+    return {"workload": f"lowest {k} modes, {nx}x{ny}-cell plane-stress mesh ({2 * nx * ny} triangles, "
+                        f"{dm.n_rows} DOF), free-free", "seconds": t, "iterations": info.iterations,
+            "block_products": info.products, "converged": info.converged,
+            "eigenvalues": [float(v) for v in lam.cpu()],
+            "max_rel_residual_elastic_modes": float(res[3:].max()) if k > 3 else None}
 
 
 def main():
@@ -326,6 +360,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--full-solve", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--modal", type=int, default=0, help="also time the lowest K modes on the 1M-triangle mesh")
     ap.add_argument("--cpu-nx", type=int, default=1024)
     ap.add_argument("--cpu-ny", type=int, default=512)
     ap.add_argument("--cpu-pcg-iters", type=int, default=20)

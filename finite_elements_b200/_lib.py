@@ -43,6 +43,8 @@ SIGNATURES = {
     "fe_dirichlet_apply": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "fe_scatter_add": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "fe_spmv": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "fe_spmm_pair": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "fe_csr_diagonal": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "fe_pcg_work_len": (_i64, [_i32, _i32]),
     "fe_pcg_cache_pattern": (C.c_int, [_vp, _vp, _vp, _i64]),
     "fe_pcg": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f64, _i32,

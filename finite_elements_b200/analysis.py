@@ -413,5 +413,36 @@ class FiniteElementAnalysis(FiniteElements):
         singular / non-SPD system raises NotImplementedError as the reference does."""
         return Result(self.mesh, list(self.solve_arrays()))
 
-    def modal_analysis(self, order, k):
-        raise NotImplementedError('modal_analysis is scheduled after the solve path (SURVEY §8f rank 1)')
+    def modal_analysis(self, order, k, constrained=False, tol=1e-9, maxit=5000, cheb_degree=None):
+        """(eigvals, eigvecs.T) of  K x = lambda M x  (analysis.py:741-796): the k 'largest'
+        (reference: eigsh(A=K, M=M, which='LM'), :779-782) or 'smallest' eigenvalues, ascending,
+        eigenvectors M-orthonormal in the rows of the second array.
+
+        Like the reference, the raw K and M are used -- boundary conditions are ignored -- unless
+        `constrained=True` (extension), which restricts the pencil to the DOFs without a Dirichlet
+        condition.  The reference's 'smallest' branch inverts the dense K (:790), singular for an
+        unconstrained mesh; here 'smallest' is the mathematically intended lower end of the same
+        pencil (rigid-body modes first when unconstrained), computed by LOBPCG on the device
+        (modal.py).  cheb_degree > 1 turns the Jacobi preconditioner of the 'smallest' branch into a
+        Chebyshev polynomial of that degree (fewer outer iterations on large meshes; None = automatic)."""
+        import torch
+        from ._lib import KIND_MASS
+        from .modal import modal_solve
+        if order not in ('largest', 'smallest'):
+            raise ValueError("Order parameter should be either 'largest' or 'smallest'")
+        if self._flatten()['magnetic']:
+            raise NotImplementedError('modal_analysis needs elements with a mass matrix (elements.py:513-536)')
+        dm = self._dm()
+        flat = self._flatten()
+        k_vals = dm.assemble(self._kind(), flat['mat'], variant=self.assembly_variant)
+        m_vals = dm.assemble(KIND_MASS, flat['mat'], variant=self.assembly_variant)
+        mask = None
+        if constrained:
+            bc_dofs, _ = self._bc_arrays()
+            mask = torch.ones(dm.n_rows, dtype=torch.float64, device=k_vals.device)
+            if len(bc_dofs):
+                mask[torch.as_tensor(np.asarray(bc_dofs, dtype=np.int64)).to(k_vals.device)] = 0.0
+        lam, vec, info = modal_solve(dm, k_vals, m_vals, int(k), order, mask=mask, tol=tol, maxit=maxit,
+                                     cheb_degree=cheb_degree)
+        self.last_modal_info = info
+        return lam.cpu().numpy(), vec.T.contiguous().cpu().numpy()

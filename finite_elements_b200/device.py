@@ -205,6 +205,30 @@ class DeviceMesh:
                               _ptr(x), _ptr(y), self.dim))
         return y
 
+    def spmm_pair(self, vals_a, vals_b, x, out_a=None, out_b=None):
+        """(A X, B X) for a row-major (n_cols, m) block X, one pass over the shared pattern
+        (vals_b None: A X only).  fe_spmm_pair."""
+        rowptr, colidx = self.csr_pattern()
+        if x.ndim != 2 or x.shape[0] != self.n_cols or not x.is_contiguous() or x.dtype != torch.float64:
+            raise ValueError("spmm_pair: X must be a contiguous float64 (n_cols, m) tensor")
+        m = int(x.shape[1])
+        ya = out_a if out_a is not None else torch.empty(self.n_rows, m, dtype=torch.float64, device=x.device)
+        yb = None
+        if vals_b is not None:
+            yb = out_b if out_b is not None else torch.empty(self.n_rows, m, dtype=torch.float64, device=x.device)
+        with torch.cuda.device(self.ctx.device):
+            check(lib.fe_spmm_pair(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals_a),
+                                   _ptr(vals_b), _ptr(x), _ptr(ya), _ptr(yb), m))
+        return ya, yb
+
+    def csr_diagonal(self, vals):
+        rowptr, colidx = self.csr_pattern()
+        d = torch.empty(self.n_rows, dtype=torch.float64, device=self.ctx.device)
+        with torch.cuda.device(self.ctx.device):
+            check(lib.fe_csr_diagonal(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals),
+                                      _ptr(d)))
+        return d
+
     def pcg_workspace(self):
         n = int(lib.fe_pcg_work_len(self.n_rows, self.n_cols))
         return torch.empty(n, dtype=torch.float64, device=self.ctx.device)

@@ -147,6 +147,18 @@ int fe_spmv(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
             const int32_t *colidx, const double *vals, const double *x, double *y,
             int32_t block_dim);
 
+/* ---- modal analysis building blocks (analysis.py:741-796) -------------------------------
+ * The reference gives K and M to scipy.sparse.linalg.eigsh (:779-782), whose Lanczos loop
+ * multiplies one vector at a time; the LOBPCG driver of the host layer works on blocks of m
+ * vectors.  y_a = A x and (when vals_b / y_b are non-NULL) y_b = B x in one pass over the
+ * pattern both matrices share.  x: double[n_cols][m] row-major, y_*: double[n_rows][m]. */
+int fe_spmm_pair(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
+                 const int32_t *colidx, const double *vals_a, const double *vals_b,
+                 const double *x, double *y_a, double *y_b, int32_t m);
+/* diag[i] = A[i][i] (0 if the entry is not stored): the Jacobi preconditioner of the block solver */
+int fe_csr_diagonal(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
+                    const int32_t *colidx, const double *vals, double *diag);
+
 /* Jacobi-preconditioned CG; replaces scipy spsolve at analysis.py:820-822 on the
  * eliminated SPD system.  x: initial guess in, solution out.  work: double[fe_pcg_work_len(n)].
  * Stops when ||r||_2 <= rtol * ||b||_2, where r is re-computed as b - A x once the recurrence

@@ -180,7 +180,7 @@ def fixtures():
                    source=f"scripts/Elasticity/beam2d_example_3.py:35-106 on InputFiles/2D/beam_2d_{lc}.msh",
                    coords=c, conn=t, group_bounds=[0, len(t)], group_params=[(30e6, 0.25, 2.7, 1)],
                    node_loads=[(tip, -1000, 2)],
-                   node_bcs=[(n, 0, d) for n in left for d in (1, 2)]), 0
+                   node_bcs=[(n, 0, d) for n in left for d in (1, 2)]), (8 if lc in ("0.5", "0.3") else 0)
     # 5. API semantics: jittered 6x4 mesh, two materials, every load / BC record type,
     #    duplicate keys (last-wins, analysis.py:42-43,:85-86), non-zero BC values
     coords, conn = structured_mesh(6, 4, jitter=0.2, seed=0)
@@ -217,7 +217,7 @@ def fixtures():
         yield dict(name=nm + "_pstress", kind="elasticity", plane="stress", source="synthetic (SURVEY §8d)",
                    coords=coords, conn=conn, group_bounds=[0, len(conn)], group_params=[steel],
                    node_loads=[(j * (nx + 1) + nx, -1000 * h, 2) for j in range(ny + 1)],
-                   node_bcs=[(j * (nx + 1), 0, d) for j in range(ny + 1) for d in (1, 2)]), 0
+                   node_bcs=[(j * (nx + 1), 0, d) for j in range(ny + 1) for d in (1, 2)]), 8
         third = (len(conn) // 3) // 2 * 2
         yield dict(name=nm + "_mag", kind="magnetic", plane=None, source="synthetic (SURVEY §8d)",
                    coords=coords, conn=conn, group_bounds=[0, third, 2 * third, len(conn)],

@@ -335,6 +335,30 @@ def jacobi_pcg(k, b, rtol=1e-8, maxit=100000, x0=None):
 
 
 # ---------------------------------------------------------------- synthetic meshes
+def modal_eigenvalues(k_mat, m_mat, k, order, free_dofs=None):
+    """k 'largest' / 'smallest' eigenvalues (ascending) and M-orthonormal eigenvectors of
+    K x = lambda M x by DENSE scipy.linalg.eigh -- the answer analysis.py:779-782
+    (eigsh(A=K, M=M, which='LM', k=k)) converges to, and the mathematically intended result of the
+    'smallest' branch (:788-794: 1 / eigs(K^-1 M), unusable as shipped because the unconstrained K
+    is singular).  free_dofs restricts the pencil to those rows/columns (constrained modes).
+    Small problems only: O(n^3)."""
+    import scipy.linalg as sla
+    kd = k_mat.toarray() if sp.issparse(k_mat) else np.asarray(k_mat)
+    md = m_mat.toarray() if sp.issparse(m_mat) else np.asarray(m_mat)
+    n = kd.shape[0]
+    idx = np.arange(n) if free_dofs is None else np.asarray(free_dofs)
+    w, v = sla.eigh(kd[np.ix_(idx, idx)], md[np.ix_(idx, idx)])
+    if order == 'largest':
+        sel = slice(len(w) - k, len(w))
+    elif order == 'smallest':
+        sel = slice(0, k)
+    else:
+        raise ValueError("Order parameter should be either 'largest' or 'smallest'")  # analysis.py:796
+    vec = np.zeros((n, k))
+    vec[idx] = v[:, sel]
+    return w[sel], vec
+
+
 def structured_mesh(nx, ny, h=None, jitter=0.0, seed=0):
     """Nodes row-major id = j*(nx+1)+i at (i h, j h), h = 1/ny; each cell ->
     T0 = [(i,j),(i+1,j),(i,j+1)], T1 = [(i+1,j+1),(i+1,j),(i,j+1)]
