@@ -84,6 +84,15 @@ struct P2PDev {
   uint4 *red[kMaxRanks];
   uint4 *ghost[kMaxRanks];
 };
+// Device copy of a rank's halo description (ctx->p2p_halo), read by the kernels that push
+// interface values: ghost j of this rank (parity par) lives in cell ghost[rank][2 j + par].
+struct HaloDev {
+  int n_nbr, n_send, n_ghost;
+  unsigned ticket;
+  int nbr_rank[kMaxRanks];
+  int send_ptr[kMaxRanks + 1];
+  int dst_off[kMaxRanks];
+};
 }  // namespace fe
 
 struct fe_ctx {
@@ -175,11 +184,30 @@ __device__ __forceinline__ bool ll_try(const uint4 *cell, unsigned seq, double *
   *out = __longlong_as_double((long long)(((unsigned long long)b << 32) | a));
   return fa == seq && fb == seq;
 }
+// Spins until the cell carries `seq`.  A peer that never delivers (crashed rank, mismatched call
+// sequence) must not hang the GPU: after ~30 s of back-off polling the wait gives up and returns
+// NaN, which the PCG kernels turn into FE_ERR_BREAKDOWN (p.Ap not finite).
 __device__ __forceinline__ double ll_wait(const uint4 *cell, unsigned seq) {
   double v;
-  while (!ll_try(cell, seq, &v)) {
+  for (int fast = 0; fast < 4096; ++fast)
+    if (ll_try(cell, seq, &v)) return v;
+  for (long long slow = 0; slow < (1ll << 27); ++slow) {
+    if (ll_try(cell, seq, &v)) return v;
+    __nanosleep(200);
   }
-  return v;
+  return __longlong_as_double(0x7ff8000000000000ll);
+}
+// Stores this rank's interface values of `vec` into the neighbours' ghost cells (peer stores over
+// NVLink); `t0`/`stride` spread the send list over the calling threads.
+__device__ __forceinline__ void halo_push(const P2PDev *pp, const HaloDev *hd, const int32_t *__restrict__ send_idx,
+                                          const double *__restrict__ vec, unsigned seq, int t0, int stride) {
+  const int n_send = hd->n_send;
+  for (int i = t0; i < n_send; i += stride) {
+    int k = 0;
+    while (i >= hd->send_ptr[k + 1]) ++k;
+    ll_store(pp->ghost[hd->nbr_rank[k]] + 2 * (size_t)(hd->dst_off[k] + (i - hd->send_ptr[k])) + (seq & 1),
+             vec[send_idx[i]], seq);
+  }
 }
 #endif
 

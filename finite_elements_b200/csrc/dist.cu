@@ -99,14 +99,6 @@ int halo_exchange(fe_ctx *ctx, cudaStream_t s, const HaloPlan *h, double *vec, i
 // ---------------------------------------------------------------------------------------
 // peer-memory transport (no NCCL inside the PCG loop)
 // ---------------------------------------------------------------------------------------
-struct HaloDev {  // device copy of the halo description, in ctx->p2p_halo
-  int n_nbr, n_send, n_ghost;
-  unsigned ticket;
-  int nbr_rank[kMaxRanks];
-  int send_ptr[kMaxRanks + 1];
-  int dst_off[kMaxRanks];
-};
-
 // One launch per exchange.  Every thread first stores its share of the interface values straight
 // into the neighbours' ghost cells (peer stores over NVLink, LL cells: no fence, no flag), then
 // waits for its share of this rank's own ghost cells and moves them behind `vec`.  The wait is per
@@ -114,14 +106,9 @@ struct HaloDev {  // device copy of the halo description, in ctx->p2p_halo
 __global__ void __launch_bounds__(256) k_halo_ll(P2PDev *pp, HaloDev *hd, const int32_t *__restrict__ send_idx,
                                                 const double *__restrict__ vec, double *__restrict__ vec_tail) {
   const unsigned seq = pp->halo_seq + 1, par = seq & 1;  // cell of ghost j and parity: 2 j + par
-  const int n_send = hd->n_send, n_ghost = hd->n_ghost;
+  const int n_ghost = hd->n_ghost;
   const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int i = t0; i < n_send; i += stride) {
-    int k = 0;
-    while (i >= hd->send_ptr[k + 1]) ++k;
-    ll_store(pp->ghost[hd->nbr_rank[k]] + 2 * (size_t)(hd->dst_off[k] + (i - hd->send_ptr[k])) + par,
-             vec[send_idx[i]], seq);
-  }
+  halo_push(pp, hd, send_idx, vec, seq, t0, stride);
   const uint4 *mine = pp->ghost[pp->rank] + par;
   for (int i = t0; i < n_ghost; i += stride) vec_tail[i] = ll_wait(mine + 2 * (size_t)i, seq);
   __syncthreads();

@@ -280,10 +280,15 @@ static int reducing_grid(fe_ctx *ctx, int64_t work_items, int items_per_cta) {
 template <bool DOT>
 static int launch_spmv(fe_ctx *ctx, cudaStream_t s, int lpr, int32_t n_rows, const int32_t *rowptr,
                        const int32_t *colidx, const double *vals, const double *x, double *y, double *partials,
-                       PcgState *st, const StreamPlan *sp = nullptr) {
+                       PcgState *st, const StreamPlan *sp = nullptr, const HaloPlan *fused_halo = nullptr) {
   if (sp && sp->on) {  // persistent TMA-streamed kernel (PCG)
-    k_spmv_stream<DOT><<<sp->grid, kStreamThreads, sp->smem, s>>>(n_rows / 2, sp->T, sp->cap, sp->bptr, sp->bidx,
-                                                                   vals, x, y, partials, st);
+    if (fused_halo)    // peer-memory transport: the exchange of x's interface values rides in the kernel
+      k_spmv_stream<DOT, true><<<sp->grid, kStreamThreads, sp->smem, s>>>(
+          n_rows / 2, sp->T, sp->cap, sp->bptr, sp->bidx, vals, x, y, partials, st, ctx->p2p_dev,
+          (HaloDev *)ctx->p2p_halo.ptr, fused_halo->send_idx);
+    else
+      k_spmv_stream<DOT, false><<<sp->grid, kStreamThreads, sp->smem, s>>>(
+          n_rows / 2, sp->T, sp->cap, sp->bptr, sp->bidx, vals, x, y, partials, st, nullptr, nullptr, nullptr);
     FE_LAUNCH_CHECK(ctx);
     return FE_OK;
   }
@@ -485,13 +490,21 @@ struct PcgLaunch {
   StreamPlan sp;
 
   // r = b - A x, p = D^-1 r, sums[1..3] = (r.z, r.r, b.b); converged flag from the TRUE residual
+  // the streamed SpMV of the peer-memory transport carries the halo exchange itself
+  bool fused() const { return dist && p2p && sp.on && halo->n_nbr > 0; }
+  int exchange(double *vec) {
+    if (!dist || fused()) return FE_OK;
+    return p2p ? halo_exchange_p2p(ctx, s, halo, vec, n_rows) : halo_exchange(ctx, s, halo, vec, n_rows);
+  }
+
   int true_residual_start() {
     int rc;
     k_copy<<<reducing_grid(ctx, n_rows, 1024), 256, 0, s>>>(n_rows, x, p);
     FE_LAUNCH_CHECK(ctx);
-    if (dist && (rc = (p2p ? halo_exchange_p2p(ctx, s, halo, p, n_rows) : halo_exchange(ctx, s, halo, p, n_rows))))
+    if ((rc = exchange(p))) return rc;
+    if ((rc = launch_spmv<false>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st, &sp,
+                                 fused() ? halo : nullptr)))
       return rc;
-    if ((rc = launch_spmv<false>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st, &sp))) return rc;
     k_pcg_init<<<vgrid, kRedBlock, 0, s>>>(n_rows, b, q, dinv, r, p, partials, st);
     FE_LAUNCH_CHECK(ctx);
     if (dist && !p2p && (rc = allreduce_sum(ctx, s, st->sums + 1, 3))) return rc;
@@ -502,9 +515,10 @@ struct PcgLaunch {
 
   int iteration(int parity) {
     int rc;
-    if (dist && (rc = (p2p ? halo_exchange_p2p(ctx, s, halo, p, n_rows) : halo_exchange(ctx, s, halo, p, n_rows))))
+    if ((rc = exchange(p))) return rc;
+    if ((rc = launch_spmv<true>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st, &sp,
+                                fused() ? halo : nullptr)))
       return rc;
-    if ((rc = launch_spmv<true>(ctx, s, lpr, n_rows, rowptr, colidx, vals, p, q, partials, st, &sp))) return rc;
     if (dist && !p2p && (rc = allreduce_sum(ctx, s, st->sums + 0, 1))) return rc;
     k_pcg_update<<<vgrid, kRedBlock, 0, s>>>(n_rows, parity, p, q, dinv, x, r, partials, st);
     FE_LAUNCH_CHECK(ctx);
@@ -634,8 +648,10 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
     const int cap = (T * (h_max_deg > 0 ? h_max_deg : 1) + 3) & ~3;
     const size_t smem = stream_smem_bytes(T, cap);
     if (smem <= 110 * 1024) {
-      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       L.sp.on = true;
       L.sp.T = T;
       L.sp.cap = cap;
@@ -670,7 +686,7 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
         cudaGraphExec_t exec;
         if ((rc = get_chunk_graph(L, kChunk, &exec))) return rc;
         FE_CUDA(cudaGraphLaunch(exec, s));
-        ctx->launches += (3 + (L.p2p ? 1 : 0)) * kChunk;
+        ctx->launches += (3 + ((L.p2p && !L.fused()) ? 1 : 0)) * kChunk;
         it += kChunk;
         local += kChunk;
       } else {

@@ -50,11 +50,22 @@ constexpr int kStreamStages = 3;
 constexpr int kStreamPtrInts = (kStreamTile + 1 + 3) & ~3;       // bptr slice copied per tile (16 B units)
 
 // smem: [full[S], empty[S] mbarriers][S x kStreamPtrInts ints][S x cap x 32 B vals][S x (cap+8) x 4 B bidx]
-template <bool DOT>
+// Value pair of ghost node g (columns n_nodes + g) straight from this rank's LL cells: the SpMV of
+// the peer-memory transport never waits for a separate exchange kernel -- only the lanes whose
+// column is a ghost wait, and only until that one neighbour value has landed.
+__device__ __forceinline__ double2 ghost_pair(const uint4 *cells /* + parity */, int32_t g, unsigned seq) {
+  return make_double2(ll_wait(cells + 4 * (size_t)g, seq), ll_wait(cells + 4 * (size_t)g + 2, seq));
+}
+
+// HALO: multi-GPU peer-memory transport.  Every CTA first pushes its share of this rank's interface
+// values of x to the neighbours' ghost cells (halo_push), then streams its tiles; columns >= n_nodes
+// are read from the ghost cells (ghost_pair).  The last CTA to finish bumps the exchange counter.
+template <bool DOT, bool HALO>
 __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream(
     int32_t n_nodes, int /*T == kStreamTile*/, int cap /* blocks per stage */, const int32_t *__restrict__ bptr,
     const int32_t *__restrict__ bidx, const double *__restrict__ vals, const double *__restrict__ x,
-    double *__restrict__ y, double *__restrict__ partials, PcgState *__restrict__ st) {
+    double *__restrict__ y, double *__restrict__ partials, PcgState *__restrict__ st, P2PDev *pp, HaloDev *hd,
+    const int32_t *__restrict__ send_idx) {
   constexpr int T = kStreamTile, S = kStreamStages, GROUPS = kStreamGroups, PASSES = 2;
   __shared__ double red[kStreamThreads / 32];
   if (DOT && (st->converged | st->breakdown)) return;
@@ -69,6 +80,17 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream(
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int n_tiles = (n_nodes + T - 1) / T;
+  unsigned hseq = 0;
+  const uint4 *gcells = nullptr;
+  if (HALO) {
+    hseq = pp->halo_seq + 1;
+    gcells = pp->ghost[pp->rank] + (hseq & 1);
+    // only the first CTAs push: they are dispatched first, so a CTA that waits for a neighbour's
+    // values never waits for a push that is itself waiting for an SM
+    const int pushers = min((int)gridDim.x, 32);
+    if ((int)blockIdx.x < pushers)
+      halo_push(pp, hd, send_idx, x, hseq, blockIdx.x * kStreamThreads + tid, pushers * kStreamThreads);
+  }
   if (tid == 0) {
     for (int i = 0; i < S; ++i) {
       ptx::mbar_init(&full[i], 1);
@@ -133,13 +155,19 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream(
       }
 #pragma unroll
       for (int p = 0; p < PASSES; ++p) xv[p] = __ldg(x2 + c[p]);  // ... then every gather of x in flight
+      if (HALO) {
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p)
+          if (c[p] >= n_nodes) xv[p] = ghost_pair(gcells, c[p] - n_nodes, hseq);
+      }
       double a0[PASSES], a1[PASSES];
 #pragma unroll
       for (int p = 0; p < PASSES; ++p) {
         a0[p] = v0[p].x * xv[p].x + v0[p].y * xv[p].y;
         a1[p] = v1[p].x * xv[p].x + v1[p].y * xv[p].y;
         for (int k = lane + 8; k < deg[p]; k += 8) {  // valence > 8
-          const double2 xx = __ldg(x2 + is[s[p] + k]);
+          const int32_t ck = is[s[p] + k];
+          const double2 xx = (HALO && ck >= n_nodes) ? ghost_pair(gcells, ck - n_nodes, hseq) : __ldg(x2 + ck);
           const double2 w0 = vs[2 * s[p] + k], w1 = vs[2 * s[p] + deg[p] + k];
           a0[p] += w0.x * xx.x + w0.y * xx.y;
           a1[p] += w1.x * xx.x + w1.y * xx.y;
@@ -169,6 +197,13 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream(
   if (DOT) {
     const double loc[1] = {dot};
     publish_and_reduce<1, kStreamThreads>(loc, partials, st, 0, red);
+  }
+  if (HALO) {  // every CTA has read halo_seq once the last one gets here
+    __syncthreads();
+    if (tid == 0 && atomicAdd(&hd->ticket, 1u) == gridDim.x - 1) {
+      hd->ticket = 0;
+      pp->halo_seq = hseq;
+    }
   }
 }
 
