@@ -178,19 +178,35 @@ def run_gpu(args):
     coords, conn = structured_mesh_torch(nx, ny, dev)
     n_el, n_nodes = conn.shape[0], coords.shape[0]
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    magnetic = args.kind == "magnetic"
+    if magnetic:
+        # SURVEY §8d magnetic config: mu = 4 pi 1e-7 * {1e5, 1, 5e4} in three equal x-bands
+        # (scripts/Magnetic/finite_element_beam.py:17-19), A = 0 on the right edge, source on two elements
+        from finite_elements_b200.device import KIND_MAGNETIC
+        KIND, dim = KIND_MAGNETIC, 1
+        mu0 = 4e-7 * np.pi
+        mat_np = np.array([[mu0 * 1e5, 0, 0, 0], [mu0, 0, 0, 0], [mu0 * 5e4, 0, 0, 0]])
+        cell_i = (torch.arange(n_el, device=dev) // 2) % nx
+        mat_id = (cell_i * 3 // nx).to(torch.int32)
+    else:
+        KIND, dim, mat_np, mat_id = KIND_ELAST_PSTRESS, 2, MAT, None
 
     t0 = time.perf_counter()
-    dm = DeviceMesh(coords, conn, None, dim=2, device=local_rank, ctx=ctx)
+    dm = DeviceMesh(coords, conn, mat_id, dim=dim, device=local_rank, ctx=ctx)
     rowptr, colidx = dm.csr_pattern()
     torch.cuda.synchronize()
     plan_ms = 1e3 * (time.perf_counter() - t0)
     n, nnz = dm.n_rows, dm.nnz
 
     left = torch.arange(ny + 1, device=dev) * (nx + 1)
-    bc = torch.stack([2 * left, 2 * left + 1], dim=1).reshape(-1).int()
-    bc_val = torch.zeros(bc.numel(), dtype=torch.float64, device=dev)
     f = torch.zeros(n, dtype=torch.float64, device=dev)
-    f[2 * (left + nx) + 1] = -1000.0 / ny
+    if magnetic:
+        bc = (left + nx).int()
+        f[conn[:2].reshape(-1).long()] = 2.5e9   # the nodal shares an ElementsLoad of 1e10 leaves (SURVEY a-7)
+    else:
+        bc = torch.stack([2 * left, 2 * left + 1], dim=1).reshape(-1).int()
+        f[2 * (left + nx) + 1] = -1000.0 / ny
+    bc_val = torch.zeros(bc.numel(), dtype=torch.float64, device=dev)
     vals = torch.empty(nnz, dtype=torch.float64, device=dev)
     rhs = torch.empty_like(f)
     x = torch.zeros_like(f)
@@ -203,7 +219,7 @@ def run_gpu(args):
         # not the CPU's launch latency)
         torch.cuda._sleep(200_000)
         a0.record()
-        dm.assemble(KIND_ELAST_PSTRESS, MAT_DEV, out=vals, variant=args.variant)
+        dm.assemble(KIND, MAT_DEV, out=vals, variant=args.variant)
         a1.record()
         rhs.copy_(f)
         dm.dirichlet(vals, rhs, bc, bc_val)
@@ -214,7 +230,7 @@ def run_gpu(args):
         if timers is not None:
             timers.append((a0, a1, p0, p1))
 
-    MAT_DEV = torch.as_tensor(MAT).to(dev)
+    MAT_DEV = torch.as_tensor(mat_np).to(dev)
     sampler = ClockSampler(local_rank)
     sampler.start()
     for _ in range(max(args.warmup, 3)):
@@ -247,7 +263,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         dm.coords.copy_(h_coords, non_blocking=True)                 # H2D: geometry of this step
-        dm.assemble(KIND_ELAST_PSTRESS, MAT_DEV, out=vals, variant=args.variant)
+        dm.assemble(KIND, MAT_DEV, out=vals, variant=args.variant)
         h_vals.copy_(vals, non_blocking=True)                        # D2H: the assembled matrix values
         torch.cuda.synchronize()
         t1 = time.perf_counter()
@@ -265,13 +281,13 @@ def run_gpu(args):
     # ---- one full solve to 1e-8 (reported, outside the timed steps) -------------------
     solve = None
     if args.full_solve:
-        dm.assemble(KIND_ELAST_PSTRESS, MAT_DEV, out=vals, variant=args.variant)
+        dm.assemble(KIND, MAT_DEV, out=vals, variant=args.variant)
         rhs.copy_(f)
         dm.dirichlet(vals, rhs, bc, bc_val)
         x.zero_()
         q0, q1 = ev(), ev()
         q0.record()
-        _, iters, relres = dm.pcg(vals, rhs, x=x, rtol=1e-8, work=work, raise_on_maxit=False)
+        _, iters, relres = dm.pcg(vals, rhs, x=x, rtol=1e-8, work=work, raise_on_maxit=False, maxit=200000)
         q1.record()
         torch.cuda.synchronize()
         true_res = float(torch.linalg.norm(rhs - dm.spmv(vals, x)) / torch.linalg.norm(rhs))
@@ -281,10 +297,11 @@ def run_gpu(args):
 
     # ---- BASELINE configs[4]: lowest modes of K x = lambda M x on the 1 M-triangle mesh (LOBPCG) ----
     modal = None
-    if args.modal > 0:
+    if args.modal > 0 and not magnetic:
         modal = run_modal(args.modal, 1024, 512, local_rank)
 
     peak, peak_kind = measured_peak_hbm()
+    default_workload = (nx, ny) == (4096, 2048) and not magnetic   # the ncu traffic constants belong to it
     a_bytes, p_bytes = asm_bytes(n_el, n_nodes, nnz), pcg_bytes_per_iter(n, nnz)
     asm_gbs = a_bytes / t_asm / 1e9
     pcg_gbs = p_bytes * args.pcg_iters / t_pcg / 1e9
@@ -292,7 +309,7 @@ def run_gpu(args):
         "metric": METRIC, "value": n_el / t_asm / 1e6, "unit": "Melem/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"S16M-family structured plane-stress mesh {nx}x{ny} cells: {n_el} triangles, "
+        "config": {"workload": f"S16M-family structured {'magnetostatic (3 mu bands)' if magnetic else 'plane-stress'} mesh {nx}x{ny} cells: {n_el} triangles, "
                                f"{n_nodes} nodes, {n} DOF, nnz {nnz}; step = numeric assembly + Dirichlet + "
                                f"{args.pcg_iters} Jacobi-PCG iterations",
                    "nx": nx, "ny": ny, "pcg_iters_per_step": args.pcg_iters, "l2": "inputs_larger_than_l2",
@@ -301,10 +318,13 @@ def run_gpu(args):
         "pcg": {"dof_iters_per_s": n * args.pcg_iters / t_pcg, "ms_per_iter": 1e3 * t_pcg / args.pcg_iters,
                 "iters": args.pcg_iters, "algorithmic_bytes_per_iter": p_bytes,
                 "roofline": {"bound": "hbm", "achieved": pcg_gbs, "peak": peak, "unit": "GB/s",
-                             "frac": pcg_gbs / peak, "traffic": SPMV_TRAFFIC_NCU, "peak_kind": peak_kind,
-                             "kernel": "k_spmv_stream<1> (+ k_pcg_update, k_pcg_pupdate)"}},
+                             "frac": pcg_gbs / peak, "traffic": SPMV_TRAFFIC_NCU if default_workload else None,
+                             "peak_kind": peak_kind,
+                             "kernel": ("k_spmv<8,1>" if magnetic else "k_spmv_stream<1,0>") +
+                                       " (+ k_pcg_update, k_pcg_pupdate)"}},
         "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
-                     "traffic": ASM_TRAFFIC_NCU, "peak_kind": peak_kind, "kernel": "k_assemble_fan<0>"},
+                     "traffic": ASM_TRAFFIC_NCU if default_workload else None, "peak_kind": peak_kind,
+                     "kernel": "k_assemble_fan<2>" if magnetic else "k_assemble_fan<0>"},
         "e2e": {"value": n_el / np.mean(e2e_asm) / 1e6, "unit": "Melem/s",
                 "h2d_bytes_per_step": int(h_coords.numel() * 8 + h_rhs.numel() * 8),
                 "d2h_bytes_per_step": int(h_vals.numel() * 8 + h_x.numel() * 8),
@@ -358,9 +378,12 @@ def main():
     ap.add_argument("--ny", type=int, default=2048)
     ap.add_argument("--pcg-iters", type=int, default=50)
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--kind", default="plane_stress", choices=["plane_stress", "magnetic"],
+                    help="magnetic = BASELINE configs[1] scaled up (1 GPU only); the headline metric is plane_stress")
     ap.add_argument("--full-solve", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--modal", type=int, default=0, help="also time the lowest K modes on the 1M-triangle mesh")
+    ap.add_argument("--modal", type=int, default=10,
+                    help="also time the lowest K modes of K x = lambda M x on the 1M-triangle mesh (BASELINE configs[4]); 0 = skip")
     ap.add_argument("--cpu-nx", type=int, default=1024)
     ap.add_argument("--cpu-ny", type=int, default=512)
     ap.add_argument("--cpu-pcg-iters", type=int, default=20)

@@ -44,6 +44,7 @@ SIGNATURES = {
     "fe_scatter_add": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "fe_spmv": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32]),
     "fe_spmm_pair": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "fe_cheb_step": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _i32]),
     "fe_csr_diagonal": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "fe_pcg_work_len": (_i64, [_i32, _i32]),
     "fe_pcg_cache_pattern": (C.c_int, [_vp, _vp, _vp, _i64]),

@@ -189,8 +189,10 @@ __device__ __forceinline__ bool ll_try(const uint4 *cell, unsigned seq, double *
 // NaN, which the PCG kernels turn into FE_ERR_BREAKDOWN (p.Ap not finite).
 __device__ __forceinline__ double ll_wait(const uint4 *cell, unsigned seq) {
   double v;
+#pragma unroll 1
   for (int fast = 0; fast < 4096; ++fast)
     if (ll_try(cell, seq, &v)) return v;
+#pragma unroll 1
   for (long long slow = 0; slow < (1ll << 27); ++slow) {
     if (ll_try(cell, seq, &v)) return v;
     __nanosleep(200);

@@ -374,12 +374,41 @@ __global__ void __launch_bounds__(kRedBlock) k_pcg_update(int32_t n, int parity,
   }
   const double alpha = st->rz[parity] / pq;
   double loc[2] = {0.0, 0.0};
-  for (int64_t i = (int64_t)blockIdx.x * kRedBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kRedBlock) {
-    const double ri = r[i] - alpha * q[i];
-    x[i] += alpha * p[i];
-    r[i] = ri;
-    loc[0] += ri * (dinv[i] * ri);
-    loc[1] += ri * ri;
+  // A CTA walks chunks of U x 256 consecutive elements; a thread's U elements sit 256 apart, so all
+  // 5 U loads use one base address per array plus immediate offsets and are issued before the first
+  // dependent FMA.  Accumulation order is fixed by (chunk, u): deterministic.
+  constexpr int U = 4;
+  const int64_t n_chunks = (n + U * kRedBlock - 1) / (U * kRedBlock);
+#pragma unroll 1
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int64_t base = chunk * (U * kRedBlock) + threadIdx.x;
+    if (base + (U - 1) * kRedBlock < n) {
+      double rv[U], qv[U], xv[U], pv[U], dv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        rv[u] = r[base + u * kRedBlock];
+        qv[u] = __ldg(q + base + u * kRedBlock);
+        xv[u] = x[base + u * kRedBlock];
+        pv[u] = __ldg(p + base + u * kRedBlock);
+        dv[u] = __ldg(dinv + base + u * kRedBlock);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double ri = rv[u] - alpha * qv[u];
+        x[base + u * kRedBlock] = xv[u] + alpha * pv[u];
+        r[base + u * kRedBlock] = ri;
+        loc[0] += ri * (dv[u] * ri);
+        loc[1] += ri * ri;
+      }
+    } else {
+      for (int64_t i = base; i < n; i += kRedBlock) {
+        const double ri = r[i] - alpha * q[i];
+        x[i] += alpha * p[i];
+        r[i] = ri;
+        loc[0] += ri * (dinv[i] * ri);
+        loc[1] += ri * ri;
+      }
+    }
   }
   publish_and_reduce<2>(loc, partials, st, 1, red);
 }
@@ -392,8 +421,25 @@ __global__ void __launch_bounds__(256) k_pcg_pupdate(int32_t n, int parity, cons
   reduced_sums<2>(st, 1, t2);  // (r.z, r.r)
   const double rz_new = t2[0];
   const double beta = rz_new / st->rz[parity];
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
-    p[i] = dinv[i] * r[i] + beta * p[i];
+  constexpr int U = 4;  // chunks of U x 256 elements as in k_pcg_update: 3 U loads in flight per thread
+  const int64_t n_chunks = (n + U * 256 - 1) / (U * 256);
+#pragma unroll 1
+  for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int64_t base = chunk * (U * 256) + threadIdx.x;
+    if (base + (U - 1) * 256 < n) {
+      double rv[U], pv[U], dv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        rv[u] = __ldg(r + base + u * 256);
+        pv[u] = p[base + u * 256];
+        dv[u] = __ldg(dinv + base + u * 256);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) p[base + u * 256] = dv[u] * rv[u] + beta * pv[u];
+    } else {
+      for (int64_t i = base; i < n; i += 256) p[i] = dinv[i] * r[i] + beta * p[i];
+    }
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     st->rz[parity ^ 1] = rz_new;
     st->iters += 1;

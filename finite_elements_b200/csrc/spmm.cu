@@ -7,57 +7,100 @@
 // from HBM once per block: Y_A = A X and, in the same pass over the shared pattern, Y_B = B X.
 //
 // Layout: X is double[n_cols][m] row-major (a torch (n, m) tensor), so the m values a matrix entry
-// needs are contiguous.  G = 4/8/16/32 lanes own one row; lane l owns column l of the block.  Each
-// step of the row loop reads one (col, a, b) triple -- the same address in all G lanes, i.e. one
-// broadcast transaction -- and one coalesced m-wide row of X (L2/L1 resident: the rows of X
-// touched by neighbouring matrix rows overlap almost completely).  No reduction across lanes is
-// needed, and every output element is produced by one thread in a fixed order (deterministic).
+// needs are contiguous.  G lanes own one row; a lane owns CPL = 4, 2 or 1 adjacent columns of the
+// block (the widest that divides m), so per matrix entry it issues one broadcast load of the
+// (col, a, b) triple and ONE 32/16/8-byte load of X for CPL FMAs -- the first version (one column per
+// lane) was bound by load instructions, not by memory (ncu: 19 % DRAM, 68 % L1).  The rows of X
+// touched by neighbouring matrix rows overlap almost completely (L1/L2 resident).  No reduction
+// across lanes is needed, and every output element is produced by one thread in a fixed order
+// (deterministic).
 // HBM bytes per call: (8 or 16) nnz + 4 nnz + 4 n + 8 m n_cols (X once) + 8 m n (per output).
 #include "common.cuh"
 
 namespace fe {
 
-template <int G, bool PAIR>
+// CPL columns per lane (1, 2 or 4: one 8-, 16- or 32-byte load of X per matrix entry), G lanes per
+// row.  EPI selects what happens to y = A x in the epilogue:
+//   0  Y_A = y (and Y_B = B x when PAIR)
+//   1  one step of the Chebyshev iteration (modal.py: chebyshev_preconditioner), all row-local:
+//        z += x_row;  r -= y;  x_out = c1 x_row + c2 dinv[row] r
+//      (x_out is a different buffer: other rows are still gathering from x)
+template <int CPL, int G, bool PAIR, int EPI>
 __global__ void __launch_bounds__(256) k_spmm(int32_t n_rows, int32_t m, const int32_t *__restrict__ rowptr,
                                              const int32_t *__restrict__ colidx, const double *__restrict__ va,
                                              const double *__restrict__ vb, const double *__restrict__ X,
-                                             double *__restrict__ YA, double *__restrict__ YB) {
+                                             double *__restrict__ YA, double *__restrict__ YB,
+                                             const double *__restrict__ dinv, double *__restrict__ r,
+                                             double *__restrict__ z, double c1, double c2) {
   const int64_t row = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
   const int lane = threadIdx.x % G;
   if (row >= n_rows) return;
   const int32_t s = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
-  for (int c0 = 0; c0 < m; c0 += G) {  // blocks wider than G lanes: one more pass over the row
-    const int col = c0 + lane;
-    const bool on = col < m;
+  for (int c0 = 0; c0 < m; c0 += G * CPL) {  // blocks wider than G * CPL: one more pass over the row
+    const int col = c0 + lane * CPL;
+    const bool on = col < m;                 // m % CPL == 0: a lane is fully on or fully off
     const double *xc = X + (on ? col : 0);
-    double accA = 0.0, accB = 0.0;
+    double accA[CPL], accB[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) accA[q] = accB[q] = 0.0;
+    auto load_x = [&](int32_t c, double *x) {
+      const double *src = xc + (int64_t)c * m;
+      if (CPL == 4) {
+        const double2 lo = __ldg(reinterpret_cast<const double2 *>(src));
+        const double2 hi = __ldg(reinterpret_cast<const double2 *>(src) + 1);
+        x[0] = lo.x, x[1] = lo.y, x[2 % CPL] = hi.x, x[3 % CPL] = hi.y;
+      } else if (CPL == 2) {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(src));
+        x[0] = v.x, x[1 % CPL] = v.y;
+      } else {
+        x[0] = __ldg(src);
+      }
+    };
     int32_t j = s;
-    for (; j + 4 <= e; j += 4) {  // four entries in flight
-      int32_t c[4];
-      double a[4], b[4], x[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        c[u] = __ldg(colidx + j + u);
-        a[u] = __ldg(va + j + u);
-        b[u] = PAIR ? __ldg(vb + j + u) : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) x[u] = on ? __ldg(xc + (int64_t)c[u] * m) : 0.0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        accA += a[u] * x[u];
-        if (PAIR) accB += b[u] * x[u];
-      }
-    }
-    for (; j < e; ++j) {
-      const int32_t c = __ldg(colidx + j);
-      const double x = on ? __ldg(xc + (int64_t)c * m) : 0.0;
-      accA += __ldg(va + j) * x;
-      if (PAIR) accB += __ldg(vb + j) * x;
-    }
     if (on) {
-      YA[row * m + col] = accA;
-      if (PAIR) YB[row * m + col] = accB;
+      for (; j + 2 <= e; j += 2) {  // two entries in flight
+        int32_t c[2];
+        double a[2], b[2], x[2][CPL];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          c[u] = __ldg(colidx + j + u);
+          a[u] = __ldg(va + j + u);
+          b[u] = PAIR ? __ldg(vb + j + u) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) load_x(c[u], x[u]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            accA[q] += a[u] * x[u][q];
+            if (PAIR) accB[q] += b[u] * x[u][q];
+          }
+      }
+      for (; j < e; ++j) {
+        double x[CPL];
+        load_x(__ldg(colidx + j), x);
+        const double a = __ldg(va + j), b = PAIR ? __ldg(vb + j) : 0.0;
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          accA[q] += a * x[q];
+          if (PAIR) accB[q] += b * x[q];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+        const int64_t o = row * m + col + q;
+        if (EPI == 0) {
+          YA[o] = accA[q];
+          if (PAIR) YB[o] = accB[q];
+        } else {
+          const double xr = __ldg(X + o);
+          const double rr = r[o] - accA[q];
+          z[o] += xr;
+          r[o] = rr;
+          YA[o] = c1 * xr + c2 * (__ldg(dinv + row) * rr);
+        }
+      }
     }
   }
 }
@@ -73,6 +116,41 @@ __global__ void __launch_bounds__(256) k_csr_diag(int32_t n_rows, const int32_t 
   diag[row] = d;
 }
 
+static void spmm_shape(int m, int *cpl, int *g) {
+  *cpl = (m % 4 == 0) ? 4 : ((m % 2 == 0) ? 2 : 1);
+  const int lanes = (m + *cpl - 1) / *cpl;
+  *g = lanes <= 1 ? 1 : (lanes <= 2 ? 2 : (lanes <= 4 ? 4 : (lanes <= 8 ? 8 : (lanes <= 16 ? 16 : 32))));
+}
+
+template <bool PAIR, int EPI>
+static void spmm_launch(cudaStream_t s, int32_t n_rows, int32_t m, const int32_t *rowptr, const int32_t *colidx,
+                        const double *va, const double *vb, const double *x, double *ya, double *yb,
+                        const double *dinv, double *r, double *z, double c1, double c2) {
+  int cpl, g;
+  spmm_shape(m, &cpl, &g);
+  const int grid = grid_for((int64_t)n_rows * g, 256);
+#define FE_SPMM(CPL, G) \
+  k_spmm<CPL, G, PAIR, EPI><<<grid, 256, 0, s>>>(n_rows, m, rowptr, colidx, va, vb, x, ya, yb, dinv, r, z, c1, c2)
+#define FE_SPMM_G(CPL)                    \
+  switch (g) {                            \
+    case 1: FE_SPMM(CPL, 1); break;       \
+    case 2: FE_SPMM(CPL, 2); break;       \
+    case 4: FE_SPMM(CPL, 4); break;       \
+    case 8: FE_SPMM(CPL, 8); break;       \
+    case 16: FE_SPMM(CPL, 16); break;     \
+    default: FE_SPMM(CPL, 32); break;     \
+  }
+  if (cpl == 4) {
+    FE_SPMM_G(4)
+  } else if (cpl == 2) {
+    FE_SPMM_G(2)
+  } else {
+    FE_SPMM_G(1)
+  }
+#undef FE_SPMM_G
+#undef FE_SPMM
+}
+
 }  // namespace fe
 
 using namespace fe;
@@ -84,24 +162,28 @@ int fe_spmm_pair(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowpt
   FE_REQUIRE(ctx && rowptr && colidx && vals_a && x && y_a, "fe_spmm_pair: NULL argument");
   FE_REQUIRE((vals_b == nullptr) == (y_b == nullptr), "fe_spmm_pair: vals_b and y_b go together");
   FE_REQUIRE(m >= 1 && m <= 1024, "fe_spmm_pair: block width %d outside [1, 1024]", m);
+  FE_REQUIRE(((uintptr_t)x & 15) == 0, "fe_spmm_pair: x must be 16-byte aligned");
   if (n_rows <= 0) return FE_OK;
   cudaStream_t s = as_stream(stream);
-  const int g = m <= 4 ? 4 : (m <= 8 ? 8 : (m <= 16 ? 16 : 32));
-  const int grid = grid_for((int64_t)n_rows * g, 256);
-#define FE_SPMM(G)                                                                                        \
-  do {                                                                                                    \
-    if (vals_b)                                                                                           \
-      k_spmm<G, true><<<grid, 256, 0, s>>>(n_rows, m, rowptr, colidx, vals_a, vals_b, x, y_a, y_b);        \
-    else                                                                                                  \
-      k_spmm<G, false><<<grid, 256, 0, s>>>(n_rows, m, rowptr, colidx, vals_a, nullptr, x, y_a, nullptr); \
-  } while (0)
-  switch (g) {
-    case 4: FE_SPMM(4); break;
-    case 8: FE_SPMM(8); break;
-    case 16: FE_SPMM(16); break;
-    default: FE_SPMM(32); break;
-  }
-#undef FE_SPMM
+  if (vals_b)
+    spmm_launch<true, 0>(s, n_rows, m, rowptr, colidx, vals_a, vals_b, x, y_a, y_b, nullptr, nullptr, nullptr, 0, 0);
+  else
+    spmm_launch<false, 0>(s, n_rows, m, rowptr, colidx, vals_a, nullptr, x, y_a, nullptr, nullptr, nullptr, nullptr, 0,
+                          0);
+  FE_LAUNCH_CHECK(ctx);
+  return FE_OK;
+}
+
+int fe_cheb_step(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr, const int32_t *colidx,
+                 const double *vals, const double *dinv, const double *d_in, double *d_out, double *r, double *z,
+                 double c1, double c2, int32_t m) {
+  FE_REQUIRE(ctx && rowptr && colidx && vals && dinv && d_in && d_out && r && z, "fe_cheb_step: NULL argument");
+  FE_REQUIRE(d_in != d_out, "fe_cheb_step: d_out must not alias d_in (rows are still gathering from it)");
+  FE_REQUIRE(m >= 1 && m <= 1024, "fe_cheb_step: block width %d outside [1, 1024]", m);
+  FE_REQUIRE(((uintptr_t)d_in & 15) == 0, "fe_cheb_step: d_in must be 16-byte aligned");
+  if (n_rows <= 0) return FE_OK;
+  spmm_launch<false, 1>(as_stream(stream), n_rows, m, rowptr, colidx, vals, nullptr, d_in, d_out, nullptr, dinv, r, z,
+                        c1, c2);
   FE_LAUNCH_CHECK(ctx);
   return FE_OK;
 }

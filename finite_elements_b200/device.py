@@ -221,6 +221,17 @@ class DeviceMesh:
                                    _ptr(vals_b), _ptr(x), _ptr(ya), _ptr(yb), m))
         return ya, yb
 
+    def cheb_step(self, vals, dinv, d_in, d_out, r, z, c1, c2):
+        """z += d_in; r -= A d_in; d_out = c1 d_in + c2 dinv r on (n, m) blocks, one pass.  fe_cheb_step."""
+        rowptr, colidx = self.csr_pattern()
+        for t in (d_in, d_out, r, z):
+            if t.shape != d_in.shape or not t.is_contiguous() or t.dtype != torch.float64:
+                raise ValueError("cheb_step: blocks must be contiguous float64 tensors of one shape")
+        with torch.cuda.device(self.ctx.device):
+            check(lib.fe_cheb_step(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals),
+                                   _ptr(dinv), _ptr(d_in), _ptr(d_out), _ptr(r), _ptr(z), float(c1), float(c2),
+                                   int(d_in.shape[1])))
+
     def csr_diagonal(self, vals):
         rowptr, colidx = self.csr_pattern()
         d = torch.empty(self.n_rows, dtype=torch.float64, device=self.ctx.device)

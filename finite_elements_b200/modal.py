@@ -45,27 +45,33 @@ def _b_orthonormalize(v, bv, av=None):
     return v @ t, bv @ t, (av @ t if av is not None else None)
 
 
-def chebyshev_preconditioner(apply_a, dinv, lmax, degree, ratio=30.0):
+def chebyshev_preconditioner(apply_a, dinv, lmax, degree, ratio=30.0, fused_step=None):
     """T r ~ A^-1 r: `degree` steps of the Chebyshev iteration for D^-1 A on [lmax/ratio, lmax]
     (Saad, Iterative Methods, alg. 12.1), started from zero.  A fixed polynomial in A, hence a
-    symmetric positive definite operator as LOBPCG requires; each step is one block product."""
+    symmetric positive definite operator as LOBPCG requires; each step is one block product.
+    fused_step(d_in, d_out, r, z, c1, c2) -- DeviceMesh.cheb_step -- does a whole step in one kernel."""
     lmin = lmax / ratio
     theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
     sigma1 = theta / delta
 
     def apply(r):
-        r = r.clone()
+        r = r.clone() if fused_step is None else r.contiguous().clone()
         rho = 1.0 / sigma1
         d = (dinv[:, None] * r) / theta
         z = torch.zeros_like(r)
-        for i in range(degree):
-            z += d
-            if i + 1 == degree:
-                break
-            r -= apply_a(d)
+        d_next = torch.empty_like(d) if fused_step is not None else None
+        for i in range(degree - 1):
             rho_new = 1.0 / (2.0 * sigma1 - rho)
-            d = (rho_new * rho) * d + (2.0 * rho_new / delta) * (dinv[:, None] * r)
+            c1, c2 = rho_new * rho, 2.0 * rho_new / delta
+            if fused_step is not None:
+                fused_step(d, d_next, r, z, c1, c2)
+                d, d_next = d_next, d
+            else:
+                z += d
+                r -= apply_a(d)
+                d = c1 * d + c2 * (dinv[:, None] * r)
             rho = rho_new
+        z += d
         return z
     return apply
 
@@ -278,7 +284,8 @@ def modal_solve(dm, k_vals, m_vals, k, order, *, mask=None, tol=1e-9, maxit=5000
             apply_k = lambda v: dm.spmm_pair(k_vals, None, v.contiguous())[0]  # noqa: E731
             ones = torch.ones(n, 1, dtype=torch.float64, device=dev)
             lmax = gershgorin_lmax(dm.spmm_pair(k_vals.abs(), None, ones)[0][:, 0], dinv)
-            precond = chebyshev_preconditioner(apply_k, dinv, lmax, cheb_degree, cheb_ratio)
+            fused = lambda d, dn, r, z, c1, c2: dm.cheb_step(k_vals, dinv, d, dn, r, z, c1, c2)  # noqa: E731
+            precond = chebyshev_preconditioner(apply_k, dinv, lmax, cheb_degree, cheb_ratio, fused_step=fused)
         else:
             precond = lambda r: dinv[:, None] * r  # noqa: E731
     lam, vec, info = lobpcg(apply_pair, n, k, dev, largest=largest, precond=precond, mask=mask, tol=tol,

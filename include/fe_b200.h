@@ -155,6 +155,13 @@ int fe_spmv(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
 int fe_spmm_pair(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
                  const int32_t *colidx, const double *vals_a, const double *vals_b,
                  const double *x, double *y_a, double *y_b, int32_t m);
+/* One step of the Chebyshev iteration that preconditions the block eigensolver, fused into the
+ * block product (all of it is row-local once y = A d_in is known):
+ *   z += d_in;  r -= A d_in;  d_out = c1 d_in + c2 diag(dinv) r          (blocks are [n][m])
+ * d_out must not alias d_in. */
+int fe_cheb_step(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
+                 const int32_t *colidx, const double *vals, const double *dinv, const double *d_in,
+                 double *d_out, double *r, double *z, double c1, double c2, int32_t m);
 /* diag[i] = A[i][i] (0 if the entry is not stored): the Jacobi preconditioner of the block solver */
 int fe_csr_diagonal(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
                     const int32_t *colidx, const double *vals, double *diag);

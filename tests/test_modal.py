@@ -160,6 +160,41 @@ def test_gpu_spmm_pair_vs_scipy():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("width", [1, 6, 10, 12])
+def test_gpu_fused_chebyshev_step_vs_unfused(width):
+    """fe_cheb_step == the three torch statements it replaces; the whole preconditioner agrees with
+    the unfused one built on fe_spmm_pair."""
+    from finite_elements_b200.device import DeviceMesh, KIND_ELAST_PSTRESS
+    from finite_elements_b200.modal import chebyshev_preconditioner, gershgorin_lmax
+    fx = Fixture("gmsh_beam_0.1")
+    dm = DeviceMesh(fx.coords, fx.conn, fx.mat_id, dim=2)
+    kv = dm.assemble(KIND_ELAST_PSTRESS, fx.mat)
+    k = dm.to_scipy(kv)
+    n = dm.n_rows
+    dinv = 1.0 / dm.csr_diagonal(kv)
+    rng = np.random.default_rng(5)
+    d, r, z = (torch.as_tensor(rng.standard_normal((n, width))).cuda() for _ in range(3))
+    d_out = torch.empty_like(d)
+    r0, z0 = r.clone(), z.clone()
+    dm.cheb_step(kv, dinv, d, d_out, r, z, 0.37, 1.9)
+    r_ref = r0.cpu().numpy() - k @ d.cpu().numpy()
+    assert np.max(np.abs(r.cpu().numpy() - r_ref)) <= 1e-13 * np.abs(r_ref).max()
+    assert torch.equal(z, z0 + d)
+    d_ref = 0.37 * d.cpu().numpy() + 1.9 * dinv.cpu().numpy()[:, None] * r_ref
+    assert np.max(np.abs(d_out.cpu().numpy() - d_ref)) <= 1e-13 * np.abs(d_ref).max()
+    with pytest.raises(ValueError):
+        dm.cheb_step(kv, dinv, d, d, r, z, 0.1, 0.2)
+    apply_k = lambda v: dm.spmm_pair(kv, None, v.contiguous())[0]  # noqa: E731
+    ones = torch.ones(n, 1, dtype=torch.float64, device="cuda")
+    lmax = gershgorin_lmax(dm.spmm_pair(kv.abs(), None, ones)[0][:, 0], dinv)
+    fused = lambda a, b, c, e, c1, c2: dm.cheb_step(kv, dinv, a, b, c, e, c1, c2)  # noqa: E731
+    res = torch.as_tensor(rng.standard_normal((n, width))).cuda()
+    t_plain = chebyshev_preconditioner(apply_k, dinv, lmax, 7, 30.0)(res)
+    t_fused = chebyshev_preconditioner(apply_k, dinv, lmax, 7, 30.0, fused_step=fused)(res)
+    assert float((t_plain - t_fused).abs().max()) <= 1e-12 * float(t_plain.abs().max())
+
+
+@pytest.mark.gpu
 def test_gpu_modal_mid_size_properties():
     """256 x 128 cells (66 k DOF): no dense oracle; the pairs must satisfy the pencil (independent
     fe_spmv), be M-orthonormal, start with three rigid-body modes, and agree with scipy's
