@@ -281,6 +281,17 @@ template <bool DOT>
 static int launch_spmv(fe_ctx *ctx, cudaStream_t s, int lpr, int32_t n_rows, const int32_t *rowptr,
                        const int32_t *colidx, const double *vals, const double *x, double *y, double *partials,
                        PcgState *st, const StreamPlan *sp = nullptr, const HaloPlan *fused_halo = nullptr) {
+  if (sp && sp->on && sp->scalar) {  // persistent TMA-streamed kernel, scalar CSR (1 DOF per node)
+    if (fused_halo)
+      k_spmv_stream1<DOT, true><<<sp->grid, kStreamThreads, sp->smem, s>>>(
+          n_rows, sp->cap, rowptr, colidx, vals, x, y, partials, st, ctx->p2p_dev, (HaloDev *)ctx->p2p_halo.ptr,
+          fused_halo->send_idx);
+    else
+      k_spmv_stream1<DOT, false><<<sp->grid, kStreamThreads, sp->smem, s>>>(n_rows, sp->cap, rowptr, colidx, vals, x,
+                                                                            y, partials, st, nullptr, nullptr, nullptr);
+    FE_LAUNCH_CHECK(ctx);
+    return FE_OK;
+  }
   if (sp && sp->on) {  // persistent TMA-streamed kernel (PCG)
     if (fused_halo)    // peer-memory transport: the exchange of x's interface values rides in the kernel
       k_spmv_stream<DOT, true><<<sp->grid, kStreamThreads, sp->smem, s>>>(
@@ -580,7 +591,7 @@ struct PcgLaunch {
 static int get_chunk_graph(PcgLaunch &L, int len, cudaGraphExec_t *out) {
   fe_ctx *ctx = L.ctx;
   const void *key[8] = {L.rowptr, L.colidx, L.vals, L.x, L.r, L.st, (void *)(intptr_t)L.n_rows,
-                        (void *)(intptr_t)(len * 128 + (L.lpr & 31) + (L.sp.on ? 32 : 0) + (L.p2p ? 64 : 0))};
+                        (void *)(intptr_t)(len * 256 + (L.lpr & 31) + (L.sp.on ? 32 : 0) + (L.p2p ? 64 : 0) + (L.sp.scalar ? 128 : 0))};
   if (ctx->pcg_graph && memcmp(key, ctx->pcg_graph_key, sizeof(key)) == 0) {
     *out = (cudaGraphExec_t)ctx->pcg_graph;
     return FE_OK;
@@ -703,6 +714,45 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
       L.sp.cap = cap;
       L.sp.smem = smem;
       const int n_tiles = (n_nodes + T - 1) / T;
+      L.sp.grid = n_tiles < 2 * ctx->num_sms ? n_tiles : 2 * ctx->num_sms;
+    }
+  }
+
+  if (L.lpr != kBlock2 && n_rows > 0 && getenv("FE_B200_NO_STREAM") == nullptr &&
+      ((uintptr_t)vals & 15) == 0 && ((uintptr_t)colidx & 15) == 0 && ((uintptr_t)rowptr & 15) == 0) {
+    // scalar CSR: the streamed kernel works on rowptr / colidx as they are; only the largest tile
+    // (in entries) is needed to size the ring
+    if ((rc = ctx->scratch_c.reserve(256))) return rc;
+    int *tile_max = (int *)ctx->scratch_c.ptr;
+    const bool cached = ctx->bp_token != 0 && ctx->bp_rowptr == rowptr && ctx->bp_colidx == colidx &&
+                        ctx->bp_built_token == ctx->bp_token && ctx->bp_built_rows == -2 - n_rows;
+    int h_tile_max = ctx->bp_max_deg;
+    if (!cached) {
+      ctx->bp_built_token = 0;
+      const int n_tiles = (n_rows + kStream1Tile - 1) / kStream1Tile;
+      FE_CUDA(cudaMemsetAsync(tile_max, 0, sizeof(int), s));
+      k_tile_max_entries<<<grid_for(n_tiles, 256), 256, 0, s>>>(n_rows, kStream1Tile, rowptr, tile_max);
+      FE_LAUNCH_CHECK(ctx);
+      FE_CUDA(cudaMemcpyAsync(&h_tile_max, tile_max, sizeof(int), cudaMemcpyDeviceToHost, s));
+      FE_CUDA(cudaStreamSynchronize(s));
+      if (ctx->bp_token != 0 && ctx->bp_rowptr == rowptr && ctx->bp_colidx == colidx) {
+        ctx->bp_built_token = ctx->bp_token;
+        ctx->bp_built_rows = -2 - n_rows;  // (negative: scalar-path entry, never equal to a block-path one)
+        ctx->bp_max_deg = h_tile_max;
+      }
+    }
+    const int cap = ((h_tile_max > 0 ? h_tile_max : 1) + 3) & ~3;
+    const size_t smem = stream1_smem_bytes(cap);
+    if (smem <= 110 * 1024) {
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream1<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream1<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream1<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream1<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      L.sp.on = true;
+      L.sp.scalar = true;
+      L.sp.cap = cap;
+      L.sp.smem = smem;
+      const int n_tiles = (n_rows + kStream1Tile - 1) / kStream1Tile;
       L.sp.grid = n_tiles < 2 * ctx->num_sms ? n_tiles : 2 * ctx->num_sms;
     }
   }

@@ -207,8 +207,184 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream(
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// The same streaming structure for scalar CSR (1 DOF per node: magnetostatics).  rowptr / colidx
+// ARE the node-level pattern, so nothing is pre-extracted.  A tile = T1 consecutive rows = one
+// contiguous slice of vals (8 B per entry) and one of colidx (4 B per entry); rows are lighter than
+// 2x2-block rows (7 entries = 84 B on a structured mesh), so a tile has 4 passes of 60 rows.
+// 8 lanes per row, one entry per lane: LDS.64 (value), LDS.32 (column), LDG.64 (x), one FMA.
+// HBM bytes per call: 12 nnz + 4 n (rowptr) + 8 n (x) + 8 n (y) -- SURVEY §8d's SpMV figure.
+// ---------------------------------------------------------------------------------------
+constexpr int kStream1Passes = 4;
+constexpr int kStream1Tile = kStream1Passes * kStreamGroups;   // 240 rows
+constexpr int kStream1PtrInts = (kStream1Tile + 1 + 3) & ~3;
+
+template <bool DOT, bool HALO>
+__global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream1(
+    int32_t n_rows, int cap /* entries per stage */, const int32_t *__restrict__ rowptr,
+    const int32_t *__restrict__ colidx, const double *__restrict__ vals, const double *__restrict__ x,
+    double *__restrict__ y, double *__restrict__ partials, PcgState *__restrict__ st, P2PDev *pp, HaloDev *hd,
+    const int32_t *__restrict__ send_idx) {
+  constexpr int T = kStream1Tile, S = kStreamStages, GROUPS = kStreamGroups, PASSES = kStream1Passes;
+  __shared__ double red[kStreamThreads / 32];
+  if (DOT && (st->converged | st->breakdown)) return;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *empty = full + S;
+  constexpr size_t kHdr = 128;
+  int32_t *ptr_s = reinterpret_cast<int32_t *>(smem + kHdr);
+  constexpr size_t ptr_bytes = (kHdr + (size_t)S * kStream1PtrInts * sizeof(int32_t) + 127) / 128 * 128;
+  double *vals_s = reinterpret_cast<double *>(smem + ptr_bytes);                       // S x (cap + 2) doubles
+  int32_t *idx_s = reinterpret_cast<int32_t *>(smem + ptr_bytes + (size_t)S * (cap + 2) * 8);  // S x (cap + 8) ints
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tiles = (n_rows + T - 1) / T;
+  unsigned hseq = 0;
+  const uint4 *gcells = nullptr;
+  if (HALO) {
+    hseq = pp->halo_seq + 1;
+    gcells = pp->ghost[pp->rank] + (hseq & 1);
+    const int pushers = min((int)gridDim.x, 32);
+    if ((int)blockIdx.x < pushers)
+      halo_push(pp, hd, send_idx, x, hseq, blockIdx.x * kStreamThreads + tid, pushers * kStreamThreads);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], kStreamConsumerWarps);
+    }
+    ptx::mbar_init_fence();
+  }
+  __syncthreads();
+
+  double dot = 0.0;
+  if (warp == kStreamConsumerWarps) {
+    // producer warp: lane 0 hands the tile's pointer / value / index slices to the TMA engine.  The
+    // 16-byte granularity of bulk copies would read a few elements past the END of the caller's
+    // arrays on the last two tiles, so those are copied by the whole warp with exact bounds.
+    const int pl = tid & 31;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+      const int stage = j % S, use = j / S;
+      if (use > 0) {
+        if (pl == 0) ptx::mbar_wait(&empty[stage], (uint32_t)((use - 1) & 1));
+        __syncwarp();
+      }
+      const int32_t r0 = tile * T, r1 = min(r0 + T, n_rows);
+      const int32_t b0 = __ldg(rowptr + r0), b1 = __ldg(rowptr + r1);
+      const int32_t av = b0 & ~1, ai = b0 & ~3;  // 16-byte aligned starts of the two slices
+      if (tile < n_tiles - 2) {
+        if (pl == 0) {
+          const uint32_t nv = ((uint32_t)(b1 - av) + 1u) & ~1u, ni = ((uint32_t)(b1 - ai) + 3u) & ~3u;
+          const bool any = b1 > b0;
+          ptx::mbar_expect_tx(&full[stage], kStream1PtrInts * 4u + (any ? nv * 8u + ni * 4u : 0u));
+          ptx::bulk_load(ptr_s + stage * kStream1PtrInts, rowptr + r0, kStream1PtrInts * 4u, &full[stage]);
+          if (any) {
+            ptx::bulk_load(vals_s + (size_t)stage * (cap + 2), vals + av, nv * 8u, &full[stage]);
+            ptx::bulk_load(idx_s + (size_t)stage * (cap + 8), colidx + ai, ni * 4u, &full[stage]);
+          }
+        }
+      } else {
+        for (int i = pl; i <= r1 - r0; i += 32) ptr_s[stage * kStream1PtrInts + i] = __ldg(rowptr + r0 + i);
+        for (int i = pl; i < b1 - b0; i += 32) {
+          vals_s[(size_t)stage * (cap + 2) + (b0 - av) + i] = __ldg(vals + b0 + i);
+          idx_s[(size_t)stage * (cap + 8) + (b0 - ai) + i] = __ldg(colidx + b0 + i);
+        }
+        __syncwarp();                                   // the lanes' stores ordered before lane 0's arrive
+        if (pl == 0) ptx::mbar_arrive(&full[stage]);    // (release) -- no transaction bytes on this phase
+      }
+    }
+  } else {
+    const int grp = tid >> 3, lane = tid & 7;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+      const int stage = j % S, use = j / S;
+      ptx::mbar_wait(&full[stage], (uint32_t)(use & 1));
+      const int32_t r0 = tile * T;
+      const int nn = min(T, n_rows - r0);
+      const int32_t *ps = ptr_s + stage * kStream1PtrInts;
+      const int32_t b0 = ps[0];
+      const double *vs = vals_s + (size_t)stage * (cap + 2) + (b0 - (b0 & ~1));
+      const int32_t *is = idx_s + (size_t)stage * (cap + 8) + (b0 - (b0 & ~3));
+
+      int32_t s[PASSES], deg[PASSES], c[PASSES];
+      double v[PASSES], xv[PASSES];
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {  // all shared-memory reads of the tile first ...
+        const int i = grp + p * GROUPS;
+        s[p] = 0;
+        deg[p] = 0;
+        if (i < nn) {
+          s[p] = ps[i] - b0;
+          deg[p] = ps[i + 1] - ps[i];
+        }
+        const bool act = lane < deg[p];
+        c[p] = act ? is[s[p] + lane] : 0;
+        v[p] = act ? vs[s[p] + lane] : 0.0;
+      }
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) xv[p] = __ldg(x + c[p]);  // ... then every gather of x in flight
+      if (HALO) {
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p)
+          if (c[p] >= n_rows) xv[p] = ll_wait(gcells + 2 * (size_t)(c[p] - n_rows), hseq);
+      }
+      double a[PASSES];
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {
+        a[p] = v[p] * xv[p];
+        for (int k = lane + 8; k < deg[p]; k += 8) {  // more than 8 entries in the row
+          const int32_t ck = is[s[p] + k];
+          const double xx = (HALO && ck >= n_rows) ? ll_wait(gcells + 2 * (size_t)(ck - n_rows), hseq) : __ldg(x + ck);
+          a[p] += vs[s[p] + k] * xx;
+        }
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) ptx::mbar_arrive(&empty[stage]);
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) a[p] += __shfl_xor_sync(0xffffffffu, a[p], o);
+        const int i = grp + p * GROUPS;
+        if (lane == 0 && i < nn) {
+          y[r0 + i] = a[p];
+          if (DOT) dot += a[p] * x[r0 + i];
+        }
+      }
+    }
+  }
+  if (DOT) {
+    const double loc[1] = {dot};
+    publish_and_reduce<1, kStreamThreads>(loc, partials, st, 0, red);
+  }
+  if (HALO) {
+    __syncthreads();
+    if (tid == 0 && atomicAdd(&hd->ticket, 1u) == gridDim.x - 1) {
+      hd->ticket = 0;
+      pp->halo_seq = hseq;
+    }
+  }
+}
+
+// max over the tiles of the streamed scalar kernel of (entries in the tile): sizes its ring stages
+__global__ void __launch_bounds__(256) k_tile_max_entries(int32_t n_rows, int32_t tile, const int32_t *__restrict__ rowptr,
+                                                         int *__restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t r0 = t * tile;
+  if (r0 >= n_rows) return;
+  const int64_t r1 = r0 + tile < n_rows ? r0 + tile : n_rows;
+  const int cnt = rowptr[r1] - rowptr[r0];
+  if (cnt > *reinterpret_cast<volatile int *>(out)) atomicMax(out, cnt);
+}
+
+static size_t stream1_smem_bytes(int cap) {
+  const size_t ptr_bytes = (128 + (size_t)kStreamStages * kStream1PtrInts * sizeof(int32_t) + 127) / 128 * 128;
+  return ptr_bytes + (size_t)kStreamStages * (cap + 2) * 8 + (size_t)kStreamStages * (cap + 8) * 4;
+}
+
 struct StreamPlan {
   bool on = false;
+  bool scalar = false;  // k_spmv_stream1 (1 DOF per node) instead of the 2x2-block kernel
   int T = 0, cap = 0, grid = 0;
   size_t smem = 0;
   int32_t *bptr = nullptr, *bidx = nullptr;

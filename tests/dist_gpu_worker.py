@@ -22,6 +22,7 @@ sys.path.insert(0, ROOT)
 def main():
     nx = int(sys.argv[1]) if len(sys.argv) > 1 else 96
     ny = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    magnetic = len(sys.argv) > 3 and sys.argv[3] == "mag"   # 1 DOF per node: scalar-CSR kernels
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -29,39 +30,51 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
 
-    from finite_elements_b200.device import DeviceMesh, KIND_ELAST_PSTRESS
+    from finite_elements_b200.device import DeviceMesh, KIND_ELAST_PSTRESS, KIND_MAGNETIC
     from finite_elements_b200.dist import DistributedMesh, partition_bounds, local_problem, localize_dofs
     from finite_elements_b200.mesh import structured_mesh
 
     coords, conn = structured_mesh(nx, ny, jitter=0.2, seed=7)
     n_nodes = len(coords)
-    mat = np.array([[210e9, 0.25, 1.0, 7860.0], [70e9, 0.33, 0.5, 2700.0]])
-    mat_id = (np.arange(len(conn)) % 2).astype(np.int32)
+    if magnetic:
+        kind, dim = KIND_MAGNETIC, 1
+        mu0 = 4e-7 * np.pi
+        mat = np.array([[mu0 * 100.0, 0, 0, 0], [mu0, 0, 0, 0], [mu0 * 30.0, 0, 0, 0]])
+        mat_id = (np.arange(len(conn)) % 3).astype(np.int32)
+    else:
+        kind, dim = KIND_ELAST_PSTRESS, 2
+        mat = np.array([[210e9, 0.25, 1.0, 7860.0], [70e9, 0.33, 0.5, 2700.0]])
+        mat_id = (np.arange(len(conn)) % 2).astype(np.int32)
     # deliberately NOT aligned to grid lines: ranks cut through the middle of a line
     bounds = partition_bounds(n_nodes, world, align=1)
     lo, hi = bounds[rank], bounds[rank + 1]
-    lp = local_problem(torch.as_tensor(conn).to(dev), lo, hi, bounds, 2)
+    lp = local_problem(torch.as_tensor(conn).to(dev), lo, hi, bounds, dim)
     gid = lp.node_gid
     dmesh = DistributedMesh(torch.as_tensor(coords).to(dev)[gid], lp,
                             torch.as_tensor(mat_id).to(dev)[lp.elem_sel], device=local_rank)
     dm = dmesh.dm
-    vals = dm.assemble(KIND_ELAST_PSTRESS, mat)
+    vals = dm.assemble(kind, mat)
 
     # global problem on every rank's own GPU (small) as the single-GPU reference
-    gm = DeviceMesh(coords, conn, mat_id, dim=2, device=local_rank)
-    gvals = gm.assemble(KIND_ELAST_PSTRESS, mat)
+    gm = DeviceMesh(coords, conn, mat_id, dim=dim, device=local_rank)
+    gvals = gm.assemble(kind, mat)
     k_glob = gm.to_scipy(gvals)
     k_loc = dm.to_scipy(vals)
-    gd = (gid.cpu().numpy()[:, None] * 2 + np.arange(2)[None, :]).reshape(-1)
+    gd = (gid.cpu().numpy()[:, None] * dim + np.arange(dim)[None, :]).reshape(-1)
     sub = k_glob[gd[:dm.n_rows]][:, gd]
     diff = abs(k_loc - sub)
     scale = abs(k_glob).max()
     assert diff.max() <= 1e-14 * scale, f"rank {rank}: local rows differ from global rows ({diff.max() / scale:.2e})"
 
     lines = np.arange(ny + 1) * (nx + 1)
-    bc_g = np.stack([2 * lines, 2 * lines + 1], axis=1).reshape(-1)
-    f_g = np.zeros(2 * n_nodes)
-    f_g[2 * (lines + nx) + 1] = -1000.0 / ny
+    if magnetic:
+        bc_g = lines + nx                      # A = 0 on the right edge
+        f_g = np.zeros(n_nodes)
+        f_g[conn[:6].reshape(-1)] = 2.5e3      # source on the first few elements
+    else:
+        bc_g = np.stack([2 * lines, 2 * lines + 1], axis=1).reshape(-1)
+        f_g = np.zeros(2 * n_nodes)
+        f_g[2 * (lines + nx) + 1] = -1000.0 / ny
     bc_l, _ = localize_dofs(lp, bc_g)
     f = torch.as_tensor(f_g[gd[:dm.n_rows]].copy()).to(dev)
     rhs = f.clone()
@@ -84,7 +97,7 @@ def main():
     t = torch.tensor([err], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"DIST-OK world={world} mesh={nx}x{ny} iters={iters} (single GPU {iters_g}) max_err={t.item():.2e} "
+        print(f"DIST-OK world={world} {'magnetic ' if magnetic else ''}mesh={nx}x{ny} iters={iters} (single GPU {iters_g}) max_err={t.item():.2e} "
               f"neighbours={len(lp.nbr_rank)}")
     dist.barrier()
     dist.destroy_process_group()
