@@ -184,11 +184,21 @@ int fe_dist_p2p_export(fe_ctx *ctx, int32_t n_ghost_dofs, void *handle64) {
              kMaxRanks);
   FE_CUDA(cudaSetDevice(ctx->device));
   FE_CUDA(cudaDeviceSynchronize());
+  const bool had_block = ctx->p2p_buf != nullptr;
   for (int r = 0; r < kMaxRanks; ++r) {
     if (ctx->p2p_peer[r] && ctx->p2p_peer[r] != ctx->p2p_buf) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
     ctx->p2p_peer[r] = nullptr;
   }
-  if (ctx->p2p_buf) cudaFree(ctx->p2p_buf);
+  if (had_block) {
+    // a second mesh in the same process group: nobody frees its old block before EVERY rank has
+    // unmapped it (the call is collective, like fe_dist_init)
+    int rc = ctx->scratch_b.reserve(256);
+    if (rc) return rc;
+    FE_CUDA(cudaMemset(ctx->scratch_b.ptr, 0, sizeof(double)));
+    if ((rc = allreduce_sum(ctx, nullptr, (double *)ctx->scratch_b.ptr, 1))) return rc;
+    FE_CUDA(cudaDeviceSynchronize());
+    cudaFree(ctx->p2p_buf);
+  }
   ctx->p2p_buf = nullptr;
   size_t off_ghost;
   ctx->p2p_bytes = p2p_block_bytes(ctx->nranks, n_ghost_dofs, &off_ghost);
