@@ -14,6 +14,7 @@ FE_ERR_ARG, FE_ERR_CUDA, FE_ERR_NCCL = -1, -2, -3
 FE_ERR_NOT_CONVERGED, FE_ERR_BREAKDOWN, FE_ERR_UNSUPPORTED = -4, -5, -6
 
 KIND_ELAST_PSTRESS, KIND_ELAST_PSTRAIN, KIND_MAGNETIC, KIND_MASS = 0, 1, 2, 3
+KIND_ELAST_TET, KIND_MASS_TET = 4, 5
 
 
 class NotConverged(RuntimeError):
@@ -43,6 +44,8 @@ SIGNATURES = {
     "fe_dirichlet_apply": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "fe_scatter_add": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "fe_spmv": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "fe_tet_elem_matrices": (C.c_int, [_vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fe_tet_assemble": (C.c_int, [_vp, _vp, C.c_int, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fe_spmm_pair": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
     "fe_cheb_step": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _i32]),
     "fe_csr_diagonal": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),

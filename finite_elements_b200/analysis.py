@@ -106,16 +106,25 @@ class FiniteElements(DessiaObject):
         return self._flat
 
     def _kind(self):
-        from ._lib import KIND_ELAST_PSTRESS, KIND_ELAST_PSTRAIN, KIND_MAGNETIC
+        from ._lib import KIND_ELAST_PSTRESS, KIND_ELAST_PSTRAIN, KIND_MAGNETIC, KIND_ELAST_TET
         if self._flatten()['magnetic']:
             return KIND_MAGNETIC
         fe_elements.check_plane_flags(self.plane_strain, self.plane_stress)
+        if self.dimension == 3:   # tetrahedra: the flags are checked but do not enter (elements.py:753-771)
+            return KIND_ELAST_TET
         return KIND_ELAST_PSTRAIN if self.plane_strain else KIND_ELAST_PSTRESS
+
+    def _mass_kind(self):
+        from ._lib import KIND_MASS, KIND_MASS_TET
+        return KIND_MASS_TET if self.dimension == 3 else KIND_MASS
 
     def _dm(self):
         if self._device_mesh is None:
-            from .device import DeviceMesh
+            from .device import DeviceMesh, DeviceMesh3D
             flat = self._flatten()
+            if self.dimension == 3:
+                self._device_mesh = DeviceMesh3D(flat['coords'], flat['conn'], flat['mat_id'], device=self.device)
+                return self._device_mesh
             self._device_mesh = DeviceMesh(flat['coords'], flat['conn'], flat['mat_id'], dim=self.dimension,
                                            device=self.device)
         return self._device_mesh
@@ -163,9 +172,10 @@ class FiniteElements(DessiaObject):
         flat = self._flatten()
         data = dm.element_matrices(kind, flat['mat']).cpu().numpy().reshape(-1)
         dim = self.dimension
-        dofs = (flat['conn'].astype(np.int64)[:, :, None] * dim + np.arange(dim)[None, None, :]).reshape(-1, 3 * dim)
-        row_ind = np.repeat(dofs, 3 * dim, axis=1).reshape(-1)
-        col_ind = np.tile(dofs, (1, 3 * dim)).reshape(-1)
+        npe = flat['conn'].shape[1]   # 3 (triangles) or 4 (tetrahedra) nodes per element
+        dofs = (flat['conn'].astype(np.int64)[:, :, None] * dim + np.arange(dim)[None, None, :]).reshape(-1, npe * dim)
+        row_ind = np.repeat(dofs, npe * dim, axis=1).reshape(-1)
+        col_ind = np.tile(dofs, (1, npe * dim)).reshape(-1)
         return list(data), list(row_ind), list(col_ind)
 
     def k_matrix_data(self):
@@ -173,8 +183,7 @@ class FiniteElements(DessiaObject):
         return self._matrix_data(self._kind())
 
     def m_matrix_data(self):
-        from ._lib import KIND_MASS
-        return self._matrix_data(KIND_MASS)
+        return self._matrix_data(self._mass_kind())
 
     def _assembled(self, kind):
         dm = self._dm()
@@ -202,12 +211,10 @@ class FiniteElements(DessiaObject):
         return self._assembled(self._kind()).tocsc()
 
     def m_matrix_dense(self):
-        from ._lib import KIND_MASS
-        return self._assembled(KIND_MASS).toarray()
+        return self._assembled(self._mass_kind()).toarray()
 
     def m_matrix_sparse(self):
-        from ._lib import KIND_MASS
-        return self._assembled(KIND_MASS).tocsc()
+        return self._assembled(self._mass_kind()).tocsc()
 
     def matrix_dense(self, method_name):
         if method_name == 'k_matrix_data':
@@ -426,7 +433,6 @@ class FiniteElementAnalysis(FiniteElements):
         (modal.py).  cheb_degree > 1 turns the Jacobi preconditioner of the 'smallest' branch into a
         Chebyshev polynomial of that degree (fewer outer iterations on large meshes; None = automatic)."""
         import torch
-        from ._lib import KIND_MASS
         from .modal import modal_solve
         if order not in ('largest', 'smallest'):
             raise ValueError("Order parameter should be either 'largest' or 'smallest'")
@@ -435,7 +441,7 @@ class FiniteElementAnalysis(FiniteElements):
         dm = self._dm()
         flat = self._flatten()
         k_vals = dm.assemble(self._kind(), flat['mat'], variant=self.assembly_variant)
-        m_vals = dm.assemble(KIND_MASS, flat['mat'], variant=self.assembly_variant)
+        m_vals = dm.assemble(self._mass_kind(), flat['mat'], variant=self.assembly_variant)
         mask = None
         if constrained:
             bc_dofs, _ = self._bc_arrays()

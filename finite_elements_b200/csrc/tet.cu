@@ -1,0 +1,181 @@
+// Linear tetrahedra, 3 DOF per node: the element arithmetic of
+// ElasticityTetrahedralElement3D (elements.py:663-876) and the deterministic row-owner assembly
+// of its global matrices.
+//
+//   B = 1/(6V) [[a_i,0,0],[0,b_i,0],[0,0,c_i],[b_i,a_i,0],[0,c_i,b_i],[c_i,0,a_i]]   elements.py:719-751
+//   D = E/((1+nu)(1-2nu)) [[1-nu,nu,nu,.],[nu,1-nu,nu,.],[nu,nu,1-nu,.],[., (1-2nu)/2 I3]]   :773-797
+//   Ke = V B^T D B                                                                     :809-828
+//   Me = rho V / 20 ((1 + delta_ij) (x) I3)                                            :830-857
+// With g_i = grad N_i = (a_i, b_i, c_i) / (6V), lam = D_12 and mu = D_44, the 3x3 block of nodes
+// (i, j) of V B^T D B is  V [ lam g_i g_j^T + mu g_j g_i^T + mu (g_i . g_j) I ]  -- evaluated in
+// registers, the 6x12 B is never formed.
+//
+// First version of the 3D path: the symbolic phase (corner lists, node adjacency) is prepared by
+// the host layer with device-side sorts; the numeric phase below is the analogue of the 2D
+// "variant 1" kernel -- one thread owns a node's three CSR rows, visits its incident elements in
+// ascending element order and accumulates the (node, neighbour) blocks in place: no atomics, the
+// summation order is fixed, two runs are bit-identical.  Not tuned yet (no shared-memory staging).
+#include "common.cuh"
+#include "elem.cuh"
+
+namespace fe {
+
+struct TetGeom {
+  double g[4][3];  // grad N_i
+  double vol;      // |det [1 x y z]| / 6  (volmdlr TetrahedralElement.volume)
+};
+
+__device__ __forceinline__ TetGeom tet_geom(const double *__restrict__ coords, int n0, int n1, int n2, int n3) {
+  const double x0 = coords[3 * (int64_t)n0], y0 = coords[3 * (int64_t)n0 + 1], z0 = coords[3 * (int64_t)n0 + 2];
+  // edge vectors from vertex 0
+  const double ax = coords[3 * (int64_t)n1] - x0, ay = coords[3 * (int64_t)n1 + 1] - y0, az = coords[3 * (int64_t)n1 + 2] - z0;
+  const double bx = coords[3 * (int64_t)n2] - x0, by = coords[3 * (int64_t)n2 + 1] - y0, bz = coords[3 * (int64_t)n2 + 2] - z0;
+  const double cx = coords[3 * (int64_t)n3] - x0, cy = coords[3 * (int64_t)n3 + 1] - y0, cz = coords[3 * (int64_t)n3 + 2] - z0;
+  // rows of the inverse of J = [a; b; c] are grad N_1..3 (N_i(p_j) = delta_ij); grad N_0 = -(sum)
+  const double c1x = by * cz - bz * cy, c1y = bz * cx - bx * cz, c1z = bx * cy - by * cx;  // b x c
+  const double c2x = cy * az - cz * ay, c2y = cz * ax - cx * az, c2z = cx * ay - cy * ax;  // c x a
+  const double c3x = ay * bz - az * by, c3y = az * bx - ax * bz, c3z = ax * by - ay * bx;  // a x b
+  const double det = ax * c1x + ay * c1y + az * c1z;                                       // a . (b x c) = 6 V signed
+  const double inv = 1.0 / det;
+  TetGeom t;
+  t.g[1][0] = c1x * inv, t.g[1][1] = c1y * inv, t.g[1][2] = c1z * inv;
+  t.g[2][0] = c2x * inv, t.g[2][1] = c2y * inv, t.g[2][2] = c2z * inv;
+  t.g[3][0] = c3x * inv, t.g[3][1] = c3y * inv, t.g[3][2] = c3z * inv;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) t.g[0][d] = -(t.g[1][d] + t.g[2][d] + t.g[3][d]);
+  t.vol = fabs(det) / 6.0;
+  return t;
+}
+
+// (lam V, mu V) for the stiffness, (rho V / 20, -) for the mass
+struct TetMat {
+  double p0, p1;
+};
+
+__device__ __forceinline__ TetMat tet_material(int kind, const double *__restrict__ mat, int mid, double vol) {
+  const double e_mod = mat[4 * mid + 0], nu = mat[4 * mid + 1], rho = mat[4 * mid + 3];
+  TetMat m;
+  if (kind == FE_ELAST_TET) {
+    const double coeff = e_mod / ((1 + nu) * (1 - 2 * nu));  // elements.py:794
+    m.p0 = coeff * nu * vol;
+    m.p1 = coeff * ((1 - 2 * nu) / 2) * vol;
+  } else {
+    m.p0 = (rho * vol) / 20;  // elements.py:854
+    m.p1 = 0.0;
+  }
+  return m;
+}
+
+// 3x3 block (v, j) of the element matrix, row-major in out[9]
+__device__ __forceinline__ void tet_block(int kind, const TetGeom &t, const TetMat &m, int v, int j, double out[9]) {
+  if (kind == FE_ELAST_TET) {
+    const double dot = t.g[v][0] * t.g[j][0] + t.g[v][1] * t.g[j][1] + t.g[v][2] * t.g[j][2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        out[3 * a + b] = m.p0 * t.g[v][a] * t.g[j][b] + m.p1 * t.g[v][b] * t.g[j][a] + (a == b ? m.p1 * dot : 0.0);
+  } else {
+    const double d = (v == j) ? 2.0 * m.p0 : m.p0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) out[q] = (q % 4 == 0) ? d : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_tet_elem_matrices(int kind, int64_t n_elems, const double *__restrict__ coords,
+                                                          const int32_t *__restrict__ conn,
+                                                          const int32_t *__restrict__ mat_id,
+                                                          const double *__restrict__ mat, double *__restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elems) return;
+  const int4 c = *reinterpret_cast<const int4 *>(conn + 4 * e);
+  const TetGeom t = tet_geom(coords, c.x, c.y, c.z, c.w);
+  const TetMat m = tet_material(kind, mat, mat_id ? mat_id[e] : 0, t.vol);
+  double *o = out + 144 * e;
+  for (int v = 0; v < 4; ++v)
+    for (int j = 0; j < 4; ++j) {
+      double b[9];
+      tet_block(kind, t, m, v, j, b);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) o[(3 * v + a) * 12 + 3 * j + q] = b[3 * a + q];
+    }
+}
+
+// One thread per owned node.  corner_elem[corner_ptr[i] .. corner_ptr[i+1]) = the elements incident
+// to node i in ascending order; adj[adj_ptr[i] .. adj_ptr[i+1]) = its sorted neighbour nodes (incl.
+// itself).  vals holds the node's three rows back to back: row r at 9 adj_ptr[i] + r * 3 deg, the
+// block towards neighbour slot k in columns 3k .. 3k+2 (the layout csr3 of the host layer exports).
+__global__ void __launch_bounds__(128) k_tet_assemble(int kind, int32_t n_owned, const int32_t *__restrict__ corner_ptr,
+                                                     const int32_t *__restrict__ corner_elem,
+                                                     const int32_t *__restrict__ adj_ptr,
+                                                     const int32_t *__restrict__ adj, const double *__restrict__ coords,
+                                                     const int32_t *__restrict__ conn,
+                                                     const int32_t *__restrict__ mat_id,
+                                                     const double *__restrict__ mat, double *__restrict__ vals) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_owned) return;
+  const int32_t a0 = adj_ptr[i], deg = adj_ptr[i + 1] - a0;
+  double *rows = vals + 9 * (int64_t)a0;
+  for (int q = 0; q < 9 * deg; ++q) rows[q] = 0.0;
+  for (int32_t cidx = corner_ptr[i]; cidx < corner_ptr[i + 1]; ++cidx) {
+    const int32_t e = corner_elem[cidx];
+    const int4 c = *reinterpret_cast<const int4 *>(conn + 4 * (int64_t)e);
+    const int nodes[4] = {c.x, c.y, c.z, c.w};
+    const TetGeom t = tet_geom(coords, c.x, c.y, c.z, c.w);
+    const TetMat m = tet_material(kind, mat, mat_id ? mat_id[e] : 0, t.vol);
+    for (int v = 0; v < 4; ++v) {
+      if (nodes[v] != i) continue;  // (a degenerate element listing the node twice adds both corners)
+      for (int j = 0; j < 4; ++j) {
+        int lo = 0, hi = deg - 1;  // slot of nodes[j] in the sorted neighbour list
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (adj[a0 + mid] < nodes[j]) lo = mid + 1; else hi = mid;
+        }
+        double b[9];
+        tet_block(kind, t, m, v, j, b);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) rows[a * 3 * deg + 3 * lo + q] += b[3 * a + q];
+      }
+    }
+  }
+}
+
+}  // namespace fe
+
+using namespace fe;
+
+extern "C" {
+
+int fe_tet_elem_matrices(fe_ctx *ctx, void *stream, int kind, int64_t n_elems, const double *coords,
+                         const int32_t *conn, const int32_t *mat_id, const double *mat, int32_t n_mat, double *out) {
+  FE_REQUIRE(ctx && coords && conn && mat && out, "fe_tet_elem_matrices: NULL argument");
+  FE_REQUIRE(kind == FE_ELAST_TET || kind == FE_MASS_TET, "fe_tet_elem_matrices: kind %d is not a tetrahedral kind", kind);
+  FE_REQUIRE(n_elems >= 0 && n_mat > 0, "fe_tet_elem_matrices: bad sizes");
+  FE_REQUIRE(((uintptr_t)conn & 15) == 0, "fe_tet_elem_matrices: conn must be 16-byte aligned");
+  if (n_elems == 0) return FE_OK;
+  k_tet_elem_matrices<<<grid_for(n_elems, 128), 128, 0, as_stream(stream)>>>(kind, n_elems, coords, conn, mat_id, mat,
+                                                                           out);
+  FE_LAUNCH_CHECK(ctx);
+  return FE_OK;
+}
+
+int fe_tet_assemble(fe_ctx *ctx, void *stream, int kind, int32_t n_owned_nodes, const int32_t *corner_ptr,
+                    const int32_t *corner_elem, const int32_t *adj_ptr, const int32_t *adj, const double *coords,
+                    const int32_t *conn, const int32_t *mat_id, const double *mat, int32_t n_mat, double *vals) {
+  FE_REQUIRE(ctx && corner_ptr && corner_elem && adj_ptr && adj && coords && conn && mat && vals,
+             "fe_tet_assemble: NULL argument");
+  FE_REQUIRE(kind == FE_ELAST_TET || kind == FE_MASS_TET, "fe_tet_assemble: kind %d is not a tetrahedral kind", kind);
+  FE_REQUIRE(n_owned_nodes >= 0 && n_mat > 0, "fe_tet_assemble: bad sizes");
+  FE_REQUIRE(((uintptr_t)conn & 15) == 0, "fe_tet_assemble: conn must be 16-byte aligned");
+  if (n_owned_nodes == 0) return FE_OK;
+  k_tet_assemble<<<grid_for(n_owned_nodes, 128), 128, 0, as_stream(stream)>>>(
+      kind, n_owned_nodes, corner_ptr, corner_elem, adj_ptr, adj, coords, conn, mat_id, mat, vals);
+  FE_LAUNCH_CHECK(ctx);
+  return FE_OK;
+}
+
+}  // extern "C"

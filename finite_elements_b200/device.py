@@ -10,10 +10,13 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import check, lib, KIND_ELAST_PSTRESS, KIND_ELAST_PSTRAIN, KIND_MAGNETIC, KIND_MASS  # noqa: F401
+from ._lib import (check, lib, KIND_ELAST_PSTRESS, KIND_ELAST_PSTRAIN, KIND_MAGNETIC, KIND_MASS,  # noqa: F401
+                   KIND_ELAST_TET, KIND_MASS_TET)
 
 
 def kind_dim(kind):
+    if kind in (KIND_ELAST_TET, KIND_MASS_TET):
+        return 3
     return 1 if kind == KIND_MAGNETIC else 2
 
 
@@ -90,6 +93,12 @@ class DeviceMesh:
         self._token = DeviceMesh._tokens   # identifies this mesh's immutable CSR pattern to the solver
 
     _tokens = 0
+
+    @property
+    def block_dim(self):
+        """What the solve entry points may assume about the CSR (fe_b200.h): 2 = rows come in
+        (2i, 2i+1) pairs sharing one column list of (2m, 2m+1) pairs; 1 = nothing."""
+        return self.dim if self.dim in (1, 2) else 1
 
     def _vouch_pattern(self):
         """fe_pcg_cache_pattern: the CSR tensors of csr_pattern() live as long as this object and
@@ -202,7 +211,7 @@ class DeviceMesh:
             y = torch.empty(self.n_rows, dtype=torch.float64, device=self.ctx.device)
         with torch.cuda.device(self.ctx.device):
             check(lib.fe_spmv(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals),
-                              _ptr(x), _ptr(y), self.dim))
+                              _ptr(x), _ptr(y), self.block_dim))
         return y
 
     def spmm_pair(self, vals_a, vals_b, x, out_a=None, out_b=None):
@@ -256,7 +265,7 @@ class DeviceMesh:
         iters, relres = C.c_int32(0), C.c_double(0.0)
         with torch.cuda.device(self.ctx.device):
             rc = lib.fe_pcg(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals), _ptr(b),
-                            _ptr(x), _ptr(work), self.dim, float(rtol), int(min(maxit, 2 ** 31 - 1)), C.byref(iters),
+                            _ptr(x), _ptr(work), self.block_dim, float(rtol), int(min(maxit, 2 ** 31 - 1)), C.byref(iters),
                             C.byref(relres))
         if rc == _lib.FE_ERR_NOT_CONVERGED and not raise_on_maxit:
             return x, iters.value, relres.value
@@ -270,7 +279,7 @@ class DeviceMesh:
             work = self.pcg_workspace()
         with torch.cuda.device(self.ctx.device):
             check(lib.fe_pcg_fixed(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals),
-                                   _ptr(b), _ptr(x), _ptr(work), self.dim, int(iters)))
+                                   _ptr(b), _ptr(x), _ptr(work), self.block_dim, int(iters)))
         return x
 
     # ---- convenience ------------------------------------------------------------------
@@ -279,6 +288,132 @@ class DeviceMesh:
         rowptr, colidx = self.csr_pattern()
         return sp.csr_matrix((vals.cpu().numpy(), colidx.cpu().numpy(), rowptr.cpu().numpy()),
                              shape=(self.n_rows, self.n_cols))
+
+
+def tet_symbolic(conn64, n):
+    """Symbolic phase of the tetrahedral path on conn64 (E,4) int64, any torch device.
+    Returns (corner_ptr i64[n+1], corner_elem i32[4E], adj_ptr i64[n+1], adj i64[sum deg], deg i64[n]):
+    per-node element lists in ascending element order, and the sorted node adjacency (diagonal included)."""
+    dev = conn64.device
+    e = conn64.shape[0]
+    corner_node = conn64.reshape(-1)
+    order = torch.sort(corner_node, stable=True).indices
+    corner_elem = (order // 4).to(torch.int32).contiguous()
+    corner_ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    corner_ptr[1:] = torch.cumsum(torch.bincount(corner_node, minlength=n), 0)
+    a = conn64[:, :, None].expand(e, 4, 4).reshape(-1)
+    b = conn64[:, None, :].expand(e, 4, 4).reshape(-1)
+    diag = torch.arange(n, device=dev, dtype=torch.int64)
+    keys = torch.unique(torch.cat([a * n + b, diag * n + diag]))      # sorted
+    deg = torch.bincount(keys // n, minlength=n)
+    adj_ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    adj_ptr[1:] = torch.cumsum(deg, 0)
+    return corner_ptr, corner_elem, adj_ptr, keys % n, deg
+
+
+def tet_csr(adj_ptr, adj, deg):
+    """(rowptr i32[3n+1], colidx i32[nnz]) of the 3x3-block expansion: row 3i+r starts at
+    9 adj_ptr[i] + r * 3 deg_i and holds columns 3 adj[k] + c, k-major -- sorted, scipy-canonical."""
+    dev = adj.device
+    n = deg.numel()
+    rowptr = torch.empty(3 * n + 1, dtype=torch.int64, device=dev)
+    base = 9 * adj_ptr[:-1]
+    for r in range(3):
+        rowptr[r:3 * n:3] = base + r * 3 * deg
+    rowptr[3 * n] = 9 * adj_ptr[-1]
+    node_of_block = torch.repeat_interleave(torch.arange(n, device=dev), deg)       # per adjacency entry
+    k_in_node = torch.arange(adj.numel(), device=dev) - adj_ptr[:-1][node_of_block]
+    colidx = torch.empty(int(9 * adj_ptr[-1].item()), dtype=torch.int32, device=dev)
+    for r in range(3):
+        pos = base[node_of_block] + r * 3 * deg[node_of_block] + 3 * k_in_node
+        for c in range(3):
+            colidx[pos + c] = (3 * adj + c).to(torch.int32)
+    return rowptr.to(torch.int32).contiguous(), colidx
+
+
+class DeviceMesh3D(DeviceMesh):
+    """Linear tetrahedra, 3 DOF per node: coords f64[N,3], conn i32[E,4].
+
+    The symbolic phase -- per-node element lists, node adjacency, the scipy-canonical CSR of the 3x3
+    blocks -- is a handful of device-side sorts (torch.sort / unique_consecutive; plumbing, once per
+    mesh); the numeric phase is fe_tet_assemble / fe_tet_elem_matrices.  Everything CSR-level
+    (Dirichlet elimination, SpMV, PCG, block products) is inherited unchanged."""
+
+    def __init__(self, coords, conn, mat_id=None, device=0, ctx=None):
+        self.ctx = ctx or Context.get(device)
+        dev = self.ctx.device
+        self.coords = torch.as_tensor(np.ascontiguousarray(coords, dtype=np.float64)).to(dev) \
+            if not torch.is_tensor(coords) else coords.to(dev, torch.float64).contiguous()
+        self.conn = torch.as_tensor(np.ascontiguousarray(conn, dtype=np.int32)).to(dev) \
+            if not torch.is_tensor(conn) else conn.to(dev, torch.int32).contiguous()
+        if mat_id is None:
+            self.mat_id = None
+        else:
+            self.mat_id = torch.as_tensor(np.ascontiguousarray(mat_id, dtype=np.int32)).to(dev) \
+                if not torch.is_tensor(mat_id) else mat_id.to(dev, torch.int32).contiguous()
+        if self.coords.ndim != 2 or self.coords.shape[1] != 3:
+            raise ValueError("coords must have shape (N, 3)")
+        self.n_nodes = int(self.coords.shape[0])
+        self.n_elems = int(self.conn.shape[0])
+        if self.n_elems and (self.conn.ndim != 2 or self.conn.shape[1] != 4):
+            raise ValueError("conn must have shape (E, 4)")
+        self.n_owned = self.n_nodes
+        self.dim = 3
+        self.plan = None
+        n, e = self.n_nodes, self.n_elems
+        conn64 = self.conn.long()
+        if e and (int(conn64.min()) < 0 or int(conn64.max()) >= n):
+            raise ValueError("conn refers to a node outside [0, N)")
+        self.corner_ptr, self.corner_elem, adj_ptr, self.adj, deg = tet_symbolic(conn64, n)
+        self.nnz = int(9 * adj_ptr[-1].item())
+        if self.nnz >= 2 ** 31:
+            raise NotImplementedError("nnz does not fit int32")
+        self.adj_ptr = adj_ptr.to(torch.int32).contiguous()
+        self.corner_ptr = self.corner_ptr.to(torch.int32).contiguous()
+        self.adj = self.adj.to(torch.int32).contiguous()
+        self._deg = deg
+        self.n_rows = 3 * n
+        self.n_cols = 3 * n
+        self.max_degree = int(deg.max().item()) if n else 0
+        self.plan_bytes = int(4 * (self.corner_elem.numel() + self.adj.numel() + 2 * (n + 1)))
+        self._csr = None
+        DeviceMesh._tokens += 1
+        self._token = DeviceMesh._tokens
+
+    def __del__(self):
+        pass
+
+    def csr_pattern(self):
+        """Row 3i+r = 9 adj_ptr[i] + r * 3 deg_i, columns 3 adj[k] + c: sorted, scipy-canonical."""
+        if self._csr is None:
+            self._csr = tet_csr(self.adj_ptr.long(), self.adj.long(), self._deg)
+        return self._csr
+
+    def assemble(self, kind, mat, out=None, variant=0):
+        """Global K (KIND_ELAST_TET) or M (KIND_MASS_TET) values in csr_pattern() order.  fe_tet_assemble."""
+        m = self._mat(mat)
+        if out is None:
+            out = torch.empty(max(self.nnz, 1), dtype=torch.float64, device=self.ctx.device)[:self.nnz]
+        with torch.cuda.device(self.ctx.device):
+            check(lib.fe_tet_assemble(self.ctx.handle, _stream(), int(kind), self.n_nodes, _ptr(self.corner_ptr),
+                                      _ptr(self.corner_elem), _ptr(self.adj_ptr), _ptr(self.adj), _ptr(self.coords),
+                                      _ptr(self.conn), _ptr(self.mat_id), _ptr(m), int(m.shape[0]), _ptr(out)))
+        return out
+
+    def element_matrices(self, kind, mat):
+        """Per-element matrices f64[E, 144] (row-major 12x12).  fe_tet_elem_matrices."""
+        m = self._mat(mat)
+        out = torch.empty((self.n_elems, 144), dtype=torch.float64, device=self.ctx.device)
+        with torch.cuda.device(self.ctx.device):
+            check(lib.fe_tet_elem_matrices(self.ctx.handle, _stream(), int(kind), self.n_elems, _ptr(self.coords),
+                                           _ptr(self.conn), _ptr(self.mat_id), _ptr(m), int(m.shape[0]), _ptr(out)))
+        return out
+
+    def element_post(self, kind, mat, u):
+        raise NotImplementedError("element post-processing is implemented for triangles only")
+
+    def source_factors(self, elem_sel=None):
+        raise NotImplementedError("the reference defines no element_to_node_factors for tetrahedra")
 
 
 def solve_dirichlet_system(dm, kind, mat, load_dof, load_val, bc_dof, bc_val, rtol=1e-12, maxit=None,

@@ -206,7 +206,7 @@ class DistributedMesh:
                                  dm.n_cols, _ptr(rowptr), _ptr(colidx), _ptr(vals), _ptr(b), _ptr(x), _ptr(work),
                                  len(self._nbr), ip(self._nbr), ip(self._sp), _ptr(self.send_idx), ip(self._rp),
                                  ip(self._dst_off) if self._dst_off is not None else C.c_void_p(0),
-                                 dm.dim, float(rtol), int(maxit), int(fixed_iters), C.byref(iters), C.byref(relres))
+                                 dm.block_dim, float(rtol), int(maxit), int(fixed_iters), C.byref(iters), C.byref(relres))
         if rc != _lib.FE_ERR_NOT_CONVERGED:
             check(rc)
         return x, iters.value, relres.value

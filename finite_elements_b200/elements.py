@@ -12,7 +12,7 @@ import numpy as np
 
 from . import core
 from .core import DessiaObject
-from .mesh import TriangularElement2D
+from .mesh import TriangularElement2D, TetrahedralElement
 
 
 def _points_array(points):
@@ -156,3 +156,64 @@ class ElasticityTriangularElement2D(ElasticityElement, Element2D):
     def from_element(cls, mesh_element, elasticity_element):
         return cls(mesh_element, elasticity_element.elasticity_modulus, elasticity_element.poisson_ratio,
                    elasticity_element.mass_density, elasticity_element.thickness)
+
+
+class ElasticityTetrahedralElement3D(ElasticityElement, TetrahedralElement):
+    """Linear tetrahedron, 3 DOF per node, local DOF order [u0, v0, w0, u1, ...]
+    (elements.py:663-876).  The plane flags are accepted and ignored, as in the reference
+    (both `_d_matrix_plane_*` return the 3D matrix, :753-771)."""
+
+    def __init__(self, mesh_element, elasticity_modulus, poisson_ratio, mass_density,
+                 displacements=None, stress=None, strain=None, name=''):
+        ElasticityElement.__init__(self, mesh_element, elasticity_modulus, poisson_ratio, mass_density,
+                                   displacements=displacements, stress=stress, strain=strain, name=name)
+        TetrahedralElement.__init__(self, points=mesh_element.points, name=name)
+
+    @property
+    def dimension(self):
+        return 3
+
+    def _b_matrix(self):
+        """6 x 12 strain-displacement matrix (elements.py:719-751), post-processing helper."""
+        f = self.form_functions
+        out = np.zeros((6, 12))
+        for i in range(4):
+            a, b, c = f[i][1], f[i][2], f[i][3]
+            out[0, 3 * i], out[1, 3 * i + 1], out[2, 3 * i + 2] = a, b, c
+            out[3, 3 * i], out[3, 3 * i + 1] = b, a
+            out[4, 3 * i + 1], out[4, 3 * i + 2] = c, b
+            out[5, 3 * i], out[5, 3 * i + 2] = c, a
+        return out / (6 * self.volume)
+
+    def _d_matrix(self, plane_strain=None):
+        """elements.py:773-797."""
+        e_mod, nu = self.elasticity_modulus, self.poisson_ratio
+        d = np.zeros((6, 6))
+        d[:3, :3] = nu
+        d[np.arange(3), np.arange(3)] = 1 - nu
+        d[np.arange(3, 6), np.arange(3, 6)] = (1 - 2 * nu) / 2
+        return e_mod / ((1 + nu) * (1 - 2 * nu)) * d
+
+    def d_matrix(self, plane_strain, plane_stress):
+        check_plane_flags(plane_strain, plane_stress)
+        return self._d_matrix()
+
+    def _one(self, kind):
+        from .device import DeviceMesh3D
+        pts = np.array([[p[0], p[1], p[2]] for p in self.points], dtype=np.float64)
+        dm = DeviceMesh3D(pts, np.array([[0, 1, 2, 3]], dtype=np.int32), None)
+        row = np.array([[self.elasticity_modulus, self.poisson_ratio, 1.0, self.mass_density]], dtype=np.float64)
+        return dm.element_matrices(kind, row).cpu().numpy()[0]
+
+    def elementary_matrix(self, plane_strain, plane_stress):
+        """volume * B^T D B flattened to 144 (elements.py:809-828)."""
+        return self._one(4)
+
+    def elementary_mass_matrix(self):
+        """(rho V / 20) ((1 + delta_ij) (x) I3) flattened to 144 (elements.py:830-857)."""
+        return self._one(5)
+
+    @classmethod
+    def from_element(cls, mesh_element, elasticity_element):
+        return cls(mesh_element, elasticity_element.elasticity_modulus, elasticity_element.poisson_ratio,
+                   elasticity_element.mass_density)

@@ -5,7 +5,8 @@ The reference takes `volmdlr.mesh` objects (third-party, not vendored; SURVEY §
 (`mesh.nodes`, `mesh.node_to_index`, `mesh.elements_groups[*].elements[*].points`), so a real
 volmdlr mesh works unchanged.  This module provides
   * look-alikes of the few volmdlr classes the reference's scripts use, for environments
-    without volmdlr (Point2D / Node2D / TriangularElement2D / ElementsGroup / Mesh);
+    without volmdlr (Point2D / Node2D / TriangularElement2D / ElementsGroup / Mesh, and
+    Point3D / Node3D / TetrahedralElement for the tetrahedral path);
   * ArrayMesh: the same surface backed by flat arrays, so that million-element meshes
     never become Python objects;
   * structured_mesh(): the synthetic triangulations of SURVEY §8d;
@@ -89,6 +90,68 @@ class Node2D(Point2D):
     __slots__ = ()
 
 
+class Vector3D:
+    """x, y, z (volmdlr.Vector3D look-alike; approximate equality like the 2D points)."""
+
+    __slots__ = ("x", "y", "z", "name")
+
+    def __init__(self, x, y=None, z=None, name=''):
+        if y is None:
+            x, y, z = x[0], x[1], x[2]
+        self.x, self.y, self.z, self.name = x, y, z, name
+
+    def __getitem__(self, i):
+        return (self.x, self.y, self.z)[i]
+
+    def __iter__(self):
+        yield self.x
+        yield self.y
+        yield self.z
+
+    def __len__(self):
+        return 3
+
+    def __add__(self, other):
+        return type(self)(self.x + other[0], self.y + other[1], self.z + other[2])
+
+    def __sub__(self, other):
+        return type(self)(self.x - other[0], self.y - other[1], self.z - other[2])
+
+    def __mul__(self, k):
+        return type(self)(self.x * k, self.y * k, self.z * k)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, k):
+        return type(self)(self.x / k, self.y / k, self.z / k)
+
+    def dot(self, other):
+        return self.x * other[0] + self.y * other[1] + self.z * other[2]
+
+    def norm(self):
+        return math.sqrt(self.x * self.x + self.y * self.y + self.z * self.z)
+
+    def _key(self):
+        return (round(self.x * 1e6), round(self.y * 1e6), round(self.z * 1e6))
+
+    def __eq__(self, other):
+        return isinstance(other, Vector3D) and self._key() == other._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __repr__(self):
+        return f"{type(self).__name__}({self.x}, {self.y}, {self.z})"
+
+
+class Point3D(Vector3D):
+    __slots__ = ()
+
+
+class Node3D(Point3D):
+    __slots__ = ()
+
+
 class LinearElement:
     def __init__(self, points, interior_normal, name=''):
         self.points = points
@@ -149,6 +212,30 @@ class TriangularElement2D(TriangularElement):
         return out
 
 
+class TetrahedralElement:
+    """points, volume, center, form_functions as ElasticityTetrahedralElement3D reads them
+    (elements.py:726-749, :823, :854): volume = |det [1 x y z]| / 6 and form_functions[i] =
+    (alpha_i, a_i, b_i, c_i) with N_i = (alpha_i + a_i x + b_i y + c_i z) / (6 volume)."""
+
+    def __init__(self, points, name=''):
+        self.points = list(points)
+        self.name = name
+        a = np.array([[1.0, p[0], p[1], p[2]] for p in self.points])
+        self._det = float(np.linalg.det(a))
+        self.volume = abs(self._det) / 6.0
+        self._a = a
+
+    @property
+    def center(self):
+        p = self.points
+        return Point3D(*(sum(q[d] for q in p) / 4 for d in range(3)))
+
+    @property
+    def form_functions(self):
+        inv = np.linalg.inv(self._a)
+        return tuple(tuple(abs(self._det) * inv[:, i]) for i in range(4))
+
+
 class ElementsGroup:
     def __init__(self, elements, name=''):
         self.elements = elements
@@ -180,15 +267,17 @@ class _LazyNodes:
     def __len__(self):
         return len(self._c)
 
+    def _node(self, row):
+        return Node3D(*(float(v) for v in row)) if len(row) == 3 else Node2D(float(row[0]), float(row[1]))
+
     def __getitem__(self, i):
         if isinstance(i, slice):
-            return [Node2D(float(x), float(y)) for x, y in self._c[i]]
-        x, y = self._c[i]
-        return Node2D(float(x), float(y))
+            return [self._node(row) for row in self._c[i]]
+        return self._node(self._c[i])
 
     def __iter__(self):
-        for x, y in self._c:
-            yield Node2D(float(x), float(y))
+        for row in self._c:
+            yield self._node(row)
 
 
 class _NodeIndex:
@@ -203,8 +292,8 @@ class _NodeIndex:
             return int(node)
         if self._map is None:
             keys = np.round(self._c * 1e6).astype(np.int64)
-            self._map = {(int(a), int(b)): i for i, (a, b) in enumerate(keys)}
-        return self._map[(round(node[0] * 1e6), round(node[1] * 1e6))]
+            self._map = {tuple(int(v) for v in row): i for i, row in enumerate(keys)}
+        return self._map[tuple(round(node[d] * 1e6) for d in range(self._c.shape[1]))]
 
 
 class ArrayElement:
@@ -226,8 +315,9 @@ class ArrayMesh:
     """Flat-array mesh with the attribute surface of volmdlr.mesh.Mesh.
 
     coords f64[N,2]; conn i32[E,3]; group_bounds [0, e1, ..., E] (contiguous element groups);
-    `element_factory(group_index, TriangularElement2D) -> element` builds per-element objects
-    on demand (only small meshes ever need them); `kind` is 'elasticity' or 'magnetic' and
+    (kind 'elasticity3d': coords f64[N,3], conn i32[E,4] -- linear tetrahedra);
+    per-element objects are built on demand (only small meshes ever need them); `kind` is
+    'elasticity', 'magnetic' or 'elasticity3d' and
     `group_params` holds, per group, the flat material row the device uses
     ((E, nu, thickness, rho) or (mu, 0, 0, 0))."""
 
@@ -246,11 +336,14 @@ class ArrayMesh:
 
     @property
     def dimension(self):
-        return 2 if self.kind == 'elasticity' else 1
+        return {'elasticity': 2, 'elasticity3d': 3}.get(self.kind, 1)
 
     def element(self, index):
         """ArrayElement handle (for ElementsLoad / ElementBoundaryCondition records)."""
         n = [int(v) for v in self.conn[index]]
+        if self.kind == 'elasticity3d':
+            p = self.coords[n]
+            return ArrayElement(int(index), n, abs(float(np.linalg.det(p[1:] - p[0]))) / 6.0)
         (x1, y1), (x2, y2), (x3, y3) = self.coords[n]
         return ArrayElement(int(index), n, 0.5 * abs((x2 - x1) * (y3 - y1) - (y2 - y1) * (x3 - x1)))
 
@@ -270,6 +363,10 @@ class ArrayMesh:
                 elems = []
                 p = self.group_params[g]
                 for e in range(self.group_bounds[g], self.group_bounds[g + 1]):
+                    if self.kind == 'elasticity3d':
+                        tet = TetrahedralElement([self.nodes[int(i)] for i in self.conn[e]])
+                        elems.append(fe_elements.ElasticityTetrahedralElement3D(tet, p[0], p[1], p[3]))
+                        continue
                     tri = TriangularElement2D([self.nodes[int(i)] for i in self.conn[e]])
                     if self.kind == 'elasticity':
                         elems.append(fe_elements.ElasticityTriangularElement2D(tri, p[0], p[1], p[3], p[2]))
@@ -287,8 +384,11 @@ def flatten_mesh(mesh):
     `magnetic`.  Duck-typed on what the reference reads from volmdlr meshes."""
     if isinstance(mesh, ArrayMesh):
         return dict(coords=mesh.coords, conn=mesh.conn, mat_id=mesh.mat_id, mat=mesh.group_params,
-                    elements=None, element_index=None, magnetic=mesh.kind != 'elasticity')
-    coords = np.array([[node[0], node[1]] for node in mesh.nodes], dtype=np.float64).reshape(-1, 2)
+                    elements=None, element_index=None, magnetic=mesh.kind == 'magnetic',
+                    space_dim=mesh.coords.shape[1])
+    first = mesh.elements_groups[0].elements[0] if mesh.elements_groups and mesh.elements_groups[0].elements else None
+    sdim = 3 if first is not None and len(first.points) == 4 else 2
+    coords = np.array([[node[d] for d in range(sdim)] for node in mesh.nodes], dtype=np.float64).reshape(-1, sdim)
     conn, mat_id, rows, row_of, element_index, elements = [], [], [], {}, {}, []
     magnetic = None
     for group in mesh.elements_groups:
@@ -302,7 +402,7 @@ def flatten_mesh(mesh):
                 row = (float(element.mu_total), 0.0, 0.0, 0.0)
             else:
                 row = (float(element.elasticity_modulus), float(element.poisson_ratio),
-                       float(element.thickness), float(element.mass_density))
+                       float(getattr(element, 'thickness', 1.0)), float(element.mass_density))
             if row not in row_of:
                 row_of[row] = len(rows)
                 rows.append(row)
@@ -310,9 +410,9 @@ def flatten_mesh(mesh):
             elements.append(element)
             conn.append([mesh.node_to_index[point] for point in element.points])
             mat_id.append(row_of[row])
-    return dict(coords=coords, conn=np.array(conn, dtype=np.int32).reshape(-1, 3),
+    return dict(coords=coords, conn=np.array(conn, dtype=np.int32).reshape(-1, sdim + 1),
                 mat_id=np.array(mat_id, dtype=np.int32), mat=np.array(rows, dtype=np.float64).reshape(-1, 4),
-                elements=elements, element_index=element_index, magnetic=bool(magnetic))
+                elements=elements, element_index=element_index, magnetic=bool(magnetic), space_dim=sdim)
 
 
 # ---------------------------------------------------------------------------------------
@@ -362,9 +462,10 @@ def structured_mesh_torch(nx, ny, device, h=None, row_lo=0, row_hi=None):
     return coords, conn
 
 
-def read_gmsh41(path):
+def read_gmsh41(path, tetrahedra=False):
     """gmsh 4.1 ASCII: nodes in file order (gmsh.nodes['all_nodes'] order in
-    beam2d_example_3.py:72), 3-node triangles (element type 2).  Returns coords, conn."""
+    beam2d_example_3.py:72), 3-node triangles (element type 2) -> coords (N,2), conn (E,3); with
+    tetrahedra=True the 4-node tetrahedra (type 4, beam3d_example_2.py:59-61) -> coords (N,3), conn (E,4)."""
     with open(path) as fh:
         lines = [ln.strip() for ln in fh]
     if "$MeshFormat" not in lines or not lines[lines.index("$MeshFormat") + 1].startswith("4.1"):
@@ -379,8 +480,7 @@ def read_gmsh41(path):
         tags.extend(int(lines[k + r]) for r in range(count))
         k += count
         for r in range(count):
-            x, y = lines[k + r].split()[:2]
-            xy.append((float(x), float(y)))
+            xy.append(tuple(float(t) for t in lines[k + r].split()[:(3 if tetrahedra else 2)]))
         k += count
     if len(tags) != n_nodes:
         raise ValueError(f"{path}: node count mismatch")
@@ -392,9 +492,28 @@ def read_gmsh41(path):
     for _ in range(n_blocks):
         _, _, etype, count = (int(t) for t in lines[k].split())
         k += 1
-        if etype == 2:
+        if etype == (4 if tetrahedra else 2):
             for r in range(count):
                 t = lines[k + r].split()
-                tris.append([index_of[int(t[1])], index_of[int(t[2])], index_of[int(t[3])]])
+                tris.append([index_of[int(v)] for v in t[1:(5 if tetrahedra else 4)]])
         k += count
-    return np.array(xy, dtype=np.float64), np.array(tris, dtype=np.int32).reshape(-1, 3)
+    return np.array(xy, dtype=np.float64), np.array(tris, dtype=np.int32).reshape(-1, 4 if tetrahedra else 3)
+
+
+def structured_tet_mesh(nx, ny, nz, h=1.0, jitter=0.0, seed=0):
+    """Box of nx x ny x nz cells of size h, nodes id = (k (ny+1) + j) (nx+1) + i, every cell cut into
+    the 6 tetrahedra of the Kuhn triangulation (conforming).  Returns coords f64[N,3], conn i32[E,4]."""
+    ii, jj, kk = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    nid = (kk * (ny + 1) + jj) * (nx + 1) + ii
+    coords = np.zeros(((nx + 1) * (ny + 1) * (nz + 1), 3))
+    coords[nid.reshape(-1)] = np.stack([ii, jj, kk], axis=-1).reshape(-1, 3) * h
+    if jitter:
+        rng = np.random.default_rng(seed)
+        d = rng.uniform(-jitter * h, jitter * h, size=coords.shape)
+        inner = nid[(ii > 0) & (ii < nx) & (jj > 0) & (jj < ny) & (kk > 0) & (kk < nz)]
+        coords[inner] += d[inner]
+    c = nid[:-1, :-1, :-1].reshape(-1)
+    dx, dy, dz = 1, nx + 1, (nx + 1) * (ny + 1)
+    tets = [np.stack([c, c + a, c + a + b, c + a + b + d3], axis=1)
+            for a, b, d3 in ((dx, dy, dz), (dx, dz, dy), (dy, dx, dz), (dy, dz, dx), (dz, dx, dy), (dz, dy, dx))]
+    return coords, np.stack(tets, axis=1).reshape(-1, 4).astype(np.int32)

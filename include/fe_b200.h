@@ -58,7 +58,10 @@ enum fe_kind {
   FE_ELAST_PSTRESS = 0, /* ElasticityTriangularElement2D.elementary_matrix(False, True) */
   FE_ELAST_PSTRAIN = 1, /* ... (True, False)                                            */
   FE_MAGNETIC = 2,      /* MagneticElement2D.elementary_matrix()                        */
-  FE_MASS = 3           /* ElasticityTriangularElement2D.elementary_mass_matrix()       */
+  FE_MASS = 3,          /* ElasticityTriangularElement2D.elementary_mass_matrix()       */
+  /* linear tetrahedra, 3 DOF per node (elements.py:663-876); fe_tet_* entry points only */
+  FE_ELAST_TET = 4,     /* ElasticityTetrahedralElement3D.elementary_matrix(.., ..)     */
+  FE_MASS_TET = 5       /* ElasticityTetrahedralElement3D.elementary_mass_matrix()      */
 };
 
 int fe_version(void);
@@ -146,6 +149,25 @@ int fe_scatter_add(fe_ctx *ctx, void *stream, int32_t n, const int32_t *dof, con
 int fe_spmv(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
             const int32_t *colidx, const double *vals, const double *x, double *y,
             int32_t block_dim);
+
+/* ---- linear tetrahedra --------------------------------------------
+ * coords double[N][3], conn int32[E][4] (16-byte aligned), mat rows as above (thickness unused).
+ * out: double[E][144], row-major 12x12 in the reference's DOF order [u0,v0,w0,u1,...]
+ * (elements.py:809-828 / :830-857). */
+int fe_tet_elem_matrices(fe_ctx *ctx, void *stream, int kind, int64_t n_elems, const double *coords,
+                         const int32_t *conn, const int32_t *mat_id, const double *mat,
+                         int32_t n_mat, double *out);
+/* Global matrix values of the tetrahedral mesh; replaces the k_matrix_data / m_matrix_data loops
+ * (analysis.py:324-339, :357-365) + csr_matrix (:661) for 3 DOF per node.  The symbolic data comes
+ * from the caller: corner_elem[corner_ptr[i] .. corner_ptr[i+1]) = elements incident to node i in
+ * ascending order, adj[adj_ptr[i] .. adj_ptr[i+1]) = sorted neighbour nodes of i (itself included).
+ * vals: node i's rows 3i, 3i+1, 3i+2 back to back from 9 adj_ptr[i], each 3 deg_i long, block of
+ * neighbour slot k at columns 3k..3k+2 -- the scipy-canonical CSR of the same triplets.  One thread
+ * owns a node's rows and adds its elements in ascending order: deterministic, no atomics. */
+int fe_tet_assemble(fe_ctx *ctx, void *stream, int kind, int32_t n_owned_nodes,
+                    const int32_t *corner_ptr, const int32_t *corner_elem, const int32_t *adj_ptr,
+                    const int32_t *adj, const double *coords, const int32_t *conn,
+                    const int32_t *mat_id, const double *mat, int32_t n_mat, double *vals);
 
 /* ---- modal analysis building blocks (analysis.py:741-796) -------------------------------
  * The reference gives K and M to scipy.sparse.linalg.eigsh (:779-782), whose Lanczos loop

@@ -25,8 +25,9 @@ from oracle.numpy_oracle import structured_mesh  # noqa: E402
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
-def read_msh41_triangles(path):
-    """Minimal gmsh 4.1 ASCII reader: nodes in file order, 3-node triangles (type 2)."""
+def read_msh41_triangles(path, etype_wanted=2):
+    """Minimal gmsh 4.1 ASCII reader: nodes in file order, 3-node triangles (type 2) or, with
+    etype_wanted=4, 4-node tetrahedra (coordinates then keep z)."""
     with open(path) as fh:
         lines = [ln.strip() for ln in fh]
     i = lines.index("$Nodes") + 1
@@ -42,7 +43,7 @@ def read_msh41_triangles(path):
         i += nb
     assert len(tags) == nnodes
     tag_to_idx = {t: k for k, t in enumerate(tags)}
-    coords = np.array(xyz, dtype=np.float64)[:, :2]
+    coords = np.array(xyz, dtype=np.float64)[:, :(3 if etype_wanted == 4 else 2)]
     i = lines.index("$Elements") + 1
     nblocks = int(lines[i].split()[0])
     i += 1
@@ -50,10 +51,10 @@ def read_msh41_triangles(path):
     for _ in range(nblocks):
         _, _, etype, nb = (int(t) for t in lines[i].split())
         i += 1
-        if etype == 2:
+        if etype == etype_wanted:
             for k in range(nb):
                 t = [int(v) for v in lines[i + k].split()]
-                tris.append([tag_to_idx[v] for v in t[1:4]])
+                tris.append([tag_to_idx[v] for v in t[1:(5 if etype_wanted == 4 else 4)]])
         i += nb
     return coords, np.array(tris, dtype=np.int32)
 
@@ -81,12 +82,13 @@ def run(ns, spec, modal_k=0):
         edge_bcs=spec.get("edge_bcs", ()), element_bcs=spec.get("element_bcs", ()),
         plane_strain=plane_strain, plane_stress=plane_stress)
     out = {}
-    if kind == "elasticity":
+    if kind in ("elasticity", "elasticity3d"):
         out["ke"] = np.array([e.elementary_matrix(plane_strain, plane_stress) for e in elems])
         out["me"] = np.array([e.elementary_mass_matrix() for e in elems])
     else:
         out["ke"] = np.array([e.elementary_matrix() for e in elems], dtype=np.float64)
-    out["factors"] = np.array([e.element_to_node_factors() for e in elems], dtype=np.float64)
+    if kind != "elasticity3d":   # tetrahedra have no element_to_node_factors in the reference
+        out["factors"] = np.array([e.element_to_node_factors() for e in elems], dtype=np.float64)
     kaug = an.create_matrix()
     out.update(csr_parts(kaug, "kaug"))
     out["f"] = an.create_source_matrix()
@@ -97,7 +99,7 @@ def run(ns, spec, modal_k=0):
         out["strain"] = np.array([er.strain[e] for e in elems], dtype=np.float64)
         out["stress"] = np.array([er.stress[e] for e in elems], dtype=np.float64)
         out["energy"] = np.array([er.energy_per_element[e] for e in elems], dtype=np.float64)
-    else:
+    elif kind == "magnetic":
         mr = ns.results.MagneticResults(mesh, list(out["x"]))
         out["bfield"] = np.array([[mr.magnetic_field_per_element[e][0], mr.magnetic_field_per_element[e][1]]
                                   for e in elems], dtype=np.float64)
@@ -106,6 +108,11 @@ def run(ns, spec, modal_k=0):
                               dtype=np.int64)
     out["bc_vals"] = np.array([b.value for b in bcs], dtype=np.float64)
     out.update(csr_parts(an.k_matrix_sparse(), "k"))
+    if kind == "elasticity3d":
+        out.update(csr_parts(an.m_matrix_sparse(), "m"))
+        if modal_k:
+            vals, vecs = an.modal_analysis('largest', modal_k)
+            out["eig_largest"] = np.sort(np.real(vals))
     if kind == "elasticity":
         out.update(csr_parts(an.m_matrix_sparse(), "m"))
         if modal_k:
@@ -121,7 +128,7 @@ def spec_arrays(spec):
     mat_id = np.zeros(e_count, dtype=np.int32)
     for g in range(len(bounds) - 1):
         mat_id[bounds[g]:bounds[g + 1]] = g
-    if spec["kind"] == "elasticity":  # reference ctor order (E, nu, rho, t) -> flat (E, nu, t, rho)
+    if spec["kind"] in ("elasticity", "elasticity3d"):  # reference ctor order (E, nu, rho, t) -> flat (E, nu, t, rho)
         mat = np.array([[p[0], p[1], p[3], p[2]] for p in spec["group_params"]], dtype=np.float64)
     else:
         mat = np.array([[p[0], 0, 0, 0] for p in spec["group_params"]], dtype=np.float64)
@@ -226,10 +233,44 @@ def fixtures():
                    node_bcs=[(j * (nx + 1) + nx, 0, 1) for j in range(ny + 1)]), 0
 
 
+def fixtures_3d():
+    """P1 tetrahedra (ElasticityTetrahedralElement3D, elements.py:663-876)."""
+    from oracle.numpy_oracle import structured_tet_mesh
+    steel, alu = (210e9, 0.25, 7860, 1), (70e9, 0.33, 2700, 1)
+
+    def clamp_and_load(coords, xmax, zmax):
+        left = [n for n in range(len(coords)) if coords[n, 0] == 0]
+        tip = [n for n in range(len(coords)) if coords[n, 0] == xmax and coords[n, 2] == zmax]
+        return ([(n, -1000.0, 3) for n in tip] + [(tip[0], 250.0, 1)],
+                [(n, 0, d) for n in left for d in (1, 2, 3)])
+
+    coords, conn = structured_tet_mesh(2, 2, 2, h=1.0, jitter=0.2, seed=3)
+    loads, bcs = clamp_and_load(coords, 2.0, 2.0)
+    yield dict(name="tet_cube2_jit", kind="elasticity3d", plane="stress", source="synthetic (Kuhn cube, 2 materials)",
+               coords=coords, conn=conn, group_bounds=[0, 24, len(conn)], group_params=[steel, alu],
+               node_loads=loads, node_bcs=bcs + [(26, 1e-4, 2)]), 6
+    coords, conn = structured_tet_mesh(6, 2, 2, h=0.5, jitter=0.15, seed=4)
+    loads, bcs = clamp_and_load(coords, 3.0, 1.0)
+    yield dict(name="tet_beam6x2x2_jit", kind="elasticity3d", plane="stress", source="synthetic (Kuhn beam)",
+               coords=coords, conn=conn, group_bounds=[0, len(conn)], group_params=[steel],
+               node_loads=loads, node_bcs=bcs), 8
+    # scripts/Elasticity/beam3d_example_2.py:52-98 on the two small gmsh beams (10 x 2 x 2)
+    for lc in ("0.5", "1"):
+        path = os.path.join(ref_loader.REFERENCE_ROOT, "scripts", "InputFiles", "3D", f"beam3d_{lc}.msh")
+        c, t = read_msh41_triangles(path, etype_wanted=4)
+        loads = [(n, -1000.0, 3) for n in range(len(c)) if c[n, 0] == 10 and c[n, 2] == 2]
+        bcs = [(n, 0, d) for n in range(len(c)) if c[n, 0] == 0 for d in (1, 2, 3)]
+        yield dict(name=f"gmsh_beam3d_{lc}", kind="elasticity3d", plane="stress",
+                   source=f"scripts/Elasticity/beam3d_example_2.py:52-98 on InputFiles/3D/beam3d_{lc}.msh",
+                   coords=c, conn=t, group_bounds=[0, len(t)], group_params=[(30e6, 0.25, 2.7, 1)],
+                   node_loads=loads, node_bcs=bcs), 0
+
+
 def main():
     ns = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
-    for spec, modal_k in fixtures():
+    only3d = "--3d" in sys.argv   # (re)mint only the tetrahedral fixtures
+    for spec, modal_k in (list(fixtures_3d()) if only3d else list(fixtures()) + list(fixtures_3d())):
         out = run(ns, spec, modal_k)
         arrays = spec_arrays(spec)
         arrays.update({"ref_" + k: v for k, v in out.items()})

@@ -30,6 +30,8 @@ KIND_ELAST_PSTRESS = 0
 KIND_ELAST_PSTRAIN = 1
 KIND_MAGNETIC = 2
 KIND_MASS = 3
+KIND_ELAST_TET = 4   # ElasticityTetrahedralElement3D.elementary_matrix (3 DOF per node, conn (E,4))
+KIND_MASS_TET = 5    # ElasticityTetrahedralElement3D.elementary_mass_matrix
 
 
 def _xy(coords, conn):
@@ -127,6 +129,69 @@ def me_mass(coords, conn, mat_id, mat):
     return ((m[:, 3] * area * m[:, 2]) / 12)[:, None, None] * _MASS_PATTERN[None]
 
 
+# ---------------------------------------------------------------- §8f rank 4: P1 tetrahedra
+def tet_geometry(coords, conn):
+    """volmdlr TetrahedralElement restated (third-party, absent from /root/reference): with
+    A = rows [1, x_j, y_j, z_j], volume = |det A| / 6 and the form functions as the reference uses
+    them (elements.py:726-739, :749): tuples (alpha_i, a_i, b_i, c_i) with
+    N_i = (alpha_i + a_i x + b_i y + c_i z) / (6 V), i.e. det(A) * column i of A^-1.
+    Returns (volume (E,), form (E,4,4) with form[:, i] = (alpha_i, a_i, b_i, c_i))."""
+    p = np.asarray(coords, dtype=np.float64)[np.asarray(conn)]          # (E,4,3)
+    a = np.concatenate([np.ones(p.shape[:2] + (1,)), p], axis=2)       # (E,4,4)
+    det = np.linalg.det(a)
+    inv = np.linalg.inv(a)                                              # column i = coefficients of N_i
+    form = (inv * np.abs(det)[:, None, None]).transpose(0, 2, 1)       # 6 V * coefficients
+    return np.abs(det) / 6.0, form
+
+
+def b_matrix_tet(coords, conn):
+    """elements.py:719-751: B (E,6,12) = 1/(6 V) * [[a_i,0,0],[0,b_i,0],[0,0,c_i],[b_i,a_i,0],
+    [0,c_i,b_i],[c_i,0,a_i]] per node i."""
+    vol, form = tet_geometry(coords, conn)
+    a, b, c = form[:, :, 1], form[:, :, 2], form[:, :, 3]              # (E,4)
+    data = np.zeros((len(vol), 6, 12))
+    data[:, 0, 0::3] = a
+    data[:, 1, 1::3] = b
+    data[:, 2, 2::3] = c
+    data[:, 3, 0::3] = b
+    data[:, 3, 1::3] = a
+    data[:, 4, 1::3] = c
+    data[:, 4, 2::3] = b
+    data[:, 5, 0::3] = c
+    data[:, 5, 2::3] = a
+    return (1.0 / (6.0 * vol))[:, None, None] * data, vol               # :749
+
+
+def d_matrix_tet(e_mod, nu):
+    """elements.py:773-797 (the plane flags are ignored in 3D, :753-771)."""
+    e_mod = np.asarray(e_mod, dtype=np.float64)
+    nu = np.asarray(nu, dtype=np.float64)
+    d = np.zeros(e_mod.shape + (6, 6))
+    for i in range(3):
+        for j in range(3):
+            d[..., i, j] = np.where(i == j, 1 - nu, nu)
+        d[..., 3 + i, 3 + i] = (1 - 2 * nu) / 2
+    return (e_mod / ((1 + nu) * (1 - 2 * nu)))[..., None, None] * d     # :794-795
+
+
+def ke_tet(coords, conn, mat_id, mat):
+    """elements.py:809-828: volume * (B^T D B), row-major 12x12, DOF order [u0,v0,w0,u1,...]."""
+    bm, vol = b_matrix_tet(coords, conn)
+    m = np.asarray(mat, dtype=np.float64)[np.asarray(mat_id)]
+    d = d_matrix_tet(m[:, 0], m[:, 1])
+    return vol[:, None, None] * np.matmul(np.matmul(bm.transpose(0, 2, 1), d), bm)
+
+
+_MASS_PATTERN_TET = np.kron(np.ones((4, 4)) + np.eye(4), np.eye(3))
+
+
+def me_tet(coords, conn, mat_id, mat):
+    """elements.py:830-857: (rho * volume / 20) * ((1 + delta_ij) (x) I3)."""
+    vol, _ = tet_geometry(coords, conn)
+    m = np.asarray(mat, dtype=np.float64)[np.asarray(mat_id)]
+    return ((m[:, 3] * vol) / 20)[:, None, None] * _MASS_PATTERN_TET[None]
+
+
 # ---------------------------------------------------------------- a-6
 def element_to_node_factors(coords, conn):
     """elements.py:18-53 / :156-191: |det| * N_i(midpoint of points[1], points[2]).
@@ -142,13 +207,13 @@ def element_to_node_factors(coords, conn):
 def element_dofs(conn, dim):
     """analysis.py:714-735 with core.py:89-108: dofs[p*dim+d] = node_p*dim + d."""
     conn = np.asarray(conn, dtype=np.int64)
-    return (conn[:, :, None] * dim + np.arange(dim)[None, None, :]).reshape(len(conn), 3 * dim)
+    return (conn[:, :, None] * dim + np.arange(dim)[None, None, :]).reshape(len(conn), conn.shape[1] * dim)
 
 
 def triplet_indices(conn, dim):
     """analysis.py:722-733: row = repeat(dofs, 3*dim), col = tile(dofs, 3*dim)."""
     dofs = element_dofs(conn, dim)
-    nd = 3 * dim
+    nd = dofs.shape[1]          # 3 dim for triangles, 4 dim for tetrahedra
     rows = np.repeat(dofs, nd, axis=1)
     cols = np.tile(dofs, (1, nd))
     return rows, cols
@@ -163,10 +228,16 @@ def element_matrices(kind, coords, conn, mat_id, mat):
         return ke_magnetic(coords, conn, mat_id, mat)
     if kind == KIND_MASS:
         return me_mass(coords, conn, mat_id, mat)
+    if kind == KIND_ELAST_TET:
+        return ke_tet(coords, conn, mat_id, mat)
+    if kind == KIND_MASS_TET:
+        return me_tet(coords, conn, mat_id, mat)
     raise NotImplementedError(kind)
 
 
 def kind_dim(kind):
+    if kind in (KIND_ELAST_TET, KIND_MASS_TET):
+        return 3
     return 1 if kind == KIND_MAGNETIC else 2
 
 
@@ -378,4 +449,28 @@ def structured_mesh(nx, ny, h=None, jitter=0.0, seed=0):
     conn = np.empty((2 * nx * ny, 3), dtype=np.int32)
     conn[0::2] = np.stack([n00, n10, n01], axis=1)
     conn[1::2] = np.stack([n11, n10, n01], axis=1)
+    return coords, conn
+
+
+def structured_tet_mesh(nx, ny, nz, h=1.0, jitter=0.0, seed=0):
+    """Box [0, nx h] x [0, ny h] x [0, nz h]: nodes id = (k (ny+1) + j) (nx+1) + i, every cell cut
+    into 6 tetrahedra around the main diagonal (Kuhn triangulation; conforming across cells).
+    Interior nodes optionally displaced by U(-jitter h, jitter h)^3."""
+    ii, jj, kk = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    nid = (kk * (ny + 1) + jj) * (nx + 1) + ii
+    coords = np.zeros(((nx + 1) * (ny + 1) * (nz + 1), 3))
+    coords[nid.reshape(-1)] = np.stack([ii, jj, kk], axis=-1).reshape(-1, 3) * h
+    if jitter:
+        rng = np.random.default_rng(seed)
+        d = rng.uniform(-jitter * h, jitter * h, size=coords.shape)
+        interior = ((ii > 0) & (ii < nx) & (jj > 0) & (jj < ny) & (kk > 0) & (kk < nz))
+        idx = nid[interior]
+        coords[idx] += d[idx]
+    c = nid[:-1, :-1, :-1].reshape(-1)
+    dx, dy, dz = 1, nx + 1, (nx + 1) * (ny + 1)
+    paths = [(dx, dy, dz), (dx, dz, dy), (dy, dx, dz), (dy, dz, dx), (dz, dx, dy), (dz, dy, dx)]
+    tets = []
+    for a, b, d3 in paths:
+        tets.append(np.stack([c, c + a, c + a + b, c + a + b + d3], axis=1))
+    conn = np.stack(tets, axis=1).reshape(-1, 4).astype(np.int32)
     return coords, conn

@@ -164,9 +164,78 @@ class TriangularElement2D(TriangularElement):
         return self is o
 
 
+class Vector3D:
+    def __init__(self, x, y, z, name=''):
+        self.x, self.y, self.z = x, y, z
+        self.name = name
+
+    def __getitem__(self, i):
+        return (self.x, self.y, self.z)[i]
+
+    def __iter__(self):
+        return iter((self.x, self.y, self.z))
+
+    def __len__(self):
+        return 3
+
+    def __add__(self, o):
+        return self.__class__(self.x + o[0], self.y + o[1], self.z + o[2])
+
+    def __sub__(self, o):
+        return self.__class__(self.x - o[0], self.y - o[1], self.z - o[2])
+
+    def __mul__(self, s):
+        return self.__class__(self.x * s, self.y * s, self.z * s)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, s):
+        return self.__class__(self.x / s, self.y / s, self.z / s)
+
+    def _key(self):
+        return (int(round(self.x * 1e6)), int(round(self.y * 1e6)), int(round(self.z * 1e6)))
+
+    def __eq__(self, o):
+        return isinstance(o, Vector3D) and self._key() == o._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.x}, {self.y}, {self.z})"
+
+
+class Point3D(Vector3D):
+    pass
+
+
+class Node3D(Point3D):
+    pass
+
+
 class TetrahedralElement:
+    """volmdlr.mesh.TetrahedralElement RESTATED (third-party, not vendored).  The reference
+    consumes `.points`, `.volume` and `.form_functions` (elements.py:726-749, :823, :854): with
+    A = rows [1, x_j, y_j, z_j], volume = |det A| / 6 and form_functions[i] = (alpha_i, a_i, b_i, c_i)
+    such that N_i = (alpha_i + a_i x + b_i y + c_i z) / (6 volume) -- the only reading under which
+    the reference's B = 1/(6 V) [a_i ...] (:749) is the strain-displacement matrix of a linear
+    tetrahedron.  Ke = V B^T D B does not depend on the sign convention of the cofactors."""
+
     def __init__(self, points, name=''):
         self.points = points
+        self.name = name
+        a = np.array([[1.0, p[0], p[1], p[2]] for p in points])
+        det = np.linalg.det(a)
+        self.volume = abs(det) / 6.0
+        inv = np.linalg.inv(a)
+        self.form_functions = tuple(tuple(abs(det) * inv[:, i]) for i in range(4))
+        self.center = (points[0] + points[1] + points[2] + points[3]) / 4
+
+    def __hash__(self):
+        return id(self)
+
+    def __eq__(self, o):
+        return self is o
 
 
 class ElementsGroup:
@@ -223,8 +292,8 @@ def load():
         return _loaded["ns"]
     if not available():
         raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
-    vm = _module("volmdlr", Point2D=Point2D, Vector2D=Vector2D)
-    vmmesh = _module("volmdlr.mesh", Node2D=Node2D, TriangularElement=TriangularElement,
+    vm = _module("volmdlr", Point2D=Point2D, Vector2D=Vector2D, Point3D=Point3D, Vector3D=Vector3D)
+    vmmesh = _module("volmdlr.mesh", Node2D=Node2D, Node3D=Node3D, TriangularElement=TriangularElement,
                      TriangularElement2D=TriangularElement2D,
                      TetrahedralElement=TetrahedralElement,
                      ElementsGroup=ElementsGroup, Mesh=Mesh, LinearElement=LinearElement)
@@ -265,11 +334,19 @@ def build_reference_analysis(ns, coords, conn, groups, kind, node_loads=(), node
     edge_loads / edge_bcs: (node_index_start, node_index_end, value, dimension).
     element_bcs: (element_index, value, dimension).
     mesh.nodes is forced to the given numbering (as beam2d_example_3.py:72-73 does)."""
-    nodes = [ns.vmmesh.Node2D(float(x), float(y)) for x, y in coords]
+    if kind == "elasticity3d":
+        nodes = [ns.vmmesh.Node3D(float(x), float(y), float(z)) for x, y, z in coords]
+    else:
+        nodes = [ns.vmmesh.Node2D(float(x), float(y)) for x, y in coords]
     all_elems, egroups = [], []
     for g in groups:
         elems = []
         for e in range(g["start"], g["stop"]):
+            if kind == "elasticity3d":
+                tet = ns.vmmesh.TetrahedralElement([nodes[i] for i in conn[e]])
+                em, nu, rho, _t = g["params"]
+                elems.append(ns.elements.ElasticityTetrahedralElement3D(tet, em, nu, rho))
+                continue
             tri = ns.vmmesh.TriangularElement2D([nodes[i] for i in conn[e]])
             if kind == "elasticity":
                 em, nu, rho, t = g["params"]

@@ -9,8 +9,22 @@ import scipy.sparse as sp
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def names():
+def _all_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def _kind_of(name):
+    return json.loads(str(np.load(os.path.join(GOLDEN, name + ".npz"))["meta"]))["kind"]
+
+
+def names():
+    """The 2D fixtures (triangles: elasticity and magnetics)."""
+    return [n for n in _all_names() if _kind_of(n) != "elasticity3d"]
+
+
+def names3d():
+    """The tetrahedral fixtures."""
+    return [n for n in _all_names() if _kind_of(n) == "elasticity3d"]
 
 
 class Fixture:
@@ -21,7 +35,7 @@ class Fixture:
         self.meta = json.loads(str(z["meta"]))
         self.kind = self.meta["kind"]
         self.plane = self.meta["plane"]
-        self.dim = 2 if self.kind == "elasticity" else 1
+        self.dim = {"elasticity": 2, "elasticity3d": 3}.get(self.kind, 1)
         self.coords, self.conn = z["coords"], z["conn"]
         self.mat_id, self.mat = z["mat_id"], z["mat"]
         self.records = self.meta["records"]
@@ -46,6 +60,8 @@ class Fixture:
         from oracle import numpy_oracle as no
         if self.kind == "magnetic":
             return no.KIND_MAGNETIC
+        if self.kind == "elasticity3d":
+            return no.KIND_ELAST_TET
         return no.KIND_ELAST_PSTRAIN if self.plane == "strain" else no.KIND_ELAST_PSTRESS
 
 
@@ -77,14 +93,21 @@ def build_object_analysis(fx, with_element_records=False, **kw):
     element, load and condition records on those objects (finite_elements_b200 classes)."""
     import finite_elements_b200 as fe
     m = fe.mesh
-    nodes = [m.Node2D(float(x), float(y)) for x, y in fx.coords]
+    if fx.kind == "elasticity3d":
+        nodes = [m.Node3D(float(x), float(y), float(z)) for x, y, z in fx.coords]
+    else:
+        nodes = [m.Node2D(float(x), float(y)) for x, y in fx.coords]
     groups, elems = [], []
     bounds = fx.meta["group_bounds"]
     for g in range(len(bounds) - 1):
         ge = []
         for e in range(bounds[g], bounds[g + 1]):
-            tri = m.TriangularElement2D([nodes[i] for i in fx.conn[e]])
             p = fx.mat[g]
+            if fx.kind == "elasticity3d":
+                tet = m.TetrahedralElement([nodes[i] for i in fx.conn[e]])
+                ge.append(fe.elements.ElasticityTetrahedralElement3D(tet, p[0], p[1], p[3]))
+                continue
+            tri = m.TriangularElement2D([nodes[i] for i in fx.conn[e]])
             if fx.kind == "elasticity":
                 ge.append(fe.elements.ElasticityTriangularElement2D(tri, p[0], p[1], p[3], p[2]))
             else:

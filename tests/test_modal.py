@@ -13,9 +13,9 @@ import pytest
 import torch
 
 from oracle import numpy_oracle as no
-from tests.fixtures import Fixture, names, build_object_analysis
+from tests.fixtures import Fixture, names, names3d, build_object_analysis
 
-MODAL = [n for n in names() if "ref_eig_largest" in Fixture(n).z.files]
+MODAL = [n for n in names() + names3d() if "ref_eig_largest" in Fixture(n).z.files]
 LOBPCG_SIZED = [n for n in MODAL if Fixture(n).ndof >= 300]
 
 
