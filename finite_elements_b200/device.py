@@ -397,7 +397,8 @@ class DeviceMesh3D(DeviceMesh):
         with torch.cuda.device(self.ctx.device):
             check(lib.fe_tet_assemble(self.ctx.handle, _stream(), int(kind), self.n_nodes, _ptr(self.corner_ptr),
                                       _ptr(self.corner_elem), _ptr(self.adj_ptr), _ptr(self.adj), _ptr(self.coords),
-                                      _ptr(self.conn), _ptr(self.mat_id), _ptr(m), int(m.shape[0]), _ptr(out)))
+                                      _ptr(self.conn), _ptr(self.mat_id), _ptr(m), int(m.shape[0]), _ptr(out),
+                                      self.max_degree, int(variant)))
         return out
 
     def element_matrices(self, kind, mat):

@@ -163,11 +163,14 @@ int fe_tet_elem_matrices(fe_ctx *ctx, void *stream, int kind, int64_t n_elems, c
  * ascending order, adj[adj_ptr[i] .. adj_ptr[i+1]) = sorted neighbour nodes of i (itself included).
  * vals: node i's rows 3i, 3i+1, 3i+2 back to back from 9 adj_ptr[i], each 3 deg_i long, block of
  * neighbour slot k at columns 3k..3k+2 -- the scipy-canonical CSR of the same triplets.  One thread
- * owns a node's rows and adds its elements in ascending order: deterministic, no atomics. */
+ * owns a node's rows and adds its elements in ascending order: deterministic, no atomics.
+ * max_degree = largest neighbour count (sizes the shared-memory tile); variant 0 = automatic,
+ * 1 = accumulate in global memory, 2 = shared-memory tile + coalesced write-out (bit-identical). */
 int fe_tet_assemble(fe_ctx *ctx, void *stream, int kind, int32_t n_owned_nodes,
                     const int32_t *corner_ptr, const int32_t *corner_elem, const int32_t *adj_ptr,
                     const int32_t *adj, const double *coords, const int32_t *conn,
-                    const int32_t *mat_id, const double *mat, int32_t n_mat, double *vals);
+                    const int32_t *mat_id, const double *mat, int32_t n_mat, double *vals,
+                    int32_t max_degree, int32_t variant);
 
 /* ---- modal analysis building blocks (analysis.py:741-796) -------------------------------
  * The reference gives K and M to scipy.sparse.linalg.eigsh (:779-782), whose Lanczos loop

@@ -113,6 +113,8 @@ def test_gpu_tet_element_and_global_matrices_vs_reference(name):
     assert_csr_values_close(k, fx.csr("k"), 1e-12)            # pattern bit-exact, values 1e-12
     assert_csr_values_close(dm.to_scipy(dm.assemble(KIND_MASS_TET, fx.mat)), fx.csr("m"), 1e-12)
     assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, fx.mat))   # deterministic
+    assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, fx.mat, variant=1))   # tile == global accumulation, bitwise
+    assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, fx.mat, variant=2))
     # the assembled matrix is the ordered sum of the dumped element matrices
     dofs = no.element_dofs(fx.conn, 3)
     import scipy.sparse as sp
@@ -165,6 +167,7 @@ def test_gpu_tet_mid_size_properties():
     mid = (np.arange(len(conn)) % 2).astype(np.int32)
     dm = DeviceMesh3D(coords, conn, mid)
     kv = dm.assemble(KIND_ELAST_TET, MAT2)
+    assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, MAT2, variant=1))
     k = dm.to_scipy(kv)
     assert_csr_values_close(k, no.assemble_k(no.KIND_ELAST_TET, coords, conn, mid, MAT2), 1e-12)
     mv = dm.assemble(KIND_MASS_TET, MAT2)
