@@ -45,6 +45,7 @@ SIGNATURES = {
     "fe_scatter_add": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp]),
     "fe_spmv": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32]),
     "fe_tet_elem_matrices": (C.c_int, [_vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fe_tet_elem_post": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "fe_tet_assemble": (C.c_int, [_vp, _vp, C.c_int, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32,
                                   _i32]),
     "fe_spmm_pair": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),

@@ -107,6 +107,54 @@ __global__ void __launch_bounds__(128) k_tet_elem_matrices(int kind, int64_t n_e
     }
 }
 
+// Element post-processing of a solution u (results.py:809-830, :769-781 for 3 DOF per node):
+// out[e] = (eps_xx, eps_yy, eps_zz, gamma_xy, gamma_yz, gamma_zx,  sig_xx, sig_yy, sig_zz, tau_xy,
+// tau_yz, tau_zx,  energy) with strain = B u_e, stress = D B u_e, energy = 1/2 u_e^T Ke u_e
+// = V/2 strain . stress  (Ke = V B^T D B).
+__global__ void __launch_bounds__(128) k_tet_post(int64_t n_elems, const double *__restrict__ coords,
+                                                 const int32_t *__restrict__ conn, const int32_t *__restrict__ mat_id,
+                                                 const double *__restrict__ mat, const double *__restrict__ u,
+                                                 double *__restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elems) return;
+  const int4 c = *reinterpret_cast<const int4 *>(conn + 4 * e);
+  const int nodes[4] = {c.x, c.y, c.z, c.w};
+  const TetGeom t = tet_geom(coords, c.x, c.y, c.z, c.w);
+  double eps[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double ux = u[3 * (int64_t)nodes[i]], uy = u[3 * (int64_t)nodes[i] + 1], uz = u[3 * (int64_t)nodes[i] + 2];
+    const double a = t.g[i][0], b = t.g[i][1], cz = t.g[i][2];
+    eps[0] += a * ux;            // elements.py:741-746: the six rows of B
+    eps[1] += b * uy;
+    eps[2] += cz * uz;
+    eps[3] += b * ux + a * uy;
+    eps[4] += cz * uy + b * uz;
+    eps[5] += cz * ux + a * uz;
+  }
+  const int mid = mat_id ? mat_id[e] : 0;
+  const double e_mod = mat[4 * mid + 0], nu = mat[4 * mid + 1];
+  const double coeff = e_mod / ((1 + nu) * (1 - 2 * nu));
+  const double da = coeff * (1 - nu), db = coeff * nu, ds = coeff * ((1 - 2 * nu) / 2);
+  double sig[6];
+  sig[0] = da * eps[0] + db * eps[1] + db * eps[2];
+  sig[1] = db * eps[0] + da * eps[1] + db * eps[2];
+  sig[2] = db * eps[0] + db * eps[1] + da * eps[2];
+  sig[3] = ds * eps[3];
+  sig[4] = ds * eps[4];
+  sig[5] = ds * eps[5];
+  double w = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) w += eps[k] * sig[k];
+  double *o = out + 13 * e;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    o[k] = eps[k];
+    o[6 + k] = sig[k];
+  }
+  o[12] = 0.5 * t.vol * w;
+}
+
 // One thread per owned node.  corner_elem[corner_ptr[i] .. corner_ptr[i+1]) = the elements incident
 // to node i in ascending order; adj[adj_ptr[i] .. adj_ptr[i+1]) = its sorted neighbour nodes (incl.
 // itself).  vals holds the node's three rows back to back: row r at 9 adj_ptr[i] + r * 3 deg, the
@@ -223,6 +271,17 @@ int fe_tet_elem_matrices(fe_ctx *ctx, void *stream, int kind, int64_t n_elems, c
   if (n_elems == 0) return FE_OK;
   k_tet_elem_matrices<<<grid_for(n_elems, 128), 128, 0, as_stream(stream)>>>(kind, n_elems, coords, conn, mat_id, mat,
                                                                            out);
+  FE_LAUNCH_CHECK(ctx);
+  return FE_OK;
+}
+
+int fe_tet_elem_post(fe_ctx *ctx, void *stream, int64_t n_elems, const double *coords, const int32_t *conn,
+                     const int32_t *mat_id, const double *mat, int32_t n_mat, const double *u, double *out) {
+  FE_REQUIRE(ctx && coords && conn && mat && u && out, "fe_tet_elem_post: NULL argument");
+  FE_REQUIRE(n_elems >= 0 && n_mat > 0, "fe_tet_elem_post: bad sizes");
+  FE_REQUIRE(((uintptr_t)conn & 15) == 0, "fe_tet_elem_post: conn must be 16-byte aligned");
+  if (n_elems == 0) return FE_OK;
+  k_tet_post<<<grid_for(n_elems, 128), 128, 0, as_stream(stream)>>>(n_elems, coords, conn, mat_id, mat, u, out);
   FE_LAUNCH_CHECK(ctx);
   return FE_OK;
 }

@@ -411,7 +411,17 @@ class DeviceMesh3D(DeviceMesh):
         return out
 
     def element_post(self, kind, mat, u):
-        raise NotImplementedError("element post-processing is implemented for triangles only")
+        """f64[E,13] = (6 strains, 6 stresses, energy) of the solution u.  fe_tet_elem_post."""
+        m = self._mat(mat)
+        u = (torch.as_tensor(np.ascontiguousarray(u, dtype=np.float64)) if not torch.is_tensor(u) else u)
+        u = u.to(self.ctx.device, torch.float64).contiguous()
+        if u.numel() < self.n_nodes * 3:
+            raise ValueError("solution vector is shorter than n_nodes * dim")
+        out = torch.empty((self.n_elems, 13), dtype=torch.float64, device=self.ctx.device)
+        with torch.cuda.device(self.ctx.device):
+            check(lib.fe_tet_elem_post(self.ctx.handle, _stream(), self.n_elems, _ptr(self.coords), _ptr(self.conn),
+                                       _ptr(self.mat_id), _ptr(m), int(m.shape[0]), _ptr(u), _ptr(out)))
+        return out
 
     def source_factors(self, elem_sel=None):
         raise NotImplementedError("the reference defines no element_to_node_factors for tetrahedra")

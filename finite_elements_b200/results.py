@@ -10,7 +10,7 @@ Plotting / VTK output of the reference are out of scope.
 import numpy as np
 
 from .core import DessiaObject
-from .mesh import Vector2D, flatten_mesh
+from .mesh import Vector2D, Vector3D, flatten_mesh
 
 
 class Result(DessiaObject):
@@ -48,9 +48,12 @@ class _DevicePost(Result):
 
     def _post_array(self):
         if self._post is None:
-            from .device import DeviceMesh
+            from .device import DeviceMesh, DeviceMesh3D
             flat = self._flatten()
-            dm = DeviceMesh(flat['coords'], flat['conn'], flat['mat_id'], dim=self.dimension, device=self._device)
+            if self.dimension == 3:
+                dm = DeviceMesh3D(flat['coords'], flat['conn'], flat['mat_id'], device=self._device)
+            else:
+                dm = DeviceMesh(flat['coords'], flat['conn'], flat['mat_id'], dim=self.dimension, device=self._device)
             ndof = len(flat['coords']) * self.dimension
             u = np.real(np.asarray(self.result_vector[:ndof], dtype=np.complex128)).astype(np.float64)
             self._post = dm.element_post(self._kind(), flat['mat'], u).cpu().numpy()
@@ -79,7 +82,14 @@ class ElasticityResults(_DevicePost):
         from . import _lib
         from .elements import check_plane_flags
         check_plane_flags(self.plane_strain, self.plane_stress)
+        if self.dimension == 3:
+            return _lib.KIND_ELAST_TET
         return _lib.KIND_ELAST_PSTRAIN if self.plane_strain else _lib.KIND_ELAST_PSTRESS
+
+    @property
+    def _ncomp(self):
+        """Voigt components per element: 3 in the plane, 6 for tetrahedra."""
+        return 6 if self.dimension == 3 else 3
 
     # ---- flat accessors ------------------------------------------------------------------
     @property
@@ -89,17 +99,17 @@ class ElasticityResults(_DevicePost):
 
     @property
     def strain_array(self):
-        """f64[E,3] = (eps_xx, eps_yy, gamma_xy)."""
-        return self._post_array()[:, 0:3]
+        """f64[E,3] = (eps_xx, eps_yy, gamma_xy); tetrahedra: f64[E,6] = (xx, yy, zz, xy, yz, zx)."""
+        return self._post_array()[:, 0:self._ncomp]
 
     @property
     def stress_array(self):
-        """f64[E,3] = (sig_xx, sig_yy, tau_xy)."""
-        return self._post_array()[:, 3:6]
+        """f64[E,3] = (sig_xx, sig_yy, tau_xy); tetrahedra: the six components in the strain order."""
+        return self._post_array()[:, self._ncomp:2 * self._ncomp]
 
     @property
     def energy_array(self):
-        return self._post_array()[:, 6]
+        return self._post_array()[:, 2 * self._ncomp]
 
     # ---- the reference's dictionary-shaped accessors -------------------------------------
     @property
@@ -107,7 +117,8 @@ class ElasticityResults(_DevicePost):
         """{node: Vector2D(u_x, u_y)} (results.py:639-674)."""
         if not self._displacement_vectors_per_node:
             d = self.displacement_array
-            self._displacement_vectors_per_node = {node: Vector2D(float(d[n, 0]), float(d[n, 1]))
+            vec = Vector3D if self.dimension == 3 else Vector2D
+            self._displacement_vectors_per_node = {node: vec(*(float(v) for v in d[n]))
                                                    for n, node in enumerate(self.mesh.nodes)}
         return self._displacement_vectors_per_node
 
@@ -179,6 +190,53 @@ class ElasticityResults2D(ElasticityResults):
 
     def shear_stress_xy(self):
         return [float(v) for v in self.stress_array[:, 2]]
+
+
+class ElasticityResults3D(ElasticityResults):
+    """Tetrahedra: component dictionaries {element: value} (results.py:1468-1720)."""
+
+    def _component(self, which, k):
+        data = self.strain if which == 'strain' else self.stress
+        return {element: float(data[element][k]) for element in self._elements()}
+
+    def axial_strain_x(self):
+        return self._component('strain', 0)
+
+    def axial_strain_y(self):
+        return self._component('strain', 1)
+
+    def axial_strain_z(self):
+        return self._component('strain', 2)
+
+    def shear_strain_xy(self):
+        return self._component('strain', 3)
+
+    def shear_strain_yz(self):
+        return self._component('strain', 4)
+
+    def shear_strain_zx(self):
+        return self._component('strain', 5)
+
+    def axial_stress_x(self):
+        return self._component('stress', 0)
+
+    def axial_stress_y(self):
+        return self._component('stress', 1)
+
+    def axial_stress_z(self):
+        return self._component('stress', 2)
+
+    def shear_stress_xy(self):
+        return self._component('stress', 3)
+
+    def shear_stress_yz(self):
+        return self._component('stress', 4)
+
+    def shear_stress_zx(self):
+        return self._component('stress', 5)
+
+    def displacement_per_node_z(self):
+        return [float(v) for v in self.displacement_array[:, 2]]
 
 
 class MagneticResults(_DevicePost):

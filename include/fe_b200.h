@@ -157,6 +157,11 @@ int fe_spmv(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
 int fe_tet_elem_matrices(fe_ctx *ctx, void *stream, int kind, int64_t n_elems, const double *coords,
                          const int32_t *conn, const int32_t *mat_id, const double *mat,
                          int32_t n_mat, double *out);
+/* Element post-processing of a solution u (results.py:809-830, :769-781): out double[E][13] =
+ * (eps_xx, eps_yy, eps_zz, gamma_xy, gamma_yz, gamma_zx, the six stresses in the same order, energy). */
+int fe_tet_elem_post(fe_ctx *ctx, void *stream, int64_t n_elems, const double *coords,
+                     const int32_t *conn, const int32_t *mat_id, const double *mat, int32_t n_mat,
+                     const double *u, double *out);
 /* Global matrix values of the tetrahedral mesh; replaces the k_matrix_data / m_matrix_data loops
  * (analysis.py:324-339, :357-365) + csr_matrix (:661) for 3 DOF per node.  The symbolic data comes
  * from the caller: corner_elem[corner_ptr[i] .. corner_ptr[i+1]) = elements incident to node i in

@@ -99,6 +99,12 @@ def run(ns, spec, modal_k=0):
         out["strain"] = np.array([er.strain[e] for e in elems], dtype=np.float64)
         out["stress"] = np.array([er.stress[e] for e in elems], dtype=np.float64)
         out["energy"] = np.array([er.energy_per_element[e] for e in elems], dtype=np.float64)
+    elif kind == "elasticity3d":
+        er = ns.results.ElasticityResults3D(mesh, list(out["x"]), plane_strain, plane_stress)
+        out["strain"] = np.array([er.strain[e] for e in elems], dtype=np.float64)
+        out["stress"] = np.array([er.stress[e] for e in elems], dtype=np.float64)
+        out["energy"] = np.array([er.energy_per_element[e] for e in elems], dtype=np.float64)
+        out["disp_node1"] = np.array(list(er.displacement_vectors_per_node[mesh.nodes[1]]), dtype=np.float64)
     elif kind == "magnetic":
         mr = ns.results.MagneticResults(mesh, list(out["x"]))
         out["bfield"] = np.array([[mr.magnetic_field_per_element[e][0], mr.magnetic_field_per_element[e][1]]

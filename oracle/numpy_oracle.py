@@ -192,6 +192,19 @@ def me_tet(coords, conn, mat_id, mat):
     return ((m[:, 3] * vol) / 20)[:, None, None] * _MASS_PATTERN_TET[None]
 
 
+def post_tet(coords, conn, mat_id, mat, u):
+    """results.py:809-830 / :769-781 for tetrahedra: strain = B u_e (E,6), stress = D B u_e (E,6),
+    energy = 1/2 u_e^T Ke u_e (E,)."""
+    bm, _ = b_matrix_tet(coords, conn)
+    m = np.asarray(mat, dtype=np.float64)[np.asarray(mat_id)]
+    d = d_matrix_tet(m[:, 0], m[:, 1])
+    ue = np.asarray(u, dtype=np.float64)[element_dofs(conn, 3)]
+    strain = np.einsum('eij,ej->ei', bm, ue)
+    stress = np.einsum('eij,ej->ei', d, strain)
+    ke = ke_tet(coords, conn, mat_id, mat)
+    return strain, stress, 0.5 * np.einsum('ei,eij,ej->e', ue, ke, ue)
+
+
 # ---------------------------------------------------------------- a-6
 def element_to_node_factors(coords, conn):
     """elements.py:18-53 / :156-191: |det| * N_i(midpoint of points[1], points[2]).

@@ -80,6 +80,18 @@ def test_symbolic_phase_and_kernel_emulation_vs_oracle(dims):
         assert np.abs(vals - ref.data).max() <= 1e-13 * np.abs(ref.data).max()
 
 
+@pytest.mark.parametrize("name", TETS)
+def test_oracle_post_processing_vs_reference(name):
+    fx = Fixture(name)
+    strain, stress, energy = no.post_tet(fx.coords, fx.conn, fx.mat_id, fx.mat, fx.ref("x")[:fx.ndof])
+    assert_close_rowscaled(strain, fx.ref("strain"), 1e-12)
+    assert_close_rowscaled(stress, fx.ref("stress"), 1e-12)
+    assert np.max(np.abs(energy - fx.ref("energy"))) <= 1e-11 * np.max(np.abs(fx.ref("energy")))
+    # the kernel's route to the energy: V/2 strain . stress
+    vol, _ = no.tet_geometry(fx.coords, fx.conn)
+    assert np.max(np.abs(0.5 * vol * np.sum(strain * stress, axis=1) - energy)) <= 1e-11 * np.max(np.abs(energy))
+
+
 def test_mesh_lookalikes_vs_oracle():
     import finite_elements_b200 as fe
     coords, conn = fe.mesh.structured_tet_mesh(2, 1, 1, h=0.7, jitter=0.0)
@@ -144,6 +156,28 @@ def test_gpu_tet_api_solution_vs_reference_spsolve(name):
     assert_close_rowscaled(np.asarray(elems[1].elementary_mass_matrix())[None], fx.ref("me")[1:2], 1e-13)
     with pytest.raises(ValueError):
         type(an)(mesh, [], [], [], [], [], [], [], [], plane_strain=True, plane_stress=True).create_matrix()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", TETS)
+def test_gpu_tet_results_vs_reference(name):
+    import finite_elements_b200 as fe
+    fx = Fixture(name)
+    an, mesh, elems = build_object_analysis(fx)
+    ref_x = fx.ref("x")
+    res = fe.results.ElasticityResults3D(mesh, list(ref_x), an.plane_strain, an.plane_stress)
+    assert res.strain_array.shape == (len(fx.conn), 6)
+    assert_close_rowscaled(res.strain_array, fx.ref("strain"), 1e-11)
+    assert_close_rowscaled(res.stress_array, fx.ref("stress"), 1e-11)
+    energy = fx.ref("energy")
+    assert np.max(np.abs(res.energy_array - energy)) <= 1e-10 * np.max(np.abs(energy))
+    assert abs(res.energy - energy.sum()) <= 1e-10 * abs(energy.sum())
+    d = res.displacement_vectors_per_node[mesh.nodes[1]]
+    assert (d.x, d.y, d.z) == tuple(fx.ref("disp_node1"))
+    assert res.displacements_per_element[elems[0]] == [ref_x[3 * n + k] for n in fx.conn[0] for k in (0, 1, 2)]
+    assert np.allclose(res.strain[elems[1]], fx.ref("strain")[1], rtol=1e-9, atol=1e-11 * abs(fx.ref("strain")).max())
+    assert res.shear_stress_zx()[elems[2]] == res.stress_array[2, 5]
+    assert res.axial_strain_z()[elems[2]] == res.strain_array[2, 2] and len(res.displacement_per_node_z()) == len(fx.coords)
 
 
 @pytest.mark.gpu
