@@ -41,6 +41,13 @@ def measured_peak_hbm():
         return 6650.0, "fallback"
 
 
+def _gpu_spin(torch, cycles=200_000):
+    """~0.1 ms of device-side spinning (torch.cuda._sleep); skipped if this torch build lacks it."""
+    spin = getattr(torch.cuda, "_sleep", None)
+    if spin is not None:
+        spin(cycles)
+
+
 def asm_bytes(n_el, n_nodes, nnz):
     return 12.0 * n_el + 16.0 * n_nodes + 8.0 * nnz          # SURVEY §8d
 
@@ -217,7 +224,7 @@ def run_gpu(args):
         # the previous step ended with a host synchronisation: keep the GPU busy for ~0.1 ms so the
         # launches below are queued before it gets to them (the events then bracket device time,
         # not the CPU's launch latency)
-        torch.cuda._sleep(200_000)
+        _gpu_spin(torch)
         a0.record()
         dm.assemble(KIND, MAT_DEV, out=vals, variant=args.variant)
         a1.record()

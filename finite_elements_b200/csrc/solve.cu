@@ -815,8 +815,10 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
   if (iters_out) *iters_out = h->iters;
   if (relres_out) *relres_out = (h->sums[3] > 0.0) ? sqrt(h->sums[2] / h->sums[3]) : 0.0;
   if (h->breakdown)
-    return fail(FE_ERR_BREAKDOWN, "pcg: breakdown after %d iterations (matrix not SPD or singular: p.Ap = %g)",
-                h->iters, h->sums[0]);
+    return fail(FE_ERR_BREAKDOWN, "pcg: breakdown after %d iterations (matrix not SPD or singular: p.Ap = %g%s)",
+                h->iters, h->sums[0],
+                (h->sums[0] != h->sums[0] && L.p2p) ? "; NaN on the peer-memory transport also means a rank did not "
+                                                      "deliver within the spin-wait limit" : "");
   if (!fixed && !h->converged && !stagnated)
     return fail(FE_ERR_NOT_CONVERGED, "pcg: not converged after %d iterations (relres %.3e > %.3e)", h->iters,
                 sqrt(h->sums[2] / h->sums[3]), rtol);

@@ -212,6 +212,12 @@ class DistributedMesh:
         return x, iters.value, relres.value
 
 
+def _gpu_spin(torch_mod, cycles=200_000):
+    spin = getattr(torch_mod.cuda, "_sleep", None)
+    if spin is not None:
+        spin(cycles)
+
+
 def structured_rank_problem(nx, ny, rank, world, dev, dim=2):
     """Rank-local piece of the SURVEY §8d structured mesh, built on the device without ever
     materialising the global connectivity: node lines [j0, j1) are owned, cell rows
@@ -267,7 +273,7 @@ def bench_distributed(args, metric, mat, measured_peak_hbm, ClockSampler, asm_by
         # the previous step ended with a host synchronisation: keep the GPU busy for ~0.1 ms so the
         # launches below are queued before it gets to them (the events then bracket device time,
         # not the CPU's launch latency)
-        torch.cuda._sleep(200_000)
+        _gpu_spin(torch)
         a0.record()
         dm.assemble(KIND_ELAST_PSTRESS, mat_dev, out=vals, variant=args.variant)
         a1.record()
