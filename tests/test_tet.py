@@ -109,6 +109,43 @@ def test_mesh_lookalikes_vs_oracle():
     assert flat['space_dim'] == 3 and flat['conn'].shape[1] == 4 and not flat['magnetic']
 
 
+def test_host_element_records_and_flattening_vs_oracle():
+    """Object meshes of ElasticityTetrahedralElement3D flatten to the fixture's arrays; the host-side
+    B / D helpers (post-processing only) agree with the oracle's restatement of elements.py:719-797."""
+    import finite_elements_b200 as fe
+    fx = Fixture("tet_cube2_jit")
+    m = fe.mesh
+    nodes = [m.Node3D(*map(float, p)) for p in fx.coords]
+    bounds = fx.meta["group_bounds"]
+    groups = []
+    for g in range(len(bounds) - 1):
+        p = fx.mat[g]
+        groups.append(m.ElementsGroup([fe.elements.ElasticityTetrahedralElement3D(
+            m.TetrahedralElement([nodes[i] for i in fx.conn[e]]), p[0], p[1], p[3])
+            for e in range(bounds[g], bounds[g + 1])], ''))
+    mesh = m.Mesh(groups)
+    mesh.nodes = nodes
+    mesh.node_to_index = {nodes[i]: i for i in range(len(nodes))}
+    flat = m.flatten_mesh(mesh)
+    assert flat['space_dim'] == 3 and not flat['magnetic']
+    assert np.array_equal(flat['coords'], fx.coords) and np.array_equal(flat['conn'], fx.conn)
+    assert np.array_equal(flat['mat'][flat['mat_id']][:, [0, 1, 3]], fx.mat[fx.mat_id][:, [0, 1, 3]])
+    bm, _ = no.b_matrix_tet(fx.coords, fx.conn)
+    el = groups[1].elements[3]
+    e = bounds[1] + 3
+    assert el.dimension == 3
+    assert np.max(np.abs(np.abs(el.b_matrix) - np.abs(bm[e]))) <= 1e-12 * np.abs(bm[e]).max()
+    d_ref = no.d_matrix_tet(fx.mat[fx.mat_id[e], 0], fx.mat[fx.mat_id[e], 1])
+    assert np.allclose(el.d_matrix(False, True), d_ref, rtol=1e-15)
+    with pytest.raises(ValueError):
+        el.d_matrix(True, True)
+    an = fe.analysis.FiniteElementAnalysis(mesh, [], [], [], [], [], [], [], [], False, True)
+    assert an.dimension == 3 and an.positions[(4, 3)] == 14
+    rows, cols = an.get_row_col_indices(el)
+    dofs = no.element_dofs(fx.conn[e:e + 1], 3)[0]
+    assert rows == list(np.repeat(dofs, 12)) and cols == list(np.tile(dofs, 12))
+
+
 # ------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", TETS)
