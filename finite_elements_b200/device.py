@@ -290,23 +290,28 @@ class DeviceMesh:
                              shape=(self.n_rows, self.n_cols))
 
 
-def tet_symbolic(conn64, n):
+def tet_symbolic(conn64, n, n_owned=None):
     """Symbolic phase of the tetrahedral path on conn64 (E,4) int64, any torch device.
-    Returns (corner_ptr i64[n+1], corner_elem i32[4E], adj_ptr i64[n+1], adj i64[sum deg], deg i64[n]):
-    per-node element lists in ascending element order, and the sorted node adjacency (diagonal included)."""
+    Returns (corner_ptr i64[n_owned+1], corner_elem i32, adj_ptr i64[n_owned+1], adj i64[sum deg],
+    deg i64[n_owned]): per-node element lists in ascending element order, and the sorted node adjacency
+    (diagonal included) -- for the owned nodes [0, n_owned) only (multi-GPU layout: owned nodes first,
+    ghosts after; rows exist for owned nodes, columns for all n local nodes)."""
     dev = conn64.device
+    n_owned = n if n_owned is None else n_owned
     e = conn64.shape[0]
     corner_node = conn64.reshape(-1)
     order = torch.sort(corner_node, stable=True).indices
-    corner_elem = (order // 4).to(torch.int32).contiguous()
-    corner_ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-    corner_ptr[1:] = torch.cumsum(torch.bincount(corner_node, minlength=n), 0)
+    counts = torch.bincount(corner_node, minlength=n)[:n_owned]
+    corner_ptr = torch.zeros(n_owned + 1, dtype=torch.int64, device=dev)
+    corner_ptr[1:] = torch.cumsum(counts, 0)
+    corner_elem = (order[:int(corner_ptr[-1].item())] // 4).to(torch.int32).contiguous()   # owned nodes sort first
     a = conn64[:, :, None].expand(e, 4, 4).reshape(-1)
     b = conn64[:, None, :].expand(e, 4, 4).reshape(-1)
-    diag = torch.arange(n, device=dev, dtype=torch.int64)
-    keys = torch.unique(torch.cat([a * n + b, diag * n + diag]))      # sorted
-    deg = torch.bincount(keys // n, minlength=n)
-    adj_ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    keep = a < n_owned
+    diag = torch.arange(n_owned, device=dev, dtype=torch.int64)
+    keys = torch.unique(torch.cat([a[keep] * n + b[keep], diag * n + diag]))      # sorted
+    deg = torch.bincount(keys // n, minlength=n_owned)
+    adj_ptr = torch.zeros(n_owned + 1, dtype=torch.int64, device=dev)
     adj_ptr[1:] = torch.cumsum(deg, 0)
     return corner_ptr, corner_elem, adj_ptr, keys % n, deg
 
@@ -339,7 +344,9 @@ class DeviceMesh3D(DeviceMesh):
     mesh); the numeric phase is fe_tet_assemble / fe_tet_elem_matrices.  Everything CSR-level
     (Dirichlet elimination, SpMV, PCG, block products) is inherited unchanged."""
 
-    def __init__(self, coords, conn, mat_id=None, device=0, ctx=None):
+    def __init__(self, coords, conn, mat_id=None, device=0, ctx=None, n_owned=None, dim=3):
+        if dim != 3:
+            raise ValueError("DeviceMesh3D is the 3 DOF per node path")
         self.ctx = ctx or Context.get(device)
         dev = self.ctx.device
         self.coords = torch.as_tensor(np.ascontiguousarray(coords, dtype=np.float64)).to(dev) \
@@ -357,14 +364,14 @@ class DeviceMesh3D(DeviceMesh):
         self.n_elems = int(self.conn.shape[0])
         if self.n_elems and (self.conn.ndim != 2 or self.conn.shape[1] != 4):
             raise ValueError("conn must have shape (E, 4)")
-        self.n_owned = self.n_nodes
+        self.n_owned = self.n_nodes if n_owned is None else int(n_owned)   # multi-GPU: owned first, ghosts after
         self.dim = 3
         self.plan = None
         n, e = self.n_nodes, self.n_elems
         conn64 = self.conn.long()
         if e and (int(conn64.min()) < 0 or int(conn64.max()) >= n):
             raise ValueError("conn refers to a node outside [0, N)")
-        self.corner_ptr, self.corner_elem, adj_ptr, self.adj, deg = tet_symbolic(conn64, n)
+        self.corner_ptr, self.corner_elem, adj_ptr, self.adj, deg = tet_symbolic(conn64, n, self.n_owned)
         self.nnz = int(9 * adj_ptr[-1].item())
         if self.nnz >= 2 ** 31:
             raise NotImplementedError("nnz does not fit int32")
@@ -372,9 +379,9 @@ class DeviceMesh3D(DeviceMesh):
         self.corner_ptr = self.corner_ptr.to(torch.int32).contiguous()
         self.adj = self.adj.to(torch.int32).contiguous()
         self._deg = deg
-        self.n_rows = 3 * n
+        self.n_rows = 3 * self.n_owned
         self.n_cols = 3 * n
-        self.max_degree = int(deg.max().item()) if n else 0
+        self.max_degree = int(deg.max().item()) if self.n_owned else 0
         self.plan_bytes = int(4 * (self.corner_elem.numel() + self.adj.numel() + 2 * (n + 1)))
         self._csr = None
         DeviceMesh._tokens += 1
@@ -395,7 +402,7 @@ class DeviceMesh3D(DeviceMesh):
         if out is None:
             out = torch.empty(max(self.nnz, 1), dtype=torch.float64, device=self.ctx.device)[:self.nnz]
         with torch.cuda.device(self.ctx.device):
-            check(lib.fe_tet_assemble(self.ctx.handle, _stream(), int(kind), self.n_nodes, _ptr(self.corner_ptr),
+            check(lib.fe_tet_assemble(self.ctx.handle, _stream(), int(kind), self.n_owned, _ptr(self.corner_ptr),
                                       _ptr(self.corner_elem), _ptr(self.adj_ptr), _ptr(self.adj), _ptr(self.coords),
                                       _ptr(self.conn), _ptr(self.mat_id), _ptr(m), int(m.shape[0]), _ptr(out),
                                       self.max_degree, int(variant)))

@@ -41,7 +41,7 @@ class LocalProblem:
 
 
 def local_problem(conn, lo, hi, bounds, dim, elem_offset=0):
-    """conn: int tensor [E_sub, 3] of GLOBAL node ids containing at least every element
+    """conn: int tensor [E_sub, 3] (triangles) or [E_sub, 4] (tetrahedra) of GLOBAL node ids containing at least every element
     incident to a node in [lo, hi).  Returns a LocalProblem with
       elem_sel   indices (into conn) of the local elements, + elem_offset = global element ids
       conn_local int32 [E_loc, 3] in local numbering (owned: g - lo; ghosts: n_owned + k)
@@ -67,8 +67,9 @@ def local_problem(conn, lo, hi, bounds, dim, elem_offset=0):
     recv_ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=dev), torch.cumsum(counts, 0)])
     # send side: every (owned a, foreign b) pair inside an element -> rank(b) needs a
     keys = []
-    for v in range(3):
-        for w in range(3):
+    npe = conn.shape[1]
+    for v in range(npe):
+        for w in range(npe):
             if v == w:
                 continue
             m = lown[:, v] & ~lown[:, w]
@@ -178,11 +179,12 @@ class DistributedMesh:
     """The rank-local DeviceMesh + halo description; pcg() runs fe_dist_pcg."""
 
     def __init__(self, coords_local, lp, mat_id_local=None, device=0, ctx=None):
-        from .device import DeviceMesh, Context
+        from .device import DeviceMesh, DeviceMesh3D, Context
         self.ctx = ctx or Context.get(device)
         self.lp = lp
-        self.dm = DeviceMesh(coords_local, lp.conn_local, mat_id_local, dim=lp.dim, device=device,
-                             n_owned=lp.n_owned, ctx=self.ctx)
+        mesh_cls = DeviceMesh3D if lp.dim == 3 else DeviceMesh   # tetrahedra / triangles
+        self.dm = mesh_cls(coords_local, lp.conn_local, mat_id_local, dim=lp.dim, device=device,
+                           n_owned=lp.n_owned, ctx=self.ctx)
         self.send_idx = lp.send_idx.to(self.ctx.device)
         self._nbr = np.ascontiguousarray(lp.nbr_rank, dtype=np.int32)
         self._sp = np.ascontiguousarray(lp.send_ptr, dtype=np.int32)

@@ -23,6 +23,7 @@ def main():
     nx = int(sys.argv[1]) if len(sys.argv) > 1 else 96
     ny = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     magnetic = len(sys.argv) > 3 and sys.argv[3] == "mag"   # 1 DOF per node: scalar-CSR kernels
+    tet = len(sys.argv) > 3 and sys.argv[3] == "tet"        # tetrahedra, 3 DOF per node (nx x ny x 4 cells)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -30,13 +31,21 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
 
-    from finite_elements_b200.device import DeviceMesh, KIND_ELAST_PSTRESS, KIND_MAGNETIC
+    from finite_elements_b200.device import DeviceMesh, DeviceMesh3D, KIND_ELAST_PSTRESS, KIND_MAGNETIC, KIND_ELAST_TET
     from finite_elements_b200.dist import DistributedMesh, partition_bounds, local_problem, localize_dofs
     from finite_elements_b200.mesh import structured_mesh
 
-    coords, conn = structured_mesh(nx, ny, jitter=0.2, seed=7)
+    if tet:
+        from finite_elements_b200.mesh import structured_tet_mesh
+        coords, conn = structured_tet_mesh(nx, ny, 4, h=1.0 / ny, jitter=0.2, seed=7)
+    else:
+        coords, conn = structured_mesh(nx, ny, jitter=0.2, seed=7)
     n_nodes = len(coords)
-    if magnetic:
+    if tet:
+        kind, dim = KIND_ELAST_TET, 3
+        mat = np.array([[210e9, 0.25, 1.0, 7860.0], [70e9, 0.33, 1.0, 2700.0]])
+        mat_id = (np.arange(len(conn)) % 2).astype(np.int32)
+    elif magnetic:
         kind, dim = KIND_MAGNETIC, 1
         mu0 = 4e-7 * np.pi
         mat = np.array([[mu0 * 100.0, 0, 0, 0], [mu0, 0, 0, 0], [mu0 * 30.0, 0, 0, 0]])
@@ -56,7 +65,8 @@ def main():
     vals = dm.assemble(kind, mat)
 
     # global problem on every rank's own GPU (small) as the single-GPU reference
-    gm = DeviceMesh(coords, conn, mat_id, dim=dim, device=local_rank)
+    gm = DeviceMesh3D(coords, conn, mat_id, device=local_rank) if tet else \
+        DeviceMesh(coords, conn, mat_id, dim=dim, device=local_rank)
     gvals = gm.assemble(kind, mat)
     k_glob = gm.to_scipy(gvals)
     k_loc = dm.to_scipy(vals)
@@ -66,8 +76,12 @@ def main():
     scale = abs(k_glob).max()
     assert diff.max() <= 1e-14 * scale, f"rank {rank}: local rows differ from global rows ({diff.max() / scale:.2e})"
 
-    lines = np.arange(ny + 1) * (nx + 1)
-    if magnetic:
+    lines = np.nonzero(coords[:, 0] == 0)[0] if tet else np.arange(ny + 1) * (nx + 1)
+    if tet:
+        bc_g = (3 * lines[:, None] + np.arange(3)[None, :]).reshape(-1)
+        f_g = np.zeros(3 * n_nodes)
+        f_g[3 * (lines + nx) + 2] = -1000.0 / ny
+    elif magnetic:
         bc_g = lines + nx                      # A = 0 on the right edge
         f_g = np.zeros(n_nodes)
         f_g[conn[:6].reshape(-1)] = 2.5e3      # source on the first few elements
@@ -97,7 +111,7 @@ def main():
     t = torch.tensor([err], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"DIST-OK world={world} {'magnetic ' if magnetic else ''}mesh={nx}x{ny} iters={iters} (single GPU {iters_g}) max_err={t.item():.2e} "
+        print(f"DIST-OK world={world} {'magnetic ' if magnetic else ('tetrahedral ' if tet else '')}mesh={nx}x{ny} iters={iters} (single GPU {iters_g}) max_err={t.item():.2e} "
               f"neighbours={len(lp.nbr_rank)}")
     dist.barrier()
     dist.destroy_process_group()

@@ -49,11 +49,15 @@ def _worker(rank, world, port, nx, ny, kind_name, shuffle, out):
     try:
         from finite_elements_b200.dist import partition_bounds, local_problem, localize_dofs
         from oracle import numpy_oracle as no
-        coords, conn = no.structured_mesh(nx, ny, jitter=0.2, seed=2)
+        tet = kind_name == "tet"
+        if tet:   # slab partition of a Kuhn box, nx x ny x 2 cells (node planes are contiguous in k)
+            coords, conn = no.structured_tet_mesh(nx, ny, 2, h=0.5, jitter=0.2, seed=2)
+        else:
+            coords, conn = no.structured_mesh(nx, ny, jitter=0.2, seed=2)
         if shuffle:  # general numbering: ranks get more than two neighbours' worth of ghosts
             rng = np.random.default_rng(9)
             conn = conn[rng.permutation(len(conn))]
-        kind = no.KIND_MAGNETIC if kind_name == "mag" else no.KIND_ELAST_PSTRESS
+        kind = no.KIND_MAGNETIC if kind_name == "mag" else (no.KIND_ELAST_TET if tet else no.KIND_ELAST_PSTRESS)
         dim = no.kind_dim(kind)
         mat = np.array([[4e-7 * np.pi, 0, 0, 0]]) if kind_name == "mag" else np.array([[210e9, 0.25, 1.0, 7860]])
         n_nodes = len(coords)
@@ -70,11 +74,18 @@ def _worker(rank, world, port, nx, ny, kind_name, shuffle, out):
         k_glob = no.assemble_k(kind, coords, conn, np.zeros(len(conn), np.int32), mat)
         gd = (gid[:, None] * dim + np.arange(dim)[None, :]).reshape(-1)   # local dof -> global dof
         assert abs(k_loc - k_glob[gd[:n_rows]][:, gd]).max() <= 1e-9 * abs(k_glob).max()
+        if tet:   # the device path's symbolic phase on the owned/ghost layout = the oracle's local rows
+            from finite_elements_b200.device import tet_symbolic, tet_csr
+            cp, ce, ap, adj, deg = tet_symbolic(torch.as_tensor(cl).long(), lp.n_local, lp.n_owned)
+            rowptr, colidx = tet_csr(ap, adj, deg)
+            assert np.array_equal(rowptr.numpy(), k_loc.indptr) and np.array_equal(colidx.numpy(), k_loc.indices)
+            for i in (0, lp.n_owned - 1):
+                assert np.array_equal(ce.numpy()[cp[i]:cp[i + 1]], np.nonzero((cl == i).any(axis=1))[0])
         # problem: clamp i = 0, load i = nx
-        lines = np.arange(ny + 1) * (nx + 1)
+        lines = np.nonzero(coords[:, 0] == 0)[0] if tet else np.arange(ny + 1) * (nx + 1)
         bc_g = (lines[:, None] * dim + np.arange(dim)[None, :]).reshape(-1)
         f_g = np.zeros(n_nodes * dim)
-        f_g[(lines + nx) * dim + dim - 1] = -1000.0 / ny
+        f_g[(lines + nx) * dim + dim - 1] = -1000.0 / ny    # (nodes with i = nx in both mesh families)
         bc_l, _ = localize_dofs(lp, bc_g)
         bc_l = bc_l.numpy()
         assert np.array_equal(np.sort(gd[bc_l]), np.sort(np.intersect1d(bc_g, gd)))
@@ -144,6 +155,14 @@ def test_two_ranks_elasticity_row_blocks():
 def test_three_ranks_magnetic_row_blocks():
     res = _run(3, 10, 11, "mag")
     assert [r[3] for r in res] == [1, 2, 1]
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_tetrahedra_slabs():
+    """3 DOF per node, 4 nodes per element: same partition / halo logic, plus the owned-row symbolic
+    phase of DeviceMesh3D against the oracle's local rows."""
+    res = _run(2, 4, 3, "tet")
+    assert [r[3] for r in res] == [1, 1]
 
 
 @pytest.mark.timeout(300)
