@@ -10,7 +10,6 @@ for mode in ${MODES:-p2p nccl}; do
   run tests/dist_gpu_worker.py 96 64 > gpurun_out/dist_worker_${N}_$mode.log 2>&1; echo "[$mode] dist worker rc=$?"; grep -E "DIST-OK|Error|error" gpurun_out/dist_worker_${N}_$mode.log | head -3
   run tests/dist_gpu_worker.py 301 77 >> gpurun_out/dist_worker_${N}_$mode.log 2>&1; echo "[$mode] dist worker(301x77) rc=$?"; grep -E "DIST-OK" gpurun_out/dist_worker_${N}_$mode.log | tail -1
   run tests/dist_gpu_worker.py 301 177 mag >> gpurun_out/dist_worker_${N}_$mode.log 2>&1; echo "[$mode] dist worker(magnetic 301x177) rc=$?"; grep -E "DIST-OK" gpurun_out/dist_worker_${N}_$mode.log | tail -1
-  # (tetrahedra across ranks: host logic is covered on CPU by tests/test_dist_cpu.py; first device run pending)
   run tests/dist_gpu_worker.py 24 12 tet >> gpurun_out/dist_worker_${N}_$mode.log 2>&1; echo "[$mode] dist worker(tetrahedra 24x12x4) rc=$?"; grep -E "DIST-OK" gpurun_out/dist_worker_${N}_$mode.log | tail -1
   if [[ $mode == p2p ]]; then  # the non-fused exchange kernel (k_halo_ll) behind the fallback SpMV kernels
     FE_B200_NO_STREAM=1 run tests/dist_gpu_worker.py 96 64 > gpurun_out/dist_worker_${N}_nostream.log 2>&1; echo "[p2p, no stream] dist worker rc=$?"; grep -E "DIST-OK" gpurun_out/dist_worker_${N}_nostream.log | tail -1

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("extra", [[], ["301", "177", "mag"]])
+@pytest.mark.parametrize("extra", [[], ["301", "177", "mag"], ["24", "12", "tet"]])
 @pytest.mark.parametrize("world", [2])
 def test_distributed_solve_matches_single_gpu(world, extra):
     import torch
