@@ -409,6 +409,10 @@ class FiniteElementAnalysis(FiniteElements):
         dm.dirichlet(vals, rhs, bc_dofs, bc_vals)
         u, iters, relres = dm.pcg(vals, rhs, rtol=self.solver_rtol, maxit=self.solver_maxit)
         self.last_solve_info = dict(iterations=iters, relative_residual=relres, ndof=ndof, nnz=dm.nnz)
+        if relres > self.solver_rtol:   # accepted at attainable accuracy (fe_b200.h: <= max(100 rtol, 1e-10))
+            import warnings
+            warnings.warn(f"solve: PCG stopped at relative residual {relres:.2e} > solver_rtol "
+                          f"{self.solver_rtol:.1e} (attainable accuracy)", RuntimeWarning, stacklevel=3)
         # multipliers: rows c of  K u + lambda = f  (the eliminated copy was overwritten in place)
         dm.assemble(kind, flat['mat'], out=vals, variant=self.assembly_variant)
         residual = f - dm.spmv(vals, u)
@@ -451,4 +455,11 @@ class FiniteElementAnalysis(FiniteElements):
         lam, vec, info = modal_solve(dm, k_vals, m_vals, int(k), order, mask=mask, tol=tol, maxit=maxit,
                                      cheb_degree=cheb_degree)
         self.last_modal_info = info
+        if not info.converged:
+            # the reference's eigsh raises ArpackNoConvergence here; the partial pairs stay available
+            # through last_modal_info, but a caller must not mistake them for converged ones
+            import warnings
+            worst = float(np.max(info.residual_norms)) if info.residual_norms is not None else float('nan')
+            warnings.warn(f"modal_analysis: LOBPCG stopped after {info.iterations} iterations, worst residual "
+                          f"{worst:.2e} x the tolerance {tol:.1e}", RuntimeWarning, stacklevel=2)
         return lam.cpu().numpy(), vec.T.contiguous().cpu().numpy()

@@ -478,6 +478,8 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
   FE_REQUIRE(kind >= FE_ELAST_PSTRESS && kind <= FE_MASS, "fe_assemble: unknown kind %d", kind);
   const int dim = (kind == FE_MAGNETIC) ? 1 : 2;
   FE_REQUIRE(dim == p->dim, "fe_assemble: kind %d needs dim %d but the plan was built with dim %d", kind, dim, p->dim);
+  FE_REQUIRE(mat && n_mat > p->max_mat_id, "fe_assemble: the mesh refers to material %d but the table has %d row(s)",
+             p->max_mat_id, n_mat);
   if (p->n_owned == 0 || p->nnz == 0) return FE_OK;
   cudaStream_t st = as_stream(stream);
   MatRow *tab = nullptr;

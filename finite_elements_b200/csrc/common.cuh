@@ -110,7 +110,7 @@ struct fe_ctx {
   int bp_max_deg = 0;
   void *pinned = nullptr;  // small pinned host buffer for scalar read-back
   void *pcg_graph = nullptr;  // cached cudaGraphExec_t of one PCG iteration chunk
-  const void *pcg_graph_key[8] = {nullptr};
+  const void *pcg_graph_key[16] = {nullptr};  // every pointer / size the captured launches bake in
   void *work_stream = nullptr;  // cudaStream_t used when the caller passes a default stream
   void *work_event = nullptr;   // cudaEvent_t ordering work_stream after the caller's stream
   // multi-GPU

@@ -23,6 +23,8 @@ struct PlanFlags {
   int max_degree;  // max node valence incl. self
   int too_dense;   // valence > kMaxDegree
   int fan_irregular;  // some node's corners do not form simple fans (edge shared by > 2 elements, ...)
+  int max_mat;     // largest mat_id (negative ids are reported through bad_mat)
+  int bad_mat;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -246,10 +248,13 @@ __global__ void __launch_bounds__(128) k_node_records(int32_t n_owned, const int
 }
 
 __global__ void k_conn4(int64_t n_elems, const int32_t *__restrict__ conn, const int32_t *__restrict__ mat_id,
-                        int4 *__restrict__ conn4) {
+                        int4 *__restrict__ conn4, PlanFlags *__restrict__ flags) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_elems) return;
-  conn4[e] = make_int4(conn[3 * e], conn[3 * e + 1], conn[3 * e + 2], mat_id ? mat_id[e] : 0);
+  const int32_t mid = mat_id ? mat_id[e] : 0;
+  if (mid < 0) flags->bad_mat = 1;
+  if (mid > *reinterpret_cast<volatile int *>(&flags->max_mat)) atomicMax(&flags->max_mat, mid);  // rarely taken
+  conn4[e] = make_int4(conn[3 * e], conn[3 * e + 1], conn[3 * e + 2], mid);
 }
 
 // Scalar CSR export: row (n, d) = columns {m*dim + c : m in adj(n), c < dim}.
@@ -334,7 +339,7 @@ int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, 
   PlanFlags *flags = nullptr;
   int64_t *totals = nullptr;
   const int64_t n3 = 3 * n_elems;
-  PlanFlags hflags = {0, 0, 0, 0};
+  PlanFlags hflags = {0, 0, 0, 0, 0, 0};
   int64_t htot[3] = {0, 0, 0};
 
 #define PLAN_TRY(expr)            \
@@ -379,7 +384,7 @@ int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, 
     // 1. histogram of corners per owned node (cursor doubles as the count array)
     k_count_corners<<<grid_for(n3, 256), 256, 0, st>>>(n3, conn, n_nodes, n_owned, cursor, flags);
     PLAN_LAUNCHED();
-    k_conn4<<<grid_for(n_elems, 256), 256, 0, st>>>(n_elems, conn, mat_id, p->conn4);
+    k_conn4<<<grid_for(n_elems, 256), 256, 0, st>>>(n_elems, conn, mat_id, p->conn4, flags);
     PLAN_LAUNCHED();
   }
   PLAN_TRY(exclusive_scan_i32(ctx, st, cursor, p->corner_ptr, n_owned, totals + 0));
@@ -390,6 +395,11 @@ int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, 
     rc = fail(FE_ERR_ARG, "fe_plan_create: connectivity references a node outside [0, %d)", n_nodes);
     goto done;
   }
+  if (hflags.bad_mat) {
+    rc = fail(FE_ERR_ARG, "fe_plan_create: negative material index");
+    goto done;
+  }
+  p->max_mat_id = hflags.max_mat;
   p->n_corners = htot[0];
   PLAN_TRY(dev_alloc(&p->corner_rec, p->n_corners, &p->bytes));
   PLAN_TRY(dev_alloc(&corner_tmp, p->n_corners, nullptr));

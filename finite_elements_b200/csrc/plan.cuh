@@ -15,6 +15,7 @@ struct fe_plan {
   int64_t nnzb = 0;       // node-level adjacency entries (incl. self) over owned rows
   int64_t nnz = 0;        // nnzb * dim * dim
   int32_t max_degree = 0;
+  int32_t max_mat_id = 0;  // largest material index any element refers to (fe_assemble checks n_mat against it)
   int64_t bytes = 0;
   // node -> corners, counting-sorted by node, ascending element id within a node
   int32_t *corner_ptr = nullptr;  // [n_owned + 1]

@@ -590,8 +590,14 @@ struct PcgLaunch {
 // as the same buffers are used (bench / time-stepping loops call the solver repeatedly).
 static int get_chunk_graph(PcgLaunch &L, int len, cudaGraphExec_t *out) {
   fe_ctx *ctx = L.ctx;
-  const void *key[8] = {L.rowptr, L.colidx, L.vals, L.x, L.r, L.st, (void *)(intptr_t)L.n_rows,
-                        (void *)(intptr_t)(len * 256 + (L.lpr & 31) + (L.sp.on ? 32 : 0) + (L.p2p ? 64 : 0) + (L.sp.scalar ? 128 : 0))};
+  // Every argument the captured launches bake in: a second mesh with the same row count whose
+  // buffers land on recycled addresses must not hit a graph holding the old ring capacity, grid,
+  // block pattern or halo list.
+  const void *key[16] = {L.rowptr, L.colidx, L.vals, L.x, L.r, L.st, (void *)(intptr_t)L.n_rows,
+                         (void *)(intptr_t)(len * 256 + (L.lpr & 31) + (L.sp.on ? 32 : 0) + (L.p2p ? 64 : 0) + (L.sp.scalar ? 128 : 0)),
+                         (void *)(intptr_t)L.sp.cap, (void *)(intptr_t)L.sp.smem, (void *)(intptr_t)L.sp.grid,
+                         (void *)L.sp.bptr, (void *)L.sp.bidx, (void *)(L.halo ? L.halo->send_idx : nullptr),
+                         (void *)(intptr_t)ctx->bp_built_token, (void *)(intptr_t)L.vgrid};
   if (ctx->pcg_graph && memcmp(key, ctx->pcg_graph_key, sizeof(key)) == 0) {
     *out = (cudaGraphExec_t)ctx->pcg_graph;
     return FE_OK;
@@ -819,9 +825,15 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
                 h->iters, h->sums[0],
                 (h->sums[0] != h->sums[0] && L.p2p) ? "; NaN on the peer-memory transport also means a rank did not "
                                                       "deliver within the spin-wait limit" : "");
-  if (!fixed && !h->converged && !stagnated)
-    return fail(FE_ERR_NOT_CONVERGED, "pcg: not converged after %d iterations (relres %.3e > %.3e)", h->iters,
-                sqrt(h->sums[2] / h->sums[3]), rtol);
+  if (!fixed && !h->converged) {
+    // Attainable accuracy: restarts that no longer reduce the true residual are accepted only within
+    // a documented slack of the tolerance (fe_b200.h); anything worse is reported as not converged.
+    const double rel = (h->sums[3] > 0.0) ? sqrt(h->sums[2] / h->sums[3]) : 0.0;
+    const double slack = 100.0 * rtol > 1e-10 ? 100.0 * rtol : 1e-10;
+    if (!(stagnated && rel <= slack))
+      return fail(FE_ERR_NOT_CONVERGED, "pcg: not converged after %d iterations (relres %.3e > %.3e%s)", h->iters, rel,
+                  rtol, stagnated ? "; restarts stopped reducing the true residual" : "");
+  }
   return FE_OK;
 }
 

@@ -43,9 +43,13 @@ class Context:
 
     @classmethod
     def get(cls, device=0):
-        if device not in cls._cache:
-            cls._cache[device] = cls(device)
-        return cls._cache[device]
+        """The calling thread's context for `device` (fe_b200.h: one ctx per (thread, device) -- a ctx
+        owns scratch buffers and a cached CUDA graph that two threads must not share)."""
+        import threading
+        key = (threading.get_ident(), int(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(device)
+        return cls._cache[key]
 
     @property
     def launches(self):
@@ -288,6 +292,38 @@ class DeviceMesh:
         rowptr, colidx = self.csr_pattern()
         return sp.csr_matrix((vals.cpu().numpy(), colidx.cpu().numpy(), rowptr.cpu().numpy()),
                              shape=(self.n_rows, self.n_cols))
+
+
+def element_post_arrays(kind, coords, conn, mat_id, mat, u, device=0, ctx=None):
+    """fe_elem_post / fe_tet_elem_post on flat arrays, WITHOUT a plan: post-processing needs the
+    connectivity and the solution only, not the CSR pattern (results.py never assembles).
+    Returns f64[E,7] (plane elasticity), f64[E,2] (magnetic) or f64[E,13] (tetrahedra) on the device."""
+    ctx = ctx or Context.get(device)
+    dev = ctx.device
+
+    def up(a, dt):
+        t = torch.as_tensor(np.ascontiguousarray(a, dtype=dt)) if not torch.is_tensor(a) else a
+        return t.to(dev).contiguous()
+
+    coords, conn = up(coords, np.float64), up(conn, np.int32)
+    mat_id = None if mat_id is None else up(mat_id, np.int32)
+    mat, u = up(mat, np.float64), up(u, np.float64)
+    n_el, npe = int(conn.shape[0]), (int(conn.shape[1]) if conn.ndim == 2 else 0)
+    sdim = kind_dim(kind)
+    if coords.ndim != 2 or (n_el and npe != (4 if sdim == 3 else 3)) or mat.ndim != 2 or mat.shape[1] != 4:
+        raise ValueError("element_post_arrays: inconsistent array shapes")
+    if u.numel() < coords.shape[0] * sdim:
+        raise ValueError("solution vector is shorter than n_nodes * dim")
+    width = 13 if sdim == 3 else (2 if kind == KIND_MAGNETIC else 7)
+    out = torch.empty((n_el, width), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        if sdim == 3:
+            check(lib.fe_tet_elem_post(ctx.handle, _stream(), n_el, _ptr(coords), _ptr(conn), _ptr(mat_id), _ptr(mat),
+                                       int(mat.shape[0]), _ptr(u), _ptr(out)))
+        else:
+            check(lib.fe_elem_post(ctx.handle, _stream(), int(kind), n_el, _ptr(coords), _ptr(conn), _ptr(mat_id),
+                                   _ptr(mat), int(mat.shape[0]), _ptr(u), _ptr(out)))
+    return out
 
 
 def tet_symbolic(conn64, n, n_owned=None):

@@ -192,7 +192,7 @@ class DistributedMesh:
         init_nccl(self.ctx)
         self._dst_off = init_peer_memory(self.ctx, lp)  # None -> NCCL transport inside the loop
 
-    def pcg(self, vals, b, x=None, rtol=1e-8, maxit=None, fixed_iters=0, work=None):
+    def pcg(self, vals, b, x=None, rtol=1e-8, maxit=None, fixed_iters=0, work=None, raise_on_maxit=True):
         dm = self.dm
         rowptr, colidx = dm._vouch_pattern()
         if x is None:
@@ -209,8 +209,9 @@ class DistributedMesh:
                                  len(self._nbr), ip(self._nbr), ip(self._sp), _ptr(self.send_idx), ip(self._rp),
                                  ip(self._dst_off) if self._dst_off is not None else C.c_void_p(0),
                                  dm.block_dim, float(rtol), int(maxit), int(fixed_iters), C.byref(iters), C.byref(relres))
-        if rc != _lib.FE_ERR_NOT_CONVERGED:
-            check(rc)
+        if rc == _lib.FE_ERR_NOT_CONVERGED and not raise_on_maxit:
+            return x, iters.value, relres.value
+        check(rc)
         return x, iters.value, relres.value
 
 

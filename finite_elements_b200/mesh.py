@@ -500,6 +500,71 @@ def read_gmsh41(path, tetrahedra=False):
     return np.array(xy, dtype=np.float64), np.array(tris, dtype=np.int32).reshape(-1, 4 if tetrahedra else 3)
 
 
+def write_gmsh41(path, coords, conn, node_blocks=1, boundary_edges=(), tag_of=lambda i: i + 1):
+    """Writes coords (N,2|3) / conn (E,3|4) as gmsh 4.1 ASCII: `node_blocks` entity blocks of nodes
+    (node i of the file order carries tag `tag_of(i)`; gmsh tags need not be contiguous), an optional block of 2-node line elements (type 1, skipped by every
+    reader of surface / volume meshes) and one block of triangles (type 2) or tetrahedra (type 4)."""
+    coords = np.asarray(coords, dtype=np.float64)
+    conn = np.asarray(conn)
+    n, sdim = coords.shape
+    tets = conn.shape[1] == 4
+    xyz = np.zeros((n, 3))
+    xyz[:, :sdim] = coords
+    bounds = [n * b // node_blocks for b in range(node_blocks + 1)]
+    out = ["$MeshFormat", "4.1 0 8", "$EndMeshFormat", "$Nodes", f"{node_blocks} {n} {tag_of(0)} {tag_of(n - 1)}"]
+    for b in range(node_blocks):
+        lo, hi = bounds[b], bounds[b + 1]
+        out.append(f"{2 if b else 0} {b + 1} 0 {hi - lo}")
+        out.extend(str(tag_of(t)) for t in range(lo, hi))
+        out.extend(" ".join(repr(float(v)) for v in xyz[t]) for t in range(lo, hi))
+    out.append("$EndNodes")
+    n_lines = len(boundary_edges)
+    n_el = n_lines + len(conn)
+    out += ["$Elements", f"{2 if n_lines else 1} {n_el} 1 {n_el}"]
+    tag = 1
+    if n_lines:
+        out.append(f"1 1 1 {n_lines}")
+        for a, b in boundary_edges:
+            out.append(f"{tag} {tag_of(a)} {tag_of(b)}")
+            tag += 1
+    out.append(f"{3 if tets else 2} 1 {4 if tets else 2} {len(conn)}")
+    for row in conn:
+        out.append(f"{tag} " + " ".join(str(tag_of(int(v))) for v in row))
+        tag += 1
+    out.append("$EndElements")
+    with open(path, "w") as fh:
+        fh.write("\n".join(out) + "\n")
+
+
+class GmshParser:
+    """The part of volmdlr.gmsh_vm.GmshParser the reference's scripts use
+    (scripts/Elasticity/beam2d_example_3.py:52-73, beam3d_example_2.py:52-66): `from_file`, the
+    `nodes['all_nodes']` list in file order and the two `define_*_element_mesh` builders."""
+
+    def __init__(self, coords, conn, tetrahedra):
+        self.coords, self.conn, self.tetrahedra = coords, conn, tetrahedra
+        cls = Node3D if tetrahedra else Node2D
+        self.nodes = {'all_nodes': [cls(*(float(v) for v in row)) for row in coords]}
+
+    @classmethod
+    def from_file(cls, file_path):
+        """A file holding tetrahedra is a 3D mesh (Node3D, its surface triangles are ignored);
+        otherwise the triangles define a 2D mesh (Node2D)."""
+        coords, conn = read_gmsh41(file_path, tetrahedra=True)
+        if len(conn):
+            return cls(coords, conn, True)
+        coords, conn = read_gmsh41(file_path, tetrahedra=False)
+        return cls(coords, conn, False)
+
+    def define_triangular_element_mesh(self):
+        nodes = self.nodes['all_nodes']
+        return Mesh([ElementsGroup([TriangularElement2D([nodes[int(i)] for i in row]) for row in self.conn], '')])
+
+    def define_tetrahedron_element_mesh(self):
+        nodes = self.nodes['all_nodes']
+        return Mesh([ElementsGroup([TetrahedralElement([nodes[int(i)] for i in row]) for row in self.conn], '')])
+
+
 def structured_tet_mesh(nx, ny, nz, h=1.0, jitter=0.0, seed=0):
     """Box of nx x ny x nz cells of size h, nodes id = (k (ny+1) + j) (nx+1) + i, every cell cut into
     the 6 tetrahedra of the Kuhn triangulation (conforming).  Returns coords f64[N,3], conn i32[E,4]."""

@@ -48,15 +48,12 @@ class _DevicePost(Result):
 
     def _post_array(self):
         if self._post is None:
-            from .device import DeviceMesh, DeviceMesh3D
+            from .device import element_post_arrays   # no plan: post-processing never needs the CSR pattern
             flat = self._flatten()
-            if self.dimension == 3:
-                dm = DeviceMesh3D(flat['coords'], flat['conn'], flat['mat_id'], device=self._device)
-            else:
-                dm = DeviceMesh(flat['coords'], flat['conn'], flat['mat_id'], dim=self.dimension, device=self._device)
             ndof = len(flat['coords']) * self.dimension
             u = np.real(np.asarray(self.result_vector[:ndof], dtype=np.complex128)).astype(np.float64)
-            self._post = dm.element_post(self._kind(), flat['mat'], u).cpu().numpy()
+            self._post = element_post_arrays(self._kind(), flat['coords'], flat['conn'], flat['mat_id'], flat['mat'],
+                                             u, device=self._device).cpu().numpy()
         return self._post
 
     def _elements(self):

@@ -99,7 +99,11 @@ int fe_elem_post(fe_ctx *ctx, void *stream, int kind, int64_t n_elems, const dou
  * keyed by node, corners ordered by element id), the sorted unique node adjacency, and the
  * corner->CSR-slot map used by fe_assemble.  n_owned_nodes == n_nodes on one GPU; on a
  * rank of a partition, nodes are numbered owned-first and ghosts after, and `conn` lists
- * every element incident to an owned node.  SYNCHRONISES the stream. */
+ * every element incident to an owned node.  SYNCHRONISES the stream.
+ * Limits (FE_ERR_UNSUPPORTED beyond them): a node may have at most 255 neighbours incl. itself
+ * (slot positions are stored in 8 bits); E < 2^29; n_nodes*dim and nnz < 2^31.  The fan-ordered
+ * assembly variant additionally needs <= 32 elements per node, material ids < 2^19 and node stars
+ * that are simple fans -- meshes outside that use variant 2 / 1 automatically (same results). */
 int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned_nodes,
                    int64_t n_elems, int32_t dim, const int32_t *conn, const int32_t *mat_id,
                    fe_plan **out);
@@ -200,9 +204,9 @@ int fe_csr_diagonal(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *ro
  * eliminated SPD system.  x: initial guess in, solution out.  work: double[fe_pcg_work_len(n)].
  * Stops when ||r||_2 <= rtol * ||b||_2, where r is re-computed as b - A x once the recurrence
  * signals convergence (restart from x if the recurrence had drifted).  If restarts stop
- * reducing the true residual (attainable FP64 accuracy reached) the call returns FE_OK with
- * relres > rtol -- callers that need a hard bound compare *relres themselves.  SYNCHRONISES
- * the stream; writes iters / relres (the true relative residual). */
+ * reducing the true residual (attainable FP64 accuracy reached) the call returns FE_OK only when
+ * relres <= max(100 rtol, 1e-10); otherwise FE_ERR_NOT_CONVERGED (x, iters, relres still written).
+ * SYNCHRONISES the stream; writes iters / relres (the true relative residual). */
 int64_t fe_pcg_work_len(int32_t n_rows, int32_t n_cols);
 int fe_pcg(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr, const int32_t *colidx,
            const double *vals, const double *b, double *x, double *work, int32_t block_dim,

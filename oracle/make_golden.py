@@ -80,7 +80,7 @@ def run(ns, spec, modal_k=0):
         node_loads=spec.get("node_loads", ()), node_bcs=spec.get("node_bcs", ()),
         elements_loads=spec.get("elements_loads", ()), edge_loads=spec.get("edge_loads", ()),
         edge_bcs=spec.get("edge_bcs", ()), element_bcs=spec.get("element_bcs", ()),
-        plane_strain=plane_strain, plane_stress=plane_stress)
+        plane_strain=plane_strain, plane_stress=plane_stress, magnet_loads=spec.get("magnet_loads", ()))
     out = {}
     if kind in ("elasticity", "elasticity3d"):
         out["ke"] = np.array([e.elementary_matrix(plane_strain, plane_stress) for e in elems])
@@ -92,6 +92,10 @@ def run(ns, spec, modal_k=0):
     kaug = an.create_matrix()
     out.update(csr_parts(kaug, "kaug"))
     out["f"] = an.create_source_matrix()
+    if spec.get("magnet_loads"):   # analysis.py:556-577 on its own (data, node rows), in emission order
+        data, rows = an.source_c_matrix_magnet_loads()
+        out["magnet_data"] = np.array(data, dtype=np.float64)
+        out["magnet_rows"] = np.array(rows, dtype=np.int64)
     out["x"] = np.array(an.solve().result_vector, dtype=np.float64)
     # post-processing of the reference (results.py:809-830, :769-781, :121-152) on its own solution
     if kind == "elasticity":
@@ -139,7 +143,8 @@ def spec_arrays(spec):
     else:
         mat = np.array([[p[0], 0, 0, 0] for p in spec["group_params"]], dtype=np.float64)
     rec = {k: [list(map(_py, r)) for r in spec.get(k, ())]
-           for k in ("node_loads", "node_bcs", "elements_loads", "edge_loads", "edge_bcs", "element_bcs")}
+           for k in ("node_loads", "node_bcs", "elements_loads", "edge_loads", "edge_bcs", "element_bcs",
+                     "magnet_loads")}
     meta = dict(name=spec["name"], kind=spec["kind"], plane=spec.get("plane"), records=rec,
                 group_bounds=[int(b) for b in bounds], source=spec.get("source", ""))
     return dict(coords=np.asarray(spec["coords"], dtype=np.float64), conn=np.asarray(spec["conn"], dtype=np.int32),
@@ -222,6 +227,18 @@ def fixtures():
                node_bcs=[(nid(6, j), 0.0, 1) for j in range(5)],
                edge_bcs=[(nid(0, 0), nid(0, 1), 3.0, 1)],
                element_bcs=[(47, 2.0, 1)]), 0
+    # 5b. MagnetLoad (loads.py:105-147, analysis.py:556-577): a 2x2-cell magnet block inside the jittered
+    #     6x4 mesh (its centre node listed as non-contour), a second single-cell magnet whose
+    #     non_contour_nodes cover one whole edge (that edge must drop out), plus an ordinary source
+    cells = lambda i0, i1, j0, j1: [2 * (j * nx + i) + t for j in range(j0, j1) for i in range(i0, i1) for t in (0, 1)]  # noqa: E731
+    yield dict(name="semantics_mag_magnet", kind="magnetic", plane=None,
+               source="synthetic (MagnetLoad: loads.py:105-147, analysis.py:556-577)",
+               coords=coords, conn=conn, group_bounds=[0, 16, 32, 48],
+               group_params=[(mu0 * 1.05,), (mu0,), (mu0 * 5e4,)],
+               magnet_loads=[(cells(2, 4, 1, 3), [nid(3, 2)], 2.5e5, 7.65e5),
+                             (cells(0, 1, 3, 4), [nid(0, 3), nid(0, 4)], -1.0e5, 3.0e5)],
+               elements_loads=[([46, 47], 3e6, 1)],
+               node_bcs=[(nid(6, j), 0.0, 1) for j in range(5)] + [(nid(i, 0), 0.0, 1) for i in range(6)]), 0
     # 6. mid-size structured meshes (uniform: exact zeros in K; jittered: general geometry)
     for nm, jit in (("struct24x16", 0.0), ("struct24x16_jit", 0.2)):
         coords, conn = structured_mesh(24, 16, jitter=jit, seed=0)
@@ -276,7 +293,10 @@ def main():
     ns = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
     only3d = "--3d" in sys.argv   # (re)mint only the tetrahedral fixtures
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None   # ... or one fixture by name
     for spec, modal_k in (list(fixtures_3d()) if only3d else list(fixtures()) + list(fixtures_3d())):
+        if only is not None and spec["name"] != only:
+            continue
         out = run(ns, spec, modal_k)
         arrays = spec_arrays(spec)
         arrays.update({"ref_" + k: v for k, v in out.items()})

@@ -309,6 +309,42 @@ def loads_to_dof_records(coords, conn, dim, node_loads=(), elements_loads=(), ed
     return dedup_last_wins(dofs, vals)
 
 
+def magnet_load_records(coords, conn, magnet_loads):
+    """analysis.py:556-577 + loads.py:129-147 (MagnetLoad.contour_linear_elements).
+    magnet_loads: (elem_idx_list, non_contour_node_list, m_x, m_y).  Contour = edges of the magnet's
+    elements that occur exactly once and do not have BOTH ends in non_contour_nodes, in first-seen
+    order (element order, then edges (p0,p1), (p1,p2), (p2,p0): volmdlr's TriangularElement2D
+    .linear_elements -- third-party, restated).  Per contour edge both end nodes receive
+    M . t * length / 2 with t = (-n_y, n_x), n the unit normal pointing to the triangle's third
+    vertex (volmdlr `interior_normal`, restated); the rows are NODE indices (analysis.py:565-566),
+    added to f without de-duplication (analysis.py:701-702).  Returns (rows, values)."""
+    xy = np.asarray(coords, dtype=np.float64)
+    rows, vals = [], []
+    for idx, non_contour, mx, my in magnet_loads:
+        count, first = {}, {}
+        for j in idx:
+            n = [int(v) for v in conn[j]]
+            for i in range(3):
+                a, b, c = n[i], n[(i + 1) % 3], n[(i + 2) % 3]
+                key = frozenset((a, b))
+                count[key] = count.get(key, 0) + 1
+                if key not in first:
+                    first[key] = (a, b, c)
+        skip = set(int(v) for v in non_contour)
+        for key, (a, b, c) in first.items():
+            if count[key] != 1 or (a in skip and b in skip):
+                continue
+            t = xy[b] - xy[a]
+            nrm = np.array([-t[1], t[0]])
+            if nrm @ (xy[c] - xy[a]) < 0:
+                nrm = -nrm
+            nrm = nrm / np.hypot(nrm[0], nrm[1])
+            share = (mx * (-nrm[1]) + my * nrm[0]) * np.hypot(t[0], t[1]) / 2
+            rows += [a, b]
+            vals += [share, share]
+    return np.array(rows, dtype=np.int64), np.array(vals, dtype=np.float64)
+
+
 # ---------------------------------------------------------------- a-9
 def bcs_to_dof_records(coords, conn, dim, node_bcs=(), element_bcs=(), edge_bcs=()):
     """analysis.py:241-265 (order: node BCs, element->node :201-220, edge->node :222-239)."""

@@ -3,7 +3,7 @@
 Loads the reference's *unmodified* modules from /root/reference/finite_elements
 behind stand-ins for the three third-party packages that are absent from this
 image (volmdlr, dessia_common, matplotlib).  Used ONLY by oracle/make_golden.py
-and oracle/validate_port.py in the build container, where /root/reference
+and tests/test_oracle.py's literal-reference checks in the build container, where /root/reference
 exists; nothing here runs on the GPU box and nothing in the product imports it.
 
 What is the reference's own code and what is restated
@@ -326,13 +326,15 @@ def load():
 # --------------------------------------------------------------------------
 def build_reference_analysis(ns, coords, conn, groups, kind, node_loads=(), node_bcs=(),
                              elements_loads=(), edge_loads=(), edge_bcs=(), element_bcs=(),
-                             plane_strain=None, plane_stress=None):
+                             plane_strain=None, plane_stress=None, magnet_loads=()):
     """coords (N,2), conn (E,3) int, groups = list of dict(start, stop, params).
     kind 'elasticity': params = (E, nu, rho, t); 'magnetic': params = (mu,).
     node_loads / node_bcs: iterables of (node_index, value, dimension(1-based)).
     elements_loads: iterables of (list_of_element_indices, value, dimension).
     edge_loads / edge_bcs: (node_index_start, node_index_end, value, dimension).
     element_bcs: (element_index, value, dimension).
+    magnet_loads: (list_of_element_indices, list_of_non_contour_node_indices, m_x, m_y)
+    (loads.py:105-147; the contour edges come from the restated volmdlr `linear_elements`).
     mesh.nodes is forced to the given numbering (as beam2d_example_3.py:72-73 does)."""
     if kind == "elasticity3d":
         nodes = [ns.vmmesh.Node3D(float(x), float(y), float(z)) for x, y, z in coords]
@@ -370,6 +372,8 @@ def build_reference_analysis(ns, coords, conn, groups, kind, node_loads=(), node
     edb = [ns.conditions.EdgeBoundaryCondition(_Edge(nodes[a], nodes[b]), v, d)
            for a, b, v, d in edge_bcs]
     elb = [ns.conditions.ElementBoundaryCondition(all_elems[j], v, d) for j, v, d in element_bcs]
-    an = ns.analysis.FiniteElementAnalysis(mesh, el, edl, nl, [], [], nb, edb, elb,
+    ml = [ns.loads.MagnetLoad([all_elems[j] for j in idx], [nodes[i] for i in ncn], ns.vm.Vector2D(mx, my))
+          for idx, ncn, mx, my in magnet_loads]
+    an = ns.analysis.FiniteElementAnalysis(mesh, el, edl, nl, ml, [], nb, edb, elb,
                                            plane_strain, plane_stress)
     return an, mesh, all_elems

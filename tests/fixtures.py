@@ -43,7 +43,7 @@ class Fixture:
 
     def rec(self, key):
         out = []
-        for r in self.records[key]:
+        for r in self.records.get(key, []):
             out.append(tuple(r))
         return out
 
@@ -130,8 +130,10 @@ def build_object_analysis(fx, with_element_records=False, **kw):
     if with_element_records:
         el = [fe.loads.ElementsLoad([elems[j] for j in idx], v, d) for idx, v, d in fx.rec("elements_loads")]
         elb = [fe.conditions.ElementBoundaryCondition(elems[j], v, d) for j, v, d in fx.rec("element_bcs")]
+    ml = [fe.loads.MagnetLoad([elems[j] for j in idx], [nodes[i] for i in ncn], m.Vector2D(mx, my))
+          for idx, ncn, mx, my in fx.records.get("magnet_loads", [])]
     ps = fx.plane
-    an = fe.analysis.FiniteElementAnalysis(mesh, el, edl, nl, [], [], nb, edb, elb,
+    an = fe.analysis.FiniteElementAnalysis(mesh, el, edl, nl, ml, [], nb, edb, elb,
                                            None if ps is None else ps == "strain",
                                            None if ps is None else ps == "stress", **kw)
     return an, mesh, elems

@@ -135,3 +135,48 @@ def test_singular_system_raises_like_the_reference():
     an.solver_maxit = 200
     with pytest.raises((NotImplementedError, fe._lib.NotConverged)):
         an.solve()
+
+
+# ------------------------------------------------------------------ BASELINE configs[0] "as shipped"
+_TIP_UY = {"0.8": -0.0842551, "0.5": -0.0926325, "0.3": -0.119740, "0.18": -0.127914, "0.1": -0.132526}
+
+
+@pytest.mark.parametrize("lc", list(_TIP_UY))
+def test_beam2d_example_3_from_msh_file(lc):
+    """scripts/Elasticity/beam2d_example_3.py:52-121 driven from a .msh file through the drop-in classes
+    exactly as the script does (GmshParser -> element objects -> Mesh -> keep gmsh node order -> NodeLoad
+    at (10, 1), clamp x = 0, plane stress): solution vs the reference's spsolve (golden), tip deflection
+    vs the values the reference gives for the five meshes."""
+    import os
+    import finite_elements_b200 as fe
+    vmmesh = fe.mesh
+    fx = Fixture("gmsh_beam_" + lc)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "msh", f"gmsh_beam_{lc}.msh")
+    gmsh = fe.mesh.GmshParser.from_file(path)
+    mesh = gmsh.define_triangular_element_mesh()
+    group_elements = []
+    for group in mesh.elements_groups:
+        solid = [fe.elements.ElasticityTriangularElement2D(tri, 30 * 1e6, 0.25, 2.7, 1) for tri in group.elements]
+        group_elements.append(vmmesh.ElementsGroup(solid, ''))
+    mesh = vmmesh.Mesh(group_elements)
+    mesh.nodes = gmsh.nodes['all_nodes']                                   # keep gmsh order (:72-73)
+    mesh.node_to_index = {mesh.nodes[i]: i for i in range(len(mesh.nodes))}
+    tip = mesh.node_to_index[vmmesh.Node2D(10, 1)]
+    node_loads = [fe.loads.NodeLoad(mesh.nodes[tip], -1000, 2)]
+    bcs = []
+    for i, node in enumerate(mesh.nodes):
+        if node.x == 0:
+            bcs += [fe.conditions.NodeBoundaryCondition(mesh.nodes[i], 0, 1),
+                    fe.conditions.NodeBoundaryCondition(mesh.nodes[i], 0, 2)]
+    an = fe.analysis.FiniteElementAnalysis(mesh=mesh, element_loads=[], edge_loads=[], node_loads=node_loads,
+                                           magnet_loads=[], continuity_conditions=[], node_boundary_conditions=bcs,
+                                           edge_boundary_conditions=[], element_boundary_conditions=[],
+                                           plane_strain=False, plane_stress=True)
+    m = an.create_matrix()
+    assert_csr_values_close(m, fx.csr("kaug"), 1e-12)
+    results = an.solve()
+    x, ref_x = np.array(results.result_vector), fx.ref("x")
+    assert len(x) == len(ref_x)
+    assert np.linalg.norm(x[:fx.ndof] - ref_x[:fx.ndof]) <= 1e-8 * np.linalg.norm(ref_x[:fx.ndof])
+    er = fe.results.ElasticityResults2D(results.mesh, results.result_vector, False, True)
+    assert abs(er.displacement_vectors_per_node[mesh.nodes[tip]][1] - _TIP_UY[lc]) < 2e-6

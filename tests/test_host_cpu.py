@@ -213,3 +213,67 @@ def test_api_errors_without_device():
     b, _ = no.b_matrix(fx.coords, fx.conn)
     assert np.allclose(elems[1].b_matrix, b[1], rtol=1e-15)
     assert np.allclose(elems[0].d_matrix(False, True), no.d_matrix(30e6, 0.25, False, True))
+
+
+def test_magnet_load_rhs_matches_reference():
+    """MagnetLoad -> right-hand side (loads.py:129-147, analysis.py:556-577) against the reference's own
+    (data, rows) and source vector; pure host work, no device call (node BCs + magnet loads only)."""
+    fx = Fixture("semantics_mag_magnet")
+    an, mesh, elems = _object_analysis(fx)          # element records (ElementsLoad) need the device: left out
+    data, rows = an.source_c_matrix_magnet_loads()
+    assert rows == list(fx.ref("magnet_rows"))
+    ref = fx.ref("magnet_data")
+    assert np.allclose(data, ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
+    contour = an.magnet_loads[1].contour_linear_elements()
+    assert len(contour) == 3                         # the edge between the two non-contour nodes dropped out
+    f = an.create_source_matrix()
+    expect = np.zeros_like(f)
+    np.add.at(expect[:, 0], fx.ref("magnet_rows"), ref)
+    assert f.shape == fx.ref("f").shape and np.allclose(f, expect, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
+
+
+# ------------------------------------------------------------------ gmsh 4.1 ingestion (SURVEY §8f rank 3)
+_MSH2D = ["gmsh_beam_0.8", "gmsh_beam_0.5", "gmsh_beam_0.3", "gmsh_beam_0.18", "gmsh_beam_0.1"]
+_MSH3D = ["gmsh_beam3d_1", "gmsh_beam3d_0.5"]
+_REF_INPUT = "/root/reference/scripts/InputFiles"
+
+
+@pytest.mark.parametrize("name", _MSH2D + _MSH3D)
+def test_read_gmsh41_committed_files(name):
+    """tests/golden/msh/*.msh (several node blocks, non-contiguous tags, a line-element block) ->
+    exactly the coords / conn of the golden fixture the reference ran on."""
+    import finite_elements_b200 as fe
+    fx = Fixture(name)
+    path = os.path.join(ROOT, "tests", "golden", "msh", name + ".msh")
+    coords, conn = fe.mesh.read_gmsh41(path, tetrahedra=name in _MSH3D)
+    assert coords.dtype == np.float64 and conn.dtype == np.int32
+    assert np.array_equal(coords, fx.coords) and np.array_equal(conn, fx.conn)
+    parser = fe.mesh.GmshParser.from_file(path)
+    assert parser.tetrahedra == (name in _MSH3D) and len(parser.nodes['all_nodes']) == len(fx.coords)
+    mesh = parser.define_tetrahedron_element_mesh() if parser.tetrahedra else parser.define_triangular_element_mesh()
+    assert sum(len(g.elements) for g in mesh.elements_groups) == len(fx.conn)
+
+
+@pytest.mark.skipif(not os.path.isdir(_REF_INPUT), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("name", _MSH2D + _MSH3D)
+def test_read_gmsh41_reference_files(name):
+    """The reader on the reference's OWN .msh files (scripts/InputFiles, read in place)."""
+    import finite_elements_b200 as fe
+    fx = Fixture(name)
+    if name in _MSH3D:
+        path = os.path.join(_REF_INPUT, "3D", name.replace("gmsh_", "") + ".msh")
+    else:
+        path = os.path.join(_REF_INPUT, "2D", name.replace("gmsh_beam_", "beam_2d_") + ".msh")
+    coords, conn = fe.mesh.read_gmsh41(path, tetrahedra=name in _MSH3D)
+    assert np.array_equal(coords, fx.coords) and np.array_equal(conn, fx.conn)
+    parser = fe.mesh.GmshParser.from_file(path)
+    assert parser.tetrahedra == (name in _MSH3D)
+    assert np.array_equal(parser.conn, fx.conn)
+
+
+def test_read_gmsh41_rejects_other_formats(tmp_path):
+    import finite_elements_b200 as fe
+    p = tmp_path / "old.msh"
+    p.write_text("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n")
+    with pytest.raises(ValueError):
+        fe.mesh.read_gmsh41(str(p))

@@ -59,6 +59,11 @@ def test_augmented_system_rhs_and_solution(name):
     ld, lv = no.loads_to_dof_records(fx.coords, fx.conn, fx.dim, fx.rec("node_loads"),
                                      fx.rec("elements_loads"), fx.rec("edge_loads"))
     f = no.source_vector(fx.ndof, ld, lv, bc_vals)
+    if fx.records.get("magnet_loads"):   # analysis.py:556-577: added on top, no de-duplication
+        mr, mv = no.magnet_load_records(fx.coords, fx.conn, fx.rec("magnet_loads"))
+        assert np.array_equal(mr, fx.ref("magnet_rows"))
+        assert np.allclose(mv, fx.ref("magnet_data"), rtol=1e-13, atol=1e-13 * np.abs(mv).max())
+        np.add.at(f[:, 0], mr, mv)
     ref_f = fx.ref("f")
     assert f.shape == ref_f.shape
     assert np.allclose(f, ref_f, rtol=1e-12, atol=1e-12 * np.abs(ref_f).max())
