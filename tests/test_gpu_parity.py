@@ -315,6 +315,44 @@ def test_properties_at_baseline_sizes(nx, ny):
     assert float(u[bc.long()].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("jitter", [0.0, 0.2])
+def test_s1m_values_and_solution_vs_oracle_direct_solve(jitter):
+    """BASELINE configs[2] (S1M, 1024 x 512 cells, plane stress) against the oracle -- SURVEY §8c
+    "Oracle at scale": the assembled K (pattern bit-exact, values 1e-12 of the row maximum) and the
+    displacements against a DIRECT solve of the Dirichlet-reduced SPD system (the reference's contract
+    is spsolve, analysis.py:820-822; the reduced solve equals its Lagrange solve on the solution block,
+    tests/test_oracle.py), tolerance 1e-8 relative as north_star states.  PCG runs at rtol 1e-12
+    because a 1e-8 residual does not bound the solution error at this condition number.
+    jitter 0.2: general geometry (no exact zeros), same sizes."""
+    import scipy.sparse.linalg as spla
+    import torch
+    from finite_elements_b200.device import DeviceMesh, KIND_ELAST_PSTRESS
+    nx, ny = 1024, 512
+    coords, conn = no.structured_mesh(nx, ny, jitter=jitter, seed=0)
+    mat = np.array([[210e9, 0.25, 1.0, 7860.0]])
+    mat_id = np.zeros(len(conn), np.int32)
+    dm = DeviceMesh(coords, conn, None, dim=2)
+    vals = dm.assemble(KIND_ELAST_PSTRESS, mat)
+    k_ref = no.assemble_k(no.KIND_ELAST_PSTRESS, coords, conn, mat_id, mat)
+    assert_csr_values_close(dm.to_scipy(vals), k_ref, 1e-12)
+    if jitter:
+        return          # one direct solve is enough (23 s of SuperLU); the jittered case pins the values
+    left = np.arange(ny + 1) * (nx + 1)
+    bc = np.stack([2 * left, 2 * left + 1], axis=1).reshape(-1)
+    f = np.zeros(dm.n_rows)
+    f[2 * (left + nx) + 1] = -1000.0 / ny
+    ke, b = no.eliminate_dirichlet(k_ref, f, bc, np.zeros(len(bc)))
+    lu = spla.splu(ke.tocsc(), permc_spec='MMD_AT_PLUS_A')      # SPD: a fill-reducing symmetric ordering is safe
+    x_ref = lu.solve(b)
+    x_ref += lu.solve(b - ke @ x_ref)                            # one step of iterative refinement
+    rhs = torch.as_tensor(f).cuda()
+    dm.dirichlet(vals, rhs, bc, np.zeros(len(bc)))
+    assert np.allclose(rhs.cpu().numpy(), b, rtol=0, atol=1e-12 * np.abs(b).max())
+    u, iters, relres = dm.pcg(vals, rhs, rtol=1e-12, maxit=200000, raise_on_maxit=False)
+    err = np.linalg.norm(u.cpu().numpy() - x_ref) / np.linalg.norm(x_ref)
+    assert relres <= 1e-10 and err <= 1e-8, (iters, relres, err)
+
+
 @pytest.mark.gpu
 def test_magnetic_properties_at_s1m():
     """BASELINE configs[1] scaled up (SURVEY §8d magnetic config, 1024 x 512 cells, three mu bands):
