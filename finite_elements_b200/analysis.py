@@ -409,7 +409,7 @@ class FiniteElementAnalysis(FiniteElements):
         dm.dirichlet(vals, rhs, bc_dofs, bc_vals)
         u, iters, relres = dm.pcg(vals, rhs, rtol=self.solver_rtol, maxit=self.solver_maxit)
         self.last_solve_info = dict(iterations=iters, relative_residual=relres, ndof=ndof, nnz=dm.nnz)
-        if relres > self.solver_rtol:   # accepted at attainable accuracy (fe_b200.h: <= max(100 rtol, 1e-10))
+        if relres > self.solver_rtol:   # accepted at attainable accuracy (fe_b200.h: <= max(100 rtol, 1e-8))
             import warnings
             warnings.warn(f"solve: PCG stopped at relative residual {relres:.2e} > solver_rtol "
                           f"{self.solver_rtol:.1e} (attainable accuracy)", RuntimeWarning, stacklevel=3)

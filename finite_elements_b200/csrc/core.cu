@@ -327,6 +327,7 @@ int fe_ctx_destroy(fe_ctx *ctx) {
   ctx->scratch_a.release();
   ctx->scratch_b.release();
   ctx->scratch_c.release();
+  ctx->scratch_p.release();
   ctx->halo_send.release();
   ctx->halo_recv.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -135,6 +135,17 @@ int halo_exchange_p2p(fe_ctx *ctx, cudaStream_t s, const HaloPlan *h, double *ve
   return FE_OK;
 }
 
+// every neighbour's slice of send_idx ascending?  (the persistent PCG kernel finds a CTA's share of a
+// send list by binary search)
+__global__ void k_check_sorted(int32_t n, const int32_t *__restrict__ idx, int32_t n_seg, const int32_t *__restrict__ seg_ptr,
+                               int *__restrict__ bad) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 1 >= n) return;
+  for (int k = 1; k < n_seg; ++k)
+    if (seg_ptr[k] == i + 1) return;  // segment boundary
+  if (idx[i] >= idx[i + 1]) *bad = 1;
+}
+
 static int upload_p2p_halo(fe_ctx *ctx, cudaStream_t s, const HaloPlan *h) {
   FE_REQUIRE(h->n_nbr <= kMaxRanks, "p2p: more than %d neighbours", kMaxRanks);
   FE_REQUIRE(h->recv_ptr[h->n_nbr] <= ctx->p2p_n_ghost, "p2p: ghost block too small (%d > %d): call fe_dist_p2p_export again",
@@ -150,10 +161,20 @@ static int upload_p2p_halo(fe_ctx *ctx, cudaStream_t s, const HaloPlan *h) {
     hd.dst_off[k] = h->peer_dst_off[k];
   }
   hd.send_ptr[h->n_nbr] = h->send_ptr[h->n_nbr];
-  int rc = ctx->p2p_halo.reserve(sizeof(HaloDev));
+  int rc = ctx->p2p_halo.reserve(sizeof(HaloDev) + 16);
   if (rc) return rc;
   FE_CUDA(cudaMemcpyAsync(ctx->p2p_halo.ptr, &hd, sizeof(hd), cudaMemcpyHostToDevice, s));
+  int bad = 0;
+  if (hd.n_send > 1) {
+    int *flag = (int *)((char *)ctx->p2p_halo.ptr + sizeof(HaloDev));
+    FE_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+    k_check_sorted<<<grid_for(hd.n_send, 256), 256, 0, s>>>(hd.n_send, h->send_idx, hd.n_nbr + 1,
+                                                            ((HaloDev *)ctx->p2p_halo.ptr)->send_ptr, flag);
+    FE_LAUNCH_CHECK(ctx);
+    FE_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
   FE_CUDA(cudaStreamSynchronize(s));  // hd lives on this stack frame
+  ctx->p2p_send_sorted = !bad;
   return FE_OK;
 }
 

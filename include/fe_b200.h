@@ -205,7 +205,7 @@ int fe_csr_diagonal(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *ro
  * Stops when ||r||_2 <= rtol * ||b||_2, where r is re-computed as b - A x once the recurrence
  * signals convergence (restart from x if the recurrence had drifted).  If restarts stop
  * reducing the true residual (attainable FP64 accuracy reached) the call returns FE_OK only when
- * relres <= max(100 rtol, 1e-10); otherwise FE_ERR_NOT_CONVERGED (x, iters, relres still written).
+ * relres <= max(100 rtol, 1e-8); otherwise FE_ERR_NOT_CONVERGED (x, iters, relres still written).
  * SYNCHRONISES the stream; writes iters / relres (the true relative residual). */
 int64_t fe_pcg_work_len(int32_t n_rows, int32_t n_cols);
 int fe_pcg(fe_ctx *ctx, void *stream, int32_t n, const int32_t *rowptr, const int32_t *colidx,

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert name in L.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
     assert sorted(L.SIGNATURES) == names
     assert L.lib.fe_version() == 100
-    assert L.lib.fe_pcg_work_len(10, 14) == 44
+    assert L.lib.fe_pcg_work_len(10, 14) == 64   # 5 n_rows + n_cols
 
 
 def test_no_cpu_fallback():
