@@ -33,6 +33,7 @@ struct PcgState {
   int breakdown;
   unsigned ticket;  // last-CTA election
   P2PDev *pp;       // peer-memory all-reduce (NULL: single GPU, or NCCL between the kernels)
+  double prof[6];   // persistent kernel, CTA 0: ns spent in SpMV | barrier+reduce | vector update | barrier | init | -
 };
 
 // ---- peer-memory all-reduce, fused into the reducing kernels ------------------------------
@@ -634,14 +635,18 @@ static int get_chunk_graph(PcgLaunch &L, int len, cudaGraphExec_t *out) {
 // only verifies the true residual once the recurrence reports convergence and relaunches (restart
 // from x) if it has drifted -- the same policy as the three-kernel path below.
 // ---------------------------------------------------------------------------------------
-static int persist_grid(fe_ctx *ctx, size_t smem, int n_tiles) {
+static int persist_grid(fe_ctx *ctx, const void *kernel, size_t smem, int n_tiles) {
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_persist, kStreamThreads, smem) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kStreamThreads, smem) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   if (per_sm > 2) per_sm = 2;
-  const int cap = per_sm * ctx->num_sms;
+  int cap = per_sm * ctx->num_sms;
+  if (const char *e = getenv("FE_B200_PERSIST_GRID")) {  // debugging: fewer, longer-running CTAs
+    const int v = atoi(e);
+    if (v >= 1 && v < cap) cap = v;
+  }
   return n_tiles < cap ? n_tiles : cap;
 }
 
@@ -651,11 +656,13 @@ static int persist_solve(PcgLaunch &L, double *work, int32_t n_cols, double rtol
   cudaStream_t s = L.s;
   const int32_t n_nodes = L.n_rows / 2;
   const int n_tiles = (n_nodes + kStreamTile - 1) / kStreamTile;
-  FE_CUDA(cudaFuncSetAttribute(k_pcg_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.sp.smem));
-  const int grid = persist_grid(ctx, L.sp.smem, n_tiles);
+  const bool multi_gpu = L.dist && L.p2p;
+  const void *kernel = multi_gpu ? (const void *)k_pcg_persist<true> : (const void *)k_pcg_persist<false>;
+  FE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.sp.smem));
+  const int grid = persist_grid(ctx, kernel, L.sp.smem, n_tiles);
   if (grid < 1) return fail(FE_ERR_CUDA, "pcg: the persistent kernel does not fit an SM (%zu B of shared memory)", L.sp.smem);
   const size_t flag_bytes = ((size_t)(1 + 2 * ctx->num_sms) * sizeof(unsigned) + 255) / 256 * 256;
-  const size_t need = flag_bytes + (size_t)2 * ctx->num_sms * kPQ * sizeof(double);
+  const size_t need = flag_bytes + (size_t)(2 * ctx->num_sms + 2) * kPQ * sizeof(double);
   const void *before = ctx->scratch_p.ptr;
   int rc = ctx->scratch_p.reserve(need);
   if (rc) return rc;
@@ -686,11 +693,15 @@ static int persist_solve(PcgLaunch &L, double *work, int32_t n_cols, double rtol
   auto run = [&](int32_t it_end) -> int {
     a.it_end = it_end;
     void *params[] = {&a};
-    FE_CUDA(cudaLaunchCooperativeKernel((const void *)k_pcg_persist, dim3(grid), dim3(kStreamThreads), params, L.sp.smem, s));
+    FE_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kStreamThreads), params, L.sp.smem, s));
     ctx->launches++;
     FE_CUDA(cudaMemcpyAsync(h, L.st, sizeof(PcgState), cudaMemcpyDeviceToHost, s));
     FE_CUDA(cudaStreamSynchronize(s));
     if (h->breakdown == 2) cudaMemsetAsync(ctx->scratch_p.ptr, 0, ctx->scratch_p.bytes, s);  // barrier flags are stale
+    if (getenv("FE_B200_PERSIST_PROF") && h->iters > 0)
+      fprintf(stderr, "[k_pcg_persist rank %d grid %d] %d its, us/it: spmv %.2f | barrier+reduce %.2f | update %.2f | barrier+halo %.2f | init %.1f us\n",
+              ctx->rank, grid, h->iters, 1e-3 * h->prof[0] / h->iters, 1e-3 * h->prof[1] / h->iters, 1e-3 * h->prof[2] / h->iters,
+              1e-3 * h->prof[3] / h->iters, 1e-3 * h->prof[4]);
     return FE_OK;
   };
   constexpr int kMaxRestarts = 12;
@@ -864,11 +875,17 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
     k_extract_dinv<<<grid_for(n_rows, 256), 256, 0, s>>>(n_rows, rowptr, colidx, vals, L.dinv, st);
     FE_LAUNCH_CHECK(ctx);
   }
-  // One persistent cooperative kernel for the whole solve (2 DOF per node, streamed pattern, one GPU
-  // or the peer-memory transport); FE_B200_NO_PERSIST=1 keeps the three-kernel path for comparison.
+  // One persistent cooperative kernel for the whole solve (pcg_persist.cuh: 2 DOF per node, streamed
+  // pattern, one GPU or the peer-memory transport).  Measured (S16M, profiles/r02_*): it trades 16 n
+  // bytes of extra vector traffic per iteration (the s = A p recurrence of the single-reduction CG)
+  // for one cross-GPU round trip and three kernel boundaries -- a loss on 1-2 GPUs (0.682 vs 0.641,
+  // 0.363 vs 0.337 ms/iteration), a gain once the per-rank share is small (8 GPUs: 0.099 vs 0.103).
+  // Default: 4 ranks and more; FE_B200_PERSIST=1 / 0 forces it on / off.
   const bool aligned16 = (((uintptr_t)x | (uintptr_t)b | (uintptr_t)work | (uintptr_t)vals) & 15) == 0;
-  if (L.sp.on && !L.sp.scalar && aligned16 && (!L.dist || (L.p2p && (halo->n_nbr == 0 || ctx->p2p_send_sorted))) &&
-      getenv("FE_B200_NO_PERSIST") == nullptr)
+  bool want_persist = L.dist && ctx->nranks >= 4;
+  if (const char *e = getenv("FE_B200_PERSIST")) want_persist = atoi(e) != 0;
+  if (getenv("FE_B200_NO_PERSIST")) want_persist = false;
+  if (want_persist && L.sp.on && !L.sp.scalar && aligned16 && (!L.dist || L.p2p))
     return persist_solve(L, work, n_cols, rtol, maxit, fixed, iters_out, relres_out);
 
   if ((rc = L.true_residual_start())) return rc;
