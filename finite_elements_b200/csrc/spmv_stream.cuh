@@ -23,7 +23,7 @@
 __global__ void __launch_bounds__(256) k_block_pattern(int32_t n_nodes, const int32_t *__restrict__ rowptr,
                                                       const int32_t *__restrict__ colidx,
                                                       int32_t *__restrict__ bptr, int32_t *__restrict__ bidx,
-                                                      int *__restrict__ max_deg) {
+                                                      int *__restrict__ max_deg, unsigned char *__restrict__ diag_slot) {
   // 8 lanes per node
   const int64_t node = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;
   const int lane = threadIdx.x & 7;
@@ -38,7 +38,35 @@ __global__ void __launch_bounds__(256) k_block_pattern(int32_t n_nodes, const in
     bptr[node] = s0 >> 2;
     if (deg > *reinterpret_cast<volatile int *>(max_deg)) atomicMax(max_deg, deg);  // rarely taken
   }
-  for (int j = lane; j < deg; j += 8) bidx[(s0 >> 2) + j] = colidx[s0 + 2 * j] >> 1;
+  bool found = false;
+  for (int j = lane; j < deg; j += 8) {
+    const int32_t m = colidx[s0 + 2 * j] >> 1;
+    bidx[(s0 >> 2) + j] = m;
+    if (m == node && j < 255) {  // position of the diagonal block: k_dinv_b2 reads it instead of searching
+      diag_slot[node] = (unsigned char)j;
+      found = true;
+    }
+  }
+  if (!__any_sync(0xffu << ((threadIdx.x & 31) & ~7), found) && lane == 0) diag_slot[node] = 255;  // not stored
+}
+
+// dinv of a 2-DOF-per-node matrix from the cached diagonal positions: two 8-byte loads per node instead
+// of one thread scanning a whole row (k_extract_dinv: 0.43 ms at 16.8 M rows).
+__global__ void __launch_bounds__(256) k_dinv_b2(int32_t n_nodes, const int32_t *__restrict__ bptr,
+                                                const unsigned char *__restrict__ diag_slot,
+                                                const double *__restrict__ vals, double *__restrict__ dinv,
+                                                int *__restrict__ breakdown) {
+  const int32_t node = blockIdx.x * 256 + threadIdx.x;
+  if (node >= n_nodes) return;
+  const int32_t b0 = bptr[node], deg = bptr[node + 1] - b0;
+  const int k = diag_slot[node];
+  double d0 = 0.0, d1 = 0.0;
+  if (k < deg) {
+    d0 = vals[4 * (int64_t)b0 + 2 * k];
+    d1 = vals[4 * (int64_t)b0 + 2 * deg + 2 * k + 1];
+  }
+  if (!(d0 > 0.0) || !(d1 > 0.0)) *breakdown = 1;  // not SPD (e.g. no Dirichlet condition at all)
+  *reinterpret_cast<double2 *>(dinv + 2 * (int64_t)node) = make_double2(1.0 / d0, 1.0 / d1);
 }
 
 

@@ -133,7 +133,10 @@ int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *plan, int kind, const 
  * block that system is equivalent to symmetric elimination, done here in
  * place on the caller's CSR: rhs -= K[:,c] g, row/col c zeroed, K[c,c] = 1, rhs[c] = g.
  * bc_dof int32[n_bc] (unique; local column numbering), bc_val double[n_bc].
- * n_rows x n_cols CSR (n_cols >= n_rows; columns >= n_rows are ghost columns). */
+ * n_rows x n_cols CSR (n_cols >= n_rows; columns >= n_rows are ghost columns), columns sorted within a
+ * row and the pattern structurally symmetric on the owned block -- what fe_plan_csr produces and every
+ * finite-element matrix has; only the rows next to a condition are visited (O(n_bc * valence)).
+ * FE_B200_BC_SWEEP=1 (environment) selects a sweep over all rows that needs neither property. */
 int fe_dirichlet_apply(fe_ctx *ctx, void *stream, int32_t n_rows, int32_t n_cols,
                        const int32_t *rowptr, const int32_t *colidx, double *vals, double *rhs,
                        int32_t n_bc, const int32_t *bc_dof, const double *bc_val);

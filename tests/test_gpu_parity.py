@@ -362,6 +362,34 @@ def test_s1m_values_and_solution_vs_oracle_direct_solve(jitter):
     assert relres <= 1e-8 and err <= 1e-8, (iters, relres, err)
 
 
+@pytest.mark.parametrize("name", ["struct24x16_jit_pstress", "struct24x16_jit_mag", "gmsh_beam_0.1"])
+def test_restricted_dirichlet_equals_full_sweep(name, monkeypatch):
+    """fe_dirichlet_apply visits only the rows next to a condition (k_bc_rows); the sweep over every row it
+    replaces (FE_B200_BC_SWEEP=1) must give the same matrix and right-hand side bit for bit -- random
+    condition sets with adjacent condition nodes, non-zero values, up to a third of all DOFs."""
+    import torch
+    fx = Fixture(name)
+    dm = _dm(fx)
+    k0 = dm.assemble(_kind(fx), fx.mat)
+    rng = np.random.default_rng(5)
+    for frac in (0.002, 0.05, 0.33):
+        n_bc = max(1, int(frac * fx.ndof))
+        dofs = rng.choice(fx.ndof, size=n_bc, replace=False).astype(np.int32)
+        g = rng.standard_normal(n_bc)
+        f = torch.as_tensor(rng.standard_normal(fx.ndof)).cuda()
+        out = []
+        for sweep in (False, True):
+            if sweep:
+                monkeypatch.setenv("FE_B200_BC_SWEEP", "1")
+            else:
+                monkeypatch.delenv("FE_B200_BC_SWEEP", raising=False)
+            vals, rhs = k0.clone(), f.clone()
+            dm.dirichlet(vals, rhs, dofs, g)
+            out.append((vals, rhs))
+        assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]), frac
+        assert torch.equal(out[0][1][torch.as_tensor(dofs).long().cuda()], torch.as_tensor(g).cuda())
+
+
 @pytest.mark.parametrize("grid_cap", [0, 37, 3])
 def test_persistent_pcg_kernel_matches_three_kernel_path(grid_cap, monkeypatch):
     """pcg_persist.cuh (single-reduction CG in one cooperative kernel; the default from 4 ranks up) forced on
