@@ -27,10 +27,36 @@ sys.path.insert(0, ROOT)
 
 METRIC = "assembled Melem/s + PCG DOF-iters/s, 16M-tri plane stress"
 MAT = np.array([[210e9, 0.25, 1.0, 7860.0]])  # scripts/Elasticity/beam2d_example_2.py:35
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at S16M from the committed ncu captures
-# (profiles/r01_d_*.md): only meaningful for the default 4096x2048 workload on one GPU.
-ASM_TRAFFIC_NCU = 2.495e9    # k_assemble_fan<0>: 0.673 GB read + 1.822 GB written
-SPMV_TRAFFIC_NCU = 2.467e9   # k_spmv_stream<1>: 2.334 GB read + 0.134 GB written
+
+
+def ncu_traffic(kernels, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel(s), from the committed
+    `ncu --set full` capture of THIS workload (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py from
+    the .ncu-rep; it records the capture's commit and command).  None when no capture matches -- a number
+    is never carried over to another workload or kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            db = json.load(fh)
+        if db.get("workload") != workload:
+            return None, None
+        tot = 0.0
+        for k in kernels:
+            tot += float(db["kernels"][k]["dram_bytes"])
+        return tot, {"capture": db.get("capture"), "commit": db.get("commit"), "kernels": list(kernels)}
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
+def literal_reference_record():
+    """SURVEY §8d CPU baseline (1): the unmodified reference timed in the build container
+    (oracle/time_literal_reference.py); it cannot run on the GPU box, so the committed record is attached."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_literal_reference_cpu.json")) as fh:
+            rec = json.load(fh)
+        rec["provenance"] = "recorded: python -m oracle.time_literal_reference in the build container (not this run)"
+        return rec
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def measured_peak_hbm():
@@ -160,6 +186,113 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def _time_assembly_and_pcg(torch, dm, kind, mat_dev, f, bc, reps=5, pcg_iters=50):
+    """(assembly seconds, PCG seconds per iteration) of one device mesh, CUDA events on the current stream."""
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    vals = torch.empty(dm.nnz, dtype=torch.float64, device=f.device)
+    bc_val = torch.zeros(bc.numel(), dtype=torch.float64, device=f.device)
+    rhs, x, work = torch.empty_like(f), torch.zeros_like(f), dm.pcg_workspace()
+    ta, tp = [], []
+    for it in range(3 + reps):
+        _gpu_spin(torch)
+        a0, a1, p0, p1 = ev(), ev(), ev(), ev()
+        a0.record()
+        dm.assemble(kind, mat_dev, out=vals)
+        a1.record()
+        rhs.copy_(f)
+        dm.dirichlet(vals, rhs, bc, bc_val)
+        x.zero_()
+        p0.record()
+        dm.pcg_fixed(vals, rhs, x, pcg_iters, work=work)
+        p1.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ta.append(a0.elapsed_time(a1) * 1e-3)
+            tp.append(p0.elapsed_time(p1) * 1e-3 / pcg_iters)
+    return float(np.mean(ta)), float(np.mean(tp))
+
+
+def run_magnetic_record(nx, ny, device, peak):
+    """BASELINE configs[1] scaled to the headline mesh: scalar-potential magnetostatics (1 DOF per node), three
+    permeability bands (scripts/Magnetic/finite_element_beam.py:17-19), A = 0 on the right edge."""
+    import torch
+    from finite_elements_b200.device import DeviceMesh, KIND_MAGNETIC
+    from finite_elements_b200.mesh import structured_mesh_torch
+    dev = torch.device("cuda", device)
+    coords, conn = structured_mesh_torch(nx, ny, dev)
+    n_el, n_nodes = conn.shape[0], coords.shape[0]
+    mu0 = 4e-7 * np.pi
+    mat_dev = torch.as_tensor(np.array([[mu0 * 1e5, 0, 0, 0], [mu0, 0, 0, 0], [mu0 * 5e4, 0, 0, 0]])).to(dev)
+    mat_id = (((torch.arange(n_el, device=dev) // 2) % nx) * 3 // nx).to(torch.int32)
+    dm = DeviceMesh(coords, conn, mat_id, dim=1, device=device)
+    f = torch.zeros(dm.n_rows, dtype=torch.float64, device=dev)
+    f[conn[:2].reshape(-1).long()] = 2.5e9
+    bc = (torch.arange(ny + 1, device=dev) * (nx + 1) + nx).int()
+    t_asm, t_it = _time_assembly_and_pcg(torch, dm, KIND_MAGNETIC, mat_dev, f, bc)
+    a_bytes, p_bytes = asm_bytes(n_el, n_nodes, dm.nnz), pcg_bytes_per_iter(dm.n_rows, dm.nnz)
+    return {"workload": f"magnetostatic (1 DOF/node, 3 mu bands) {nx}x{ny} cells: {n_el} triangles, {dm.n_rows} DOF, nnz {dm.nnz}",
+            "assembly_ms": 1e3 * t_asm, "melem_per_s": n_el / t_asm / 1e6,
+            "assembly_roofline": {"bound": "hbm", "achieved": a_bytes / t_asm / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": a_bytes / t_asm / 1e9 / peak, "kernel": "k_assemble_fan<2>",
+                                  "algorithmic_bytes": a_bytes},
+            "pcg_ms_per_iter": 1e3 * t_it, "pcg_dof_iters_per_s": dm.n_rows / t_it,
+            "pcg_roofline": {"bound": "hbm", "achieved": p_bytes / t_it / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": p_bytes / t_it / 1e9 / peak, "kernel": "k_spmv_stream1 (+ k_pcg_update, k_pcg_pupdate)"}}
+
+
+def run_tet_record(nx, ny, nz, device, peak):
+    """linear tetrahedra, 3 DOF per node, on a Kuhn-triangulated box."""
+    import torch
+    from finite_elements_b200.device import DeviceMesh3D, KIND_ELAST_TET
+    from finite_elements_b200.mesh import structured_tet_mesh
+    dev = torch.device("cuda", device)
+    coords, conn = structured_tet_mesh(nx, ny, nz, h=1.0 / ny)
+    dm = DeviceMesh3D(coords, conn, None, device=device)
+    n = dm.n_rows
+    left = np.nonzero(coords[:, 0] == 0)[0]
+    bc = torch.as_tensor((3 * left[:, None] + np.arange(3)[None, :]).reshape(-1).astype(np.int32)).to(dev)
+    f = torch.zeros(n, dtype=torch.float64, device=dev)
+    f[torch.as_tensor(3 * np.nonzero(coords[:, 0] == coords[:, 0].max())[0] + 2).to(dev)] = -1000.0 / (ny * nz)
+    t_asm, t_it = _time_assembly_and_pcg(torch, dm, KIND_ELAST_TET, torch.as_tensor(MAT).to(dev), f, bc)
+    a_bytes = 16.0 * len(conn) + 24.0 * len(coords) + 8.0 * dm.nnz
+    p_bytes = pcg_bytes_per_iter(n, dm.nnz)
+    return {"workload": f"linear tetrahedra {nx}x{ny}x{nz}-cell Kuhn mesh: {len(conn)} elements, {n} DOF, nnz {dm.nnz}",
+            "assembly_ms": 1e3 * t_asm, "melem_per_s": len(conn) / t_asm / 1e6,
+            "assembly_roofline": {"bound": "hbm", "achieved": a_bytes / t_asm / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": a_bytes / t_asm / 1e9 / peak, "algorithmic_bytes": a_bytes},
+            "pcg_ms_per_iter": 1e3 * t_it, "pcg_dof_iters_per_s": n / t_it,
+            "pcg_roofline": {"bound": "hbm", "achieved": p_bytes / t_it / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": p_bytes / t_it / 1e9 / peak}}
+
+
+def run_e2e_solve(nx, ny, device):
+    """BASELINE configs[2] end to end through the drop-in class: host arrays -> FiniteElementAnalysis(ArrayMesh)
+    .solve() -> Result (host list).  Timed region: mesh H2D + symbolic phase + assembly + loads / conditions +
+    Dirichlet + Jacobi-PCG to 1e-8 + D2H of the solution.  The matrix never leaves the device."""
+    import torch
+    import finite_elements_b200 as fe
+    coords, conn = fe.mesh.structured_mesh(nx, ny)
+    mesh = fe.mesh.ArrayMesh(coords, conn, 'elasticity', MAT, [0, len(conn)])
+    h = 1.0 / ny
+    loads = [fe.loads.NodeLoad(j * (nx + 1) + nx, -1000.0 * h, 2) for j in range(ny + 1)]
+    bcs = [fe.conditions.NodeBoundaryCondition(j * (nx + 1), 0.0, d) for j in range(ny + 1) for d in (1, 2)]
+    times = []
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        an = fe.analysis.FiniteElementAnalysis(mesh, [], [], loads, [], [], bcs, [], [], plane_strain=False,
+                                               plane_stress=True, device=device, solver_rtol=1e-8)
+        x = an.solve_arrays()
+        times.append(time.perf_counter() - t0)
+    info = an.last_solve_info
+    t = float(min(times))
+    return {"workload": f"FiniteElementAnalysis(ArrayMesh {nx}x{ny} cells, {len(conn)} triangles).solve(), rtol 1e-8",
+            "seconds": t, "melem_per_s": len(conn) / t / 1e6, "iterations": info["iterations"],
+            "relative_residual": info["relative_residual"],
+            "h2d_bytes": int(coords.nbytes + conn.nbytes), "d2h_bytes": int(x.nbytes),
+            "tip_uy": float(x[2 * ((ny + 1) * (nx + 1) - 1) + 1])}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -301,6 +434,9 @@ def run_gpu(args):
         ts = q0.elapsed_time(q1) * 1e-3
         solve = {"rtol": 1e-8, "iters": iters, "relres": relres, "true_relres": true_res, "seconds": ts,
                  "dof_iters_per_s": n * iters / ts if ts > 0 else None}
+        if not magnetic:   # fingerprints of x: the N-GPU lines (dist.solution_check) must reproduce them
+            solve.update({"x_sum": float(x.sum()), "x_sumsq": float(torch.dot(x, x)),
+                          "tip_uy": float(x[2 * ((ny + 1) * (nx + 1) - 1) + 1])})
 
     # ---- BASELINE configs[4]: lowest modes of K x = lambda M x on the 1 M-triangle mesh (LOBPCG) ----
     modal = None
@@ -308,7 +444,11 @@ def run_gpu(args):
         modal = run_modal(args.modal, 1024, 512, local_rank)
 
     peak, peak_kind = measured_peak_hbm()
-    default_workload = (nx, ny) == (4096, 2048) and not magnetic   # the ncu traffic constants belong to it
+    wl_key = f"{args.kind} {nx}x{ny} x1"                       # the committed ncu capture must be of this workload
+    asm_kernel = "k_assemble_fan<2>" if magnetic else "k_assemble_fan<0>"
+    pcg_kernels = ["k_spmv_stream1<1,0>" if magnetic else "k_spmv_stream<1,0>", "k_pcg_update", "k_pcg_pupdate"]
+    asm_traffic, asm_src = ncu_traffic([asm_kernel], wl_key)
+    pcg_traffic, pcg_src = ncu_traffic(pcg_kernels, wl_key)
     a_bytes, p_bytes = asm_bytes(n_el, n_nodes, nnz), pcg_bytes_per_iter(n, nnz)
     asm_gbs = a_bytes / t_asm / 1e9
     pcg_gbs = p_bytes * args.pcg_iters / t_pcg / 1e9
@@ -325,13 +465,10 @@ def run_gpu(args):
         "pcg": {"dof_iters_per_s": n * args.pcg_iters / t_pcg, "ms_per_iter": 1e3 * t_pcg / args.pcg_iters,
                 "iters": args.pcg_iters, "algorithmic_bytes_per_iter": p_bytes,
                 "roofline": {"bound": "hbm", "achieved": pcg_gbs, "peak": peak, "unit": "GB/s",
-                             "frac": pcg_gbs / peak, "traffic": SPMV_TRAFFIC_NCU if default_workload else None,
-                             "peak_kind": peak_kind,
-                             "kernel": ("k_spmv<8,1>" if magnetic else "k_spmv_stream<1,0>") +
-                                       " (+ k_pcg_update, k_pcg_pupdate)"}},
+                             "frac": pcg_gbs / peak, "traffic": pcg_traffic, "traffic_source": pcg_src,
+                             "peak_kind": peak_kind, "kernel": " + ".join(pcg_kernels) + " (one iteration)"}},
         "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": peak, "unit": "GB/s", "frac": asm_gbs / peak,
-                     "traffic": ASM_TRAFFIC_NCU if default_workload else None, "peak_kind": peak_kind,
-                     "kernel": "k_assemble_fan<2>" if magnetic else "k_assemble_fan<0>"},
+                     "traffic": asm_traffic, "traffic_source": asm_src, "peak_kind": peak_kind, "kernel": asm_kernel},
         "e2e": {"value": n_el / np.mean(e2e_asm) / 1e6, "unit": "Melem/s",
                 "h2d_bytes_per_step": int(h_coords.numel() * 8 + h_rhs.numel() * 8),
                 "d2h_bytes_per_step": int(h_vals.numel() * 8 + h_x.numel() * 8),
@@ -341,10 +478,18 @@ def run_gpu(args):
     }
     if modal is not None:
         line["modal"] = modal
+    if args.extras and not magnetic:
+        # the other rows of SURVEY §8 measured in the same run (sub-records; the headline stays plane stress)
+        del vals, rhs, x, work, dm
+        torch.cuda.empty_cache()
+        line["magnetic"] = run_magnetic_record(nx, ny, local_rank, peak)
+        line["tetrahedra"] = run_tet_record(96, 48, 48, local_rank, peak)
+        line["e2e_solve"] = run_e2e_solve(1024, 512, local_rank)
     if not args.no_cpu_baseline:
         cb = cpu_baseline(args.cpu_nx, args.cpu_ny, args.cpu_pcg_iters)
         line["cpu_baseline"] = {"value": cb["melem_s"], "unit": "Melem/s", "cores": 1, "kind": "port",
-                                "sample": cb["sample"], "pcg_dof_iters_per_s": cb["dof_iters_s"]}
+                                "sample": cb["sample"], "pcg_dof_iters_per_s": cb["dof_iters_s"],
+                                "literal_reference": literal_reference_record()}
     print(json.dumps(line))
 
 
@@ -391,6 +536,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--modal", type=int, default=10,
                     help="also time the lowest K modes of K x = lambda M x on the 1M-triangle mesh (BASELINE configs[4]); 0 = skip")
+    ap.add_argument("--extras", type=int, default=1,
+                    help="also measure the magnetic path (same mesh), the tetrahedral path and configs[2] end to end "
+                         "through FiniteElementAnalysis.solve() as sub-records of the line; 0 = skip")
     ap.add_argument("--cpu-nx", type=int, default=1024)
     ap.add_argument("--cpu-ny", type=int, default=512)
     ap.add_argument("--cpu-pcg-iters", type=int, default=20)

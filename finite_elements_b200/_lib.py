@@ -46,8 +46,8 @@ SIGNATURES = {
     "fe_spmv": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32]),
     "fe_tet_elem_matrices": (C.c_int, [_vp, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fe_tet_elem_post": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
-    "fe_tet_assemble": (C.c_int, [_vp, _vp, C.c_int, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32,
-                                  _i32]),
+    "fe_tet_plan_create": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, C.POINTER(_vp)]),
+    "fe_tet_assemble": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _i32, _vp, _i32]),
     "fe_spmm_pair": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
     "fe_cheb_step": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _i32]),
     "fe_csr_diagonal": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),

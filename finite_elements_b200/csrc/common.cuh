@@ -102,6 +102,7 @@ struct fe_ctx {
   fe::Scratch scratch_a;   // material tables, BC flags, scan block sums
   fe::Scratch scratch_b;   // reduction partials / PCG scalars
   fe::Scratch scratch_c;   // node-level block pattern of the streamed SpMV
+  fe::Scratch scratch_g;   // fe_tet_assemble: per-element gradient table (128 B per element)
   fe::Scratch bc_map;      // fe_dirichlet_apply: column -> condition index + 1 (kept all-zero between calls)
   fe::Scratch scratch_p;   // persistent PCG kernel: barrier flags (zeroed on allocation) + per-CTA partials
   bool p2p_send_sorted = false;  // every neighbour's send list is ascending (checked when the halo is uploaded)

@@ -329,6 +329,7 @@ int fe_ctx_destroy(fe_ctx *ctx) {
   ctx->scratch_c.release();
   ctx->scratch_p.release();
   ctx->bc_map.release();
+  ctx->scratch_g.release();
   ctx->halo_send.release();
   ctx->halo_recv.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -148,14 +148,14 @@ __global__ void k_count_corners(int64_t n3, const int32_t *__restrict__ conn, in
 
 __global__ void k_fill_corners(int64_t n3, const int32_t *__restrict__ conn, int32_t n_nodes, int32_t n_owned,
                                const int32_t *__restrict__ corner_ptr, int32_t *__restrict__ cursor,
-                               int32_t *__restrict__ corner_tmp) {
+                               int32_t *__restrict__ corner_tmp, int npe = 3) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n3) return;
   const int32_t nd = conn[i];
   if (nd < 0 || nd >= n_owned) return;
   const int32_t pos = corner_ptr[nd] + atomicAdd(cursor + nd, 1);
-  const int64_t e = i / 3;
-  corner_tmp[pos] = (int32_t)((e << 2) | (i - 3 * e));
+  const int64_t e = i / npe;
+  corner_tmp[pos] = (int32_t)((e << 2) | (i - npe * e));
 }
 
 __device__ __forceinline__ void insertion_sort(int32_t *a, int n) {
@@ -311,6 +311,9 @@ int fe_plan_destroy(fe_plan *p) {
   cudaFree(p->conn4);
   cudaFree(p->fan_ptr);
   cudaFree(p->fan_rec);
+  cudaFree(p->corner_elem);
+  cudaFree(p->contrib_ptr);
+  cudaFree(p->contrib);
   delete p;
   return FE_OK;
 }
@@ -468,6 +471,224 @@ done:
 #undef PLAN_TRY
 #undef PLAN_CUDA
 #undef PLAN_LAUNCHED
+}
+
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// Linear tetrahedra (3 DOF per node): the same node-graph construction with 4 corners per element
+// (ElasticityTetrahedralElement3D, elements.py:663-876; get_row_col_indices analysis.py:714-735 for
+// 12 x 12 element matrices).  Instead of the triangles' fan records the plan lists, per off-diagonal
+// block (node, neighbour), the elements that contain both -- k_tet_assemble_slots gives every block
+// of the global matrix to one lane.
+// ---------------------------------------------------------------------------------------
+namespace fe {
+
+__global__ void __launch_bounds__(128) k_tet_node_adjacency(int32_t n_owned, const int32_t *__restrict__ conn,
+                                                           const int32_t *__restrict__ corner_ptr,
+                                                           int32_t *__restrict__ corner_tmp, int32_t *__restrict__ cand,
+                                                           int32_t *__restrict__ ndeg, int32_t *__restrict__ corner_elem,
+                                                           PlanFlags *__restrict__ flags) {
+  const int32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_owned) return;
+  const int32_t c0 = corner_ptr[n], c1 = corner_ptr[n + 1];
+  int32_t *cs = corner_tmp + c0;
+  const int nc = c1 - c0;
+  insertion_sort(cs, nc);  // (element << 2 | vertex): ascending element id
+  int32_t *cd = cand + 4 * (int64_t)c0;
+  for (int k = 0; k < nc; ++k) {
+    const int64_t e = cs[k] >> 2;
+    corner_elem[c0 + k] = (int32_t)e;
+    if (k > 0 && (cs[k - 1] >> 2) == e) flags->fan_irregular = 1;  // the element lists this node twice
+    for (int j = 0; j < 4; ++j) cd[4 * k + j] = conn[4 * e + j];
+  }
+  insertion_sort(cd, 4 * nc);
+  int m = 0;
+  for (int k = 0; k < 4 * nc; ++k)
+    if (m == 0 || cd[k] != cd[m - 1]) cd[m++] = cd[k];
+  ndeg[n] = m;
+  if (m > *reinterpret_cast<volatile int *>(&flags->max_degree)) atomicMax(&flags->max_degree, m);
+  if (m > kMaxDegree) flags->too_dense = 1;
+}
+
+// One thread per owned node, slot-major: for every neighbour slot the corners whose element holds that
+// neighbour, in ascending element order.  FILL = false counts, FILL = true writes the codes.
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_tet_contrib(int32_t n_owned, const int32_t *__restrict__ conn,
+                                                    const int32_t *__restrict__ corner_ptr,
+                                                    const int32_t *__restrict__ corner_tmp,
+                                                    const int32_t *__restrict__ cand, const int32_t *__restrict__ adj_ptr,
+                                                    int32_t *__restrict__ adj, int32_t *__restrict__ cnt,
+                                                    const int32_t *__restrict__ contrib_ptr, int32_t *__restrict__ contrib) {
+  const int32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_owned) return;
+  const int32_t c0 = corner_ptr[n], c1 = corner_ptr[n + 1];
+  const int32_t a0 = adj_ptr[n];
+  const int deg = adj_ptr[n + 1] - a0;
+  if (deg > kMaxDegree) return;
+  const int32_t *cd = cand + 4 * (int64_t)c0;
+  for (int k = 0; k < deg; ++k) {
+    const int32_t m = cd[k];
+    if (!FILL) adj[a0 + k] = m;
+    int32_t count = 0;
+    if (m != n) {
+      int32_t w = FILL ? contrib_ptr[a0 + k] : 0;
+      for (int32_t c = c0; c < c1; ++c) {
+        const int32_t code = corner_tmp[c];
+        const int64_t e = code >> 2;
+        const int v = code & 3;
+        for (int j = 0; j < 4; ++j) {
+          if (j == v || conn[4 * e + j] != m) continue;
+          if (FILL) contrib[w++] = (int32_t)((e << 4) | (v << 2) | j);
+          ++count;
+        }
+      }
+    }
+    if (!FILL) cnt[a0 + k] = count;
+  }
+}
+
+}  // namespace fe
+
+extern "C" {
+
+int fe_tet_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, int64_t n_elems, const int32_t *conn,
+                       fe_plan **out) {
+  FE_REQUIRE(ctx && out, "fe_tet_plan_create: NULL ctx/out");
+  FE_REQUIRE(n_nodes >= 0 && n_owned >= 0 && n_owned <= n_nodes, "fe_tet_plan_create: bad node counts %d/%d", n_owned, n_nodes);
+  FE_REQUIRE(n_elems >= 0 && (n_elems == 0 || conn), "fe_tet_plan_create: bad connectivity");
+  if (n_elems >= (int64_t(1) << 27)) return fail(FE_ERR_UNSUPPORTED, "fe_tet_plan_create: more than 2^27 elements");
+  if ((int64_t)n_nodes * 3 >= (int64_t(1) << 31)) return fail(FE_ERR_UNSUPPORTED, "fe_tet_plan_create: DOF count overflows int32");
+  cudaStream_t st = as_stream(stream);
+  FE_CUDA(cudaSetDevice(ctx->device));
+  fe_plan *p = new fe_plan();
+  p->ctx = ctx;
+  p->n_nodes = n_nodes;
+  p->n_owned = n_owned;
+  p->dim = 3;
+  p->npe = 4;
+  p->n_elems = n_elems;
+  int rc = FE_OK;
+  int32_t *cursor = nullptr, *corner_tmp = nullptr, *cand = nullptr, *ndeg = nullptr, *cnt = nullptr;
+  PlanFlags *flags = nullptr;
+  int64_t *totals = nullptr;
+  const int64_t n4 = 4 * n_elems;
+  PlanFlags hflags = {0, 0, 0, 0, 0, 0};
+  int64_t htot[3] = {0, 0, 0};
+#define TP_TRY(expr)            \
+  do {                          \
+    rc = (expr);                \
+    if (rc != FE_OK) goto done; \
+  } while (0)
+#define TP_CUDA(call)                                                                                       \
+  do {                                                                                                      \
+    cudaError_t e__ = (call);                                                                               \
+    if (e__ != cudaSuccess) {                                                                               \
+      rc = fail(FE_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      goto done;                                                                                            \
+    }                                                                                                       \
+  } while (0)
+#define TP_LAUNCHED()                                                                                      \
+  do {                                                                                                     \
+    ctx->launches++;                                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                                                  \
+    if (e__ != cudaSuccess) {                                                                              \
+      rc = fail(FE_ERR_CUDA, "launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__));   \
+      goto done;                                                                                           \
+    }                                                                                                      \
+  } while (0)
+  TP_TRY(dev_alloc(&p->corner_ptr, (int64_t)n_owned + 1, &p->bytes));
+  TP_TRY(dev_alloc(&p->adj_ptr, (int64_t)n_owned + 1 + 136, &p->bytes));
+  TP_TRY(dev_alloc(&cursor, (int64_t)n_owned + 1, nullptr));
+  TP_TRY(dev_alloc(&ndeg, (int64_t)n_owned + 1, nullptr));
+  TP_TRY(dev_alloc(&flags, 1, nullptr));
+  TP_TRY(dev_alloc(&totals, 3, nullptr));
+  TP_CUDA(cudaMemsetAsync(cursor, 0, ((size_t)n_owned + 1) * sizeof(int32_t), st));
+  TP_CUDA(cudaMemsetAsync(ndeg, 0, ((size_t)n_owned + 1) * sizeof(int32_t), st));
+  TP_CUDA(cudaMemsetAsync(flags, 0, sizeof(PlanFlags), st));
+  TP_CUDA(cudaMemsetAsync(totals, 0, 3 * sizeof(int64_t), st));
+  if (n_elems > 0 && n_owned > 0) {
+    k_count_corners<<<grid_for(n4, 256), 256, 0, st>>>(n4, conn, n_nodes, n_owned, cursor, flags);
+    TP_LAUNCHED();
+  }
+  TP_TRY(exclusive_scan_i32(ctx, st, cursor, p->corner_ptr, n_owned, totals + 0));
+  TP_CUDA(cudaMemcpyAsync(htot, totals, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  TP_CUDA(cudaMemcpyAsync(&hflags, flags, sizeof(PlanFlags), cudaMemcpyDeviceToHost, st));
+  TP_CUDA(cudaStreamSynchronize(st));
+  if (hflags.bad_node) {
+    rc = fail(FE_ERR_ARG, "fe_tet_plan_create: connectivity references a node outside [0, %d)", n_nodes);
+    goto done;
+  }
+  p->n_corners = htot[0];
+  TP_TRY(dev_alloc(&p->corner_elem, p->n_corners, &p->bytes));
+  TP_TRY(dev_alloc(&corner_tmp, p->n_corners, nullptr));
+  TP_TRY(dev_alloc(&cand, 4 * p->n_corners, nullptr));
+  if (p->n_corners > 0) {
+    TP_CUDA(cudaMemsetAsync(cursor, 0, ((size_t)n_owned + 1) * sizeof(int32_t), st));
+    k_fill_corners<<<grid_for(n4, 256), 256, 0, st>>>(n4, conn, n_nodes, n_owned, p->corner_ptr, cursor, corner_tmp, 4);
+    TP_LAUNCHED();
+    k_tet_node_adjacency<<<grid_for(n_owned, 128), 128, 0, st>>>(n_owned, conn, p->corner_ptr, corner_tmp, cand, ndeg,
+                                                                p->corner_elem, flags);
+    TP_LAUNCHED();
+  }
+  TP_TRY(exclusive_scan_i32(ctx, st, ndeg, p->adj_ptr, n_owned, totals + 1));
+  TP_CUDA(cudaMemcpyAsync(htot, totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  TP_CUDA(cudaMemcpyAsync(&hflags, flags, sizeof(PlanFlags), cudaMemcpyDeviceToHost, st));
+  TP_CUDA(cudaStreamSynchronize(st));
+  p->nnzb = htot[1];
+  p->nnz = p->nnzb * 9;
+  p->max_degree = hflags.max_degree;
+  p->tet_degenerate = hflags.fan_irregular != 0;
+  if (hflags.too_dense) {
+    rc = fail(FE_ERR_UNSUPPORTED, "fe_tet_plan_create: a node has %d neighbours (limit %d)", hflags.max_degree, kMaxDegree);
+    goto done;
+  }
+  if (p->nnz >= (int64_t(1) << 31)) {
+    rc = fail(FE_ERR_UNSUPPORTED, "fe_tet_plan_create: nnz = %lld overflows int32 CSR indices", (long long)p->nnz);
+    goto done;
+  }
+  TP_TRY(dev_alloc(&p->adj, p->nnzb, &p->bytes));
+  TP_TRY(dev_alloc(&cnt, p->nnzb + 1, nullptr));
+  TP_TRY(dev_alloc(&p->contrib_ptr, p->nnzb + 1, &p->bytes));
+  TP_CUDA(cudaMemsetAsync(cnt, 0, ((size_t)p->nnzb + 1) * sizeof(int32_t), st));
+  if (p->n_corners > 0) {
+    k_tet_contrib<false><<<grid_for(n_owned, 128), 128, 0, st>>>(n_owned, conn, p->corner_ptr, corner_tmp, cand, p->adj_ptr,
+                                                              p->adj, cnt, nullptr, nullptr);
+    TP_LAUNCHED();
+  }
+  TP_TRY(exclusive_scan_i32(ctx, st, cnt, p->contrib_ptr, p->nnzb, totals + 2));
+  TP_CUDA(cudaMemcpyAsync(htot, totals, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  TP_CUDA(cudaStreamSynchronize(st));
+  p->n_contrib = htot[2];
+  if (p->n_contrib >= (int64_t(1) << 31)) {
+    rc = fail(FE_ERR_UNSUPPORTED, "fe_tet_plan_create: %lld block contributions overflow int32", (long long)p->n_contrib);
+    goto done;
+  }
+  TP_TRY(dev_alloc(&p->contrib, p->n_contrib, &p->bytes));
+  if (p->n_contrib > 0) {
+    k_tet_contrib<true><<<grid_for(n_owned, 128), 128, 0, st>>>(n_owned, conn, p->corner_ptr, corner_tmp, cand, p->adj_ptr,
+                                                             p->adj, nullptr, p->contrib_ptr, p->contrib);
+    TP_LAUNCHED();
+  }
+  TP_CUDA(cudaStreamSynchronize(st));
+done:
+  cudaFree(cursor);
+  cudaFree(corner_tmp);
+  cudaFree(cand);
+  cudaFree(ndeg);
+  cudaFree(cnt);
+  cudaFree(flags);
+  cudaFree(totals);
+  if (rc != FE_OK) {
+    fe_plan_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return FE_OK;
+#undef TP_TRY
+#undef TP_CUDA
+#undef TP_LAUNCHED
 }
 
 int64_t fe_plan_nnz(const fe_plan *p) { return p ? p->nnz : 0; }

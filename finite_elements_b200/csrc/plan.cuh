@@ -35,4 +35,13 @@ struct fe_plan {
   int32_t fan_tile_max = 0;    // max records of one 32-node chunk (one warp of k_assemble_fan)
   int32_t *fan_ptr = nullptr;  // [n_owned + 1]
   int2 *fan_rec = nullptr;     // [n_fan]
+  // linear tetrahedra (npe == 4, dim == 3; fe_tet_plan_create): per OFF-DIAGONAL block (node i, slot k) the
+  // elements that hold both nodes, ascending, as (element << 4 | local vertex of i << 2 | local vertex of the
+  // neighbour) -- what k_tet_assemble_slots walks; the diagonal block is summed from the same visits
+  int32_t npe = 3;
+  int32_t *corner_elem = nullptr;   // [n_corners] element of every corner, ascending within a node (variants 1, 2)
+  int32_t *contrib_ptr = nullptr;   // [nnzb + 1]
+  int32_t *contrib = nullptr;       // [12 n_elems restricted to owned rows]
+  int64_t n_contrib = 0;
+  bool tet_degenerate = false;      // an element lists a node twice: the slot kernel is not used
 };

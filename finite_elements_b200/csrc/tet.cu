@@ -22,6 +22,7 @@
 // per SM): the fan-ordered, TMA-pipelined treatment the triangles got is the next step.
 #include "common.cuh"
 #include "elem.cuh"
+#include "plan.cuh"
 
 namespace fe {
 
@@ -279,6 +280,246 @@ __global__ void __launch_bounds__(kTetTile) k_tet_assemble_tile(
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Default: one LANE per block of the global matrix.  16 lanes share a node; lane l owns the neighbour
+// slots l, l + 16, ... and walks, for each, the plan's list of elements that hold both nodes (ascending
+// element id, fe_tet_plan_create), accumulating the 3x3 block in registers and writing it once -- no
+// shared-memory tile (the node-owner kernels above are capped at 6 warps per SM by theirs), no slot
+// search, no serial 24-element loop.  Only the two gradients a block needs are evaluated: with the
+// element relabelled (other_a, self, neighbour, other_b),  grad N_self = (b x c) / det and
+// grad N_nbr = (c x a) / det  for the edge vectors a, b, c from other_a.  The diagonal block follows from the
+// off-diagonal ones (rigid-translation null space, see the end of the kernel): fixed order, bit-reproducible.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int pick4(const int4 &c, int i) { return i == 0 ? c.x : (i == 1 ? c.y : (i == 2 ? c.z : c.w)); }
+
+#ifndef FE_TET_MINB
+#define FE_TET_MINB 3  // resident CTAs per SM the register allocation targets (80 registers; measured best of 2/3/4)
+#endif
+template <bool MASS>
+__global__ void __launch_bounds__(256, FE_TET_MINB) k_tet_assemble_slots(int32_t n_owned, const int32_t *__restrict__ adj_ptr,
+                                                           const int32_t *__restrict__ adj,
+                                                           const int32_t *__restrict__ contrib_ptr,
+                                                           const int32_t *__restrict__ contrib,
+                                                           const double *__restrict__ coords,
+                                                           const int32_t *__restrict__ conn,
+                                                           const int32_t *__restrict__ mat_id,
+                                                           const double *__restrict__ mat, double *__restrict__ vals) {
+  const int32_t node = (blockIdx.x * 256 + threadIdx.x) >> 4;
+  const int lane = threadIdx.x & 15;
+  if (node >= n_owned) return;  // (whole 16-lane groups leave together)
+  const int32_t a0 = __ldg(adj_ptr + node);
+  const int deg = __ldg(adj_ptr + node + 1) - a0;
+  double *rows = vals + 9 * (int64_t)a0;
+  const int4 *conn4 = reinterpret_cast<const int4 *>(conn);
+  // this lane's share of the sum of the node's off-diagonal blocks, parked in shared memory (one column
+  // per thread) so that it does not occupy 18 registers across the element loop
+  __shared__ double tot_s[9][256];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) tot_s[q][threadIdx.x] = 0.0;
+  int kself = -1;
+  for (int k = lane; k < deg; k += 16) {
+    if (__ldg(adj + a0 + k) == node) kself = k;
+    double acc[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+    const int32_t q0 = __ldg(contrib_ptr + a0 + k), q1 = __ldg(contrib_ptr + a0 + k + 1);
+    // software pipeline: the next entry's code and connectivity row travel while this one is evaluated
+    int32_t code = 0;
+    int4 c = make_int4(0, 0, 0, 0);
+    if (q0 < q1) {
+      code = __ldg(contrib + q0);
+      c = __ldg(conn4 + (code >> 4));
+    }
+    for (int32_t q = q0; q < q1; ++q) {
+      const int32_t e = code >> 4;
+      const int vi = (code >> 2) & 3, vj = code & 3;
+      const int4 cc = c;
+      if (q + 1 < q1) {
+        code = __ldg(contrib + q + 1);
+        c = __ldg(conn4 + (code >> 4));
+      }
+      const unsigned rest = 0xFu ^ (1u << vi) ^ (1u << vj);
+      const int oa = __ffs(rest) - 1, ob = 31 - __clz(rest);
+      const double *p0 = coords + 3 * (int64_t)pick4(cc, oa), *pi = coords + 3 * (int64_t)pick4(cc, vi);
+      const double *pj = coords + 3 * (int64_t)pick4(cc, vj), *pb = coords + 3 * (int64_t)pick4(cc, ob);
+      const double x0 = __ldg(p0), y0 = __ldg(p0 + 1), z0 = __ldg(p0 + 2);
+      const double ax = __ldg(pi) - x0, ay = __ldg(pi + 1) - y0, az = __ldg(pi + 2) - z0;
+      const double bx = __ldg(pj) - x0, by = __ldg(pj + 1) - y0, bz = __ldg(pj + 2) - z0;
+      const double cx = __ldg(pb) - x0, cy = __ldg(pb + 1) - y0, cz = __ldg(pb + 2) - z0;
+      const double ux = by * cz - bz * cy, uy = bz * cx - bx * cz, uz = bx * cy - by * cx;  // b x c
+      const double det = ax * ux + ay * uy + az * uz;                                        // 6 V, signed
+      const TetMat m = tet_material(MASS ? FE_MASS_TET : FE_ELAST_TET, mat, mat_id ? __ldg(mat_id + e) : 0, fabs(det) / 6.0);
+      if (MASS) {
+        acc[0] += m.p0;
+        acc[4] += m.p0;
+        acc[8] += m.p0;
+      } else {
+        const double inv = 1.0 / det;
+        const double gi[3] = {ux * inv, uy * inv, uz * inv};                                  // grad N_self
+        const double gj[3] = {(cy * az - cz * ay) * inv, (cz * ax - cx * az) * inv, (cx * ay - cy * ax) * inv};  // (c x a) / det
+        const double mdot = m.p1 * (gi[0] * gj[0] + gi[1] * gj[1] + gi[2] * gj[2]);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const double lr = m.p0 * gi[r], mr = m.p1 * gj[r];
+#pragma unroll
+          for (int t = 0; t < 3; ++t) acc[3 * r + t] += lr * gj[t] + mr * gi[t] + (r == t ? mdot : 0.0);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        rows[r * 3 * deg + 3 * k + t] = acc[3 * r + t];
+        tot_s[3 * r + t][threadIdx.x] += acc[3 * r + t];
+      }
+  }
+  double tot[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) tot[q] = tot_s[q][threadIdx.x];
+  // Diagonal block.  Stiffness: a rigid translation carries no force, so every block row of K sums to zero
+  // and K_ii = -(sum of the off-diagonal blocks) -- the same number as the sum of the elements' self blocks
+  // up to rounding, without evaluating them.  Consistent mass: an element gives 2 m to (i, i) and m to each
+  // of its three (i, j), so M_ii = 2/3 of the off-diagonal sum.  The 16 partial sums are added by
+  // xor-shuffles in a fixed order.
+  const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) tot[q] += __shfl_xor_sync(gmask, tot[q], o);
+  }
+  if (kself >= 0) {
+    const double f = MASS ? (2.0 / 3.0) : -1.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int t = 0; t < 3; ++t) rows[r * 3 * deg + 3 * kself + t] = f * tot[3 * r + t];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Two-pass form of the lane-per-block assembly (default).  Pass 1 evaluates every element ONCE and
+// leaves four 32-byte records h_k = (sqrt(mu V) grad N_k, lambda / mu) in a scratch table (128 B per
+// element).  Pass 2 walks the same per-block element lists and reads exactly the two records it needs,
+// each with ONE 256-bit load (LDG.E.256: one sector per lane):
+//     block(i, j) = (lambda / mu) h_i h_j^T + h_j h_i^T + (h_i . h_j) I        (= V B_i^T D B_j)
+// ncu on the earlier forms of this walk: L1TEX 95 % busy on scattered 8-byte loads (7 sector accesses per
+// visit with an unpadded table, 13 when the geometry is rebuilt from connectivity and coordinates);
+// the number of divergent accesses per visit (l1tex__data_pipe_lsu_wavefronts ~ 1 per lane access per
+// cycle and SM), not FP64 or DRAM, sets the time: 0.94 ms (round 1) -> 0.36 (rebuild) -> 0.30 ms (table)
+// on 1.33 M elements.  Staging the rows in shared memory for coalesced stores was tried and bought nothing.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_global_f64x4(double *p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+struct D4 {
+  double x, y, z, w;
+};
+__device__ __forceinline__ D4 ldg_nc_f64x4(const double *p) {
+  D4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+
+template <bool MASS>
+__global__ void __launch_bounds__(128) k_tet_gradient_table(int64_t n_elems, const double *__restrict__ coords,
+                                                           const int32_t *__restrict__ conn,
+                                                           const int32_t *__restrict__ mat_id,
+                                                           const double *__restrict__ mat, double *__restrict__ table) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elems) return;
+  const int4 c = __ldg(reinterpret_cast<const int4 *>(conn) + e);
+  const TetGeom t = tet_geom(coords, c.x, c.y, c.z, c.w);
+  const TetMat m = tet_material(MASS ? FE_MASS_TET : FE_ELAST_TET, mat, mat_id ? mat_id[e] : 0, t.vol);
+  // elasticity: m = (lambda V, mu V); mass: m.p0 = rho V / 20 rides in the fourth component
+  const double sc = MASS ? 0.0 : sqrt(m.p1);
+  const double w = MASS ? m.p0 : (m.p1 != 0.0 ? m.p0 / m.p1 : 0.0);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) st_global_f64x4(table + 16 * e + 4 * k, sc * t.g[k][0], sc * t.g[k][1], sc * t.g[k][2], w);
+}
+
+template <bool MASS>
+__device__ __forceinline__ void tet_pair_add(const D4 &hi, const D4 &hj, double (&acc)[9]) {
+  if (MASS) {
+    acc[0] += hi.w;
+    acc[4] += hi.w;
+    acc[8] += hi.w;
+  } else {
+    const double dot = hi.x * hj.x + hi.y * hj.y + hi.z * hj.z;
+    const double gi[3] = {hi.x, hi.y, hi.z}, gj[3] = {hj.x, hj.y, hj.z};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double lr = hi.w * gi[r];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[3 * r + c] += lr * gj[c] + gj[r] * gi[c] + (r == c ? dot : 0.0);
+    }
+  }
+}
+
+template <bool MASS>
+__global__ void __launch_bounds__(256, 4) k_tet_assemble_table(int32_t n_owned, const int32_t *__restrict__ adj_ptr,
+                                                              const int32_t *__restrict__ adj,
+                                                              const int32_t *__restrict__ contrib_ptr,
+                                                              const int32_t *__restrict__ contrib,
+                                                              const double *__restrict__ table, double *__restrict__ vals) {
+  const int32_t node = (blockIdx.x * 256 + threadIdx.x) >> 4;
+  const int lane = threadIdx.x & 15;
+  if (node >= n_owned) return;
+  const int32_t a0 = __ldg(adj_ptr + node);
+  const int deg = __ldg(adj_ptr + node + 1) - a0;
+  double *rows = vals + 9 * (int64_t)a0;
+  __shared__ double tot_s[9][256];  // per-lane sum of its off-diagonal blocks (kept out of the registers)
+#pragma unroll
+  for (int q = 0; q < 9; ++q) tot_s[q][threadIdx.x] = 0.0;
+  int kself = -1;
+  for (int k = lane; k < deg; k += 16) {
+    if (__ldg(adj + a0 + k) == node) kself = k;
+    double acc[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+    const int32_t q0 = __ldg(contrib_ptr + a0 + k), q1 = __ldg(contrib_ptr + a0 + k + 1);
+    // two visits in flight: both codes, then the four 256-bit record loads, then the arithmetic
+    auto rec = [&](int32_t code, int v) { return ldg_nc_f64x4(table + 16 * (int64_t)(code >> 4) + 4 * v); };
+    int32_t q = q0;
+    for (; q + 1 < q1; q += 2) {
+      const int32_t c0 = __ldg(contrib + q), c1 = __ldg(contrib + q + 1);
+      const D4 i0 = rec(c0, (c0 >> 2) & 3), j0 = MASS ? i0 : rec(c0, c0 & 3);
+      const D4 i1 = rec(c1, (c1 >> 2) & 3), j1 = MASS ? i1 : rec(c1, c1 & 3);
+      tet_pair_add<MASS>(i0, j0, acc);
+      tet_pair_add<MASS>(i1, j1, acc);
+    }
+    if (q < q1) {
+      const int32_t c0 = __ldg(contrib + q);
+      const D4 i0 = rec(c0, (c0 >> 2) & 3), j0 = MASS ? i0 : rec(c0, c0 & 3);
+      tet_pair_add<MASS>(i0, j0, acc);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        rows[r * 3 * deg + 3 * k + t] = acc[3 * r + t];
+        tot_s[3 * r + t][threadIdx.x] += acc[3 * r + t];
+      }
+  }
+  // diagonal block from the off-diagonal ones: see k_tet_assemble_slots
+  double tot[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) tot[q] = tot_s[q][threadIdx.x];
+  const unsigned gmask = 0xffffu << (threadIdx.x & 16);
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) tot[q] += __shfl_xor_sync(gmask, tot[q], o);
+  }
+  if (kself >= 0) {
+    const double f = MASS ? (2.0 / 3.0) : -1.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int t = 0; t < 3; ++t) rows[r * 3 * deg + 3 * kself + t] = f * tot[3 * r + t];
+  }
+}
+
 }  // namespace fe
 
 using namespace fe;
@@ -309,30 +550,53 @@ int fe_tet_elem_post(fe_ctx *ctx, void *stream, int64_t n_elems, const double *c
   return FE_OK;
 }
 
-int fe_tet_assemble(fe_ctx *ctx, void *stream, int kind, int32_t n_owned_nodes, const int32_t *corner_ptr,
-                    const int32_t *corner_elem, const int32_t *adj_ptr, const int32_t *adj, const double *coords,
-                    const int32_t *conn, const int32_t *mat_id, const double *mat, int32_t n_mat, double *vals,
-                    int32_t max_degree, int32_t variant) {
-  FE_REQUIRE(ctx && corner_ptr && corner_elem && adj_ptr && adj && coords && conn && mat && vals,
-             "fe_tet_assemble: NULL argument");
+int fe_tet_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind, const double *coords, const int32_t *conn,
+                    const int32_t *mat_id, const double *mat, int32_t n_mat, double *vals, int32_t variant) {
+  FE_REQUIRE(ctx && p && coords && conn && mat && (vals || p->nnz == 0), "fe_tet_assemble: NULL argument");
+  FE_REQUIRE(p->npe == 4 && p->dim == 3, "fe_tet_assemble: the plan was not built by fe_tet_plan_create");
   FE_REQUIRE(kind == FE_ELAST_TET || kind == FE_MASS_TET, "fe_tet_assemble: kind %d is not a tetrahedral kind", kind);
-  FE_REQUIRE(n_owned_nodes >= 0 && n_mat > 0, "fe_tet_assemble: bad sizes");
+  FE_REQUIRE(n_mat > 0, "fe_tet_assemble: bad sizes");
   FE_REQUIRE(((uintptr_t)conn & 15) == 0, "fe_tet_assemble: conn must be 16-byte aligned");
-  FE_REQUIRE(variant >= 0 && variant <= 2, "fe_tet_assemble: unknown variant %d", variant);
-  if (n_owned_nodes == 0) return FE_OK;
+  FE_REQUIRE(variant >= 0 && variant <= 4, "fe_tet_assemble: unknown variant %d", variant);
+  if (p->n_owned == 0 || p->nnz == 0) return FE_OK;
+  cudaStream_t st = as_stream(stream);
+  const int max_degree = p->max_degree;
   const size_t smem = (size_t)9 * (max_degree > 0 ? max_degree : 1) * kTetLD * sizeof(double);
   const bool fits = max_degree > 0 && smem <= 200 * 1024;
+  if (variant >= 3 && p->tet_degenerate)
+    return fail(FE_ERR_UNSUPPORTED, "fe_tet_assemble: the slot variant needs elements with four distinct nodes");
   if (variant == 2 && !fits)
-    return fail(FE_ERR_UNSUPPORTED, "fe_tet_assemble: the tile variant needs max_degree (got %d) and %zu B of shared memory",
-                max_degree, smem);
-  if (variant == 0) variant = fits ? 2 : 1;
-  if (variant == 2) {
+    return fail(FE_ERR_UNSUPPORTED, "fe_tet_assemble: the tile variant needs %zu B of shared memory (valence %d)", smem, max_degree);
+  if (variant == 0) variant = !p->tet_degenerate ? 4 : (fits ? 2 : 1);
+  if (variant == 4) {
+    int rc = ctx->scratch_g.reserve((size_t)p->n_elems * 16 * sizeof(double));
+    if (rc) return rc;
+    double *table = (double *)ctx->scratch_g.ptr;
+    const int g1 = grid_for(p->n_elems, 128), g2 = grid_for((int64_t)p->n_owned * 16, 256);
+    if (kind == FE_MASS_TET) {
+      k_tet_gradient_table<true><<<g1, 128, 0, st>>>(p->n_elems, coords, conn, mat_id, mat, table);
+      FE_LAUNCH_CHECK(ctx);
+      k_tet_assemble_table<true><<<g2, 256, 0, st>>>(p->n_owned, p->adj_ptr, p->adj, p->contrib_ptr, p->contrib, table, vals);
+    } else {
+      k_tet_gradient_table<false><<<g1, 128, 0, st>>>(p->n_elems, coords, conn, mat_id, mat, table);
+      FE_LAUNCH_CHECK(ctx);
+      k_tet_assemble_table<false><<<g2, 256, 0, st>>>(p->n_owned, p->adj_ptr, p->adj, p->contrib_ptr, p->contrib, table, vals);
+    }
+  } else if (variant == 3) {
+    const int grid = grid_for((int64_t)p->n_owned * 16, 256);
+    if (kind == FE_MASS_TET)
+      k_tet_assemble_slots<true><<<grid, 256, 0, st>>>(p->n_owned, p->adj_ptr, p->adj, p->contrib_ptr, p->contrib, coords, conn,
+                                                      mat_id, mat, vals);
+    else
+      k_tet_assemble_slots<false><<<grid, 256, 0, st>>>(p->n_owned, p->adj_ptr, p->adj, p->contrib_ptr, p->contrib, coords, conn,
+                                                       mat_id, mat, vals);
+  } else if (variant == 2) {
     FE_CUDA(cudaFuncSetAttribute(k_tet_assemble_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tet_assemble_tile<<<grid_for(n_owned_nodes, kTetTile), kTetTile, smem, as_stream(stream)>>>(
-        kind, n_owned_nodes, corner_ptr, corner_elem, adj_ptr, adj, coords, conn, mat_id, mat, vals);
+    k_tet_assemble_tile<<<grid_for(p->n_owned, kTetTile), kTetTile, smem, st>>>(
+        kind, p->n_owned, p->corner_ptr, p->corner_elem, p->adj_ptr, p->adj, coords, conn, mat_id, mat, vals);
   } else {
-    k_tet_assemble<<<grid_for(n_owned_nodes, 128), 128, 0, as_stream(stream)>>>(
-        kind, n_owned_nodes, corner_ptr, corner_elem, adj_ptr, adj, coords, conn, mat_id, mat, vals);
+    k_tet_assemble<<<grid_for(p->n_owned, 128), 128, 0, st>>>(kind, p->n_owned, p->corner_ptr, p->corner_elem, p->adj_ptr,
+                                                             p->adj, coords, conn, mat_id, mat, vals);
   }
   FE_LAUNCH_CHECK(ctx);
   return FE_OK;

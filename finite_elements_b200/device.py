@@ -375,10 +375,10 @@ def tet_csr(adj_ptr, adj, deg):
 class DeviceMesh3D(DeviceMesh):
     """Linear tetrahedra, 3 DOF per node: coords f64[N,3], conn i32[E,4].
 
-    The symbolic phase -- per-node element lists, node adjacency, the scipy-canonical CSR of the 3x3
-    blocks -- is a handful of device-side sorts (torch.sort / unique_consecutive; plumbing, once per
-    mesh); the numeric phase is fe_tet_assemble / fe_tet_elem_matrices.  Everything CSR-level
-    (Dirichlet elimination, SpMV, PCG, block products) is inherited unchanged."""
+    The symbolic phase (per-node element lists, node adjacency, per-block element lists, the scipy-canonical
+    CSR of the 3x3 blocks) is fe_tet_plan_create -- hand-written kernels like the triangles' fe_plan_create;
+    the numeric phase is fe_tet_assemble / fe_tet_elem_matrices.  Everything CSR-level (Dirichlet
+    elimination, SpMV, PCG, block products) is inherited unchanged."""
 
     def __init__(self, coords, conn, mat_id=None, device=0, ctx=None, n_owned=None, dim=3):
         if dim != 3:
@@ -402,35 +402,19 @@ class DeviceMesh3D(DeviceMesh):
             raise ValueError("conn must have shape (E, 4)")
         self.n_owned = self.n_nodes if n_owned is None else int(n_owned)   # multi-GPU: owned first, ghosts after
         self.dim = 3
-        self.plan = None
-        n, e = self.n_nodes, self.n_elems
-        conn64 = self.conn.long()
-        if e and (int(conn64.min()) < 0 or int(conn64.max()) >= n):
-            raise ValueError("conn refers to a node outside [0, N)")
-        self.corner_ptr, self.corner_elem, adj_ptr, self.adj, deg = tet_symbolic(conn64, n, self.n_owned)
-        self.nnz = int(9 * adj_ptr[-1].item())
-        if self.nnz >= 2 ** 31:
-            raise NotImplementedError("nnz does not fit int32")
-        self.adj_ptr = adj_ptr.to(torch.int32).contiguous()
-        self.corner_ptr = self.corner_ptr.to(torch.int32).contiguous()
-        self.adj = self.adj.to(torch.int32).contiguous()
-        self._deg = deg
-        self.n_rows = 3 * self.n_owned
-        self.n_cols = 3 * n
-        self.max_degree = int(deg.max().item()) if self.n_owned else 0
-        self.plan_bytes = int(4 * (self.corner_elem.numel() + self.adj.numel() + 2 * (n + 1)))
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            check(lib.fe_tet_plan_create(self.ctx.handle, _stream(), self.n_nodes, self.n_owned, self.n_elems,
+                                         _ptr(self.conn), C.byref(h)))
+        self.plan = h
+        self.nnz = int(lib.fe_plan_nnz(h))
+        self.n_rows = int(lib.fe_plan_n_rows(h))
+        self.n_cols = 3 * self.n_nodes
+        self.max_degree = int(lib.fe_plan_max_degree(h))
+        self.plan_bytes = int(lib.fe_plan_bytes(h))
         self._csr = None
         DeviceMesh._tokens += 1
         self._token = DeviceMesh._tokens
-
-    def __del__(self):
-        pass
-
-    def csr_pattern(self):
-        """Row 3i+r = 9 adj_ptr[i] + r * 3 deg_i, columns 3 adj[k] + c: sorted, scipy-canonical."""
-        if self._csr is None:
-            self._csr = tet_csr(self.adj_ptr.long(), self.adj.long(), self._deg)
-        return self._csr
 
     def assemble(self, kind, mat, out=None, variant=0):
         """Global K (KIND_ELAST_TET) or M (KIND_MASS_TET) values in csr_pattern() order.  fe_tet_assemble."""
@@ -438,10 +422,9 @@ class DeviceMesh3D(DeviceMesh):
         if out is None:
             out = torch.empty(max(self.nnz, 1), dtype=torch.float64, device=self.ctx.device)[:self.nnz]
         with torch.cuda.device(self.ctx.device):
-            check(lib.fe_tet_assemble(self.ctx.handle, _stream(), int(kind), self.n_owned, _ptr(self.corner_ptr),
-                                      _ptr(self.corner_elem), _ptr(self.adj_ptr), _ptr(self.adj), _ptr(self.coords),
+            check(lib.fe_tet_assemble(self.ctx.handle, _stream(), self.plan, int(kind), _ptr(self.coords),
                                       _ptr(self.conn), _ptr(self.mat_id), _ptr(m), int(m.shape[0]), _ptr(out),
-                                      self.max_degree, int(variant)))
+                                      int(variant)))
         return out
 
     def element_matrices(self, kind, mat):

@@ -189,8 +189,11 @@ class DistributedMesh:
         self._nbr = np.ascontiguousarray(lp.nbr_rank, dtype=np.int32)
         self._sp = np.ascontiguousarray(lp.send_ptr, dtype=np.int32)
         self._rp = np.ascontiguousarray(lp.recv_ptr, dtype=np.int32)
+        t0 = time.perf_counter()
         init_nccl(self.ctx)
         self._dst_off = init_peer_memory(self.ctx, lp)  # None -> NCCL transport inside the loop
+        torch.cuda.synchronize(self.ctx.device)
+        self.peer_setup_ms = 1e3 * (time.perf_counter() - t0)
 
     def pcg(self, vals, b, x=None, rtol=1e-8, maxit=None, fixed_iters=0, work=None, raise_on_maxit=True):
         dm = self.dm
@@ -236,6 +239,32 @@ def structured_rank_problem(nx, ny, rank, world, dev, dim=2):
     return lp, coords[lp.node_gid].contiguous(), bounds
 
 
+def solution_check(dmesh, lp, vals, rhs, x, nx, ny):
+    """Parity evidence carried by every multi-GPU bench line, independent of the transport the solver used:
+    the TRUE residual ||rhs - A x|| / ||rhs|| recomputed with the ghost values of x fetched over NCCL
+    (torch.distributed all_gather of the owned blocks), and fingerprints of x that must agree between runs
+    at different GPU counts: sum, sum of squares and the tip displacement u_y(node (nx, ny))."""
+    import torch.distributed as dist
+    dm = dmesh.dm
+    dev = x.device
+    world = dist.get_world_size()
+    n_own = torch.tensor([x.numel()], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n_own) for _ in range(world)]
+    dist.all_gather(sizes, n_own)
+    sizes = [int(t.item()) for t in sizes]
+    parts = [torch.empty(sz, dtype=torch.float64, device=dev) for sz in sizes]
+    dist.all_gather(parts, x.contiguous())                 # NCCL
+    xg = torch.cat(parts)                                  # global solution in global DOF order (row blocks)
+    gd = (lp.node_gid[:, None] * lp.dim + torch.arange(lp.dim, device=dev)[None, :]).reshape(-1)
+    x_local = xg[gd].contiguous()                          # owned values, then ghost values
+    res = rhs - dm.spmv(vals, x_local)
+    acc = torch.stack([torch.dot(res, res), torch.dot(rhs, rhs)])
+    dist.all_reduce(acc)                                   # NCCL
+    tip = 2 * ((ny + 1) * (nx + 1) - 1) + 1
+    return {"true_relres_nccl": float(torch.sqrt(acc[0] / acc[1])), "x_sum": float(xg.sum()),
+            "x_sumsq": float(torch.dot(xg, xg)), "tip_uy": float(xg[tip])}
+
+
 def bench_distributed(args, metric, mat, measured_peak_hbm, ClockSampler, asm_bytes, pcg_bytes_per_iter):
     """N > 1 arm of bench.py: the S16M mesh split into N row blocks (strong scaling)."""
     import json
@@ -248,13 +277,22 @@ def bench_distributed(args, metric, mat, measured_peak_hbm, ClockSampler, asm_by
     ctx = Context.get(local_rank)
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
+    # communicator set-up (ncclCommInitRank, IPC handle exchange) is timed apart from the symbolic phase
+    t0 = time.perf_counter()
+    init_nccl(ctx)
+    torch.cuda.synchronize()
+    comm_init_ms = 1e3 * (time.perf_counter() - t0)
     t0 = time.perf_counter()
     lp, coords_local, bounds = structured_rank_problem(nx, ny, rank, world, dev)
+    torch.cuda.synchronize()
+    partition_ms = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
     dmesh = DistributedMesh(coords_local, lp, None, device=local_rank, ctx=ctx)
     dm = dmesh.dm
     dm.csr_pattern()
     torch.cuda.synchronize()
-    plan_ms = 1e3 * (time.perf_counter() - t0)
+    plan_ms = 1e3 * (time.perf_counter() - t0) - dmesh.peer_setup_ms
+    comm_init_ms += dmesh.peer_setup_ms
 
     n_el_total, n_nodes_total = 2 * nx * ny, (nx + 1) * (ny + 1)
     n_total = 2 * n_nodes_total
@@ -365,6 +403,7 @@ def bench_distributed(args, metric, mat, measured_peak_hbm, ClockSampler, asm_by
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         solve = {"rtol": 1e-8, "iters": iters, "relres": relres, "seconds": ts.item(),
                  "dof_iters_per_s": n_total * iters / ts.item()}
+        solve.update(solution_check(dmesh, lp, vals, rhs, x, nx, ny))
 
     if rank == 0:
         peak, peak_kind = measured_peak_hbm()
@@ -378,10 +417,15 @@ def bench_distributed(args, metric, mat, measured_peak_hbm, ClockSampler, asm_by
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"S16M-family structured plane-stress mesh {nx}x{ny} cells "
                                    f"({n_el_total} triangles, {n_total} DOF) in {world} row blocks; step = numeric "
-                                   f"assembly + Dirichlet + {args.pcg_iters} Jacobi-PCG iterations "
-                                   "(NCCL halo send/recv + dot all-reduce)",
+                                   f"assembly (no communication) + Dirichlet + {args.pcg_iters} Jacobi-PCG iterations "
+                                   "(interface halo + dot-product all-reduce per iteration)",
                        "nx": nx, "ny": ny, "pcg_iters_per_step": args.pcg_iters, "l2": "inputs_larger_than_l2",
                        "parallelism": f"row-block x{world}", "pattern_build_ms": plan_ms,
+                       "comm_init_ms": comm_init_ms, "partition_ms": partition_ms,
+                       "pcg_kernel": "k_pcg_persist<MULTI> (one cooperative launch, single-reduction CG)"
+                       if (world >= 4 or os.environ.get("FE_B200_PERSIST") == "1") and dmesh._dst_off is not None
+                       and os.environ.get("FE_B200_PERSIST") != "0" and not os.environ.get("FE_B200_NO_PERSIST")
+                       else "k_spmv_stream + k_pcg_update + k_pcg_pupdate",
                        "transport": "peer-memory halo stores + all-reduce fused into the PCG kernels (NVLink)"
                        if dmesh._dst_off is not None else "NCCL send/recv + all-reduce"},
             "assembly": {"ms": 1e3 * t_asm, "melem_per_s": n_el_total / t_asm / 1e6, "algorithmic_bytes": a_bytes},

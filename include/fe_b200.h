@@ -169,20 +169,28 @@ int fe_tet_elem_matrices(fe_ctx *ctx, void *stream, int kind, int64_t n_elems, c
 int fe_tet_elem_post(fe_ctx *ctx, void *stream, int64_t n_elems, const double *coords,
                      const int32_t *conn, const int32_t *mat_id, const double *mat, int32_t n_mat,
                      const double *u, double *out);
+/* Symbolic phase of a tetrahedral mesh, once per mesh, entirely on the device (replaces
+ * get_row_col_indices analysis.py:714-735 for 12 x 12 element matrices and the pattern half of csr_matrix,
+ * :661): node->element lists (counting sort keyed by node, ascending element id), sorted node adjacency,
+ * and -- per off-diagonal block (node, neighbour) -- the list of elements that hold both nodes.  The plan
+ * works with fe_plan_nnz / _n_rows / _max_degree / _bytes / _csr / _destroy like a triangle plan (dim = 3:
+ * node i's rows 3i, 3i+1, 3i+2 lie back to back from 9 adj_ptr[i], each 3 deg_i long, the block of
+ * neighbour slot k at columns 3k..3k+2 -- the scipy-canonical CSR of the same triplets).  n_owned_nodes <
+ * n_nodes selects the multi-GPU layout (owned nodes first).  conn int32[E][4], 16-byte aligned.  Same
+ * limits as fe_plan_create (<= 255 neighbours per node), E < 2^27.  SYNCHRONISES the stream. */
+int fe_tet_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned_nodes,
+                       int64_t n_elems, const int32_t *conn, fe_plan **out);
 /* Global matrix values of the tetrahedral mesh; replaces the k_matrix_data / m_matrix_data loops
- * (analysis.py:324-339, :357-365) + csr_matrix (:661) for 3 DOF per node.  The symbolic data comes
- * from the caller: corner_elem[corner_ptr[i] .. corner_ptr[i+1]) = elements incident to node i in
- * ascending order, adj[adj_ptr[i] .. adj_ptr[i+1]) = sorted neighbour nodes of i (itself included).
- * vals: node i's rows 3i, 3i+1, 3i+2 back to back from 9 adj_ptr[i], each 3 deg_i long, block of
- * neighbour slot k at columns 3k..3k+2 -- the scipy-canonical CSR of the same triplets.  One thread
- * owns a node's rows and adds its elements in ascending order: deterministic, no atomics.
- * max_degree = largest neighbour count (sizes the shared-memory tile); variant 0 = automatic,
- * 1 = accumulate in global memory, 2 = shared-memory tile + coalesced write-out (bit-identical). */
-int fe_tet_assemble(fe_ctx *ctx, void *stream, int kind, int32_t n_owned_nodes,
-                    const int32_t *corner_ptr, const int32_t *corner_elem, const int32_t *adj_ptr,
-                    const int32_t *adj, const double *coords, const int32_t *conn,
-                    const int32_t *mat_id, const double *mat, int32_t n_mat, double *vals,
-                    int32_t max_degree, int32_t variant);
+ * (analysis.py:324-339, :357-365) + csr_matrix (:661) for 3 DOF per node.  Deterministic, no atomics.
+ * variant 0 = automatic; 4 = two passes: every element's gradients once into a scratch table owned by the
+ * ctx (128 B per element), then one lane per 3x3 block of the global matrix walking the plan's per-block
+ * element lists (default; needs elements with four distinct nodes); 3 = the same walk rebuilding the
+ * geometry at every visit (no scratch); 1 = one thread per node accumulating in global memory, 2 = the
+ * same through a shared-memory tile (1 and 2 are bit-identical to each other and add a block's elements
+ * in ascending order; 3 and 4 agree with them to rounding). */
+int fe_tet_assemble(fe_ctx *ctx, void *stream, const fe_plan *plan, int kind, const double *coords,
+                    const int32_t *conn, const int32_t *mat_id, const double *mat, int32_t n_mat,
+                    double *vals, int32_t variant);
 
 /* ---- modal analysis building blocks (analysis.py:741-796) -------------------------------
  * The reference gives K and M to scipy.sparse.linalg.eigsh (:779-782), whose Lanczos loop

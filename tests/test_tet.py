@@ -162,8 +162,22 @@ def test_gpu_tet_element_and_global_matrices_vs_reference(name):
     assert_csr_values_close(k, fx.csr("k"), 1e-12)            # pattern bit-exact, values 1e-12
     assert_csr_values_close(dm.to_scipy(dm.assemble(KIND_MASS_TET, fx.mat)), fx.csr("m"), 1e-12)
     assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, fx.mat))   # deterministic
-    assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, fx.mat, variant=1))   # tile == global accumulation, bitwise
-    assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, fx.mat, variant=2))
+    # the node-owner kernels: tile == global accumulation, bitwise; the default (one lane per block, other
+    # summation order and element labelling) agrees with them to rounding
+    k1 = dm.assemble(KIND_ELAST_TET, fx.mat, variant=1)
+    assert torch.equal(k1, dm.assemble(KIND_ELAST_TET, fx.mat, variant=2))
+    assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, fx.mat, variant=4))
+    k3 = dm.assemble(KIND_ELAST_TET, fx.mat, variant=3)
+    assert float((k3 - k1).abs().max()) <= 1e-13 * float(k1.abs().max())
+    assert float((kv - k1).abs().max()) <= 1e-13 * float(k1.abs().max())
+    m1 = dm.assemble(KIND_MASS_TET, fx.mat, variant=1)
+    assert float((dm.assemble(KIND_MASS_TET, fx.mat) - m1).abs().max()) <= 1e-14 * float(m1.abs().max())
+    # the device-side symbolic phase (fe_tet_plan_create) against plain torch sorts of the same connectivity
+    from finite_elements_b200.device import tet_symbolic, tet_csr
+    cp, ce, ap, adj, deg = tet_symbolic(torch.as_tensor(fx.conn).long().cuda(), len(fx.coords))
+    rp_t, ci_t = tet_csr(ap, adj, deg)
+    rp_d, ci_d = dm.csr_pattern()
+    assert torch.equal(rp_t, rp_d) and torch.equal(ci_t, ci_d)
     # the assembled matrix is the ordered sum of the dumped element matrices
     dofs = no.element_dofs(fx.conn, 3)
     import scipy.sparse as sp
@@ -238,7 +252,10 @@ def test_gpu_tet_mid_size_properties():
     mid = (np.arange(len(conn)) % 2).astype(np.int32)
     dm = DeviceMesh3D(coords, conn, mid)
     kv = dm.assemble(KIND_ELAST_TET, MAT2)
-    assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, MAT2, variant=1))
+    assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, MAT2))
+    k2 = dm.assemble(KIND_ELAST_TET, MAT2, variant=2)
+    assert torch.equal(k2, dm.assemble(KIND_ELAST_TET, MAT2, variant=1))
+    assert float((kv - k2).abs().max()) <= 1e-13 * float(k2.abs().max())
     k = dm.to_scipy(kv)
     assert_csr_values_close(k, no.assemble_k(no.KIND_ELAST_TET, coords, conn, mid, MAT2), 1e-12)
     mv = dm.assemble(KIND_MASS_TET, MAT2)
