@@ -284,13 +284,23 @@ static int launch_spmv(fe_ctx *ctx, cudaStream_t s, int lpr, int32_t n_rows, con
                        const int32_t *colidx, const double *vals, const double *x, double *y, double *partials,
                        PcgState *st, const StreamPlan *sp = nullptr, const HaloPlan *fused_halo = nullptr) {
   if (sp && sp->on && sp->scalar) {  // persistent TMA-streamed kernel, scalar CSR (1 DOF per node)
-    if (fused_halo)
-      k_spmv_stream1<DOT, true><<<sp->grid, kStreamThreads, sp->smem, s>>>(
-          n_rows, sp->cap, rowptr, colidx, vals, x, y, partials, st, ctx->p2p_dev, (HaloDev *)ctx->p2p_halo.ptr,
-          fused_halo->send_idx);
+#define FE_STREAM1(P)                                                                                                   \
+  do {                                                                                                                  \
+    if (fused_halo)                                                                                                     \
+      k_spmv_stream1<DOT, true, P><<<sp->grid, kStreamThreads, sp->smem, s>>>(                                          \
+          n_rows, sp->cap, rowptr, colidx, vals, x, y, partials, st, ctx->p2p_dev, (HaloDev *)ctx->p2p_halo.ptr,        \
+          fused_halo->send_idx);                                                                                        \
+    else                                                                                                                \
+      k_spmv_stream1<DOT, false, P><<<sp->grid, kStreamThreads, sp->smem, s>>>(n_rows, sp->cap, rowptr, colidx, vals, x, \
+                                                                               y, partials, st, nullptr, nullptr, nullptr); \
+  } while (0)
+    if (sp->passes == 4)
+      FE_STREAM1(4);
+    else if (sp->passes == 2)
+      FE_STREAM1(2);
     else
-      k_spmv_stream1<DOT, false><<<sp->grid, kStreamThreads, sp->smem, s>>>(n_rows, sp->cap, rowptr, colidx, vals, x,
-                                                                            y, partials, st, nullptr, nullptr, nullptr);
+      FE_STREAM1(1);
+#undef FE_STREAM1
     FE_LAUNCH_CHECK(ctx);
     return FE_OK;
   }
@@ -686,7 +696,7 @@ static int get_chunk_graph(PcgLaunch &L, int len, cudaGraphExec_t *out) {
                          (void *)(intptr_t)(len * 256 + (L.lpr & 31) + (L.sp.on ? 32 : 0) + (L.p2p ? 64 : 0) + (L.sp.scalar ? 128 : 0)),
                          (void *)(intptr_t)L.sp.cap, (void *)(intptr_t)L.sp.smem, (void *)(intptr_t)L.sp.grid,
                          (void *)L.sp.bptr, (void *)L.sp.bidx, (void *)(L.halo ? L.halo->send_idx : nullptr),
-                         (void *)(intptr_t)ctx->bp_built_token, (void *)(intptr_t)L.vgrid};
+                         (void *)(intptr_t)ctx->bp_built_token, (void *)(intptr_t)(L.vgrid * 8 + L.sp.passes)};
   if (ctx->pcg_graph && memcmp(key, ctx->pcg_graph_key, sizeof(key)) == 0) {
     *out = (cudaGraphExec_t)ctx->pcg_graph;
     return FE_OK;
@@ -927,6 +937,10 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
     // (in entries) is needed to size the ring
     if ((rc = ctx->scratch_c.reserve(256))) return rc;
     int *tile_max = (int *)ctx->scratch_c.ptr;
+    // rows per tile from the mean row length: 240 rows of 7 entries, 120 of <= 24, 60 of 45 (tetrahedra)
+    const double avg_row = (double)h_rowptr_end / n_rows;
+    const int passes = avg_row <= 12.0 ? 4 : (avg_row <= 24.0 ? 2 : 1);
+    const int kStream1Tile = stream1_tile(passes);
     const bool cached = ctx->bp_token != 0 && ctx->bp_rowptr == rowptr && ctx->bp_colidx == colidx &&
                         ctx->bp_built_token == ctx->bp_token && ctx->bp_built_rows == -2 - n_rows;
     int h_tile_max = ctx->bp_max_deg;
@@ -945,14 +959,25 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
       }
     }
     const int cap = ((h_tile_max > 0 ? h_tile_max : 1) + 3) & ~3;
-    const size_t smem = stream1_smem_bytes(cap);
+    const size_t smem = stream1_smem_bytes(cap, passes);
     if (smem <= 110 * 1024) {
-      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream1<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream1<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream1<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream1<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#define FE_STREAM1_ATTR(P)                                                                                                   \
+  do {                                                                                                                       \
+    FE_CUDA(cudaFuncSetAttribute(k_spmv_stream1<true, false, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    FE_CUDA(cudaFuncSetAttribute(k_spmv_stream1<false, false, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    FE_CUDA(cudaFuncSetAttribute(k_spmv_stream1<true, true, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    FE_CUDA(cudaFuncSetAttribute(k_spmv_stream1<false, true, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+  } while (0)
+      if (passes == 4)
+        FE_STREAM1_ATTR(4);
+      else if (passes == 2)
+        FE_STREAM1_ATTR(2);
+      else
+        FE_STREAM1_ATTR(1);
+#undef FE_STREAM1_ATTR
       L.sp.on = true;
       L.sp.scalar = true;
+      L.sp.passes = passes;
       L.sp.cap = cap;
       L.sp.smem = smem;
       const int n_tiles = (n_rows + kStream1Tile - 1) / kStream1Tile;

@@ -243,17 +243,19 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream(
 // 8 lanes per row, one entry per lane: LDS.64 (value), LDS.32 (column), LDG.64 (x), one FMA.
 // HBM bytes per call: 12 nnz + 4 n (rowptr) + 8 n (x) + 8 n (y) -- SURVEY §8d's SpMV figure.
 // ---------------------------------------------------------------------------------------
-constexpr int kStream1Passes = 4;
-constexpr int kStream1Tile = kStream1Passes * kStreamGroups;   // 240 rows
-constexpr int kStream1PtrInts = (kStream1Tile + 1 + 3) & ~3;
+// PASSES rows per 8-lane group and tile: 4 (240 rows) for the 7-entry rows of a scalar triangle mesh; 2 or 1
+// when the rows are long (45-entry rows of a tetrahedral mesh: a 240-row tile would not fit the ring).
+__host__ __device__ constexpr int stream1_tile(int passes) { return passes * kStreamGroups; }
+__host__ __device__ constexpr int stream1_ptr_ints(int passes) { return (stream1_tile(passes) + 1 + 3) & ~3; }
 
-template <bool DOT, bool HALO>
+template <bool DOT, bool HALO, int PASSES>
 __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream1(
     int32_t n_rows, int cap /* entries per stage */, const int32_t *__restrict__ rowptr,
     const int32_t *__restrict__ colidx, const double *__restrict__ vals, const double *__restrict__ x,
     double *__restrict__ y, double *__restrict__ partials, PcgState *__restrict__ st, P2PDev *pp, HaloDev *hd,
     const int32_t *__restrict__ send_idx) {
-  constexpr int T = kStream1Tile, S = kStreamStages, GROUPS = kStreamGroups, PASSES = kStream1Passes;
+  constexpr int T = stream1_tile(PASSES), S = kStreamStages, GROUPS = kStreamGroups;
+  constexpr int kStream1PtrInts = stream1_ptr_ints(PASSES);
   __shared__ double red[kStreamThreads / 32];
   if (DOT && (st->converged | st->breakdown)) return;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -405,14 +407,15 @@ __global__ void __launch_bounds__(256) k_tile_max_entries(int32_t n_rows, int32_
   if (cnt > *reinterpret_cast<volatile int *>(out)) atomicMax(out, cnt);
 }
 
-static size_t stream1_smem_bytes(int cap) {
-  const size_t ptr_bytes = (128 + (size_t)kStreamStages * kStream1PtrInts * sizeof(int32_t) + 127) / 128 * 128;
+static size_t stream1_smem_bytes(int cap, int passes) {
+  const size_t ptr_bytes = (128 + (size_t)kStreamStages * stream1_ptr_ints(passes) * sizeof(int32_t) + 127) / 128 * 128;
   return ptr_bytes + (size_t)kStreamStages * (cap + 2) * 8 + (size_t)kStreamStages * (cap + 8) * 4;
 }
 
 struct StreamPlan {
   bool on = false;
   bool scalar = false;  // k_spmv_stream1 (1 DOF per node) instead of the 2x2-block kernel
+  int passes = 4;       // k_spmv_stream1: rows per 8-lane group and tile (4, 2 or 1)
   int T = 0, cap = 0, grid = 0;
   size_t smem = 0;
   int32_t *bptr = nullptr, *bidx = nullptr;
