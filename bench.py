@@ -513,7 +513,33 @@ def run_modal(k, nx, ny, device):
     t = time.perf_counter() - t0
     kx, mx = dm.spmm_pair(kv, mv, vec.contiguous())
     res = torch.linalg.norm(kx - mx * lam[None, :], dim=0) / (torch.linalg.norm(kx, dim=0) + 1e-300)
-    return {"workload": f"lowest {k} modes, {nx}x{ny}-cell plane-stress mesh ({2 * nx * ny} triangles, "
+    # the dominant kernel of the path: the fused Chebyshev step (k_spmm<..., EPI = 1>) on a block of `block` columns
+    block = info.block
+    n = dm.n_rows
+    d0 = torch.randn(n, block, dtype=torch.float64, device=dev)
+    d1, rr, zz = torch.empty_like(d0), torch.randn_like(d0), torch.zeros_like(d0)
+    dinv = 1.0 / dm.csr_diagonal(kv)
+    for _ in range(3):
+        dm.cheb_step(kv, dinv, d0, d1, rr, zz, 0.5, 1e-12)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps // 2):
+        dm.cheb_step(kv, dinv, d0, d1, rr, zz, 0.5, 1e-12)
+        dm.cheb_step(kv, dinv, d1, d0, rr, zz, 0.5, 1e-12)
+    e1.record()
+    torch.cuda.synchronize()
+    t_step = e0.elapsed_time(e1) * 1e-3 / reps
+    step_bytes = 12.0 * dm.nnz + 4.0 * n + 48.0 * block * n   # vals + colidx, rowptr, (d, r, z) read + (d', r, z) written
+    peak, peak_kind = measured_peak_hbm()
+    steps = info.iterations * max(info.get("cheb_degree", 1) - 1, 1)
+    return {"roofline": {"bound": "hbm", "kernel": "k_spmm<CPL,G,0,1> (fused Chebyshev step, fe_cheb_step)",
+                         "achieved": step_bytes / t_step / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": step_bytes / t_step / 1e9 / peak, "peak_kind": peak_kind, "traffic": None,
+                         "algorithmic_bytes_per_step": step_bytes, "ms_per_step": 1e3 * t_step, "block_columns": block,
+                         "steps_in_solve": steps, "share_of_solve": steps * t_step / t if t > 0 else None},
+            "cheb_degree": info.get("cheb_degree"),
+            "workload": f"lowest {k} modes, {nx}x{ny}-cell plane-stress mesh ({2 * nx * ny} triangles, "
                         f"{dm.n_rows} DOF), free-free", "seconds": t, "iterations": info.iterations,
             "block_products": info.products, "converged": info.converged,
             "eigenvalues": [float(v) for v in lam.cpu()],

@@ -132,6 +132,20 @@ def lobpcg(apply_pair, n, k, device, *, largest=False, precond=None, mask=None, 
             bv = bv * mask[:, None]
         return av, bv
 
+    # optional section timers (FE_B200_MODAL_PROF=1: device-synchronised wall clock per section -> info["prof"])
+    import os
+    import time
+    prof = {} if os.environ.get("FE_B200_MODAL_PROF") else None
+    t_last = [0.0]
+
+    def lap(name):
+        if prof is not None:
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            if name:
+                prof[name] = prof.get(name, 0.0) + (t - t_last[0])
+            t_last[0] = t
+
     gen = torch.Generator(device="cpu").manual_seed(seed)
     x = torch.randn(n, m, generator=gen, dtype=torch.float64).to(device)
     if mask is not None:
@@ -155,6 +169,7 @@ def lobpcg(apply_pair, n, k, device, *, largest=False, precond=None, mask=None, 
     p = ap = bp = None
     rn = den = None
     for it in range(maxit):
+        lap(None)
         r = ax - bx * theta[None, :]
         rn = torch.linalg.norm(r, dim=0)
         den = (tol * (torch.linalg.norm(ax, dim=0) + theta.abs() * torch.linalg.norm(bx, dim=0))
@@ -165,12 +180,15 @@ def lobpcg(apply_pair, n, k, device, *, largest=False, precond=None, mask=None, 
             break
         act = torch.nonzero(~conv).flatten()           # soft locking: converged pairs get no new direction
         w = r[:, act]
+        lap("residual+test")
         if precond is not None:
             w = precond(w)
+        lap("preconditioner")
         if mask is not None:
             w = w * mask[:, None]
         basis, b_basis = (x, bx) if p is None else (torch.cat([x, p], 1), torch.cat([bx, bp], 1))
         out = _orthonormalize_against(w, basis, b_basis, op)
+        lap("orthonormalise W")
         info["products"] += 2
         if out is None:                                 # residual block collapsed: refresh and retry without P
             x, ax, bx, theta = rayleigh_ritz_x(x)
@@ -184,7 +202,9 @@ def lobpcg(apply_pair, n, k, device, *, largest=False, precond=None, mask=None, 
             s, a_s, b_s = torch.cat([x, w], 1), torch.cat([ax, aw], 1), torch.cat([bx, bw], 1)
         else:
             s, a_s, b_s = torch.cat([x, w, p], 1), torch.cat([ax, aw, ap], 1), torch.cat([bx, bw, bp], 1)
-        wv, c = sla.eigh(_sym(s.T @ a_s).cpu().numpy())  # S is B-orthonormal: standard problem
+        gram = _sym(s.T @ a_s)
+        lap("gram")
+        wv, c = sla.eigh(gram.cpu().numpy())  # S is B-orthonormal: standard problem
         c = c[:, :m]
         # new directions: the part of the Ritz vectors outside the old X, orthogonalised against the
         # new X in coefficient space (S orthonormal => B-inner products are Euclidean ones there)
@@ -196,6 +216,7 @@ def lobpcg(apply_pair, n, k, device, *, largest=False, precond=None, mask=None, 
         dg = np.abs(np.diag(rr))
         rank = int((dg > 1e-10 * max(dg[0], 1e-300)).sum()) if dg.size else 0
         c_t = torch.as_tensor(c, device=device)
+        lap("ritz (host)")
         if rank > 0:
             q_t = torch.as_tensor(np.ascontiguousarray(q[:, :rank]), device=device)
             p, ap, bp = s @ q_t, a_s @ q_t, b_s @ q_t
@@ -203,13 +224,17 @@ def lobpcg(apply_pair, n, k, device, *, largest=False, precond=None, mask=None, 
             p = ap = bp = None
         x, ax, bx = s @ c_t, a_s @ c_t, b_s @ c_t
         theta = torch.as_tensor(wv[:m].copy(), device=device)
+        lap("update X, P")
         if (it + 1) % refresh == 0:                     # recompute A X, B X from X: no drift
             x, ax, bx, theta = rayleigh_ritz_x(x)
             if p is not None:
                 outp = _orthonormalize_against(p, x, bx, op)
                 p, ap, bp = (None, None, None) if outp is None else outp
+            lap("refresh")
     else:
         info["iterations"] = maxit
+    if prof is not None:
+        info["prof"] = {k_: round(v_, 4) for k_, v_ in prof.items()}
     lam = sign * theta[:k]
     vec = x[:, :k]
     info["residual_norms"] = (rn[:k] / den[:k]).cpu().numpy()   # <= 1 means converged
@@ -251,10 +276,15 @@ def modal_solve(dm, k_vals, m_vals, k, order, *, mask=None, tol=1e-9, maxit=5000
     Returns (eigenvalues ascending (k,), eigenvectors (n, k) M-orthonormal, ModalInfo).
 
     cheb_degree: degree of the Chebyshev polynomial preconditioner of the 'smallest' branch (0 / 1 =
-    plain Jacobi).  None picks 24 on [lmax/250, lmax] above 20 000 DOFs: the outer iteration count of
-    the lowest modes grows like 1/h with Jacobi, a degree-d polynomial divides it by about d/1.5."""
+    plain Jacobi).  The outer iteration count of the lowest modes grows like 1/h with Jacobi and a
+    degree-d polynomial divides it by about d/1.5, while a Chebyshev step (one fused kernel) is far cheaper
+    than an outer iteration (orthogonalisations, Gram products, a host Rayleigh-Ritz): measured on the
+    1 M-triangle mesh, degree 24 / 48 / 96 = 454 / 199 / 93 outer iterations = 5.3 / 3.4 / 2.6 s.  None
+    therefore scales the degree with the mesh, d ~ 0.13 sqrt(nodes) in [24, 128] (96 at 1 M triangles),
+    on [lmax / (0.45 d^2), lmax]; below 20 000 DOFs plain Jacobi is used."""
     if cheb_degree is None:
-        cheb_degree = 24 if dm.n_rows > 20000 else 0
+        nodes = dm.n_rows / max(1, getattr(dm, "dim", 2))
+        cheb_degree = int(min(128, max(24, 8 * round(0.13 * nodes ** 0.5 / 8)))) if dm.n_rows > 20000 else 0
     if cheb_ratio is None:
         cheb_ratio = max(30.0, 0.45 * cheb_degree * cheb_degree)
     if order not in ("largest", "smallest"):
@@ -290,4 +320,5 @@ def modal_solve(dm, k_vals, m_vals, k, order, *, mask=None, tol=1e-9, maxit=5000
             precond = lambda r: dinv[:, None] * r  # noqa: E731
     lam, vec, info = lobpcg(apply_pair, n, k, dev, largest=largest, precond=precond, mask=mask, tol=tol,
                             maxit=maxit, guard=g, seed=seed, anorm=anorm)
+    info["cheb_degree"] = 0 if largest else int(cheb_degree or 0)
     return lam, vec, info
