@@ -233,7 +233,7 @@ def run_magnetic_record(nx, ny, device, peak):
     return {"workload": f"magnetostatic (1 DOF/node, 3 mu bands) {nx}x{ny} cells: {n_el} triangles, {dm.n_rows} DOF, nnz {dm.nnz}",
             "assembly_ms": 1e3 * t_asm, "melem_per_s": n_el / t_asm / 1e6,
             "assembly_roofline": {"bound": "hbm", "achieved": a_bytes / t_asm / 1e9, "peak": peak, "unit": "GB/s",
-                                  "frac": a_bytes / t_asm / 1e9 / peak, "kernel": "k_assemble_fan<2>",
+                                  "frac": a_bytes / t_asm / 1e9 / peak, "kernel": f"k_assemble_fan<2,{int(dm.fan_record_bytes == 4)}>",
                                   "algorithmic_bytes": a_bytes},
             "pcg_ms_per_iter": 1e3 * t_it, "pcg_dof_iters_per_s": dm.n_rows / t_it,
             "pcg_roofline": {"bound": "hbm", "achieved": p_bytes / t_it / 1e9, "peak": peak, "unit": "GB/s",
@@ -445,7 +445,8 @@ def run_gpu(args):
 
     peak, peak_kind = measured_peak_hbm()
     wl_key = f"{args.kind} {nx}x{ny} x1"                       # the committed ncu capture must be of this workload
-    asm_kernel = "k_assemble_fan<2>" if magnetic else "k_assemble_fan<0>"
+    r4 = int(getattr(dm, "fan_record_bytes", 8) == 4 and args.variant != 4)
+    asm_kernel = f"k_assemble_fan<{2 if magnetic else 0},{r4}>"
     pcg_kernels = ["k_spmv_stream1<1,0>" if magnetic else "k_spmv_stream<1,0>", "k_pcg_update", "k_pcg_pupdate"]
     asm_traffic, asm_src = ncu_traffic([asm_kernel], wl_key)
     pcg_traffic, pcg_src = ncu_traffic(pcg_kernels, wl_key)
@@ -460,7 +461,8 @@ def run_gpu(args):
                                f"{n_nodes} nodes, {n} DOF, nnz {nnz}; step = numeric assembly + Dirichlet + "
                                f"{args.pcg_iters} Jacobi-PCG iterations",
                    "nx": nx, "ny": ny, "pcg_iters_per_step": args.pcg_iters, "l2": "inputs_larger_than_l2",
-                   "assembly_variant": args.variant, "pattern_build_ms": plan_ms},
+                   "assembly_variant": args.variant, "fan_record_bytes": getattr(dm, "fan_record_bytes", None),
+                   "pattern_build_ms": plan_ms},
         "assembly": {"ms": 1e3 * t_asm, "melem_per_s": n_el / t_asm / 1e6, "algorithmic_bytes": a_bytes},
         "pcg": {"dof_iters_per_s": n * args.pcg_iters / t_pcg, "ms_per_iter": 1e3 * t_pcg / args.pcg_iters,
                 "iters": args.pcg_iters, "algorithmic_bytes_per_iter": p_bytes,

@@ -39,6 +39,7 @@ SIGNATURES = {
     "fe_plan_n_rows": (_i32, [_vp]),
     "fe_plan_max_degree": (_i32, [_vp]),
     "fe_plan_bytes": (_i64, [_vp]),
+    "fe_plan_fan_record_bytes": (_i32, [_vp]),
     "fe_plan_csr": (C.c_int, [_vp, _vp, _vp, _vp]),
     "fe_assemble": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _i32, _vp, C.c_int]),
     "fe_dirichlet_apply": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),

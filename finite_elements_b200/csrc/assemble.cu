@@ -204,6 +204,9 @@ __global__ void __launch_bounds__(kTile) k_assemble_tile(int32_t n_owned, const 
 #ifndef FE_FAN_MINB
 #define FE_FAN_MINB 5  // resident CTAs per SM the register allocation targets (96 registers, no spills)
 #endif
+#ifndef FE_FAN_MINB_SCALAR
+#define FE_FAN_MINB_SCALAR 6  // the scalar (magnetic) instance needs 76 registers
+#endif
 
 struct FanFlags {
   static constexpr uint32_t SEED = 1, ADD_CARRY = 2, HOLD_A = 4, LAST = 8, ADD_FIRST = 16;
@@ -266,27 +269,67 @@ constexpr int kFanWarps = kFanThreads / 32;
 constexpr int kFanChunk = 32;
 constexpr int kFanPtrInts = (kFanChunk + 1 + 3) & ~3;  // 36
 
-__host__ __device__ inline size_t fan_stage_bytes(int rec_cap) {
-  return ((size_t)2 * kFanPtrInts * sizeof(int32_t) + (size_t)rec_cap * sizeof(int2) + 15) / 16 * 16;
+// Record format of the fan walk: the plan's 8-byte records, or their 4-byte form (plan.cuh) with the
+// per-node header word in a third pointer slice of the ring stage.
+template <bool R4>
+struct FanRec;
+template <>
+struct FanRec<false> {
+  using T = int2;
+  static constexpr int kAlign = 2;  // records per 16 bytes
+  static __device__ __forceinline__ T none() { return make_int2(0, 0); }
+  static __device__ __forceinline__ int32_t nbr(T r, int32_t /*self*/, int32_t /*n_owned*/) { return r.x; }
+  static __device__ __forceinline__ uint32_t k(T r) { return (uint32_t)r.y & 255; }
+  static __device__ __forceinline__ bool seed(T r) { return (uint32_t)r.y & (FanFlags::SEED << 8); }
+  static __device__ __forceinline__ bool add_carry(T r) { return (uint32_t)r.y & (FanFlags::ADD_CARRY << 8); }
+  static __device__ __forceinline__ bool last(T r) { return (uint32_t)r.y & (FanFlags::LAST << 8); }
+  static __device__ __forceinline__ bool add_first(T r) { return (uint32_t)r.y & (FanFlags::ADD_FIRST << 8); }
+  static __device__ __forceinline__ int kself(T r, uint32_t /*hdr*/) { return (uint32_t)r.y >> 13; }
+  static __device__ __forceinline__ int mat(T r, uint32_t /*hdr*/) { return (uint32_t)r.y >> 13; }
+};
+template <>
+struct FanRec<true> {
+  using T = uint32_t;
+  static constexpr int kAlign = 4;
+  static __device__ __forceinline__ T none() { return 0u; }
+  static __device__ __forceinline__ int32_t nbr(T r, int32_t self, int32_t n_owned) {
+    return (r & (FAN4_GHOST << 8)) ? n_owned + (int32_t)(r >> 14) : self + ((int32_t)r >> 14);
+  }
+  static __device__ __forceinline__ uint32_t k(T r) { return r & 255; }
+  static __device__ __forceinline__ bool seed(T r) { return r & (FAN4_SEED << 8); }
+  static __device__ __forceinline__ bool add_carry(T r) { return r & (FAN4_ADD_CARRY << 8); }
+  static __device__ __forceinline__ bool last(T r) { return r & (FAN4_LAST << 8); }
+  static __device__ __forceinline__ bool add_first(T r) { return r & (FAN4_ADD_FIRST << 8); }
+  static __device__ __forceinline__ int kself(T /*r*/, uint32_t hdr) { return hdr & 255; }
+  static __device__ __forceinline__ int mat(T r, uint32_t hdr) {
+    return (r & (FAN4_MAT1 << 8)) ? (int)(hdr >> 20) : (int)((hdr >> 8) & 4095);
+  }
+};
+
+__host__ __device__ inline size_t fan_stage_bytes(int rec_cap, bool r4) {
+  return ((size_t)(r4 ? 3 : 2) * kFanPtrInts * sizeof(int32_t) + (size_t)rec_cap * (r4 ? 4 : 8) + 15) / 16 * 16;
 }
-__host__ __device__ inline size_t fan_warp_bytes(int rec_cap, int warp_slot_bytes) {
-  return (32 + 2 * fan_stage_bytes(rec_cap) + (size_t)warp_slot_bytes + 127) / 128 * 128;
+__host__ __device__ inline size_t fan_warp_bytes(int rec_cap, int warp_slot_bytes, bool r4) {
+  return (32 + 2 * fan_stage_bytes(rec_cap, r4) + (size_t)warp_slot_bytes + 127) / 128 * 128;
 }
 
-template <int KC>
-__global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
-    int32_t n_owned, const int32_t *__restrict__ fan_ptr, const int2 *__restrict__ fan_rec,
-    const int32_t *__restrict__ adj_ptr, const double2 *__restrict__ coords, const MatRow *__restrict__ tab,
-    double *__restrict__ vals, int rec_cap, int warp_slot_bytes) {
+template <int KC, bool R4>
+__global__ void __launch_bounds__(kFanThreads, (KC == 2 ? FE_FAN_MINB_SCALAR : FE_FAN_MINB)) k_assemble_fan(
+    int32_t n_owned, const int32_t *__restrict__ fan_ptr, const typename FanRec<R4>::T *__restrict__ fan_rec,
+    const uint32_t *__restrict__ fan_hdr, const int32_t *__restrict__ adj_ptr, const double2 *__restrict__ coords,
+    const MatRow *__restrict__ tab, double *__restrict__ vals, int rec_cap, int warp_slot_bytes) {
   using Ops = FanOps<KC>;
   using Val = typename Ops::Val;
   using Slot = typename Ops::Slot;
+  using RO = FanRec<R4>;
+  using Rec = typename RO::T;
   constexpr int SPB = (KC == 2) ? 1 : 2;  // Slots per node-level block
+  constexpr int kPtrSlices = R4 ? 3 : 2;  // adj_ptr, fan_ptr (, fan_hdr)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *wbase = smem_raw + (size_t)warp * fan_warp_bytes(rec_cap, warp_slot_bytes);
+  unsigned char *wbase = smem_raw + (size_t)warp * fan_warp_bytes(rec_cap, warp_slot_bytes, R4);
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
-  const size_t stage_bytes = fan_stage_bytes(rec_cap);
+  const size_t stage_bytes = fan_stage_bytes(rec_cap, R4);
   int32_t *ep = reinterpret_cast<int32_t *>(wbase + 16);  // [2][2] record-range end points (LDGSTS)
   unsigned char *stage0 = wbase + 32;
   Slot *acc = reinterpret_cast<Slot *>(stage0 + 2 * stage_bytes);
@@ -312,13 +355,14 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
   };
   auto issue = [&](int chunk, int stage, int32_t r0, int32_t r1) {
     const int32_t n0 = chunk * kFanChunk;
-    const int32_t base = r0 & ~1;  // 16-byte aligned start of the record copy
-    const uint32_t rec_bytes = (uint32_t)((r1 - base + 1) >> 1) * 16u;
+    const int32_t base = r0 & ~(RO::kAlign - 1);  // 16-byte aligned start of the record copy
+    const uint32_t rec_bytes = (uint32_t)((r1 - base + RO::kAlign - 1) / RO::kAlign) * 16u;
     unsigned char *st = stage0 + stage * stage_bytes;
-    ptx::mbar_expect_tx(&full[stage], 2u * kFanPtrInts * 4u + rec_bytes);
+    ptx::mbar_expect_tx(&full[stage], (uint32_t)kPtrSlices * kFanPtrInts * 4u + rec_bytes);
     ptx::bulk_load(st, adj_ptr + n0, kFanPtrInts * 4u, &full[stage]);
     ptx::bulk_load(st + kFanPtrInts * 4, fan_ptr + n0, kFanPtrInts * 4u, &full[stage]);
-    if (rec_bytes) ptx::bulk_load(st + 2 * kFanPtrInts * 4, fan_rec + base, rec_bytes, &full[stage]);
+    if (R4) ptx::bulk_load(st + 2 * kFanPtrInts * 4, fan_hdr + n0, kFanPtrInts * 4u, &full[stage]);
+    if (rec_bytes) ptx::bulk_load(st + kPtrSlices * kFanPtrInts * 4, fan_rec + base, rec_bytes, &full[stage]);
   };
   int chunk = blockIdx.x * kFanWarps + warp;
   if (lane == 0 && chunk < n_chunks) {
@@ -335,20 +379,22 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
 
   // ---- per-thread state of the chunk about to be computed (filled by begin_chunk)
   struct Item {
-    int2 rec;
+    Rec rec;
     double2 p;
   };
   Item ia, ib, ic;  // three rotating sets: current, previous, and the gather two steps ahead
-  ia.rec = ib.rec = ic.rec = make_int2(0, 0);
+  ia.rec = ib.rec = ic.rec = RO::none();
   ia.p = ib.p = ic.p = make_double2(0.0, 0.0);
   double2 ps = make_double2(0.0, 0.0);
-  const int2 *recs = nullptr;
+  const Rec *recs = nullptr;
   Slot *my = acc;
   int f = 0, fe = 0, deg = 0;
+  int32_t self = 0;
+  uint32_t hdr = 0;
   auto fetch = [&](int i, Item &it) {
     if (i < fe) {
       it.rec = recs[i];
-      it.p = __ldg(coords + it.rec.x);
+      it.p = __ldg(coords + RO::nbr(it.rec, self, n_owned));
     }
   };
   // Waits for the chunk's ring slot and puts the first gathers in flight.
@@ -360,16 +406,18 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     const unsigned char *st = stage0 + stage * stage_bytes;
     const int32_t *a_sl = reinterpret_cast<const int32_t *>(st);
     const int32_t *f_sl = a_sl + kFanPtrInts;
-    recs = reinterpret_cast<const int2 *>(st + 2 * kFanPtrInts * 4);
-    const int32_t base = f_sl[0] & ~1;
+    recs = reinterpret_cast<const Rec *>(st + kPtrSlices * kFanPtrInts * 4);
+    const int32_t base = f_sl[0] & ~(RO::kAlign - 1);
     const int32_t out_lo = a_sl[0];
     f = fe = deg = 0;
+    self = n0 + lane;
     if (lane < n_in) {
-      ps = __ldg(coords + n0 + lane);
+      ps = __ldg(coords + self);
       f = f_sl[lane] - base;
       fe = f_sl[lane + 1] - base;
       deg = a_sl[lane + 1] - a_sl[lane];
       my = acc + SPB * (a_sl[lane] - out_lo);
+      if (R4) hdr = reinterpret_cast<const uint32_t *>(f_sl + kFanPtrInts)[lane];
     }
     fetch(f, ia);
     fetch(f + 1, ib);
@@ -387,13 +435,12 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     MatRow m = {0.0, 0.0, 0.0, 0.0};
     Val diag = Ops::zero(), carry = Ops::zero();
     auto process = [&](const Item &cur, const Item &prev) {
-      const uint32_t y = (uint32_t)cur.rec.y;
-      const uint32_t fl = (y >> 8) & 31;
-      if (fl & FanFlags::SEED) {
-        kself = y >> 13;
+      const Rec rc = cur.rec;
+      if (RO::seed(rc)) {
+        kself = RO::kself(rc, hdr);
         return;
       }
-      const int mid = y >> 13;
+      const int mid = RO::mat(rc, hdr);
       if (mid != cur_mat) {
         m = tab[mid];
         cur_mat = mid;
@@ -402,13 +449,13 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
       Val r[3];
       Ops::rows(g, m, r);
       Ops::add(diag, r[0]);
-      if (fl & FanFlags::ADD_CARRY) Ops::add(r[1], carry);
+      if (RO::add_carry(rc)) Ops::add(r[1], carry);
       // (a closed fan's first block waits in its slot; the last step completes it there)
-      Ops::store(my, deg, (uint32_t)prev.rec.y & 255, 1, r[1]);
+      Ops::store(my, deg, RO::k(prev.rec), 1, r[1]);
       carry = r[2];
-      if (fl & FanFlags::LAST) {
-        if (fl & FanFlags::ADD_FIRST) Ops::add(r[2], Ops::load(my, deg, y & 255));
-        Ops::store(my, deg, y & 255, 1, r[2]);
+      if (RO::last(rc)) {
+        if (RO::add_first(rc)) Ops::add(r[2], Ops::load(my, deg, RO::k(rc)));
+        Ops::store(my, deg, RO::k(rc), 1, r[2]);
       }
     };
     while (true) {
@@ -460,8 +507,11 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
 }
 
 static int fan_warp_slot_bytes(int dim, int max_degree) { return dim * dim * max_degree * kFanChunk * 8; }
-static size_t fan_smem_bytes(int dim, int max_degree, int rec_cap) {
-  return kFanWarps * fan_warp_bytes(rec_cap, fan_warp_slot_bytes(dim, max_degree));
+static int fan_rec_cap(int fan_tile_max, bool r4) {  // alignment slack + round-up of the 16-byte copy
+  return r4 ? ((fan_tile_max + 7) & ~3) : ((fan_tile_max + 3) & ~1);
+}
+static size_t fan_smem_bytes(int dim, int max_degree, int fan_tile_max, bool r4) {
+  return kFanWarps * fan_warp_bytes(fan_rec_cap(fan_tile_max, r4), fan_warp_slot_bytes(dim, max_degree), r4);
 }
 
 static size_t tile_smem_bytes(int dim, int max_degree) {
@@ -487,11 +537,15 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
   if (rc) return rc;
   const double2 *xy = reinterpret_cast<const double2 *>(coords);
   const int grid = grid_for(p->n_owned, kTile);
-  const int rec_cap = (p->fan_tile_max + 3) & ~1;  // +1 alignment slack, +1 over-read, even
+  // variant 3 = fan walk (4-byte records when the plan could build them), 4 = fan walk on the 8-byte records
+  bool r4 = p->fan_compact_ok && variant != 4;
   size_t smem = tile_smem_bytes(dim, p->max_degree);
-  const size_t smem_fan = fan_smem_bytes(dim, p->max_degree, rec_cap);
   const size_t smem_limit = 200 * 1024;
+  if (r4 && fan_smem_bytes(dim, p->max_degree, p->fan_tile_max, true) > smem_limit) r4 = false;
+  const size_t smem_fan = fan_smem_bytes(dim, p->max_degree, p->fan_tile_max, r4);
+  const int rec_cap = fan_rec_cap(p->fan_tile_max, r4);
   if (variant == 0) variant = (p->fan_ok && smem_fan <= smem_limit) ? 3 : ((smem <= smem_limit) ? 2 : 1);
+  if (variant == 4) variant = 3;
   if (variant == 3) smem = smem_fan;
   if (variant == 3 && !p->fan_ok)
     return fail(FE_ERR_UNSUPPORTED, "fe_assemble: the fan variant needs a mesh whose node stars are simple fans");
@@ -500,16 +554,25 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
                 p->max_degree);
   FE_REQUIRE(variant >= 1 && variant <= 3, "fe_assemble: unknown variant %d", variant);
 
+#define FE_FAN_LAUNCH(KC, R4, RECS)                                                                              \
+  do {                                                                                                          \
+    constexpr int minb = (KC == 2) ? FE_FAN_MINB_SCALAR : FE_FAN_MINB;                                          \
+    FE_CUDA(cudaFuncSetAttribute(k_assemble_fan<KC, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    const int fgrid = grid < minb * ctx->num_sms ? grid : minb * ctx->num_sms;                                  \
+    k_assemble_fan<KC, R4><<<fgrid, kFanThreads, smem, st>>>(p->n_owned, p->fan_ptr, RECS, p->fan_hdr,          \
+                                                             p->adj_ptr, xy, tab, vals, rec_cap,                \
+                                                             fan_warp_slot_bytes(dim, p->max_degree));          \
+  } while (0)
 #define FE_ASM_LAUNCH(KC)                                                                                       \
   do {                                                                                                          \
     if (variant == 1) {                                                                                         \
       k_assemble_global<KC><<<grid, kTile, 0, st>>>(p->n_owned, p->corner_ptr, p->corner_rec, p->adj_ptr,        \
                                                     p->conn4, xy, tab, vals);                                   \
     } else if (variant == 3) {                                                                                  \
-      FE_CUDA(cudaFuncSetAttribute(k_assemble_fan<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      const int fgrid = grid < FE_FAN_MINB * ctx->num_sms ? grid : FE_FAN_MINB * ctx->num_sms;                  \
-      k_assemble_fan<KC><<<fgrid, kFanThreads, smem, st>>>(p->n_owned, p->fan_ptr, p->fan_rec, p->adj_ptr, xy,  \
-                                                           tab, vals, rec_cap, fan_warp_slot_bytes(dim, p->max_degree)); \
+      if (r4)                                                                                                   \
+        FE_FAN_LAUNCH(KC, true, p->fan_rec4);                                                                   \
+      else                                                                                                      \
+        FE_FAN_LAUNCH(KC, false, p->fan_rec);                                                                   \
     } else {                                                                                                    \
       FE_CUDA(cudaFuncSetAttribute(k_assemble_tile<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_assemble_tile<KC><<<grid, kTile, smem, st>>>(p->n_owned, p->corner_ptr, p->corner_rec, p->adj_ptr,       \
@@ -524,6 +587,7 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
   else
     FE_ASM_LAUNCH(0);
 #undef FE_ASM_LAUNCH
+#undef FE_FAN_LAUNCH
   FE_LAUNCH_CHECK(ctx);
   return FE_OK;
 }

@@ -286,6 +286,50 @@ __global__ void k_fan_tile_max(int32_t n_owned, const int32_t *__restrict__ fan_
   if (cnt > *reinterpret_cast<volatile int *>(out)) atomicMax(out, cnt);
 }
 
+// 8-byte fan records -> 4-byte words + one header word per node (layout in plan.cuh).  One thread per node.
+__global__ void __launch_bounds__(128) k_fan_compact(int32_t n_owned, const int32_t *__restrict__ fan_ptr,
+                                                    const int2 *__restrict__ rec, uint32_t *__restrict__ rec4,
+                                                    uint32_t *__restrict__ hdr, int *__restrict__ bad) {
+  const int32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_owned) return;
+  const int32_t f0 = fan_ptr[n], f1 = fan_ptr[n + 1];
+  uint32_t kself = 0;
+  int mat0 = -1, mat1 = -1;
+  for (int32_t f = f0; f < f1; ++f) {
+    const int2 r = rec[f];
+    const uint32_t y = (uint32_t)r.y;
+    const uint32_t k = y & 255, fl = (y >> 8) & 31, hi = y >> 13;
+    uint32_t f4 = (fl & FAN_SEED ? FAN4_SEED : 0u) | (fl & FAN_ADD_CARRY ? FAN4_ADD_CARRY : 0u) |
+                  (fl & FAN_LAST ? FAN4_LAST : 0u) | (fl & FAN_ADD_FIRST ? FAN4_ADD_FIRST : 0u);
+    uint32_t field;
+    if (r.x >= n_owned) {  // ghost column (multi-GPU layout: owned first, ghosts after): index among the ghosts
+      f4 |= FAN4_GHOST;
+      field = (uint32_t)(r.x - n_owned);
+      if (field >= (1u << kFan4FieldBits)) *bad = 1;
+    } else {
+      const int32_t delta = r.x - n;
+      if (delta < -(1 << (kFan4FieldBits - 1)) || delta >= (1 << (kFan4FieldBits - 1))) *bad = 1;
+      field = (uint32_t)delta & ((1u << kFan4FieldBits) - 1u);
+    }
+    if (fl & FAN_SEED) {
+      kself = hi;
+    } else {
+      const int mid = (int)hi;
+      if (mat0 < 0 || mid == mat0) {
+        mat0 = mid;
+      } else if (mat1 < 0 || mid == mat1) {
+        mat1 = mid;
+        f4 |= FAN4_MAT1;
+      } else {
+        *bad = 1;  // a third material around one node
+      }
+      if (mid >= 4096) *bad = 1;
+    }
+    rec4[f] = k | (f4 << 8) | (field << 14);
+  }
+  hdr[n] = kself | ((uint32_t)(mat0 < 0 ? 0 : mat0) << 8) | ((uint32_t)(mat1 < 0 ? 0 : mat1) << 20);
+}
+
 template <typename T>
 static int dev_alloc(T **p, int64_t count, int64_t *bytes_acc) {
   size_t b = (size_t)(count > 0 ? count : 1) * sizeof(T);
@@ -311,6 +355,8 @@ int fe_plan_destroy(fe_plan *p) {
   cudaFree(p->conn4);
   cudaFree(p->fan_ptr);
   cudaFree(p->fan_rec);
+  cudaFree(p->fan_rec4);
+  cudaFree(p->fan_hdr);
   cudaFree(p->corner_elem);
   cudaFree(p->contrib_ptr);
   cudaFree(p->contrib);
@@ -453,6 +499,17 @@ int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, 
   }
   PLAN_CUDA(cudaStreamSynchronize(st));
   if (p->fan_ok) p->fan_tile_max = hflags.max_degree;
+  if (p->fan_ok && n_owned > 0 && p->n_fan > 0) {  // compact (4-byte) copy of the fan records when they fit
+    PLAN_TRY(dev_alloc(&p->fan_rec4, p->n_fan + 8, &p->bytes));  // +8: 16-byte staging over-read
+    PLAN_TRY(dev_alloc(&p->fan_hdr, (int64_t)n_owned + 136, &p->bytes));  // +136: slice over-read
+    PLAN_CUDA(cudaMemsetAsync(&flags->bad_node, 0, sizeof(int), st));
+    k_fan_compact<<<grid_for(n_owned, 128), 128, 0, st>>>(n_owned, p->fan_ptr, p->fan_rec, p->fan_rec4, p->fan_hdr,
+                                                         &flags->bad_node);
+    PLAN_LAUNCHED();
+    PLAN_CUDA(cudaMemcpyAsync(&hflags, flags, sizeof(PlanFlags), cudaMemcpyDeviceToHost, st));
+    PLAN_CUDA(cudaStreamSynchronize(st));
+    p->fan_compact_ok = hflags.bad_node == 0;
+  }
 
 done:
   cudaFree(cursor);
@@ -695,6 +752,7 @@ int64_t fe_plan_nnz(const fe_plan *p) { return p ? p->nnz : 0; }
 int32_t fe_plan_n_rows(const fe_plan *p) { return p ? p->n_owned * p->dim : 0; }
 int32_t fe_plan_max_degree(const fe_plan *p) { return p ? p->max_degree : 0; }
 int64_t fe_plan_bytes(const fe_plan *p) { return p ? p->bytes : 0; }
+int32_t fe_plan_fan_record_bytes(const fe_plan *p) { return (p && p->fan_ok) ? (p->fan_compact_ok ? 4 : 8) : 0; }
 
 int fe_plan_csr(const fe_plan *p, void *stream, int32_t *rowptr, int32_t *colidx) {
   FE_REQUIRE(p && rowptr && (colidx || p->nnz == 0), "fe_plan_csr: NULL argument");

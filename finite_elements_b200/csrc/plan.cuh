@@ -4,6 +4,8 @@
 #include "common.cuh"
 
 namespace fe {
+constexpr int kFan4FieldBits = 18;
+enum : uint32_t { FAN4_SEED = 1, FAN4_ADD_CARRY = 2, FAN4_ADD_FIRST = 4, FAN4_LAST = 8, FAN4_MAT1 = 16, FAN4_GHOST = 32 };
 constexpr int kTile = 128;  // nodes (= threads) per CTA of the tiled assembly kernels
 }
 
@@ -35,6 +37,15 @@ struct fe_plan {
   int32_t fan_tile_max = 0;    // max records of one 32-node chunk (one warp of k_assemble_fan)
   int32_t *fan_ptr = nullptr;  // [n_owned + 1]
   int2 *fan_rec = nullptr;     // [n_fan]
+  // the same records in 4 bytes (plan.cu: k_fan_compact) when the numbering is banded (|neighbour - node| <
+  // 2^17 for owned neighbours, fewer than 2^18 ghosts) and no node star holds more than two materials
+  // (ids < 4096): half the record traffic of the assembly kernel.
+  //   word        = k | FAN4_* flags << 8 | field << 14;  field = neighbour - node (signed 18 bit), or with
+  //                 FAN4_GHOST the neighbour's index among the ghost columns (neighbour - n_owned)
+  //   fan_hdr[i]  = k_self | mat0 << 8 | mat1 << 20       (FAN4_MAT1 selects mat1 for a step)
+  bool fan_compact_ok = false;
+  uint32_t *fan_rec4 = nullptr;  // [n_fan]
+  uint32_t *fan_hdr = nullptr;   // [n_owned]
   // linear tetrahedra (npe == 4, dim == 3; fe_tet_plan_create): per OFF-DIAGONAL block (node i, slot k) the
   // elements that hold both nodes, ascending, as (element << 4 | local vertex of i << 2 | local vertex of the
   // neighbour) -- what k_tet_assemble_slots walks; the diagonal block is summed from the same visits

@@ -92,6 +92,7 @@ class DeviceMesh:
         self.n_cols = self.n_nodes * self.dim
         self.max_degree = int(lib.fe_plan_max_degree(h))
         self.plan_bytes = int(lib.fe_plan_bytes(h))
+        self.fan_record_bytes = int(lib.fe_plan_fan_record_bytes(h))
         self._csr = None
         DeviceMesh._tokens += 1
         self._token = DeviceMesh._tokens   # identifies this mesh's immutable CSR pattern to the solver

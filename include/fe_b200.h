@@ -112,6 +112,10 @@ int64_t fe_plan_nnz(const fe_plan *plan);        /* nnz of the (n_owned*dim) x (
 int32_t fe_plan_n_rows(const fe_plan *plan);     /* n_owned_nodes * dim                         */
 int32_t fe_plan_max_degree(const fe_plan *plan); /* max node valence incl. self                  */
 int64_t fe_plan_bytes(const fe_plan *plan);      /* device bytes held by the plan                */
+/* Bytes per fan record fe_assemble's default variant will read: 4 (compact records: banded numbering,
+ * |neighbour - node| < 2^17 on the owned block and < 2^18 ghost columns, at most two materials with ids
+ * < 4096 around any node), 8 otherwise, 0 when the mesh has no fan ordering (variants 2 / 1). */
+int32_t fe_plan_fan_record_bytes(const fe_plan *plan);
 /* Canonical CSR pattern (sorted columns, explicit zeros kept): bit-exact with
  * scipy.sparse.csr_matrix((data,(row,col))) of analysis.py:661 on the K block.
  * rowptr int32[n_rows+1], colidx int32[nnz]. */
@@ -124,7 +128,8 @@ int fe_plan_csr(const fe_plan *plan, void *stream, int32_t *rowptr, int32_t *col
  * fully overwritten.  variant: 0 = default (fastest available), 1 = generic row-owner
  * kernel (accumulates in global memory), 2 = shared-memory staged tiles, 3 = fan-ordered
  * traversal + staged tiles (needs node stars that are simple fans, i.e. no edge shared by
- * more than two elements; FE_ERR_UNSUPPORTED otherwise -- variant 0 then picks 2). */
+ * more than two elements; FE_ERR_UNSUPPORTED otherwise -- variant 0 then picks 2), 4 = variant 3
+ * forced onto the 8-byte fan records (bit-identical to 3; for tests and A/B timing). */
 int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *plan, int kind, const double *coords,
                 const double *mat, int32_t n_mat, double *vals, int variant);
 

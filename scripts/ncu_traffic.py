@@ -23,18 +23,21 @@ def short(name):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--rep", required=True)
+    ap.add_argument("--rep", required=True, nargs="+", help="one or more .ncu-rep files of the same workload")
     ap.add_argument("--workload", required=True)
     ap.add_argument("--capture", default="")
     ap.add_argument("--command", default="")
     ap.add_argument("--out", default="profiles/ncu_traffic.json")
     a = ap.parse_args()
-    raw = subprocess.run(["ncu", "-i", a.rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    h, units = rows[0], rows[1]
-    ir, iw, it = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("gpu__time_duration.sum")
     kernels = {}
-    for r in rows[2:]:
+    allrows = []
+    for rep in a.rep:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        h, units = rows[0], rows[1]
+        allrows += [(h, units, r) for r in rows[2:]]
+    for h, units, r in allrows:
+        ir, iw, it = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("gpu__time_duration.sum")
         k = short(r[h.index("Kernel Name")])
         if k in kernels:
             continue

@@ -66,6 +66,9 @@ def test_pattern_bit_exact_and_values(name):
     v0 = dm.assemble(_kind(fx), fx.mat, variant=0)
     assert np.array_equal(v1.cpu().numpy(), v2.cpu().numpy()), "element-order variants must agree bit for bit"
     assert np.array_equal(v0.cpu().numpy(), v3.cpu().numpy()), "default = fan variant on a manifold mesh"
+    v4 = dm.assemble(_kind(fx), fx.mat, variant=4)   # the same walk on the 8-byte records
+    assert dm.fan_record_bytes in (4, 8)
+    assert np.array_equal(v3.cpu().numpy(), v4.cpu().numpy()), "4-byte and 8-byte fan records must agree bit for bit"
     assert_csr_values_close(dm.to_scipy(v3), dm.to_scipy(v2), 1e-14)  # vertex relabelling: last-ulp only
     assert_csr_values_close(dm.to_scipy(v2), ref_k, 1e-12)
     assert_csr_values_close(dm.to_scipy(v3), ref_k, 1e-12)
@@ -243,6 +246,37 @@ def test_non_manifold_and_bowtie_fall_back_from_fan_variant():
     k_ref = no.assemble_k(no.KIND_MAGNETIC, coords, conn, np.zeros(3, np.int32), np.array([[2.0, 0, 0, 0]]))
     assert_csr_values_close(dm1.to_scipy(dm1.assemble(no.KIND_MAGNETIC, np.array([[2.0, 0, 0, 0]]), variant=3)),
                             k_ref, 1e-12)
+
+
+def test_compact_fan_records_and_their_fallbacks():
+    """4-byte fan records (plan.cu: k_fan_compact) need a banded numbering and at most two materials around a
+    node; outside that the plan keeps the 8-byte records.  Same values either way."""
+    from oracle import numpy_oracle as no
+    from finite_elements_b200.device import DeviceMesh
+    mat = np.array([[1.0, 0.3, 1.0, 1.0], [2.5, 0.25, 1.0, 0.5], [0.7, 0.1, 1.0, 2.0]])
+    coords, conn = no.structured_mesh(40, 24, jitter=0.2, seed=3)
+    two = (np.arange(len(conn)) >= len(conn) // 2).astype(np.int32)      # two bands: <= 2 materials per star
+    three = (np.arange(len(conn)) % 3).astype(np.int32)                   # three materials around most nodes
+    for kind, dim in ((no.KIND_ELAST_PSTRESS, 2), (no.KIND_MAGNETIC, 1)):
+        m = mat if dim == 2 else np.array([[1.0, 0, 0, 0], [50.0, 0, 0, 0], [3.0, 0, 0, 0]])
+        for mat_id, rb in ((two, 4), (three, 8)):
+            dm = DeviceMesh(coords, conn, mat_id, dim=dim)
+            assert dm.fan_record_bytes == rb
+            v3 = dm.assemble(kind, m, variant=3)
+            assert np.array_equal(v3.cpu().numpy(), dm.assemble(kind, m, variant=4).cpu().numpy())
+            assert_csr_values_close(dm.to_scipy(v3), no.assemble_k(kind, coords, conn, mat_id, m), 1e-12)
+    # a numbering that is not banded: neighbours further than 2^17 apart
+    coords, conn = no.structured_mesh(420, 400, jitter=0.1, seed=5)
+    perm = np.random.default_rng(7).permutation(len(coords))
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    coords_p, conn_p = coords[perm], inv[conn].astype(np.int32)
+    mid = np.zeros(len(conn), np.int32)
+    dm = DeviceMesh(coords_p, conn_p, mid, dim=2)
+    assert dm.fan_record_bytes == 8
+    assert DeviceMesh(coords, conn, mid, dim=2).fan_record_bytes == 4
+    k_ref = no.assemble_k(no.KIND_ELAST_PSTRESS, coords_p, conn_p, mid, mat)
+    assert_csr_values_close(dm.to_scipy(dm.assemble(no.KIND_ELAST_PSTRESS, mat)), k_ref, 1e-12)
 
 
 def test_error_mapping():
