@@ -202,27 +202,41 @@ __global__ void __launch_bounds__(kTile) k_assemble_tile(int32_t n_owned, const 
 // relabelling, rounding differs in the last ulp from the element-order kernels (tests: 1e-14
 // between variants).
 #ifndef FE_FAN_MINB
-#define FE_FAN_MINB 5  // resident CTAs per SM the register allocation targets (96 registers, no spills)
-#endif
-#ifndef FE_FAN_MINB_SCALAR
-#define FE_FAN_MINB_SCALAR 6  // the scalar (magnetic) instance needs 76 registers
+#define FE_FAN_MINB 3  // resident CTAs per SM the register allocation targets (shared memory allows 3 at valence 7)
 #endif
 
 struct FanFlags {
   static constexpr uint32_t SEED = 1, ADD_CARRY = 2, HOLD_A = 4, LAST = 8, ADD_FIRST = 16;
 };
 
+// Per-kind arithmetic of one fan step.  With e1 = prev - self and e2 = cur - self (the element is (self, prev,
+// cur)) the reference's coefficients (elements.py:403-408) are
+//   beta_self = e1.y - e2.y, gamma_self = e2.x - e1.x;  beta_prev = e2.y, gamma_prev = -e2.x;
+//   beta_cur = -e1.y, gamma_cur = e1.x;  det = e1.x e2.y - e1.y e2.x  (= 2 A, signed)
+// and area / det^2 = 1 / (2 |det|).  step() ADDS the element's block towards `prev` to pb (which arrives holding
+// the previous element's share, the carry) and returns the block towards `cur` in cb.  The diagonal block is not
+// evaluated: every block row of Ke sums to zero (rigid translation / constant potential), so K_ii = -(sum of
+// the row's off-diagonal blocks); for the consistent mass matrix M_ii = +(that sum).
 template <int KC>
-struct FanOps;  // per-kind value type of one (node, neighbour) block
+struct FanOps;
 
 template <>
-struct FanOps<2> {  // magnetic: scalar entries
+struct FanOps<2> {  // magnetic: scalar entries, Ke_ij = (1/mu) (beta_i beta_j + gamma_i gamma_j) / (2 |det|)
   using Val = double;
   using Slot = double;
   static __device__ __forceinline__ Val zero() { return 0.0; }
-  static __device__ __forceinline__ void rows(const TriGeom &g, const MatRow &m, Val r[3]) { mag_row(g, m, 0, r); }
+  static __device__ __forceinline__ void step(const double2 &e1, const double2 &e2, const MatRow &m, Val &pb, Val &cb) {
+    const double b0 = e1.y - e2.y, g0 = e2.x - e1.x;
+    const double det = e1.x * e2.y - e1.y * e2.x;
+    const double s = (0.5 * m.p0) * fabs(1.0 / det);
+    const double sb = s * b0, sg = s * g0;
+    pb = fma(sb, e2.y, pb);
+    pb = fma(-sg, e2.x, pb);
+    cb = sg * e1.x - sb * e1.y;
+  }
   static __device__ __forceinline__ void add(Val &a, const Val &b) { a += b; }
-  static __device__ __forceinline__ void store(Slot *my, int /*deg*/, int k, int ld, const Val &v) { my[k * ld] = v; }
+  static __device__ __forceinline__ void diag_acc(Val &d, const Val &b) { d -= b; }
+  static __device__ __forceinline__ void store(Slot *my, int /*deg*/, int k, const Val &v) { my[k] = v; }
   static __device__ __forceinline__ Val load(const Slot *my, int /*deg*/, int k) { return my[k]; }
 };
 
@@ -231,11 +245,36 @@ struct FanOps {  // elasticity (0) / mass (1): 2x2 blocks, stored as two double2
   using Val = Blk2;
   using Slot = double2;
   static __device__ __forceinline__ Val zero() { return Blk2{0.0, 0.0, 0.0, 0.0}; }
-  static __device__ __forceinline__ void rows(const TriGeom &g, const MatRow &m, Val r[3]) {
-    if (KC == 0)
-      elast_row_blocks(g, m, 0, r);
-    else
-      mass_row_blocks(g, m, 0, r);
+  static __device__ __forceinline__ void step(const double2 &e1, const double2 &e2, const MatRow &m, Val &pb, Val &cb) {
+    const double det = e1.x * e2.y - e1.y * e2.x;
+    if (KC == 1) {  // rho t / 12 * area on the off-diagonal blocks' diagonals
+      const double s = (0.5 * m.p0) * fabs(det);
+      pb.k00 += s;
+      pb.k11 += s;
+      cb = Blk2{s, 0.0, 0.0, s};
+      return;
+    }
+    // Ke(self, j) = t A B_self^T D B_j (elements.py:466-511), t in the material row
+    const double b0 = e1.y - e2.y, g0 = e2.x - e1.x;
+    const double s = 0.5 * fabs(1.0 / det);
+    const double tb = s * b0, tg = s * g0;
+    const double cb_ = m.p0 * tb, cg = m.p0 * tg;  // c t
+    const double ab = m.p1 * tb, ag = m.p1 * tg;   // a t
+    const double sb = m.p2 * tb, sg = m.p2 * tg;   // b t (shear)
+    // j = prev: beta = e2.y, gamma = -e2.x
+    pb.k00 = fma(cb_, e2.y, pb.k00);
+    pb.k00 = fma(-sg, e2.x, pb.k00);
+    pb.k01 = fma(sg, e2.y, pb.k01);
+    pb.k01 = fma(-ab, e2.x, pb.k01);
+    pb.k10 = fma(ag, e2.y, pb.k10);
+    pb.k10 = fma(-sb, e2.x, pb.k10);
+    pb.k11 = fma(sb, e2.y, pb.k11);
+    pb.k11 = fma(-cg, e2.x, pb.k11);
+    // j = cur: beta = -e1.y, gamma = e1.x
+    cb.k00 = sg * e1.x - cb_ * e1.y;
+    cb.k01 = ab * e1.x - sg * e1.y;
+    cb.k10 = sb * e1.x - ag * e1.y;
+    cb.k11 = cg * e1.x - sb * e1.y;
   }
   static __device__ __forceinline__ void add(Val &a, const Val &b) {
     a.k00 += b.k00;
@@ -243,9 +282,20 @@ struct FanOps {  // elasticity (0) / mass (1): 2x2 blocks, stored as two double2
     a.k10 += b.k10;
     a.k11 += b.k11;
   }
-  static __device__ __forceinline__ void store(Slot *my, int deg, int k, int ld, const Val &v) {
-    my[k * ld] = make_double2(v.k00, v.k01);
-    my[(deg + k) * ld] = make_double2(v.k10, v.k11);
+  static __device__ __forceinline__ void diag_acc(Val &d, const Val &b) {
+    if (KC == 1) {
+      d.k00 += b.k00;
+      d.k11 += b.k11;
+    } else {
+      d.k00 -= b.k00;
+      d.k01 -= b.k01;
+      d.k10 -= b.k10;
+      d.k11 -= b.k11;
+    }
+  }
+  static __device__ __forceinline__ void store(Slot *my, int deg, int k, const Val &v) {
+    my[k] = make_double2(v.k00, v.k01);
+    my[deg + k] = make_double2(v.k10, v.k11);
   }
   static __device__ __forceinline__ Val load(const Slot *my, int deg, int k) {
     const double2 u = my[k], w = my[deg + k];
@@ -256,14 +306,18 @@ struct FanOps {  // elasticity (0) / mass (1): 2x2 blocks, stored as two double2
 // Persistent kernel in which every WARP is an independent software pipeline over 32-node
 // chunks (chunk = global warp id, + total warps, ...); warps never synchronise with each other.
 //  * Input ring per warp (2 stages, one mbarrier each): while chunk c is computed, lane 0 has
-//    already handed chunk c+1 to the TMA engine -- the two pointer slices (adj_ptr, fan_ptr: 36
-//    ints each) and the chunk's contiguous record range -- and the record-range end points of
-//    chunk c+2 are travelling towards its registers.  The dependent pointer -> record round
-//    trips are off the critical path.
+//    already handed chunk c+1 to the TMA engine -- the pointer slices (adj_ptr, fan_ptr, fan_hdr: 36
+//    words each), the chunk's own coordinates and its contiguous record range -- and the end points
+//    of chunk c+2's record range are travelling towards lane 0's registers.
+//  * Neighbour coordinates: at the top of chunk c every lane walks the records of ITS node of chunk
+//    c+1 (already in the ring) and issues one 16-byte cp.async per record into the stage's
+//    coordinate array -- a whole chunk (>= 7 steps) ahead of their use.  ncu on the previous form
+//    (register prefetch two steps ahead): 4.2 of 9.9 stall cycles per issue were long-scoreboard
+//    waits on these gathers, ~1500 cycles per step and warp at 0.46 ms.  The walk itself now reads
+//    only shared memory.
 //  * Output: each warp owns a private sub-tile, the exact image of its 32 nodes' slice of
-//    `vals`, and hands it to the TMA engine with one bulk store; the first coordinate gathers of
-//    chunk c+1 are issued BEFORE the warp waits for that store to finish reading shared memory.
-// smem per warp: full[2] | end points int[2][2] | 2 x { a_slice[36], f_slice[36], recs[rec_cap] } | sub-tile
+//    `vals`, and hands it to the TMA engine with one bulk store.
+// smem per warp: full[2] | 2 x { a_slice[36], f_slice[36], (hdr[36]), self_xy[32], recs[rec_cap], xy[rec_cap] } | sub-tile
 constexpr int kFanThreads = kTile;  // 128 = 4 independent warps
 constexpr int kFanWarps = kFanThreads / 32;
 constexpr int kFanChunk = 32;
@@ -277,44 +331,52 @@ template <>
 struct FanRec<false> {
   using T = int2;
   static constexpr int kAlign = 2;  // records per 16 bytes
-  static __device__ __forceinline__ T none() { return make_int2(0, 0); }
   static __device__ __forceinline__ int32_t nbr(T r, int32_t /*self*/, int32_t /*n_owned*/) { return r.x; }
   static __device__ __forceinline__ uint32_t k(T r) { return (uint32_t)r.y & 255; }
   static __device__ __forceinline__ bool seed(T r) { return (uint32_t)r.y & (FanFlags::SEED << 8); }
-  static __device__ __forceinline__ bool add_carry(T r) { return (uint32_t)r.y & (FanFlags::ADD_CARRY << 8); }
   static __device__ __forceinline__ bool last(T r) { return (uint32_t)r.y & (FanFlags::LAST << 8); }
   static __device__ __forceinline__ bool add_first(T r) { return (uint32_t)r.y & (FanFlags::ADD_FIRST << 8); }
   static __device__ __forceinline__ int kself(T r, uint32_t /*hdr*/) { return (uint32_t)r.y >> 13; }
-  static __device__ __forceinline__ int mat(T r, uint32_t /*hdr*/) { return (uint32_t)r.y >> 13; }
+  static __device__ __forceinline__ int first_mat(uint32_t /*hdr*/) { return -1; }
+  static __device__ __forceinline__ bool new_mat(T r, uint32_t /*hdr*/, int &cur) {
+    const int mid = (uint32_t)r.y >> 13;
+    const bool ch = mid != cur;
+    cur = mid;
+    return ch;
+  }
 };
 template <>
 struct FanRec<true> {
   using T = uint32_t;
   static constexpr int kAlign = 4;
-  static __device__ __forceinline__ T none() { return 0u; }
   static __device__ __forceinline__ int32_t nbr(T r, int32_t self, int32_t n_owned) {
-    return (r & (FAN4_GHOST << 8)) ? n_owned + (int32_t)(r >> 14) : self + ((int32_t)r >> 14);
+    return ((r & (FAN4_GHOST << 8)) ? n_owned : self) + ((int32_t)r >> 14);
   }
   static __device__ __forceinline__ uint32_t k(T r) { return r & 255; }
   static __device__ __forceinline__ bool seed(T r) { return r & (FAN4_SEED << 8); }
-  static __device__ __forceinline__ bool add_carry(T r) { return r & (FAN4_ADD_CARRY << 8); }
   static __device__ __forceinline__ bool last(T r) { return r & (FAN4_LAST << 8); }
   static __device__ __forceinline__ bool add_first(T r) { return r & (FAN4_ADD_FIRST << 8); }
   static __device__ __forceinline__ int kself(T /*r*/, uint32_t hdr) { return hdr & 255; }
-  static __device__ __forceinline__ int mat(T r, uint32_t hdr) {
-    return (r & (FAN4_MAT1 << 8)) ? (int)(hdr >> 20) : (int)((hdr >> 8) & 4095);
+  static __device__ __forceinline__ int first_mat(uint32_t hdr) { return (hdr >> 8) & 4095; }
+  static __device__ __forceinline__ bool new_mat(T r, uint32_t hdr, int &cur) {
+    if (!(r & (FAN4_MATSW << 8))) return false;
+    const int m0 = (hdr >> 8) & 4095, m1 = hdr >> 20;
+    cur = (cur == m0) ? m1 : m0;
+    return true;
   }
 };
 
 __host__ __device__ inline size_t fan_stage_bytes(int rec_cap, bool r4) {
-  return ((size_t)(r4 ? 3 : 2) * kFanPtrInts * sizeof(int32_t) + (size_t)rec_cap * (r4 ? 4 : 8) + 15) / 16 * 16;
+  // pointer slices | own coordinates | records | neighbour coordinates (16-byte aligned pieces)
+  return (size_t)(r4 ? 3 : 2) * kFanPtrInts * sizeof(int32_t) + kFanChunk * 16 +
+         ((size_t)rec_cap * (r4 ? 4 : 8) + 15) / 16 * 16 + (size_t)rec_cap * 16;
 }
 __host__ __device__ inline size_t fan_warp_bytes(int rec_cap, int warp_slot_bytes, bool r4) {
   return (32 + 2 * fan_stage_bytes(rec_cap, r4) + (size_t)warp_slot_bytes + 127) / 128 * 128;
 }
 
 template <int KC, bool R4>
-__global__ void __launch_bounds__(kFanThreads, (KC == 2 ? FE_FAN_MINB_SCALAR : FE_FAN_MINB)) k_assemble_fan(
+__global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     int32_t n_owned, const int32_t *__restrict__ fan_ptr, const typename FanRec<R4>::T *__restrict__ fan_rec,
     const uint32_t *__restrict__ fan_hdr, const int32_t *__restrict__ adj_ptr, const double2 *__restrict__ coords,
     const MatRow *__restrict__ tab, double *__restrict__ vals, int rec_cap, int warp_slot_bytes) {
@@ -325,12 +387,13 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? FE_FAN_MINB_SCALAR : F
   using Rec = typename RO::T;
   constexpr int SPB = (KC == 2) ? 1 : 2;  // Slots per node-level block
   constexpr int kPtrSlices = R4 ? 3 : 2;  // adj_ptr, fan_ptr (, fan_hdr)
+  constexpr int kSelfOff = kPtrSlices * kFanPtrInts * 4, kRecOff = kSelfOff + kFanChunk * 16;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *wbase = smem_raw + (size_t)warp * fan_warp_bytes(rec_cap, warp_slot_bytes, R4);
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
   const size_t stage_bytes = fan_stage_bytes(rec_cap, R4);
-  int32_t *ep = reinterpret_cast<int32_t *>(wbase + 16);  // [2][2] record-range end points (LDGSTS)
+  const size_t xy_off = kRecOff + ((size_t)rec_cap * sizeof(Rec) + 15) / 16 * 16;
   unsigned char *stage0 = wbase + 32;
   Slot *acc = reinterpret_cast<Slot *>(stage0 + 2 * stage_bytes);
 
@@ -343,167 +406,150 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? FE_FAN_MINB_SCALAR : F
   }
   __syncwarp();
 
-  // ---- lane 0: the TMA loads of a chunk.  The end points of its record range are fetched one
-  //      chunk ahead with cp.async (global -> shared, no registers held across the compute loop).
-  auto request_endpoints = [&](int chunk, int slot) {
-    if (chunk < n_chunks) {
-      const int32_t n0 = chunk * kFanChunk;
-      ptx::cp_async4(ep + 2 * slot, fan_ptr + n0);
-      ptx::cp_async4(ep + 2 * slot + 1, fan_ptr + min(n0 + kFanChunk, n_owned));
-    }
-    ptx::cp_async_commit();
-  };
+  // ---- lane 0: the TMA loads of a chunk, given the end points [r0, r1) of its record range
   auto issue = [&](int chunk, int stage, int32_t r0, int32_t r1) {
     const int32_t n0 = chunk * kFanChunk;
     const int32_t base = r0 & ~(RO::kAlign - 1);  // 16-byte aligned start of the record copy
     const uint32_t rec_bytes = (uint32_t)((r1 - base + RO::kAlign - 1) / RO::kAlign) * 16u;
+    const uint32_t self_bytes = (uint32_t)min(kFanChunk, n_owned - n0) * 16u;
     unsigned char *st = stage0 + stage * stage_bytes;
-    ptx::mbar_expect_tx(&full[stage], (uint32_t)kPtrSlices * kFanPtrInts * 4u + rec_bytes);
+    ptx::mbar_expect_tx(&full[stage], (uint32_t)kPtrSlices * kFanPtrInts * 4u + self_bytes + rec_bytes);
     ptx::bulk_load(st, adj_ptr + n0, kFanPtrInts * 4u, &full[stage]);
     ptx::bulk_load(st + kFanPtrInts * 4, fan_ptr + n0, kFanPtrInts * 4u, &full[stage]);
     if (R4) ptx::bulk_load(st + 2 * kFanPtrInts * 4, fan_hdr + n0, kFanPtrInts * 4u, &full[stage]);
-    if (rec_bytes) ptx::bulk_load(st + kPtrSlices * kFanPtrInts * 4, fan_rec + base, rec_bytes, &full[stage]);
+    ptx::bulk_load(st + kSelfOff, coords + n0, self_bytes, &full[stage]);
+    if (rec_bytes) ptx::bulk_load(st + kRecOff, fan_rec + base, rec_bytes, &full[stage]);
   };
-  int chunk = blockIdx.x * kFanWarps + warp;
-  if (lane == 0 && chunk < n_chunks) {
-    // chunks 0 and 1 of this warp: direct loads (start-up only); chunk 2's end points requested
-    for (int q = 0; q < 2; ++q) {
-      const int c = chunk + q * chunk_stride;
-      if (c < n_chunks) {
-        const int32_t n0 = c * kFanChunk;
-        issue(c, q, __ldg(fan_ptr + n0), __ldg(fan_ptr + min(n0 + kFanChunk, n_owned)));
-      }
+  auto endpoints = [&](int chunk, int32_t &r0, int32_t &r1) {
+    if (chunk < n_chunks) {
+      const int32_t n0 = chunk * kFanChunk;
+      r0 = __ldg(fan_ptr + n0);
+      r1 = __ldg(fan_ptr + min(n0 + kFanChunk, n_owned));
     }
-    request_endpoints(chunk + 2 * chunk_stride, 0);
+  };
+  // ---- every lane: the neighbour coordinates of its node of `chunk` (whose ring slot must be full)
+  auto gather = [&](int chunk, int stage) {
+    const int32_t n0 = chunk * kFanChunk;
+    unsigned char *st = stage0 + stage * stage_bytes;
+    const int32_t *f_sl = reinterpret_cast<const int32_t *>(st) + kFanPtrInts;
+    const Rec *rc = reinterpret_cast<const Rec *>(st + kRecOff);
+    double2 *xy = reinterpret_cast<double2 *>(st + xy_off);
+    if (lane < min(kFanChunk, n_owned - n0)) {
+      const int32_t base = f_sl[0] & ~(RO::kAlign - 1);
+      const int i1 = f_sl[lane + 1] - base;
+      for (int i = f_sl[lane] - base; i < i1; ++i) ptx::cp_async16(xy + i, coords + RO::nbr(rc[i], n0 + lane, n_owned));
+    }
+  };
+
+  int chunk = blockIdx.x * kFanWarps + warp;
+  int32_t ep0 = 0, ep1 = 0;  // lane 0: record range of the chunk after the next one
+  if (chunk < n_chunks) {
+    if (lane == 0) {
+      // chunks 0 and 1 of this warp: direct loads (start-up only)
+      for (int q = 0; q < 2; ++q) {
+        const int c = chunk + q * chunk_stride;
+        endpoints(c, ep0, ep1);
+        if (c < n_chunks) issue(c, q, ep0, ep1);
+      }
+      endpoints(chunk + 2 * chunk_stride, ep0, ep1);
+    }
+    ptx::mbar_wait(&full[0], 0);
+    gather(chunk, 0);
+    ptx::cp_async_commit();
   }
 
-  // ---- per-thread state of the chunk about to be computed (filled by begin_chunk)
-  struct Item {
-    Rec rec;
-    double2 p;
-  };
-  Item ia, ib, ic;  // three rotating sets: current, previous, and the gather two steps ahead
-  ia.rec = ib.rec = ic.rec = RO::none();
-  ia.p = ib.p = ic.p = make_double2(0.0, 0.0);
-  double2 ps = make_double2(0.0, 0.0);
-  const Rec *recs = nullptr;
-  Slot *my = acc;
-  int f = 0, fe = 0, deg = 0;
-  int32_t self = 0;
-  uint32_t hdr = 0;
-  auto fetch = [&](int i, Item &it) {
-    if (i < fe) {
-      it.rec = recs[i];
-      it.p = __ldg(coords + RO::nbr(it.rec, self, n_owned));
+  for (int j = 0; chunk < n_chunks; chunk += chunk_stride, j = (j + 1) & 3) {  // stage = j & 1, barrier parity = j >> 1
+    const int stage = j & 1;
+    const int next = chunk + chunk_stride;
+    if (next < n_chunks) {
+      ptx::mbar_wait(&full[stage ^ 1], (uint32_t)(((j + 1) >> 1) & 1));
+      gather(next, stage ^ 1);
     }
-  };
-  // Waits for the chunk's ring slot and puts the first gathers in flight.
-  auto begin_chunk = [&](int c, int jj) {
-    const int stage = jj & 1;
-    ptx::mbar_wait(&full[stage], (uint32_t)((jj >> 1) & 1));
-    const int32_t n0 = c * kFanChunk;
+    ptx::cp_async_commit();  // (an empty group keeps the count: one group per chunk)
+
+    // ---- this thread's node
+    const int32_t n0 = chunk * kFanChunk;
     const int n_in = min(kFanChunk, n_owned - n0);
     const unsigned char *st = stage0 + stage * stage_bytes;
     const int32_t *a_sl = reinterpret_cast<const int32_t *>(st);
     const int32_t *f_sl = a_sl + kFanPtrInts;
-    recs = reinterpret_cast<const Rec *>(st + kPtrSlices * kFanPtrInts * 4);
-    const int32_t base = f_sl[0] & ~(RO::kAlign - 1);
+    const Rec *recs = reinterpret_cast<const Rec *>(st + kRecOff);
+    const double2 *xy = reinterpret_cast<const double2 *>(st + xy_off);
     const int32_t out_lo = a_sl[0];
-    f = fe = deg = 0;
-    self = n0 + lane;
+    const int32_t out_len = a_sl[n_in] - out_lo;  // node-level block range of this chunk
+    int f = 0, fe = 0, deg = 0;
+    uint32_t hdr = 0;
+    double2 ps = make_double2(0.0, 0.0);
+    Slot *my = acc;
     if (lane < n_in) {
-      ps = __ldg(coords + self);
+      const int32_t base = f_sl[0] & ~(RO::kAlign - 1);
       f = f_sl[lane] - base;
       fe = f_sl[lane + 1] - base;
       deg = a_sl[lane + 1] - a_sl[lane];
       my = acc + SPB * (a_sl[lane] - out_lo);
+      ps = reinterpret_cast<const double2 *>(st + kSelfOff)[lane];
       if (R4) hdr = reinterpret_cast<const uint32_t *>(f_sl + kFanPtrInts)[lane];
     }
-    fetch(f, ia);
-    fetch(f + 1, ib);
-  };
+    // the previous chunk's bulk store must have drained the sub-tile; this chunk's gathers must have landed
+    if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
+    ptx::cp_async_wait_group<1>();
+    __syncwarp();
 
-  int j = 0;  // ring position mod 4: stage = j & 1, barrier parity = (j >> 1) & 1
-  if (chunk < n_chunks) begin_chunk(chunk, 0);
-  for (; chunk < n_chunks; chunk += chunk_stride, j = (j + 1) & 3) {
-    const int stage = j & 1;
-    const int next = chunk + chunk_stride;
-
-    // ---- the fan walk of this thread's node (records + neighbour coordinates, 3 rotating sets)
-    const bool any = f < fe;
-    int kself = 0, cur_mat = -1;
-    MatRow m = {0.0, 0.0, 0.0, 0.0};
-    Val diag = Ops::zero(), carry = Ops::zero();
-    auto process = [&](const Item &cur, const Item &prev) {
-      const Rec rc = cur.rec;
-      if (RO::seed(rc)) {
-        kself = RO::kself(rc, hdr);
-        return;
+    // ---- the fan walk (records and neighbour coordinates from shared memory)
+    if (f < fe) {
+      int kself = 0, cur_mat = RO::first_mat(hdr);
+      MatRow m = {0.0, 0.0, 0.0, 0.0};
+      if (R4) m = tab[cur_mat];
+      Val diag = Ops::zero(), carry = Ops::zero();
+      double2 e1 = make_double2(0.0, 0.0);
+      Rec prev_rec = recs[f];
+      for (; f < fe; ++f) {
+        const Rec rc = recs[f];
+        const double2 p = xy[f];
+        const double2 e2 = make_double2(p.x - ps.x, p.y - ps.y);
+        if (RO::seed(rc)) {  // a chain starts: its first neighbour, nothing carried
+          kself = RO::kself(rc, hdr);
+          carry = Ops::zero();
+        } else {
+          if (RO::new_mat(rc, hdr, cur_mat)) m = tab[cur_mat];
+          Val cb;
+          Ops::step(e1, e2, m, carry, cb);  // carry: now the finished block towards the previous neighbour
+          // (a closed fan's first block waits in its slot; the last step completes it there)
+          Ops::store(my, deg, RO::k(prev_rec), carry);
+          Ops::diag_acc(diag, carry);
+          carry = cb;
+          if (RO::last(rc)) {
+            Ops::diag_acc(diag, cb);
+            if (RO::add_first(rc)) Ops::add(cb, Ops::load(my, deg, RO::k(rc)));
+            Ops::store(my, deg, RO::k(rc), cb);
+          }
+        }
+        e1 = e2;
+        prev_rec = rc;
       }
-      const int mid = RO::mat(rc, hdr);
-      if (mid != cur_mat) {
-        m = tab[mid];
-        cur_mat = mid;
-      }
-      const TriGeom g = tri_geom(ps, prev.p, cur.p);
-      Val r[3];
-      Ops::rows(g, m, r);
-      Ops::add(diag, r[0]);
-      if (RO::add_carry(rc)) Ops::add(r[1], carry);
-      // (a closed fan's first block waits in its slot; the last step completes it there)
-      Ops::store(my, deg, RO::k(prev.rec), 1, r[1]);
-      carry = r[2];
-      if (RO::last(rc)) {
-        if (RO::add_first(rc)) Ops::add(r[2], Ops::load(my, deg, RO::k(rc)));
-        Ops::store(my, deg, RO::k(rc), 1, r[2]);
-      }
-    };
-    while (true) {
-      if (f >= fe) break;
-      process(ia, ic);
-      fetch(f + 2, ic);
-      ++f;
-      if (f >= fe) break;
-      process(ib, ia);
-      fetch(f + 2, ia);
-      ++f;
-      if (f >= fe) break;
-      process(ic, ib);
-      fetch(f + 2, ib);
-      ++f;
+      Ops::store(my, deg, kself, diag);
     }
-    if (any) Ops::store(my, deg, kself, 1, diag);
 
     // ---- the sub-tile is complete: the exact image of vals[dim^2 * out_lo ...)
     ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy
     __syncwarp();
-    int32_t out_lo, out_len;  // node-level block range of this chunk (slice still in the ring slot)
-    {
-      const int32_t *a_sl = reinterpret_cast<const int32_t *>(stage0 + stage * stage_bytes);
-      out_lo = a_sl[0];
-      out_len = a_sl[min(kFanChunk, n_owned - chunk * kFanChunk)] - out_lo;
-    }
     if (KC == 2) {
       // 1 DOF per node: the destination is only 8-byte aligned -> plain coalesced copy
       const double *src = reinterpret_cast<const double *>(acc);
       double *dst = vals + out_lo;
       for (int q = lane; q < out_len; q += 32) dst[q] = src[q];
+      __syncwarp();
     } else if (lane == 0 && out_len > 0) {
       ptx::bulk_store(vals + 4 * (int64_t)out_lo, acc, (uint32_t)out_len * 32u);  // one TMA bulk store
     }
     if (lane == 0) {
       // this warp is done with ring slot `stage`: refill it with the chunk after the next one
-      // (its end points were requested a whole chunk ago and sit in ep[stage])
       const int nn = next + chunk_stride;
-      ptx::cp_async_wait_all();
-      if (nn < n_chunks) issue(nn, stage, ep[2 * stage], ep[2 * stage + 1]);
-      request_endpoints(nn + chunk_stride, stage ^ 1);
+      if (nn < n_chunks) issue(nn, stage, ep0, ep1);
+      endpoints(nn + chunk_stride, ep0, ep1);
     }
-    // first gathers of the next chunk go out before we wait for the store to drain the sub-tile
-    if (next < n_chunks) begin_chunk(next, (j + 1) & 3);
-    if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
-    __syncwarp();
   }
+  if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
 }
 
 static int fan_warp_slot_bytes(int dim, int max_degree) { return dim * dim * max_degree * kFanChunk * 8; }
@@ -556,8 +602,10 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
 
 #define FE_FAN_LAUNCH(KC, R4, RECS)                                                                              \
   do {                                                                                                          \
-    constexpr int minb = (KC == 2) ? FE_FAN_MINB_SCALAR : FE_FAN_MINB;                                          \
+    int minb = FE_FAN_MINB;                                                                                     \
     FE_CUDA(cudaFuncSetAttribute(k_assemble_fan<KC, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    FE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&minb, k_assemble_fan<KC, R4>, kFanThreads, smem));   \
+    if (minb < 1) minb = 1;                                                                                     \
     const int fgrid = grid < minb * ctx->num_sms ? grid : minb * ctx->num_sms;                                  \
     k_assemble_fan<KC, R4><<<fgrid, kFanThreads, smem, st>>>(p->n_owned, p->fan_ptr, RECS, p->fan_hdr,          \
                                                              p->adj_ptr, xy, tab, vals, rec_cap,                \

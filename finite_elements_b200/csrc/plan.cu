@@ -294,34 +294,30 @@ __global__ void __launch_bounds__(128) k_fan_compact(int32_t n_owned, const int3
   if (n >= n_owned) return;
   const int32_t f0 = fan_ptr[n], f1 = fan_ptr[n + 1];
   uint32_t kself = 0;
-  int mat0 = -1, mat1 = -1;
+  int mat0 = -1, mat1 = -1, cur = -1;
   for (int32_t f = f0; f < f1; ++f) {
     const int2 r = rec[f];
     const uint32_t y = (uint32_t)r.y;
     const uint32_t k = y & 255, fl = (y >> 8) & 31, hi = y >> 13;
-    uint32_t f4 = (fl & FAN_SEED ? FAN4_SEED : 0u) | (fl & FAN_ADD_CARRY ? FAN4_ADD_CARRY : 0u) |
-                  (fl & FAN_LAST ? FAN4_LAST : 0u) | (fl & FAN_ADD_FIRST ? FAN4_ADD_FIRST : 0u);
-    uint32_t field;
+    uint32_t f4 = (fl & FAN_SEED ? FAN4_SEED : 0u) | (fl & FAN_LAST ? FAN4_LAST : 0u) |
+                  (fl & FAN_ADD_FIRST ? FAN4_ADD_FIRST : 0u);
+    int32_t delta = r.x - n;
     if (r.x >= n_owned) {  // ghost column (multi-GPU layout: owned first, ghosts after): index among the ghosts
       f4 |= FAN4_GHOST;
-      field = (uint32_t)(r.x - n_owned);
-      if (field >= (1u << kFan4FieldBits)) *bad = 1;
-    } else {
-      const int32_t delta = r.x - n;
-      if (delta < -(1 << (kFan4FieldBits - 1)) || delta >= (1 << (kFan4FieldBits - 1))) *bad = 1;
-      field = (uint32_t)delta & ((1u << kFan4FieldBits) - 1u);
+      delta = r.x - n_owned;
     }
+    if (delta < -(1 << (kFan4FieldBits - 1)) || delta >= (1 << (kFan4FieldBits - 1))) *bad = 1;
+    const uint32_t field = (uint32_t)delta & ((1u << kFan4FieldBits) - 1u);
     if (fl & FAN_SEED) {
       kself = hi;
     } else {
       const int mid = (int)hi;
-      if (mat0 < 0 || mid == mat0) {
-        mat0 = mid;
-      } else if (mat1 < 0 || mid == mat1) {
-        mat1 = mid;
-        f4 |= FAN4_MAT1;
-      } else {
-        *bad = 1;  // a third material around one node
+      if (mat0 < 0) mat0 = cur = mid;
+      if (mid != cur) {
+        if (mat1 < 0 && mid != mat0) mat1 = mid;
+        if (mid != mat0 && mid != mat1) *bad = 1;  // a third material around one node
+        f4 |= FAN4_MATSW;
+        cur = mid;
       }
       if (mid >= 4096) *bad = 1;
     }
@@ -357,6 +353,13 @@ int fe_plan_destroy(fe_plan *p) {
   cudaFree(p->fan_rec);
   cudaFree(p->fan_rec4);
   cudaFree(p->fan_hdr);
+  cudaFree(p->tile_eptr);
+  cudaFree(p->tile_nptr);
+  cudaFree(p->tile_elist);
+  cudaFree(p->tile_erec);
+  cudaFree(p->tile_nodes);
+  cudaFree(p->contrib16);
+  cudaFree(p->tet_kself);
   cudaFree(p->corner_elem);
   cudaFree(p->contrib_ptr);
   cudaFree(p->contrib);
@@ -606,6 +609,175 @@ __global__ void __launch_bounds__(128) k_tet_contrib(int32_t n_owned, const int3
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Tiles of the staged assembly (plan.cuh): one CTA per tile of kTetStageNodes owned nodes.
+//  * elements: a corner (node i, element e) of the tile's corner range is the element's FIRST appearance
+//    when i is the smallest tile node of e; first appearances are numbered by an exclusive scan
+//    -> tile-local element index (order: by node, then ascending element id).
+//  * nodes: the tile's adjacency range, sorted (bitonic, shared memory) and made unique.
+//  * contribution codes: the element of every code is looked up in the corner list of its smallest tile
+//    node and replaced by the tile-local index.
+// FILL = false counts (tile_ecnt, tile_ncnt, maxima), FILL = true writes the lists.
+// ---------------------------------------------------------------------------------------
+constexpr int kTetStageCornerCap = 2048;  // corners per tile (16 nodes: <= 128 elements per node on average)
+constexpr int kTetStageAdjCap = 2048;     // adjacency entries per tile
+struct TetStageFlags {
+  int bad, max_elems, max_nodes, max_contrib, max_adj;
+};
+
+__device__ __forceinline__ int tile_first_node(const int32_t *__restrict__ conn, int64_t e, int32_t n0, int32_t n1) {
+  int32_t imin = INT32_MAX;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const int32_t m = conn[4 * e + v];
+    if (m >= n0 && m < n1 && m < imin) imin = m;
+  }
+  return imin;
+}
+
+// exclusive scan of the 0/1 flags in s[0..n) by 256 threads; s[c] becomes prefix | flag << 31; returns the total
+__device__ int tile_scan_flags(int32_t *s, int n, int32_t *part) {
+  const int tid = threadIdx.x;
+  const int per = (n + 255) / 256, beg = min(tid * per, n), end = min(beg + per, n);
+  int sum = 0;
+  for (int c = beg; c < end; ++c) sum += s[c];
+  part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int t = 0; t < 256; ++t) {
+      const int v = part[t];
+      part[t] = run;
+      run += v;
+    }
+    part[256] = run;
+  }
+  __syncthreads();
+  int run = part[tid];
+  for (int c = beg; c < end; ++c) {
+    const int f = s[c];
+    s[c] = run | (f ? (int32_t)0x80000000 : 0);
+    run += f;
+  }
+  __syncthreads();
+  return part[256];
+}
+
+__device__ __forceinline__ int lower_bound_i32(const int32_t *a, int n, int32_t key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_tet_stage_tiles(
+    int32_t n_owned, const int32_t *__restrict__ conn, const int32_t *__restrict__ corner_ptr,
+    const int32_t *__restrict__ corner_elem, const int32_t *__restrict__ adj_ptr, const int32_t *__restrict__ adj,
+    const int32_t *__restrict__ contrib_ptr, const int32_t *__restrict__ contrib, int32_t *__restrict__ tile_ecnt,
+    int32_t *__restrict__ tile_ncnt, const int32_t *__restrict__ tile_eptr, const int32_t *__restrict__ tile_nptr,
+    int32_t *__restrict__ tile_elist, ushort4 *__restrict__ tile_erec, int32_t *__restrict__ tile_nodes,
+    uint16_t *__restrict__ contrib16, uint8_t *__restrict__ kself, TetStageFlags *__restrict__ flags) {
+  __shared__ int32_t s_pre[kTetStageCornerCap];
+  __shared__ int32_t s_sort[kTetStageAdjCap];
+  __shared__ int32_t s_uflag[kTetStageAdjCap];
+  __shared__ int32_t s_uniq[kTetStageAdjCap];
+  __shared__ int32_t s_cptr[kTetStageNodes + 1];
+  __shared__ int32_t s_part[257];
+  const int tid = threadIdx.x;
+  const int32_t tile = blockIdx.x, n0 = tile * kTetStageNodes, n1 = min(n0 + kTetStageNodes, n_owned);
+  const int nt = n1 - n0;
+  if (tid <= nt) s_cptr[tid] = corner_ptr[n0 + tid];
+  __syncthreads();
+  const int32_t c0 = s_cptr[0];
+  const int nc = s_cptr[nt] - c0;
+  const int32_t a0 = adj_ptr[n0];
+  const int na = adj_ptr[n1] - a0;
+  const int32_t q0 = contrib_ptr[a0];
+  const int nq = contrib_ptr[a0 + na] - q0;
+  if (nc > kTetStageCornerCap || na > kTetStageAdjCap) {  // (uniform across the CTA)
+    if (tid == 0) flags->bad = 1;
+    return;
+  }
+  // ---- elements: first appearances within the tile
+  for (int c = tid; c < nc; c += 256) {
+    int lo = 0, hi = nt - 1;  // node of the corner: last i with s_cptr[i] <= c0 + c
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_cptr[mid] <= c0 + c) lo = mid; else hi = mid - 1;
+    }
+    s_pre[c] = tile_first_node(conn, corner_elem[c0 + c], n0, n1) == n0 + lo;
+  }
+  __syncthreads();
+  const int ne = tile_scan_flags(s_pre, nc, s_part);
+  // ---- nodes: sorted unique adjacency of the tile
+  int npad = 1;
+  while (npad < na) npad <<= 1;
+  for (int k = tid; k < npad; k += 256) s_sort[k] = k < na ? adj[a0 + k] : INT32_MAX;
+  __syncthreads();
+  for (int size = 2; size <= npad; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int k = tid; k < npad; k += 256) {
+        const int partner = k ^ stride;
+        if (partner > k) {
+          const bool up = (k & size) == 0;
+          const int32_t x = s_sort[k], y = s_sort[partner];
+          if ((x > y) == up) {
+            s_sort[k] = y;
+            s_sort[partner] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int k = tid; k < na; k += 256) s_uflag[k] = (k == 0 || s_sort[k] != s_sort[k - 1]);
+  __syncthreads();
+  const int nn = tile_scan_flags(s_uflag, na, s_part);
+  for (int k = tid; k < na; k += 256)
+    if (s_uflag[k] < 0) s_uniq[s_uflag[k] & 0x7fffffff] = s_sort[k];
+  __syncthreads();
+  if (!FILL) {
+    if (tid == 0) {
+      tile_ecnt[tile] = ne;
+      tile_ncnt[tile] = nn;
+      atomicMax(&flags->max_elems, ne);
+      atomicMax(&flags->max_nodes, nn);
+      atomicMax(&flags->max_contrib, nq);
+      atomicMax(&flags->max_adj, na);
+      if (ne > 4095 || nn > 65535) flags->bad = 1;
+    }
+    return;
+  }
+  const int32_t eb = tile_eptr[tile], nb = tile_nptr[tile];
+  for (int k = tid; k < nn; k += 256) tile_nodes[nb + k] = s_uniq[k];
+  for (int c = tid; c < nc; c += 256) {
+    if (s_pre[c] >= 0) continue;
+    const int le = s_pre[c] & 0x7fffffff;
+    const int64_t e = corner_elem[c0 + c];
+    tile_elist[eb + le] = (int32_t)e;
+    ushort4 r;
+    r.x = (unsigned short)lower_bound_i32(s_uniq, nn, conn[4 * e + 0]);
+    r.y = (unsigned short)lower_bound_i32(s_uniq, nn, conn[4 * e + 1]);
+    r.z = (unsigned short)lower_bound_i32(s_uniq, nn, conn[4 * e + 2]);
+    r.w = (unsigned short)lower_bound_i32(s_uniq, nn, conn[4 * e + 3]);
+    tile_erec[eb + le] = r;
+  }
+  if (tid < nt) {
+    const int32_t i = n0 + tid, b0 = adj_ptr[i], d = adj_ptr[i + 1] - b0;
+    kself[i] = (uint8_t)(d > 0 ? lower_bound_i32(adj + b0, d, i) : 0);
+  }
+  for (int q = tid; q < nq; q += 256) {
+    const int32_t code = contrib[q0 + q];
+    const int32_t e = code >> 4;
+    const int li = tile_first_node(conn, e, n0, n1) - n0;
+    const int32_t cb = s_cptr[li];
+    const int cpos = cb + lower_bound_i32(corner_elem + cb, s_cptr[li + 1] - cb, e) - c0;
+    contrib16[q0 + q] = (uint16_t)(((s_pre[cpos] & 0x7fffffff) << 4) | (code & 15));
+  }
+}
+
 }  // namespace fe
 
 extern "C" {
@@ -627,9 +799,10 @@ int fe_tet_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_own
   p->npe = 4;
   p->n_elems = n_elems;
   int rc = FE_OK;
-  int32_t *cursor = nullptr, *corner_tmp = nullptr, *cand = nullptr, *ndeg = nullptr, *cnt = nullptr;
+  int32_t *cursor = nullptr, *corner_tmp = nullptr, *cand = nullptr, *ndeg = nullptr, *cnt = nullptr, *tcnt = nullptr;
   PlanFlags *flags = nullptr;
-  int64_t *totals = nullptr;
+  TetStageFlags *sflags = nullptr;
+  int64_t *totals = nullptr, *stot = nullptr;
   const int64_t n4 = 4 * n_elems;
   PlanFlags hflags = {0, 0, 0, 0, 0, 0};
   int64_t htot[3] = {0, 0, 0};
@@ -729,7 +902,50 @@ int fe_tet_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_own
     TP_LAUNCHED();
   }
   TP_CUDA(cudaStreamSynchronize(st));
+  // ---- tiles of the staged assembly variant
+  if (!p->tet_degenerate && n_owned > 0 && p->n_contrib > 0) {
+    TetStageFlags hs = {0, 0, 0, 0, 0};
+    int64_t hst[2] = {0, 0};
+    p->n_tiles = (n_owned + kTetStageNodes - 1) / kTetStageNodes;
+    TP_TRY(dev_alloc(&sflags, 1, nullptr));
+    TP_TRY(dev_alloc(&stot, 2, nullptr));
+    TP_TRY(dev_alloc(&tcnt, 2 * ((int64_t)p->n_tiles + 1), nullptr));
+    TP_TRY(dev_alloc(&p->tile_eptr, (int64_t)p->n_tiles + 1, &p->bytes));
+    TP_TRY(dev_alloc(&p->tile_nptr, (int64_t)p->n_tiles + 1, &p->bytes));
+    TP_CUDA(cudaMemsetAsync(sflags, 0, sizeof(TetStageFlags), st));
+    TP_CUDA(cudaMemsetAsync(tcnt, 0, 2 * ((size_t)p->n_tiles + 1) * sizeof(int32_t), st));
+    k_tet_stage_tiles<false><<<p->n_tiles, 256, 0, st>>>(n_owned, conn, p->corner_ptr, p->corner_elem, p->adj_ptr, p->adj,
+                                                        p->contrib_ptr, p->contrib, tcnt, tcnt + p->n_tiles + 1, nullptr,
+                                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sflags);
+    TP_LAUNCHED();
+    TP_TRY(exclusive_scan_i32(ctx, st, tcnt, p->tile_eptr, p->n_tiles, stot + 0));
+    TP_TRY(exclusive_scan_i32(ctx, st, tcnt + p->n_tiles + 1, p->tile_nptr, p->n_tiles, stot + 1));
+    TP_CUDA(cudaMemcpyAsync(hst, stot, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    TP_CUDA(cudaMemcpyAsync(&hs, sflags, sizeof(TetStageFlags), cudaMemcpyDeviceToHost, st));
+    TP_CUDA(cudaStreamSynchronize(st));
+    if (!hs.bad && hst[0] < (int64_t(1) << 31) && hst[1] < (int64_t(1) << 31)) {
+      TP_TRY(dev_alloc(&p->tile_elist, hst[0], &p->bytes));
+      TP_TRY(dev_alloc(&p->tile_erec, hst[0], &p->bytes));
+      TP_TRY(dev_alloc(&p->tile_nodes, hst[1], &p->bytes));
+      TP_TRY(dev_alloc(&p->contrib16, p->n_contrib + 8, &p->bytes));
+      TP_TRY(dev_alloc(&p->tet_kself, (int64_t)n_owned, &p->bytes));
+      k_tet_stage_tiles<true><<<p->n_tiles, 256, 0, st>>>(n_owned, conn, p->corner_ptr, p->corner_elem, p->adj_ptr, p->adj,
+                                                         p->contrib_ptr, p->contrib, nullptr, nullptr, p->tile_eptr,
+                                                         p->tile_nptr, p->tile_elist, p->tile_erec, p->tile_nodes,
+                                                         p->contrib16, p->tet_kself, sflags);
+      TP_LAUNCHED();
+      TP_CUDA(cudaStreamSynchronize(st));
+      p->tile_elems_max = hs.max_elems;
+      p->tile_nodes_max = hs.max_nodes;
+      p->tile_contrib_max = hs.max_contrib;
+      p->tile_adj_max = hs.max_adj;
+      p->tet_stage_ok = true;
+    }
+  }
 done:
+  cudaFree(sflags);
+  cudaFree(stot);
+  cudaFree(tcnt);
   cudaFree(cursor);
   cudaFree(corner_tmp);
   cudaFree(cand);

@@ -5,7 +5,8 @@
 
 namespace fe {
 constexpr int kFan4FieldBits = 18;
-enum : uint32_t { FAN4_SEED = 1, FAN4_ADD_CARRY = 2, FAN4_ADD_FIRST = 4, FAN4_LAST = 8, FAN4_MAT1 = 16, FAN4_GHOST = 32 };
+enum : uint32_t { FAN4_SEED = 1, FAN4_MATSW = 2, FAN4_ADD_FIRST = 4, FAN4_LAST = 8, FAN4_GHOST = 32 };
+constexpr int kTetStageNodes = 16;  // owned nodes per tile of the staged tetrahedral assembly (tet.cu)
 constexpr int kTile = 128;  // nodes (= threads) per CTA of the tiled assembly kernels
 }
 
@@ -38,11 +39,12 @@ struct fe_plan {
   int32_t *fan_ptr = nullptr;  // [n_owned + 1]
   int2 *fan_rec = nullptr;     // [n_fan]
   // the same records in 4 bytes (plan.cu: k_fan_compact) when the numbering is banded (|neighbour - node| <
-  // 2^17 for owned neighbours, fewer than 2^18 ghosts) and no node star holds more than two materials
+  // 2^17 for owned neighbours, fewer than 2^17 ghosts) and no node star holds more than two materials
   // (ids < 4096): half the record traffic of the assembly kernel.
-  //   word        = k | FAN4_* flags << 8 | field << 14;  field = neighbour - node (signed 18 bit), or with
-  //                 FAN4_GHOST the neighbour's index among the ghost columns (neighbour - n_owned)
-  //   fan_hdr[i]  = k_self | mat0 << 8 | mat1 << 20       (FAN4_MAT1 selects mat1 for a step)
+  //   word        = k | FAN4_* flags << 8 | field << 14;  field (signed 18 bit) = neighbour - node, or with
+  //                 FAN4_GHOST neighbour - n_owned (its index among the ghost columns)
+  //   fan_hdr[i]  = k_self | mat0 << 8 | mat1 << 20;  a node's walk starts on mat0 and FAN4_MATSW on a step
+  //                 switches to the other material before the step is evaluated
   bool fan_compact_ok = false;
   uint32_t *fan_rec4 = nullptr;  // [n_fan]
   uint32_t *fan_hdr = nullptr;   // [n_owned]
@@ -55,4 +57,18 @@ struct fe_plan {
   int32_t *contrib = nullptr;       // [12 n_elems restricted to owned rows]
   int64_t n_contrib = 0;
   bool tet_degenerate = false;      // an element lists a node twice: the slot kernel is not used
+  // staged variant (k_tet_assemble_staged): tiles of kTetStageNodes consecutive owned nodes.  Per tile the distinct
+  // nodes and elements its rows touch (an element belongs to the tile of every owned node it holds), the elements'
+  // connectivity in tile-local node numbers, and the contribution codes re-based on the tile-local element
+  // index -- everything the kernel stages in shared memory arrives as contiguous, coalesced slices.
+  bool tet_stage_ok = false;         // false: a tile exceeds the 12-bit element / 16-bit node index or the caps
+  int32_t n_tiles = 0;
+  int32_t *tile_eptr = nullptr;      // [n_tiles + 1] -> tile_elist / tile_erec
+  int32_t *tile_nptr = nullptr;      // [n_tiles + 1] -> tile_nodes
+  int32_t *tile_elist = nullptr;     // global element id (material lookup)
+  ushort4 *tile_erec = nullptr;      // the element's four nodes as positions in the tile's node list
+  int32_t *tile_nodes = nullptr;     // ascending global node ids
+  uint16_t *contrib16 = nullptr;     // [n_contrib] tile-local element index << 4 | vi << 2 | vj
+  uint8_t *tet_kself = nullptr;      // [n_owned] position of the node in its own adjacency row
+  int32_t tile_elems_max = 0, tile_nodes_max = 0, tile_contrib_max = 0, tile_adj_max = 0;
 };

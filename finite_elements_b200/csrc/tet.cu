@@ -31,12 +31,12 @@ struct TetGeom {
   double vol;      // |det [1 x y z]| / 6  (volmdlr TetrahedralElement.volume)
 };
 
-__device__ __forceinline__ TetGeom tet_geom(const double *__restrict__ coords, int n0, int n1, int n2, int n3) {
-  const double x0 = coords[3 * (int64_t)n0], y0 = coords[3 * (int64_t)n0 + 1], z0 = coords[3 * (int64_t)n0 + 2];
+__device__ __forceinline__ TetGeom tet_geom_xyz(double x0, double y0, double z0, double x1, double y1, double z1, double x2,
+                                                double y2, double z2, double x3, double y3, double z3) {
   // edge vectors from vertex 0
-  const double ax = coords[3 * (int64_t)n1] - x0, ay = coords[3 * (int64_t)n1 + 1] - y0, az = coords[3 * (int64_t)n1 + 2] - z0;
-  const double bx = coords[3 * (int64_t)n2] - x0, by = coords[3 * (int64_t)n2 + 1] - y0, bz = coords[3 * (int64_t)n2 + 2] - z0;
-  const double cx = coords[3 * (int64_t)n3] - x0, cy = coords[3 * (int64_t)n3 + 1] - y0, cz = coords[3 * (int64_t)n3 + 2] - z0;
+  const double ax = x1 - x0, ay = y1 - y0, az = z1 - z0;
+  const double bx = x2 - x0, by = y2 - y0, bz = z2 - z0;
+  const double cx = x3 - x0, cy = y3 - y0, cz = z3 - z0;
   // rows of the inverse of J = [a; b; c] are grad N_1..3 (N_i(p_j) = delta_ij); grad N_0 = -(sum)
   const double c1x = by * cz - bz * cy, c1y = bz * cx - bx * cz, c1z = bx * cy - by * cx;  // b x c
   const double c2x = cy * az - cz * ay, c2y = cz * ax - cx * az, c2z = cx * ay - cy * ax;  // c x a
@@ -51,6 +51,12 @@ __device__ __forceinline__ TetGeom tet_geom(const double *__restrict__ coords, i
   for (int d = 0; d < 3; ++d) t.g[0][d] = -(t.g[1][d] + t.g[2][d] + t.g[3][d]);
   t.vol = fabs(det) / 6.0;
   return t;
+}
+
+__device__ __forceinline__ TetGeom tet_geom(const double *__restrict__ coords, int n0, int n1, int n2, int n3) {
+  const double *p0 = coords + 3 * (int64_t)n0, *p1 = coords + 3 * (int64_t)n1;
+  const double *p2 = coords + 3 * (int64_t)n2, *p3 = coords + 3 * (int64_t)n3;
+  return tet_geom_xyz(p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
 }
 
 // (lam V, mu V) for the stiffness, (rho V / 20, -) for the mass
@@ -520,6 +526,136 @@ __global__ void __launch_bounds__(256, 4) k_tet_assemble_table(int32_t n_owned, 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Staged form (default): one CTA per tile of kTetStageNodes consecutive nodes, everything through shared
+// memory.  The table walk above is bound by the L1's rate for scattered sectors (ncu: ~1 sector per clock and
+// SM, 109 M sectors per launch); here the only scattered global loads left are one coordinate triple per tile
+// node, every other input is a contiguous slice prepared by the plan (plan.cu: k_tet_stage_tiles):
+//   stage  : coordinates of the tile's nodes, contribution offsets and 16-bit codes -> shared memory
+//   phase A: every element of the tile is evaluated once (one thread each) from the staged coordinates into
+//            four 32-byte records (sqrt(mu V) grad N_k, lambda / mu) in shared memory
+//   phase B: one lane per block walks its code list (LDS.U16) and reads the two records it needs with two
+//            LDS.128 each; blocks land in the shared-memory image of the tile's slice of vals
+//   diag   : nine lanes per node add the row's off-diagonal blocks in slot order (K_ii = -sum, M_ii = 2/3 sum)
+//   store  : the image is copied out with fully coalesced stores.
+// An element is evaluated once per tile it touches (~3x on a Kuhn mesh numbered lexicographically).
+// ---------------------------------------------------------------------------------------
+constexpr int kTetStageThreads = kTetStageNodes * 16;
+
+struct TetStageSmem {
+  size_t grad, out, xyz, cptr, aptr, codes, total;
+};
+__host__ __device__ inline TetStageSmem tet_stage_smem(int ne_max, int na_max, int nn_max, int nq_max) {
+  TetStageSmem s;
+  s.grad = 0;
+  s.out = s.grad + (size_t)ne_max * 128;
+  s.xyz = s.out + (size_t)na_max * 72;
+  s.cptr = s.xyz + (size_t)nn_max * 24;
+  s.aptr = s.cptr + ((size_t)na_max + 2) / 2 * 8;
+  s.codes = s.aptr + ((size_t)kTetStageNodes + 2) / 2 * 8;
+  s.total = (s.codes + (size_t)nq_max * 2 + 15) / 16 * 16;
+  return s;
+}
+
+template <bool MASS>
+__global__ void __launch_bounds__(kTetStageThreads, 3) k_tet_assemble_staged(
+    int32_t n_owned, const int32_t *__restrict__ adj_ptr, const int32_t *__restrict__ contrib_ptr,
+    const uint16_t *__restrict__ contrib16, const int32_t *__restrict__ tile_eptr, const int32_t *__restrict__ tile_nptr,
+    const int32_t *__restrict__ tile_elist, const ushort4 *__restrict__ tile_erec, const int32_t *__restrict__ tile_nodes,
+    const uint8_t *__restrict__ kself, const double *__restrict__ coords, const int32_t *__restrict__ mat_id,
+    const double *__restrict__ mat, double *__restrict__ vals, int ne_max, int na_max, int nn_max, int nq_max) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const TetStageSmem L = tet_stage_smem(ne_max, na_max, nn_max, nq_max);
+  double *s_grad = reinterpret_cast<double *>(smem_raw + L.grad);
+  double *s_out = reinterpret_cast<double *>(smem_raw + L.out);
+  double *s_xyz = reinterpret_cast<double *>(smem_raw + L.xyz);
+  int32_t *s_cptr = reinterpret_cast<int32_t *>(smem_raw + L.cptr);
+  int32_t *s_aptr = reinterpret_cast<int32_t *>(smem_raw + L.aptr);
+  uint16_t *s_codes = reinterpret_cast<uint16_t *>(smem_raw + L.codes);
+
+  const int tid = threadIdx.x;
+  const int32_t tile = blockIdx.x, n0 = tile * kTetStageNodes, n1 = min(n0 + kTetStageNodes, n_owned);
+  const int nt = n1 - n0;
+  const int32_t a0 = __ldg(adj_ptr + n0);
+  const int na = __ldg(adj_ptr + n1) - a0;
+  const int32_t eb = __ldg(tile_eptr + tile), nb = __ldg(tile_nptr + tile);
+  const int ne = __ldg(tile_eptr + tile + 1) - eb, nn = __ldg(tile_nptr + tile + 1) - nb;
+  const int32_t q0 = __ldg(contrib_ptr + a0);
+  const int nq = __ldg(contrib_ptr + a0 + na) - q0;
+  // ---- stage
+  if (tid <= nt) s_aptr[tid] = __ldg(adj_ptr + n0 + tid) - a0;
+  for (int k = tid; k <= na; k += kTetStageThreads) s_cptr[k] = __ldg(contrib_ptr + a0 + k) - q0;
+  for (int k = tid; k < 3 * nn; k += kTetStageThreads) {
+    const int nd = k / 3;
+    s_xyz[k] = __ldg(coords + 3 * (int64_t)__ldg(tile_nodes + nb + nd) + (k - 3 * nd));
+  }
+  for (int k = tid; k < nq; k += kTetStageThreads) s_codes[k] = __ldg(contrib16 + q0 + k);
+  __syncthreads();
+  // ---- phase A: the tile's elements, once each
+  for (int le = tid; le < ne; le += kTetStageThreads) {
+    const ushort4 r = __ldg(tile_erec + eb + le);
+    const double *p0 = s_xyz + 3 * r.x, *p1 = s_xyz + 3 * r.y, *p2 = s_xyz + 3 * r.z, *p3 = s_xyz + 3 * r.w;
+    const TetGeom t = tet_geom_xyz(p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
+    const int mid = mat_id ? __ldg(mat_id + __ldg(tile_elist + eb + le)) : 0;
+    const TetMat m = tet_material(MASS ? FE_MASS_TET : FE_ELAST_TET, mat, mid, t.vol);
+    const double sc = MASS ? 0.0 : sqrt(m.p1);
+    const double w = MASS ? m.p0 : (m.p1 != 0.0 ? m.p0 / m.p1 : 0.0);
+    double2 *g = reinterpret_cast<double2 *>(s_grad + 16 * le);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      g[2 * k] = make_double2(sc * t.g[k][0], sc * t.g[k][1]);
+      g[2 * k + 1] = make_double2(sc * t.g[k][2], w);
+    }
+  }
+  __syncthreads();
+  // ---- phase B: one lane per block
+  const int nl = tid >> 4, lane = tid & 15;
+  int al = 0, deg = 0;
+  if (nl < nt) {
+    al = s_aptr[nl];
+    deg = s_aptr[nl + 1] - al;
+  }
+  double *rows = s_out + 9 * al;
+  for (int k = lane; k < deg; k += 16) {
+    double acc[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+    const int qb = s_cptr[al + k + 1];
+    for (int q = s_cptr[al + k]; q < qb; ++q) {
+      const uint32_t code = s_codes[q];
+      const double2 *gi = reinterpret_cast<const double2 *>(s_grad + 16 * (code >> 4) + 4 * ((code >> 2) & 3));
+      const double2 *gj = reinterpret_cast<const double2 *>(s_grad + 16 * (code >> 4) + 4 * (code & 3));
+      const double2 i0 = gi[0], i1 = gi[1];
+      const D4 hi = {i0.x, i0.y, i1.x, i1.y};
+      D4 hj = hi;
+      if (!MASS) {
+        const double2 j0 = gj[0], j1 = gj[1];
+        hj = D4{j0.x, j0.y, j1.x, j1.y};
+      }
+      tet_pair_add<MASS>(hi, hj, acc);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int t = 0; t < 3; ++t) rows[r * 3 * deg + 3 * k + t] = acc[3 * r + t];
+  }
+  __syncwarp();
+  // ---- diagonal block from the off-diagonal ones (see k_tet_assemble_slots), slot order
+  if (lane < 9 && deg > 0) {
+    const int ks = __ldg(kself + n0 + nl);
+    const int r = lane / 3, t = lane - 3 * r;
+    const double *row = rows + r * 3 * deg + t;
+    double sum = 0.0;
+    for (int k = 0; k < deg; ++k)
+      if (k != ks) sum += row[3 * k];
+    rows[r * 3 * deg + 3 * ks + t] = (MASS ? (2.0 / 3.0) : -1.0) * sum;
+  }
+  __syncthreads();
+  // ---- store the image of vals[9 a0 .. 9 (a0 + na))
+  double *dst = vals + 9 * (int64_t)a0;
+  for (int k = tid; k < 9 * na; k += kTetStageThreads) dst[k] = s_out[k];
+}
+
 }  // namespace fe
 
 using namespace fe;
@@ -557,7 +693,7 @@ int fe_tet_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind, const
   FE_REQUIRE(kind == FE_ELAST_TET || kind == FE_MASS_TET, "fe_tet_assemble: kind %d is not a tetrahedral kind", kind);
   FE_REQUIRE(n_mat > 0, "fe_tet_assemble: bad sizes");
   FE_REQUIRE(((uintptr_t)conn & 15) == 0, "fe_tet_assemble: conn must be 16-byte aligned");
-  FE_REQUIRE(variant >= 0 && variant <= 4, "fe_tet_assemble: unknown variant %d", variant);
+  FE_REQUIRE(variant >= 0 && variant <= 5, "fe_tet_assemble: unknown variant %d", variant);
   if (p->n_owned == 0 || p->nnz == 0) return FE_OK;
   cudaStream_t st = as_stream(stream);
   const int max_degree = p->max_degree;
@@ -567,8 +703,27 @@ int fe_tet_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind, const
     return fail(FE_ERR_UNSUPPORTED, "fe_tet_assemble: the slot variant needs elements with four distinct nodes");
   if (variant == 2 && !fits)
     return fail(FE_ERR_UNSUPPORTED, "fe_tet_assemble: the tile variant needs %zu B of shared memory (valence %d)", smem, max_degree);
-  if (variant == 0) variant = !p->tet_degenerate ? 4 : (fits ? 2 : 1);
-  if (variant == 4) {
+  const TetStageSmem sl = tet_stage_smem(p->tile_elems_max, p->tile_adj_max, p->tile_nodes_max, p->tile_contrib_max);
+  const bool stage_fits = p->tet_stage_ok && sl.total <= 200 * 1024;
+  if (variant == 5 && !stage_fits)
+    return fail(FE_ERR_UNSUPPORTED, "fe_tet_assemble: the staged variant needs tiles of <= 4095 elements within %d B of shared memory",
+                200 * 1024);
+  if (variant == 0) variant = stage_fits ? 5 : (!p->tet_degenerate ? 4 : (fits ? 2 : 1));
+  if (variant == 5) {
+#define FE_TET_STAGED(MASS)                                                                                          \
+  do {                                                                                                               \
+    FE_CUDA(cudaFuncSetAttribute(k_tet_assemble_staged<MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total)); \
+    k_tet_assemble_staged<MASS><<<p->n_tiles, kTetStageThreads, sl.total, st>>>(                                      \
+        p->n_owned, p->adj_ptr, p->contrib_ptr, p->contrib16, p->tile_eptr, p->tile_nptr, p->tile_elist, p->tile_erec, \
+        p->tile_nodes, p->tet_kself, coords, mat_id, mat, vals, p->tile_elems_max, p->tile_adj_max, p->tile_nodes_max, \
+        p->tile_contrib_max);                                                                                        \
+  } while (0)
+    if (kind == FE_MASS_TET)
+      FE_TET_STAGED(true);
+    else
+      FE_TET_STAGED(false);
+#undef FE_TET_STAGED
+  } else if (variant == 4) {
     int rc = ctx->scratch_g.reserve((size_t)p->n_elems * 16 * sizeof(double));
     if (rc) return rc;
     double *table = (double *)ctx->scratch_g.ptr;

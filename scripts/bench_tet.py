@@ -14,6 +14,7 @@ sys.path.insert(0, ROOT)
 from finite_elements_b200.device import DeviceMesh3D, KIND_ELAST_TET  # noqa: E402
 from finite_elements_b200.mesh import structured_tet_mesh  # noqa: E402
 
+VARIANT = int(os.environ.get('FE_TET_VARIANT', '0'))
 nx, ny, nz = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (96, 48, 48)
 coords, conn = structured_tet_mesh(nx, ny, nz, h=1.0 / ny)
 mat = torch.as_tensor(np.array([[210e9, 0.25, 1.0, 7860.0]])).cuda()
@@ -23,14 +24,14 @@ rowptr, colidx = dm.csr_pattern()
 vals = torch.empty(dm.nnz, dtype=torch.float64, device="cuda")
 ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 for _ in range(3):
-    dm.assemble(KIND_ELAST_TET, mat, out=vals)
+    dm.assemble(KIND_ELAST_TET, mat, out=vals, variant=VARIANT)
 torch.cuda.synchronize()
 t = []
 for _ in range(5):
     torch.cuda._sleep(200_000)
     a, b = ev(), ev()
     a.record()
-    dm.assemble(KIND_ELAST_TET, mat, out=vals)
+    dm.assemble(KIND_ELAST_TET, mat, out=vals, variant=VARIANT)
     b.record()
     torch.cuda.synchronize()
     t.append(a.elapsed_time(b) * 1e-3)

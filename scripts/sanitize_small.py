@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Small assemblies of every kind for `compute-sanitizer --tool memcheck python scripts/sanitize_small.py`."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from finite_elements_b200 import mesh  # noqa: E402
+from finite_elements_b200.device import (DeviceMesh, DeviceMesh3D, KIND_ELAST_PSTRESS, KIND_MAGNETIC, KIND_MASS,  # noqa: E402
+                                         KIND_ELAST_TET, KIND_MASS_TET)
+
+coords, conn = mesh.structured_mesh(67, 33, jitter=0.1, seed=1)
+mid = (np.arange(len(conn)) >= len(conn) // 2).astype(np.int32)
+mat = np.array([[1.0, 0.3, 1.0, 1.0], [2.0, 0.25, 0.5, 2.0]])
+dm = DeviceMesh(coords, conn, mid, dim=2)
+for v in (0, 4, 2, 1):
+    k = dm.assemble(KIND_ELAST_PSTRESS, mat, variant=v)
+    m = dm.assemble(KIND_MASS, mat, variant=v)
+dm1 = DeviceMesh(coords, conn, mid, dim=1)
+for v in (0, 4):
+    dm1.assemble(KIND_MAGNETIC, np.array([[1.0, 0, 0, 0], [30.0, 0, 0, 0]]), variant=v)
+c3, t3 = mesh.structured_tet_mesh(9, 7, 5, h=0.5, jitter=0.15, seed=4)
+d3 = DeviceMesh3D(c3, t3, (np.arange(len(t3)) % 2).astype(np.int32))
+m3 = np.array([[210e9, 0.25, 1.0, 7860.0], [70e9, 0.3, 1.0, 2700.0]])
+for v in (0, 5, 4, 3, 2, 1):
+    d3.assemble(KIND_ELAST_TET, m3, variant=v)
+    d3.assemble(KIND_MASS_TET, m3, variant=v)
+torch.cuda.synchronize()
+print("sanitize_small: done", float(k.abs().sum()), dm.fan_record_bytes)
