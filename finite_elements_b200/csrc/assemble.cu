@@ -305,23 +305,28 @@ struct FanOps {  // elasticity (0) / mass (1): 2x2 blocks, stored as two double2
 
 // Persistent kernel in which every WARP is an independent software pipeline over 32-node
 // chunks (chunk = global warp id, + total warps, ...); warps never synchronise with each other.
-//  * Input ring per warp (2 stages, one mbarrier each): while chunk c is computed, lane 0 has
-//    already handed chunk c+1 to the TMA engine -- the pointer slices (adj_ptr, fan_ptr, fan_hdr: 36
-//    words each), the chunk's own coordinates and its contiguous record range -- and the end points
-//    of chunk c+2's record range are travelling towards lane 0's registers.
-//  * Neighbour coordinates: at the top of chunk c every lane walks the records of ITS node of chunk
-//    c+1 (already in the ring) and issues one 16-byte cp.async per record into the stage's
-//    coordinate array -- a whole chunk (>= 7 steps) ahead of their use.  ncu on the previous form
-//    (register prefetch two steps ahead): 4.2 of 9.9 stall cycles per issue were long-scoreboard
-//    waits on these gathers, ~1500 cycles per step and warp at 0.46 ms.  The walk itself now reads
-//    only shared memory.
+//  * Input ring per warp (kFanStages stages, one mbarrier each), filled by the TMA engine: the pointer
+//    slices of a chunk (adj_ptr, fan_ptr, fan_hdr: 36 words each), its own coordinates and its contiguous
+//    record range.  A stage is refilled as soon as its chunk is done, i.e. kFanStages - 1 chunks before the
+//    data is first touched (ncu on the 2-stage form: 14 % of all stall samples sat on the mbarrier wait).
+//    The end points of the record range a refill needs are fetched one chunk earlier with cp.async
+//    (global -> shared: no load is in flight into a register across the loop's back edge).
+//  * Neighbour coordinates: one 16-byte gather per fan step, issued two steps ahead into three rotating
+//    register sets; the first two gathers of a chunk are issued a whole chunk ahead (at the top of the
+//    previous chunk's walk), so the walk starts without waiting for them (17 % of the samples before).
 //  * Output: each warp owns a private sub-tile, the exact image of its 32 nodes' slice of
 //    `vals`, and hands it to the TMA engine with one bulk store.
-// smem per warp: full[2] | 2 x { a_slice[36], f_slice[36], (hdr[36]), self_xy[32], recs[rec_cap], xy[rec_cap] } | sub-tile
+// smem per warp: full[<=4] | end points int[2][2] | kFanStages x { a_slice[36], f_slice[36], (hdr[36]), self_xy[32], recs[rec_cap] } | sub-tile
 constexpr int kFanThreads = kTile;  // 128 = 4 independent warps
 constexpr int kFanWarps = kFanThreads / 32;
 constexpr int kFanChunk = 32;
 constexpr int kFanPtrInts = (kFanChunk + 1 + 3) & ~3;  // 36
+#ifndef FE_FAN_STAGES
+#define FE_FAN_STAGES 3
+#endif
+constexpr int kFanStages = FE_FAN_STAGES;
+static_assert(kFanStages >= 2 && kFanStages <= 4, "ring depth");
+constexpr int kFanHdrBytes = 64;  // barriers + end points
 
 // Record format of the fan walk: the plan's 8-byte records, or their 4-byte form (plan.cuh) with the
 // per-node header word in a third pointer slice of the ring stage.
@@ -367,12 +372,12 @@ struct FanRec<true> {
 };
 
 __host__ __device__ inline size_t fan_stage_bytes(int rec_cap, bool r4) {
-  // pointer slices | own coordinates | records | neighbour coordinates (16-byte aligned pieces)
+  // pointer slices | own coordinates | records (16-byte aligned pieces)
   return (size_t)(r4 ? 3 : 2) * kFanPtrInts * sizeof(int32_t) + kFanChunk * 16 +
-         ((size_t)rec_cap * (r4 ? 4 : 8) + 15) / 16 * 16 + (size_t)rec_cap * 16;
+         ((size_t)rec_cap * (r4 ? 4 : 8) + 15) / 16 * 16;
 }
 __host__ __device__ inline size_t fan_warp_bytes(int rec_cap, int warp_slot_bytes, bool r4) {
-  return (32 + 2 * fan_stage_bytes(rec_cap, r4) + (size_t)warp_slot_bytes + 127) / 128 * 128;
+  return (kFanHdrBytes + kFanStages * fan_stage_bytes(rec_cap, r4) + (size_t)warp_slot_bytes + 127) / 128 * 128;
 }
 
 template <int KC, bool R4>
@@ -392,16 +397,16 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *wbase = smem_raw + (size_t)warp * fan_warp_bytes(rec_cap, warp_slot_bytes, R4);
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
+  int32_t *ep = reinterpret_cast<int32_t *>(wbase + 32);  // [2][2] record-range end points (LDGSTS)
   const size_t stage_bytes = fan_stage_bytes(rec_cap, R4);
-  const size_t xy_off = kRecOff + ((size_t)rec_cap * sizeof(Rec) + 15) / 16 * 16;
-  unsigned char *stage0 = wbase + 32;
-  Slot *acc = reinterpret_cast<Slot *>(stage0 + 2 * stage_bytes);
+  unsigned char *stage0 = wbase + kFanHdrBytes;
+  Slot *acc = reinterpret_cast<Slot *>(stage0 + kFanStages * stage_bytes);
 
   const int n_chunks = (n_owned + kFanChunk - 1) / kFanChunk;
   const int chunk_stride = gridDim.x * kFanWarps;
   if (lane == 0) {
-    ptx::mbar_init(&full[0], 1);
-    ptx::mbar_init(&full[1], 1);
+#pragma unroll
+    for (int q = 0; q < kFanStages; ++q) ptx::mbar_init(&full[q], 1);
     ptx::mbar_init_fence();
   }
   __syncwarp();
@@ -420,115 +425,148 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     ptx::bulk_load(st + kSelfOff, coords + n0, self_bytes, &full[stage]);
     if (rec_bytes) ptx::bulk_load(st + kRecOff, fan_rec + base, rec_bytes, &full[stage]);
   };
-  auto endpoints = [&](int chunk, int32_t &r0, int32_t &r1) {
+  auto request_endpoints = [&](int chunk, int slot) {
     if (chunk < n_chunks) {
       const int32_t n0 = chunk * kFanChunk;
-      r0 = __ldg(fan_ptr + n0);
-      r1 = __ldg(fan_ptr + min(n0 + kFanChunk, n_owned));
+      ptx::cp_async4(ep + 2 * slot, fan_ptr + n0);
+      ptx::cp_async4(ep + 2 * slot + 1, fan_ptr + min(n0 + kFanChunk, n_owned));
+    }
+    ptx::cp_async_commit();
+  };
+  // ---- every lane: record range of its node in a (full) ring stage and its first two gathers
+  struct Item {
+    Rec rec;
+    double2 p;
+  };
+  auto lane_range = [&](int chunk, int stage, int &f0, int &f1) {
+    const unsigned char *st = stage0 + stage * stage_bytes;
+    const int32_t *f_sl = reinterpret_cast<const int32_t *>(st) + kFanPtrInts;
+    f0 = f1 = 0;
+    if (lane < min(kFanChunk, n_owned - chunk * kFanChunk)) {
+      const int32_t base = f_sl[0] & ~(RO::kAlign - 1);
+      f0 = f_sl[lane] - base;
+      f1 = f_sl[lane + 1] - base;
     }
   };
-  // ---- every lane: the neighbour coordinates of its node of `chunk` (whose ring slot must be full)
-  auto gather = [&](int chunk, int stage) {
-    const int32_t n0 = chunk * kFanChunk;
-    unsigned char *st = stage0 + stage * stage_bytes;
-    const int32_t *f_sl = reinterpret_cast<const int32_t *>(st) + kFanPtrInts;
-    const Rec *rc = reinterpret_cast<const Rec *>(st + kRecOff);
-    double2 *xy = reinterpret_cast<double2 *>(st + xy_off);
-    if (lane < min(kFanChunk, n_owned - n0)) {
-      const int32_t base = f_sl[0] & ~(RO::kAlign - 1);
-      const int i1 = f_sl[lane + 1] - base;
-      for (int i = f_sl[lane] - base; i < i1; ++i) ptx::cp_async16(xy + i, coords + RO::nbr(rc[i], n0 + lane, n_owned));
-    }
+  auto first_gathers = [&](int chunk, int stage, double2 &pa, double2 &pb) {
+    int f0, f1;
+    lane_range(chunk, stage, f0, f1);
+    const Rec *rc = reinterpret_cast<const Rec *>(stage0 + stage * stage_bytes + kRecOff);
+    const int32_t self = chunk * kFanChunk + lane;
+    if (f0 < f1) pa = __ldg(coords + RO::nbr(rc[f0], self, n_owned));
+    if (f0 + 1 < f1) pb = __ldg(coords + RO::nbr(rc[f0 + 1], self, n_owned));
   };
 
   int chunk = blockIdx.x * kFanWarps + warp;
-  int32_t ep0 = 0, ep1 = 0;  // lane 0: record range of the chunk after the next one
+  double2 npa = make_double2(0.0, 0.0), npb = npa;  // first two neighbour coordinates of the NEXT chunk
   if (chunk < n_chunks) {
     if (lane == 0) {
-      // chunks 0 and 1 of this warp: direct loads (start-up only)
-      for (int q = 0; q < 2; ++q) {
+      // the first kFanStages chunks of this warp: direct loads of the end points (start-up only)
+      for (int q = 0; q < kFanStages; ++q) {
         const int c = chunk + q * chunk_stride;
-        endpoints(c, ep0, ep1);
-        if (c < n_chunks) issue(c, q, ep0, ep1);
+        if (c < n_chunks) {
+          const int32_t n0 = c * kFanChunk;
+          issue(c, q, __ldg(fan_ptr + n0), __ldg(fan_ptr + min(n0 + kFanChunk, n_owned)));
+        }
       }
-      endpoints(chunk + 2 * chunk_stride, ep0, ep1);
+      request_endpoints(chunk + kFanStages * chunk_stride, 0);
     }
     ptx::mbar_wait(&full[0], 0);
-    gather(chunk, 0);
-    ptx::cp_async_commit();
+    first_gathers(chunk, 0, npa, npb);
   }
 
-  for (int j = 0; chunk < n_chunks; chunk += chunk_stride, j = (j + 1) & 3) {  // stage = j & 1, barrier parity = j >> 1
-    const int stage = j & 1;
+  // ring position j in [0, 2 kFanStages): stage = j % kFanStages, barrier parity = j / kFanStages
+  for (int j = 0; chunk < n_chunks; chunk += chunk_stride, j = (j + 1 == 2 * kFanStages) ? 0 : j + 1) {
+    const int stage = (j >= kFanStages) ? j - kFanStages : j;
     const int next = chunk + chunk_stride;
-    if (next < n_chunks) {
-      ptx::mbar_wait(&full[stage ^ 1], (uint32_t)(((j + 1) >> 1) & 1));
-      gather(next, stage ^ 1);
-    }
-    ptx::cp_async_commit();  // (an empty group keeps the count: one group per chunk)
 
-    // ---- this thread's node
+    // ---- this thread's node (its ring stage was waited for one chunk ago)
     const int32_t n0 = chunk * kFanChunk;
     const int n_in = min(kFanChunk, n_owned - n0);
     const unsigned char *st = stage0 + stage * stage_bytes;
     const int32_t *a_sl = reinterpret_cast<const int32_t *>(st);
-    const int32_t *f_sl = a_sl + kFanPtrInts;
     const Rec *recs = reinterpret_cast<const Rec *>(st + kRecOff);
-    const double2 *xy = reinterpret_cast<const double2 *>(st + xy_off);
     const int32_t out_lo = a_sl[0];
     const int32_t out_len = a_sl[n_in] - out_lo;  // node-level block range of this chunk
-    int f = 0, fe = 0, deg = 0;
+    const int32_t self = n0 + lane;
+    int f, fe, deg = 0;
+    lane_range(chunk, stage, f, fe);
     uint32_t hdr = 0;
     double2 ps = make_double2(0.0, 0.0);
     Slot *my = acc;
     if (lane < n_in) {
-      const int32_t base = f_sl[0] & ~(RO::kAlign - 1);
-      f = f_sl[lane] - base;
-      fe = f_sl[lane + 1] - base;
       deg = a_sl[lane + 1] - a_sl[lane];
       my = acc + SPB * (a_sl[lane] - out_lo);
       ps = reinterpret_cast<const double2 *>(st + kSelfOff)[lane];
-      if (R4) hdr = reinterpret_cast<const uint32_t *>(f_sl + kFanPtrInts)[lane];
+      if (R4) hdr = reinterpret_cast<const uint32_t *>(a_sl + 2 * kFanPtrInts)[lane];
     }
-    // the previous chunk's bulk store must have drained the sub-tile; this chunk's gathers must have landed
+    Item ia, ib, ic;  // three rotating sets: current, previous, and the gather two steps ahead
+    ia.p = npa;
+    ib.p = npb;
+    ic.p = make_double2(0.0, 0.0);
+    ia.rec = ib.rec = ic.rec = recs[0];
+    if (f < fe) ia.rec = recs[f];
+    if (f + 1 < fe) ib.rec = recs[f + 1];
+    auto fetch = [&](int i, Item &it) {
+      if (i < fe) {
+        it.rec = recs[i];
+        it.p = __ldg(coords + RO::nbr(it.rec, self, n_owned));
+      }
+    };
+    // ---- the next chunk: wait for its ring stage (refilled kFanStages - 1 chunks ago), first gathers out
+    if (next < n_chunks) {
+      const int jn = (j + 1 == 2 * kFanStages) ? 0 : j + 1;
+      const int sn = (jn >= kFanStages) ? jn - kFanStages : jn;
+      ptx::mbar_wait(&full[sn], (uint32_t)(jn >= kFanStages));
+      first_gathers(next, sn, npa, npb);
+    }
+    // the previous chunk's bulk store must have drained the sub-tile
     if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
-    ptx::cp_async_wait_group<1>();
     __syncwarp();
 
-    // ---- the fan walk (records and neighbour coordinates from shared memory)
-    if (f < fe) {
-      int kself = 0, cur_mat = RO::first_mat(hdr);
-      MatRow m = {0.0, 0.0, 0.0, 0.0};
-      if (R4) m = tab[cur_mat];
-      Val diag = Ops::zero(), carry = Ops::zero();
-      double2 e1 = make_double2(0.0, 0.0);
-      Rec prev_rec = recs[f];
-      for (; f < fe; ++f) {
-        const Rec rc = recs[f];
-        const double2 p = xy[f];
-        const double2 e2 = make_double2(p.x - ps.x, p.y - ps.y);
-        if (RO::seed(rc)) {  // a chain starts: its first neighbour, nothing carried
-          kself = RO::kself(rc, hdr);
-          carry = Ops::zero();
-        } else {
-          if (RO::new_mat(rc, hdr, cur_mat)) m = tab[cur_mat];
-          Val cb;
-          Ops::step(e1, e2, m, carry, cb);  // carry: now the finished block towards the previous neighbour
-          // (a closed fan's first block waits in its slot; the last step completes it there)
-          Ops::store(my, deg, RO::k(prev_rec), carry);
-          Ops::diag_acc(diag, carry);
-          carry = cb;
-          if (RO::last(rc)) {
-            Ops::diag_acc(diag, cb);
-            if (RO::add_first(rc)) Ops::add(cb, Ops::load(my, deg, RO::k(rc)));
-            Ops::store(my, deg, RO::k(rc), cb);
-          }
-        }
-        e1 = e2;
-        prev_rec = rc;
+    // ---- the fan walk
+    const bool any = f < fe;
+    int kself = 0, cur_mat = RO::first_mat(hdr);
+    MatRow m = {0.0, 0.0, 0.0, 0.0};
+    if (R4 && any) m = tab[cur_mat];
+    Val diag = Ops::zero(), carry = Ops::zero();
+    auto process = [&](const Item &cur, const Item &prev) {
+      const Rec rc = cur.rec;
+      if (RO::seed(rc)) {  // a chain starts: its first neighbour, nothing carried
+        kself = RO::kself(rc, hdr);
+        carry = Ops::zero();
+        return;
       }
-      Ops::store(my, deg, kself, diag);
+      if (RO::new_mat(rc, hdr, cur_mat)) m = tab[cur_mat];
+      const double2 e1 = make_double2(prev.p.x - ps.x, prev.p.y - ps.y);
+      const double2 e2 = make_double2(cur.p.x - ps.x, cur.p.y - ps.y);
+      Val cb;
+      Ops::step(e1, e2, m, carry, cb);  // carry: now the finished block towards the previous neighbour
+      // (a closed fan's first block waits in its slot; the last step completes it there)
+      Ops::store(my, deg, RO::k(prev.rec), carry);
+      Ops::diag_acc(diag, carry);
+      carry = cb;
+      if (RO::last(rc)) {
+        Ops::diag_acc(diag, cb);
+        if (RO::add_first(rc)) Ops::add(cb, Ops::load(my, deg, RO::k(rc)));
+        Ops::store(my, deg, RO::k(rc), cb);
+      }
+    };
+    while (true) {
+      if (f >= fe) break;
+      process(ia, ic);
+      fetch(f + 2, ic);
+      ++f;
+      if (f >= fe) break;
+      process(ib, ia);
+      fetch(f + 2, ia);
+      ++f;
+      if (f >= fe) break;
+      process(ic, ib);
+      fetch(f + 2, ib);
+      ++f;
     }
+    if (any) Ops::store(my, deg, kself, diag);
 
     // ---- the sub-tile is complete: the exact image of vals[dim^2 * out_lo ...)
     ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy
@@ -543,10 +581,12 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
       ptx::bulk_store(vals + 4 * (int64_t)out_lo, acc, (uint32_t)out_len * 32u);  // one TMA bulk store
     }
     if (lane == 0) {
-      // this warp is done with ring slot `stage`: refill it with the chunk after the next one
-      const int nn = next + chunk_stride;
-      if (nn < n_chunks) issue(nn, stage, ep0, ep1);
-      endpoints(nn + chunk_stride, ep0, ep1);
+      // this warp is done with ring slot `stage`: refill it with the chunk kFanStages ahead
+      // (its end points were requested a whole chunk ago and sit in ep[j & 1])
+      const int nn = chunk + kFanStages * chunk_stride;
+      ptx::cp_async_wait_all();
+      if (nn < n_chunks) issue(nn, stage, ep[2 * (j & 1)], ep[2 * (j & 1) + 1]);
+      request_endpoints(nn + chunk_stride, (j & 1) ^ 1);
     }
   }
   if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();

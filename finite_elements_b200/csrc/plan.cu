@@ -355,6 +355,7 @@ int fe_plan_destroy(fe_plan *p) {
   cudaFree(p->fan_hdr);
   cudaFree(p->tile_eptr);
   cudaFree(p->tile_nptr);
+  cudaFree(p->tile_desc);
   cudaFree(p->tile_elist);
   cudaFree(p->tile_erec);
   cudaFree(p->tile_nodes);
@@ -679,7 +680,8 @@ __global__ void __launch_bounds__(256) k_tet_stage_tiles(
     const int32_t *__restrict__ contrib_ptr, const int32_t *__restrict__ contrib, int32_t *__restrict__ tile_ecnt,
     int32_t *__restrict__ tile_ncnt, const int32_t *__restrict__ tile_eptr, const int32_t *__restrict__ tile_nptr,
     int32_t *__restrict__ tile_elist, ushort4 *__restrict__ tile_erec, int32_t *__restrict__ tile_nodes,
-    uint16_t *__restrict__ contrib16, uint8_t *__restrict__ kself, TetStageFlags *__restrict__ flags) {
+    uint16_t *__restrict__ contrib16, uint8_t *__restrict__ kself, int4 *__restrict__ tile_desc,
+    TetStageFlags *__restrict__ flags) {
   __shared__ int32_t s_pre[kTetStageCornerCap];
   __shared__ int32_t s_sort[kTetStageAdjCap];
   __shared__ int32_t s_uflag[kTetStageAdjCap];
@@ -751,6 +753,10 @@ __global__ void __launch_bounds__(256) k_tet_stage_tiles(
     return;
   }
   const int32_t eb = tile_eptr[tile], nb = tile_nptr[tile];
+  if (tid == 0) {
+    tile_desc[2 * tile] = make_int4(a0, na, eb, ne);
+    tile_desc[2 * tile + 1] = make_int4(nb, nn, q0, nq);
+  }
   for (int k = tid; k < nn; k += 256) tile_nodes[nb + k] = s_uniq[k];
   for (int c = tid; c < nc; c += 256) {
     if (s_pre[c] >= 0) continue;
@@ -916,7 +922,7 @@ int fe_tet_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_own
     TP_CUDA(cudaMemsetAsync(tcnt, 0, 2 * ((size_t)p->n_tiles + 1) * sizeof(int32_t), st));
     k_tet_stage_tiles<false><<<p->n_tiles, 256, 0, st>>>(n_owned, conn, p->corner_ptr, p->corner_elem, p->adj_ptr, p->adj,
                                                         p->contrib_ptr, p->contrib, tcnt, tcnt + p->n_tiles + 1, nullptr,
-                                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sflags);
+                                                        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sflags);
     TP_LAUNCHED();
     TP_TRY(exclusive_scan_i32(ctx, st, tcnt, p->tile_eptr, p->n_tiles, stot + 0));
     TP_TRY(exclusive_scan_i32(ctx, st, tcnt + p->n_tiles + 1, p->tile_nptr, p->n_tiles, stot + 1));
@@ -924,6 +930,7 @@ int fe_tet_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_own
     TP_CUDA(cudaMemcpyAsync(&hs, sflags, sizeof(TetStageFlags), cudaMemcpyDeviceToHost, st));
     TP_CUDA(cudaStreamSynchronize(st));
     if (!hs.bad && hst[0] < (int64_t(1) << 31) && hst[1] < (int64_t(1) << 31)) {
+      TP_TRY(dev_alloc(&p->tile_desc, 2 * (int64_t)p->n_tiles, &p->bytes));
       TP_TRY(dev_alloc(&p->tile_elist, hst[0], &p->bytes));
       TP_TRY(dev_alloc(&p->tile_erec, hst[0], &p->bytes));
       TP_TRY(dev_alloc(&p->tile_nodes, hst[1], &p->bytes));
@@ -932,7 +939,7 @@ int fe_tet_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_own
       k_tet_stage_tiles<true><<<p->n_tiles, 256, 0, st>>>(n_owned, conn, p->corner_ptr, p->corner_elem, p->adj_ptr, p->adj,
                                                          p->contrib_ptr, p->contrib, nullptr, nullptr, p->tile_eptr,
                                                          p->tile_nptr, p->tile_elist, p->tile_erec, p->tile_nodes,
-                                                         p->contrib16, p->tet_kself, sflags);
+                                                         p->contrib16, p->tet_kself, p->tile_desc, sflags);
       TP_LAUNCHED();
       TP_CUDA(cudaStreamSynchronize(st));
       p->tile_elems_max = hs.max_elems;

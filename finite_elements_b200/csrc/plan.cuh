@@ -65,6 +65,8 @@ struct fe_plan {
   int32_t n_tiles = 0;
   int32_t *tile_eptr = nullptr;      // [n_tiles + 1] -> tile_elist / tile_erec
   int32_t *tile_nptr = nullptr;      // [n_tiles + 1] -> tile_nodes
+  int4 *tile_desc = nullptr;         // [2 n_tiles] (adj offset, adj length, element offset, elements), (node offset,
+                                     // nodes, contribution offset, contributions): all a CTA needs to address its slices
   int32_t *tile_elist = nullptr;     // global element id (material lookup)
   ushort4 *tile_erec = nullptr;      // the element's four nodes as positions in the tile's node list
   int32_t *tile_nodes = nullptr;     // ascending global node ids

@@ -541,6 +541,8 @@ __global__ void __launch_bounds__(256, 4) k_tet_assemble_table(int32_t n_owned, 
 // An element is evaluated once per tile it touches (~3x on a Kuhn mesh numbered lexicographically).
 // ---------------------------------------------------------------------------------------
 constexpr int kTetStageThreads = kTetStageNodes * 16;
+constexpr int kTetGradStride = 13;  // doubles per element in shared memory: 4 x (sqrt(mu V) grad N_k) + lambda / mu
+                                    // (odd stride: elements spread over all banks; 128 B records aliased 8-way)
 
 struct TetStageSmem {
   size_t grad, out, xyz, cptr, aptr, codes, total;
@@ -548,7 +550,7 @@ struct TetStageSmem {
 __host__ __device__ inline TetStageSmem tet_stage_smem(int ne_max, int na_max, int nn_max, int nq_max) {
   TetStageSmem s;
   s.grad = 0;
-  s.out = s.grad + (size_t)ne_max * 128;
+  s.out = s.grad + ((size_t)ne_max * kTetGradStride * 8 + 15) / 16 * 16;
   s.xyz = s.out + (size_t)na_max * 72;
   s.cptr = s.xyz + (size_t)nn_max * 24;
   s.aptr = s.cptr + ((size_t)na_max + 2) / 2 * 8;
@@ -558,12 +560,12 @@ __host__ __device__ inline TetStageSmem tet_stage_smem(int ne_max, int na_max, i
 }
 
 template <bool MASS>
-__global__ void __launch_bounds__(kTetStageThreads, 3) k_tet_assemble_staged(
+__global__ void __launch_bounds__(kTetStageThreads, 4) k_tet_assemble_staged(
     int32_t n_owned, const int32_t *__restrict__ adj_ptr, const int32_t *__restrict__ contrib_ptr,
-    const uint16_t *__restrict__ contrib16, const int32_t *__restrict__ tile_eptr, const int32_t *__restrict__ tile_nptr,
-    const int32_t *__restrict__ tile_elist, const ushort4 *__restrict__ tile_erec, const int32_t *__restrict__ tile_nodes,
-    const uint8_t *__restrict__ kself, const double *__restrict__ coords, const int32_t *__restrict__ mat_id,
-    const double *__restrict__ mat, double *__restrict__ vals, int ne_max, int na_max, int nn_max, int nq_max) {
+    const uint16_t *__restrict__ contrib16, const int4 *__restrict__ tile_desc, const int32_t *__restrict__ tile_elist,
+    const ushort4 *__restrict__ tile_erec, const int32_t *__restrict__ tile_nodes, const uint8_t *__restrict__ kself,
+    const double *__restrict__ coords, const int32_t *__restrict__ mat_id, const double *__restrict__ mat,
+    double *__restrict__ vals, int ne_max, int na_max, int nn_max, int nq_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const TetStageSmem L = tet_stage_smem(ne_max, na_max, nn_max, nq_max);
   double *s_grad = reinterpret_cast<double *>(smem_raw + L.grad);
@@ -576,37 +578,50 @@ __global__ void __launch_bounds__(kTetStageThreads, 3) k_tet_assemble_staged(
   const int tid = threadIdx.x;
   const int32_t tile = blockIdx.x, n0 = tile * kTetStageNodes, n1 = min(n0 + kTetStageNodes, n_owned);
   const int nt = n1 - n0;
-  const int32_t a0 = __ldg(adj_ptr + n0);
-  const int na = __ldg(adj_ptr + n1) - a0;
-  const int32_t eb = __ldg(tile_eptr + tile), nb = __ldg(tile_nptr + tile);
-  const int ne = __ldg(tile_eptr + tile + 1) - eb, nn = __ldg(tile_nptr + tile + 1) - nb;
-  const int32_t q0 = __ldg(contrib_ptr + a0);
-  const int nq = __ldg(contrib_ptr + a0 + na) - q0;
-  // ---- stage
-  if (tid <= nt) s_aptr[tid] = __ldg(adj_ptr + n0 + tid) - a0;
-  for (int k = tid; k <= na; k += kTetStageThreads) s_cptr[k] = __ldg(contrib_ptr + a0 + k) - q0;
+  // one descriptor per tile (plan.cu): every slice below is addressed from it -- one dependent load, not three
+  const int4 d0 = __ldg(tile_desc + 2 * tile), d1 = __ldg(tile_desc + 2 * tile + 1);
+  const int32_t a0 = d0.x, eb = d0.z, nb = d1.x, q0 = d1.z;
+  const int na = d0.y, ne = d0.w, nn = d1.y, nq = d1.w;
+  // ---- stage (all loads independent of each other except coordinates <- node list)
+  ushort4 er0 = make_ushort4(0, 0, 0, 0), er1 = er0;  // this thread's elements of phase A
+  int32_t eg0 = 0, eg1 = 0;
+  if (tid < ne) {
+    er0 = __ldg(tile_erec + eb + tid);
+    if (mat_id) eg0 = __ldg(tile_elist + eb + tid);
+  }
+  if (tid + kTetStageThreads < ne) {
+    er1 = __ldg(tile_erec + eb + tid + kTetStageThreads);
+    if (mat_id) eg1 = __ldg(tile_elist + eb + tid + kTetStageThreads);
+  }
   for (int k = tid; k < 3 * nn; k += kTetStageThreads) {
     const int nd = k / 3;
     s_xyz[k] = __ldg(coords + 3 * (int64_t)__ldg(tile_nodes + nb + nd) + (k - 3 * nd));
   }
+  if (tid <= nt) s_aptr[tid] = __ldg(adj_ptr + n0 + tid) - a0;
+  for (int k = tid; k <= na; k += kTetStageThreads) s_cptr[k] = __ldg(contrib_ptr + a0 + k) - q0;
   for (int k = tid; k < nq; k += kTetStageThreads) s_codes[k] = __ldg(contrib16 + q0 + k);
+  const int mid0 = (mat_id && tid < ne) ? __ldg(mat_id + eg0) : 0;
+  const int mid1 = (mat_id && tid + kTetStageThreads < ne) ? __ldg(mat_id + eg1) : 0;
   __syncthreads();
   // ---- phase A: the tile's elements, once each
-  for (int le = tid; le < ne; le += kTetStageThreads) {
-    const ushort4 r = __ldg(tile_erec + eb + le);
+  auto evaluate = [&](int le, const ushort4 r, int mid) {
     const double *p0 = s_xyz + 3 * r.x, *p1 = s_xyz + 3 * r.y, *p2 = s_xyz + 3 * r.z, *p3 = s_xyz + 3 * r.w;
     const TetGeom t = tet_geom_xyz(p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
-    const int mid = mat_id ? __ldg(mat_id + __ldg(tile_elist + eb + le)) : 0;
     const TetMat m = tet_material(MASS ? FE_MASS_TET : FE_ELAST_TET, mat, mid, t.vol);
     const double sc = MASS ? 0.0 : sqrt(m.p1);
-    const double w = MASS ? m.p0 : (m.p1 != 0.0 ? m.p0 / m.p1 : 0.0);
-    double2 *g = reinterpret_cast<double2 *>(s_grad + 16 * le);
+    double *g = s_grad + kTetGradStride * le;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      g[2 * k] = make_double2(sc * t.g[k][0], sc * t.g[k][1]);
-      g[2 * k + 1] = make_double2(sc * t.g[k][2], w);
+      g[3 * k] = sc * t.g[k][0];
+      g[3 * k + 1] = sc * t.g[k][1];
+      g[3 * k + 2] = sc * t.g[k][2];
     }
-  }
+    g[12] = MASS ? m.p0 : (m.p1 != 0.0 ? m.p0 / m.p1 : 0.0);
+  };
+  if (tid < ne) evaluate(tid, er0, mid0);
+  if (tid + kTetStageThreads < ne) evaluate(tid + kTetStageThreads, er1, mid1);
+  for (int le = tid + 2 * kTetStageThreads; le < ne; le += kTetStageThreads)
+    evaluate(le, __ldg(tile_erec + eb + le), mat_id ? __ldg(mat_id + __ldg(tile_elist + eb + le)) : 0);
   __syncthreads();
   // ---- phase B: one lane per block
   const int nl = tid >> 4, lane = tid & 15;
@@ -623,15 +638,11 @@ __global__ void __launch_bounds__(kTetStageThreads, 3) k_tet_assemble_staged(
     const int qb = s_cptr[al + k + 1];
     for (int q = s_cptr[al + k]; q < qb; ++q) {
       const uint32_t code = s_codes[q];
-      const double2 *gi = reinterpret_cast<const double2 *>(s_grad + 16 * (code >> 4) + 4 * ((code >> 2) & 3));
-      const double2 *gj = reinterpret_cast<const double2 *>(s_grad + 16 * (code >> 4) + 4 * (code & 3));
-      const double2 i0 = gi[0], i1 = gi[1];
-      const D4 hi = {i0.x, i0.y, i1.x, i1.y};
+      const double *ge = s_grad + kTetGradStride * (code >> 4);
+      const double *gi = ge + 3 * ((code >> 2) & 3), *gj = ge + 3 * (code & 3);
+      const D4 hi = {gi[0], gi[1], gi[2], ge[12]};
       D4 hj = hi;
-      if (!MASS) {
-        const double2 j0 = gj[0], j1 = gj[1];
-        hj = D4{j0.x, j0.y, j1.x, j1.y};
-      }
+      if (!MASS) hj = D4{gj[0], gj[1], gj[2], 0.0};
       tet_pair_add<MASS>(hi, hj, acc);
     }
 #pragma unroll
@@ -714,7 +725,7 @@ int fe_tet_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind, const
   do {                                                                                                               \
     FE_CUDA(cudaFuncSetAttribute(k_tet_assemble_staged<MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total)); \
     k_tet_assemble_staged<MASS><<<p->n_tiles, kTetStageThreads, sl.total, st>>>(                                      \
-        p->n_owned, p->adj_ptr, p->contrib_ptr, p->contrib16, p->tile_eptr, p->tile_nptr, p->tile_elist, p->tile_erec, \
+        p->n_owned, p->adj_ptr, p->contrib_ptr, p->contrib16, p->tile_desc, p->tile_elist, p->tile_erec,             \
         p->tile_nodes, p->tet_kself, coords, mat_id, mat, vals, p->tile_elems_max, p->tile_adj_max, p->tile_nodes_max, \
         p->tile_contrib_max);                                                                                        \
   } while (0)
