@@ -202,12 +202,23 @@ __global__ void __launch_bounds__(kTile) k_assemble_tile(int32_t n_owned, const 
 // relabelling, rounding differs in the last ulp from the element-order kernels (tests: 1e-14
 // between variants).
 #ifndef FE_FAN_MINB
-#define FE_FAN_MINB 3  // resident CTAs per SM the register allocation targets (shared memory allows 3 at valence 7)
+#define FE_FAN_MINB 5  // resident CTAs (of 2 warps) per SM the register allocation targets; shared memory allows 5 at valence 7
 #endif
 
 struct FanFlags {
   static constexpr uint32_t SEED = 1, ADD_CARRY = 2, HOLD_A = 4, LAST = 8, ADD_FIRST = 16;
 };
+
+// 1 / d to ~1 ulp without the slow-path branch of the compiler's division: MUFU.RCP64H seed (>= 20 bits)
+// and two Newton steps.  |d| is an element's 2 x area: never subnormal or huge on a mesh that has a K.
+__device__ __forceinline__ double fan_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  return fma(y, e, y);
+}
 
 // Per-kind arithmetic of one fan step.  With e1 = prev - self and e2 = cur - self (the element is (self, prev,
 // cur)) the reference's coefficients (elements.py:403-408) are
@@ -228,7 +239,7 @@ struct FanOps<2> {  // magnetic: scalar entries, Ke_ij = (1/mu) (beta_i beta_j +
   static __device__ __forceinline__ void step(const double2 &e1, const double2 &e2, const MatRow &m, Val &pb, Val &cb) {
     const double b0 = e1.y - e2.y, g0 = e2.x - e1.x;
     const double det = e1.x * e2.y - e1.y * e2.x;
-    const double s = (0.5 * m.p0) * fabs(1.0 / det);
+    const double s = (0.5 * m.p0) * fabs(fan_rcp(det));
     const double sb = s * b0, sg = s * g0;
     pb = fma(sb, e2.y, pb);
     pb = fma(-sg, e2.x, pb);
@@ -256,7 +267,7 @@ struct FanOps {  // elasticity (0) / mass (1): 2x2 blocks, stored as two double2
     }
     // Ke(self, j) = t A B_self^T D B_j (elements.py:466-511), t in the material row
     const double b0 = e1.y - e2.y, g0 = e2.x - e1.x;
-    const double s = 0.5 * fabs(1.0 / det);
+    const double s = 0.5 * fabs(fan_rcp(det));
     const double tb = s * b0, tg = s * g0;
     const double cb_ = m.p0 * tb, cg = m.p0 * tg;  // c t
     const double ab = m.p1 * tb, ag = m.p1 * tg;   // a t
@@ -304,28 +315,34 @@ struct FanOps {  // elasticity (0) / mass (1): 2x2 blocks, stored as two double2
 };
 
 // Persistent kernel in which every WARP is an independent software pipeline over 32-node
-// chunks (chunk = global warp id, + total warps, ...); warps never synchronise with each other.
-//  * Input ring per warp (kFanStages stages, one mbarrier each), filled by the TMA engine: the pointer
+// chunks (chunk = global warp id, + total warps, ...); warps never synchronise with each other and
+// the walk touches nothing but shared memory and registers.
+//  * Input ring per warp (kFanStages = 3 stages, one mbarrier each), filled by the TMA engine: the pointer
 //    slices of a chunk (adj_ptr, fan_ptr, fan_hdr: 36 words each), its own coordinates and its contiguous
-//    record range.  A stage is refilled as soon as its chunk is done, i.e. kFanStages - 1 chunks before the
-//    data is first touched (ncu on the 2-stage form: 14 % of all stall samples sat on the mbarrier wait).
-//    The end points of the record range a refill needs are fetched one chunk earlier with cp.async
-//    (global -> shared: no load is in flight into a register across the loop's back edge).
-//  * Neighbour coordinates: one 16-byte gather per fan step, issued two steps ahead into three rotating
-//    register sets; the first two gathers of a chunk are issued a whole chunk ahead (at the top of the
-//    previous chunk's walk), so the walk starts without waiting for them (17 % of the samples before).
-//  * Output: each warp owns a private sub-tile, the exact image of its 32 nodes' slice of
-//    `vals`, and hands it to the TMA engine with one bulk store.
-// smem per warp: full[<=4] | end points int[2][2] | kFanStages x { a_slice[36], f_slice[36], (hdr[36]), self_xy[32], recs[rec_cap] } | sub-tile
-constexpr int kFanThreads = kTile;  // 128 = 4 independent warps
-constexpr int kFanWarps = kFanThreads / 32;
+//    record range.  A stage is refilled as soon as its chunk is done; the end points of the record range
+//    a refill needs are fetched one chunk earlier with cp.async (global -> shared: no load is in flight
+//    into a register across the loop's back edge -- ptxas waits for those at the branch).
+//  * Neighbour coordinates: at the top of chunk c every lane walks the records of ITS node of chunk
+//    c+1 (already in the ring) and issues one 16-byte cp.async per record into one of two coordinate
+//    arrays -- a whole chunk ahead of their use, tracked by cp.async groups, not by register scoreboards
+//    (register prefetch two steps ahead: 17 % of the stall samples on the first gathers of a chunk and
+//    false scoreboard dependencies between the prefetch sets, ncu r02 captures L and N).
+//  * Walk: the first record of a node is the seed of its fan; a node with a single fan (all but
+//    boundary corners and bow-ties) runs a loop without flag tests, two steps per trip with the
+//    carry / edge registers swapping roles; other nodes take the general loop.
+//  * Output: each warp owns a private sub-tile, the exact image of its 32 nodes' slice of `vals`,
+//    and copies it out itself with coalesced 128-bit stores (a TMA bulk store kept the sub-tile busy
+//    until the store engine had drained it: 9 % of the samples).
+// smem per warp: full[3] | end points int[2][2] | 3 x { a_slice[36], f_slice[36], (hdr[36]), self_xy[32], recs[rec_cap] }
+//                | 2 x xy[rec_cap] | sub-tile
+#ifndef FE_FAN_WARPS
+#define FE_FAN_WARPS 2
+#endif
+constexpr int kFanWarps = FE_FAN_WARPS;  // independent warps per CTA
+constexpr int kFanThreads = kFanWarps * 32;
 constexpr int kFanChunk = 32;
 constexpr int kFanPtrInts = (kFanChunk + 1 + 3) & ~3;  // 36
-#ifndef FE_FAN_STAGES
-#define FE_FAN_STAGES 3
-#endif
-constexpr int kFanStages = FE_FAN_STAGES;
-static_assert(kFanStages >= 2 && kFanStages <= 4, "ring depth");
+constexpr int kFanStages = 3;
 constexpr int kFanHdrBytes = 64;  // barriers + end points
 
 // Record format of the fan walk: the plan's 8-byte records, or their 4-byte form (plan.cuh) with the
@@ -342,6 +359,7 @@ struct FanRec<false> {
   static __device__ __forceinline__ bool last(T r) { return (uint32_t)r.y & (FanFlags::LAST << 8); }
   static __device__ __forceinline__ bool add_first(T r) { return (uint32_t)r.y & (FanFlags::ADD_FIRST << 8); }
   static __device__ __forceinline__ int kself(T r, uint32_t /*hdr*/) { return (uint32_t)r.y >> 13; }
+  static __device__ __forceinline__ bool multi(T /*r*/) { return true; }  // (no flag in this format: general loop)
   static __device__ __forceinline__ int first_mat(uint32_t /*hdr*/) { return -1; }
   static __device__ __forceinline__ bool new_mat(T r, uint32_t /*hdr*/, int &cur) {
     const int mid = (uint32_t)r.y >> 13;
@@ -362,6 +380,7 @@ struct FanRec<true> {
   static __device__ __forceinline__ bool last(T r) { return r & (FAN4_LAST << 8); }
   static __device__ __forceinline__ bool add_first(T r) { return r & (FAN4_ADD_FIRST << 8); }
   static __device__ __forceinline__ int kself(T /*r*/, uint32_t hdr) { return hdr & 255; }
+  static __device__ __forceinline__ bool multi(T r) { return r & (FAN4_MULTI << 8); }
   static __device__ __forceinline__ int first_mat(uint32_t hdr) { return (hdr >> 8) & 4095; }
   static __device__ __forceinline__ bool new_mat(T r, uint32_t hdr, int &cur) {
     if (!(r & (FAN4_MATSW << 8))) return false;
@@ -377,7 +396,8 @@ __host__ __device__ inline size_t fan_stage_bytes(int rec_cap, bool r4) {
          ((size_t)rec_cap * (r4 ? 4 : 8) + 15) / 16 * 16;
 }
 __host__ __device__ inline size_t fan_warp_bytes(int rec_cap, int warp_slot_bytes, bool r4) {
-  return (kFanHdrBytes + kFanStages * fan_stage_bytes(rec_cap, r4) + (size_t)warp_slot_bytes + 127) / 128 * 128;
+  return (kFanHdrBytes + kFanStages * fan_stage_bytes(rec_cap, r4) + 2 * (size_t)rec_cap * 16 +
+          (size_t)warp_slot_bytes + 127) / 128 * 128;
 }
 
 template <int KC, bool R4>
@@ -400,7 +420,8 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
   int32_t *ep = reinterpret_cast<int32_t *>(wbase + 32);  // [2][2] record-range end points (LDGSTS)
   const size_t stage_bytes = fan_stage_bytes(rec_cap, R4);
   unsigned char *stage0 = wbase + kFanHdrBytes;
-  Slot *acc = reinterpret_cast<Slot *>(stage0 + kFanStages * stage_bytes);
+  double2 *xy0 = reinterpret_cast<double2 *>(stage0 + kFanStages * stage_bytes);
+  Slot *acc = reinterpret_cast<Slot *>(xy0 + 2 * rec_cap);
 
   const int n_chunks = (n_owned + kFanChunk - 1) / kFanChunk;
   const int chunk_stride = gridDim.x * kFanWarps;
@@ -431,16 +452,10 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
       ptx::cp_async4(ep + 2 * slot, fan_ptr + n0);
       ptx::cp_async4(ep + 2 * slot + 1, fan_ptr + min(n0 + kFanChunk, n_owned));
     }
-    ptx::cp_async_commit();
   };
-  // ---- every lane: record range of its node in a (full) ring stage and its first two gathers
-  struct Item {
-    Rec rec;
-    double2 p;
-  };
+  // ---- every lane: record range of its node in a (full) ring stage; the gathers of that node
   auto lane_range = [&](int chunk, int stage, int &f0, int &f1) {
-    const unsigned char *st = stage0 + stage * stage_bytes;
-    const int32_t *f_sl = reinterpret_cast<const int32_t *>(st) + kFanPtrInts;
+    const int32_t *f_sl = reinterpret_cast<const int32_t *>(stage0 + stage * stage_bytes) + kFanPtrInts;
     f0 = f1 = 0;
     if (lane < min(kFanChunk, n_owned - chunk * kFanChunk)) {
       const int32_t base = f_sl[0] & ~(RO::kAlign - 1);
@@ -448,17 +463,15 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
       f1 = f_sl[lane + 1] - base;
     }
   };
-  auto first_gathers = [&](int chunk, int stage, double2 &pa, double2 &pb) {
+  auto gather = [&](int chunk, int stage, double2 *xy) {
     int f0, f1;
     lane_range(chunk, stage, f0, f1);
     const Rec *rc = reinterpret_cast<const Rec *>(stage0 + stage * stage_bytes + kRecOff);
     const int32_t self = chunk * kFanChunk + lane;
-    if (f0 < f1) pa = __ldg(coords + RO::nbr(rc[f0], self, n_owned));
-    if (f0 + 1 < f1) pb = __ldg(coords + RO::nbr(rc[f0 + 1], self, n_owned));
+    for (int i = f0; i < f1; ++i) ptx::cp_async16(xy + i, coords + RO::nbr(rc[i], self, n_owned));
   };
 
   int chunk = blockIdx.x * kFanWarps + warp;
-  double2 npa = make_double2(0.0, 0.0), npb = npa;  // first two neighbour coordinates of the NEXT chunk
   if (chunk < n_chunks) {
     if (lane == 0) {
       // the first kFanStages chunks of this warp: direct loads of the end points (start-up only)
@@ -472,23 +485,32 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
       request_endpoints(chunk + kFanStages * chunk_stride, 0);
     }
     ptx::mbar_wait(&full[0], 0);
-    first_gathers(chunk, 0, npa, npb);
+    gather(chunk, 0, xy0);
+    ptx::cp_async_commit();  // group of chunk 0: its gathers (+ lane 0: the first end points)
   }
 
-  // ring position j in [0, 2 kFanStages): stage = j % kFanStages, barrier parity = j / kFanStages
-  for (int j = 0; chunk < n_chunks; chunk += chunk_stride, j = (j + 1 == 2 * kFanStages) ? 0 : j + 1) {
+  // ring position j in [0, 6): stage = j % 3, barrier parity = j / 3, coordinate array = j & 1
+  for (int j = 0; chunk < n_chunks; chunk += chunk_stride, j = (j == 5) ? 0 : j + 1) {
     const int stage = (j >= kFanStages) ? j - kFanStages : j;
     const int next = chunk + chunk_stride;
+    // ---- the next chunk: its ring stage was refilled two chunks ago; put its gathers in flight
+    if (next < n_chunks) {
+      const int jn = (j == 5) ? 0 : j + 1;
+      const int sn = (jn >= kFanStages) ? jn - kFanStages : jn;
+      ptx::mbar_wait(&full[sn], (uint32_t)(jn >= kFanStages));
+      gather(next, sn, xy0 + ((j & 1) ^ 1) * rec_cap);
+    }
+    ptx::cp_async_commit();  // one group per chunk (lane 0: + the end points requested at the end of the last trip)
 
-    // ---- this thread's node (its ring stage was waited for one chunk ago)
+    // ---- this thread's node
     const int32_t n0 = chunk * kFanChunk;
     const int n_in = min(kFanChunk, n_owned - n0);
     const unsigned char *st = stage0 + stage * stage_bytes;
     const int32_t *a_sl = reinterpret_cast<const int32_t *>(st);
     const Rec *recs = reinterpret_cast<const Rec *>(st + kRecOff);
+    const double2 *xy = xy0 + (j & 1) * rec_cap;
     const int32_t out_lo = a_sl[0];
     const int32_t out_len = a_sl[n_in] - out_lo;  // node-level block range of this chunk
-    const int32_t self = n0 + lane;
     int f, fe, deg = 0;
     lane_range(chunk, stage, f, fe);
     uint32_t hdr = 0;
@@ -500,96 +522,102 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
       ps = reinterpret_cast<const double2 *>(st + kSelfOff)[lane];
       if (R4) hdr = reinterpret_cast<const uint32_t *>(a_sl + 2 * kFanPtrInts)[lane];
     }
-    Item ia, ib, ic;  // three rotating sets: current, previous, and the gather two steps ahead
-    ia.p = npa;
-    ib.p = npb;
-    ic.p = make_double2(0.0, 0.0);
-    ia.rec = ib.rec = ic.rec = recs[0];
-    if (f < fe) ia.rec = recs[f];
-    if (f + 1 < fe) ib.rec = recs[f + 1];
-    auto fetch = [&](int i, Item &it) {
-      if (i < fe) {
-        it.rec = recs[i];
-        it.p = __ldg(coords + RO::nbr(it.rec, self, n_owned));
-      }
-    };
-    // ---- the next chunk: wait for its ring stage (refilled kFanStages - 1 chunks ago), first gathers out
-    if (next < n_chunks) {
-      const int jn = (j + 1 == 2 * kFanStages) ? 0 : j + 1;
-      const int sn = (jn >= kFanStages) ? jn - kFanStages : jn;
-      ptx::mbar_wait(&full[sn], (uint32_t)(jn >= kFanStages));
-      first_gathers(next, sn, npa, npb);
-    }
-    // the previous chunk's bulk store must have drained the sub-tile
-    if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
-    __syncwarp();
+    ptx::cp_async_wait_group<1>();  // everything but the group just committed: this chunk's gathers have landed
 
     // ---- the fan walk
-    const bool any = f < fe;
-    int kself = 0, cur_mat = RO::first_mat(hdr);
-    MatRow m = {0.0, 0.0, 0.0, 0.0};
-    if (R4 && any) m = tab[cur_mat];
-    Val diag = Ops::zero(), carry = Ops::zero();
-    auto process = [&](const Item &cur, const Item &prev) {
-      const Rec rc = cur.rec;
-      if (RO::seed(rc)) {  // a chain starts: its first neighbour, nothing carried
-        kself = RO::kself(rc, hdr);
-        carry = Ops::zero();
-        return;
+    if (f < fe) {
+      int cur_mat = RO::first_mat(hdr);
+      MatRow m = {0.0, 0.0, 0.0, 0.0};
+      if (R4) m = tab[cur_mat];
+      Val diag = Ops::zero();
+      Rec rp = recs[f];  // the seed of the node's first fan
+      int kself = RO::kself(rp, hdr);
+      const double2 p0 = xy[f];
+      double2 ea = make_double2(p0.x - ps.x, p0.y - ps.y);
+      Val X = Ops::zero(), Y;
+      if (!RO::multi(rp)) {
+        // single fan: records f+1 .. fe-1 are its steps, the last one closes or ends it
+        int i = f + 1;
+        for (; i + 1 < fe; i += 2) {
+          const Rec r1 = recs[i], r2 = recs[i + 1];
+          const double2 p1 = xy[i], p2 = xy[i + 1];
+          const double2 e1 = make_double2(p1.x - ps.x, p1.y - ps.y), e2 = make_double2(p2.x - ps.x, p2.y - ps.y);
+          if (RO::new_mat(r1, hdr, cur_mat)) m = tab[cur_mat];
+          Ops::step(ea, e1, m, X, Y);  // X: the finished block towards the previous neighbour
+          Ops::store(my, deg, RO::k(rp), X);
+          Ops::diag_acc(diag, X);
+          if (RO::new_mat(r2, hdr, cur_mat)) m = tab[cur_mat];
+          Ops::step(e1, e2, m, Y, X);
+          Ops::store(my, deg, RO::k(r1), Y);
+          Ops::diag_acc(diag, Y);
+          rp = r2;
+          ea = e2;
+        }
+        if (i < fe) {
+          const Rec r1 = recs[i];
+          const double2 p1 = xy[i];
+          const double2 e1 = make_double2(p1.x - ps.x, p1.y - ps.y);
+          if (RO::new_mat(r1, hdr, cur_mat)) m = tab[cur_mat];
+          Ops::step(ea, e1, m, X, Y);
+          Ops::store(my, deg, RO::k(rp), X);
+          Ops::diag_acc(diag, X);
+          X = Y;
+          rp = r1;
+        }
+        // X: the last element's block towards the last neighbour (a closed fan's first block waits in its slot)
+        if (fe - f > 1) {
+          Ops::diag_acc(diag, X);
+          if (RO::add_first(rp)) Ops::add(X, Ops::load(my, deg, RO::k(rp)));
+          Ops::store(my, deg, RO::k(rp), X);
+        }
+      } else {
+        // general walk: several fans around the node (boundary corners, bow-ties) or 8-byte records
+        for (int i = f + 1; i < fe; ++i) {
+          const Rec rc = recs[i];
+          const double2 p = xy[i];
+          const double2 e2 = make_double2(p.x - ps.x, p.y - ps.y);
+          if (RO::seed(rc)) {  // a chain starts: its first neighbour, nothing carried
+            kself = RO::kself(rc, hdr);
+            X = Ops::zero();
+          } else {
+            if (RO::new_mat(rc, hdr, cur_mat)) m = tab[cur_mat];
+            Ops::step(ea, e2, m, X, Y);
+            Ops::store(my, deg, RO::k(rp), X);
+            Ops::diag_acc(diag, X);
+            X = Y;
+            if (RO::last(rc)) {
+              Ops::diag_acc(diag, Y);
+              if (RO::add_first(rc)) Ops::add(Y, Ops::load(my, deg, RO::k(rc)));
+              Ops::store(my, deg, RO::k(rc), Y);
+            }
+          }
+          ea = e2;
+          rp = rc;
+        }
       }
-      if (RO::new_mat(rc, hdr, cur_mat)) m = tab[cur_mat];
-      const double2 e1 = make_double2(prev.p.x - ps.x, prev.p.y - ps.y);
-      const double2 e2 = make_double2(cur.p.x - ps.x, cur.p.y - ps.y);
-      Val cb;
-      Ops::step(e1, e2, m, carry, cb);  // carry: now the finished block towards the previous neighbour
-      // (a closed fan's first block waits in its slot; the last step completes it there)
-      Ops::store(my, deg, RO::k(prev.rec), carry);
-      Ops::diag_acc(diag, carry);
-      carry = cb;
-      if (RO::last(rc)) {
-        Ops::diag_acc(diag, cb);
-        if (RO::add_first(rc)) Ops::add(cb, Ops::load(my, deg, RO::k(rc)));
-        Ops::store(my, deg, RO::k(rc), cb);
-      }
-    };
-    while (true) {
-      if (f >= fe) break;
-      process(ia, ic);
-      fetch(f + 2, ic);
-      ++f;
-      if (f >= fe) break;
-      process(ib, ia);
-      fetch(f + 2, ia);
-      ++f;
-      if (f >= fe) break;
-      process(ic, ib);
-      fetch(f + 2, ib);
-      ++f;
+      Ops::store(my, deg, kself, diag);
     }
-    if (any) Ops::store(my, deg, kself, diag);
-
-    // ---- the sub-tile is complete: the exact image of vals[dim^2 * out_lo ...)
-    ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy
     __syncwarp();
+
+    // ---- the sub-tile is complete, the exact image of vals[dim^2 * out_lo ...): coalesced copy-out
     if (KC == 2) {
-      // 1 DOF per node: the destination is only 8-byte aligned -> plain coalesced copy
-      const double *src = reinterpret_cast<const double *>(acc);
+      const double *src = reinterpret_cast<const double *>(acc);  // 1 DOF per node: only 8-byte aligned
       double *dst = vals + out_lo;
       for (int q = lane; q < out_len; q += 32) dst[q] = src[q];
-      __syncwarp();
-    } else if (lane == 0 && out_len > 0) {
-      ptx::bulk_store(vals + 4 * (int64_t)out_lo, acc, (uint32_t)out_len * 32u);  // one TMA bulk store
+    } else {
+      const double2 *src = reinterpret_cast<const double2 *>(acc);
+      double2 *dst = reinterpret_cast<double2 *>(vals + 4 * (int64_t)out_lo);
+      for (int q = lane; q < 2 * out_len; q += 32) dst[q] = src[q];
     }
     if (lane == 0) {
-      // this warp is done with ring slot `stage`: refill it with the chunk kFanStages ahead
-      // (its end points were requested a whole chunk ago and sit in ep[j & 1])
+      // this warp is done with ring slot `stage`: refill it with the chunk kFanStages ahead (its end points were
+      // requested a whole chunk ago, in ep[j & 1], and belong to a group the wait above has retired)
       const int nn = chunk + kFanStages * chunk_stride;
-      ptx::cp_async_wait_all();
       if (nn < n_chunks) issue(nn, stage, ep[2 * (j & 1)], ep[2 * (j & 1) + 1]);
       request_endpoints(nn + chunk_stride, (j & 1) ^ 1);
     }
+    __syncwarp();
   }
-  if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
 }
 
 static int fan_warp_slot_bytes(int dim, int max_degree) { return dim * dim * max_degree * kFanChunk * 8; }

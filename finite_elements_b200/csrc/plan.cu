@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(128) k_fan_compact(int32_t n_owned, const int3
   if (n >= n_owned) return;
   const int32_t f0 = fan_ptr[n], f1 = fan_ptr[n + 1];
   uint32_t kself = 0;
-  int mat0 = -1, mat1 = -1, cur = -1;
+  int mat0 = -1, mat1 = -1, cur = -1, n_seeds = 0;
   for (int32_t f = f0; f < f1; ++f) {
     const int2 r = rec[f];
     const uint32_t y = (uint32_t)r.y;
@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(128) k_fan_compact(int32_t n_owned, const int3
     const uint32_t field = (uint32_t)delta & ((1u << kFan4FieldBits) - 1u);
     if (fl & FAN_SEED) {
       kself = hi;
+      ++n_seeds;
     } else {
       const int mid = (int)hi;
       if (mat0 < 0) mat0 = cur = mid;
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(128) k_fan_compact(int32_t n_owned, const int3
     }
     rec4[f] = k | (f4 << 8) | (field << 14);
   }
+  if (n_seeds > 1) rec4[f0] |= FAN4_MULTI << 8;
   hdr[n] = kself | ((uint32_t)(mat0 < 0 ? 0 : mat0) << 8) | ((uint32_t)(mat1 < 0 ? 0 : mat1) << 20);
 }
 

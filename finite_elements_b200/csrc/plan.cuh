@@ -5,7 +5,7 @@
 
 namespace fe {
 constexpr int kFan4FieldBits = 18;
-enum : uint32_t { FAN4_SEED = 1, FAN4_MATSW = 2, FAN4_ADD_FIRST = 4, FAN4_LAST = 8, FAN4_GHOST = 32 };
+enum : uint32_t { FAN4_SEED = 1, FAN4_MATSW = 2, FAN4_ADD_FIRST = 4, FAN4_LAST = 8, FAN4_MULTI = 16, FAN4_GHOST = 32 };
 constexpr int kTetStageNodes = 16;  // owned nodes per tile of the staged tetrahedral assembly (tet.cu)
 constexpr int kTile = 128;  // nodes (= threads) per CTA of the tiled assembly kernels
 }
@@ -44,7 +44,8 @@ struct fe_plan {
   //   word        = k | FAN4_* flags << 8 | field << 14;  field (signed 18 bit) = neighbour - node, or with
   //                 FAN4_GHOST neighbour - n_owned (its index among the ghost columns)
   //   fan_hdr[i]  = k_self | mat0 << 8 | mat1 << 20;  a node's walk starts on mat0 and FAN4_MATSW on a step
-  //                 switches to the other material before the step is evaluated
+  //                 switches to the other material before the step is evaluated; FAN4_MULTI on a node's first
+  //                 record: more than one fan around the node (the kernel's general loop)
   bool fan_compact_ok = false;
   uint32_t *fan_rec4 = nullptr;  // [n_fan]
   uint32_t *fan_hdr = nullptr;   // [n_owned]
