@@ -452,6 +452,8 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
       ptx::cp_async4(ep + 2 * slot, fan_ptr + n0);
       ptx::cp_async4(ep + 2 * slot + 1, fan_ptr + min(n0 + kFanChunk, n_owned));
     }
+    ptx::cp_async_commit();  // a group of its own, OLDER than the gathers committed at the top of the next trip:
+                             // that trip's wait_group<1> retires it before the end points are read
   };
   // ---- every lane: record range of its node in a (full) ring stage; the gathers of that node
   auto lane_range = [&](int chunk, int stage, int &f0, int &f1) {
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
     }
     ptx::mbar_wait(&full[0], 0);
     gather(chunk, 0, xy0);
-    ptx::cp_async_commit();  // group of chunk 0: its gathers (+ lane 0: the first end points)
+    ptx::cp_async_commit();  // group of chunk 0's gathers
   }
 
   // ring position j in [0, 6): stage = j % 3, barrier parity = j / 3, coordinate array = j & 1
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
       ptx::mbar_wait(&full[sn], (uint32_t)(jn >= kFanStages));
       gather(next, sn, xy0 + ((j & 1) ^ 1) * rec_cap);
     }
-    ptx::cp_async_commit();  // one group per chunk (lane 0: + the end points requested at the end of the last trip)
+    ptx::cp_async_commit();  // one group of gathers per chunk
 
     // ---- this thread's node
     const int32_t n0 = chunk * kFanChunk;
