@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(kTile) k_assemble_tile(int32_t n_owned, const 
 // Element geometry is evaluated in (self, prev, next) vertex order -- Ke is invariant under
 // relabelling, rounding differs in the last ulp from the element-order kernels (tests: 1e-14
 // between variants).
+#ifndef FE_FAN_DEFAULT_DESIGN
+#define FE_FAN_DEFAULT_DESIGN 0  // 0 = register walk (fan_regwalk.cuh), 1 = all-asynchronous (k_assemble_fan)
+#endif
 #ifndef FE_FAN_MINB
 #define FE_FAN_MINB 5  // resident CTAs (of 2 warps) per SM the register allocation targets; shared memory allows 5 at valence 7
 #endif
@@ -622,12 +625,28 @@ __global__ void __launch_bounds__(kFanThreads, FE_FAN_MINB) k_assemble_fan(
   }
 }
 
+#include "fan_regwalk.cuh"
+
 static int fan_warp_slot_bytes(int dim, int max_degree) { return dim * dim * max_degree * kFanChunk * 8; }
 static int fan_rec_cap(int fan_tile_max, bool r4) {  // alignment slack + round-up of the 16-byte copy
   return r4 ? ((fan_tile_max + 7) & ~3) : ((fan_tile_max + 3) & ~1);
 }
 static size_t fan_smem_bytes(int dim, int max_degree, int fan_tile_max, bool r4) {
   return kFanWarps * fan_warp_bytes(fan_rec_cap(fan_tile_max, r4), fan_warp_slot_bytes(dim, max_degree), r4);
+}
+
+static int rw_rec_cap(int fan_tile_max, bool r4) { return r4 ? ((fan_tile_max + 7) & ~3) : ((fan_tile_max + 3) & ~1); }
+static size_t rw_smem_bytes(int dim, int max_degree, int fan_tile_max, bool r4) {
+  return kRwWarps * rw_warp_bytes(rw_rec_cap(fan_tile_max, r4), fan_warp_slot_bytes(dim, max_degree), r4);
+}
+// FE_B200_FAN_DESIGN=rw selects the register-walk kernel (fan_regwalk.cuh), =async the all-asynchronous one
+static int fan_design() {
+  static int d = -1;
+  if (d < 0) {
+    const char *e = getenv("FE_B200_FAN_DESIGN");
+    d = (e && e[0] == 'a') ? 1 : ((e && e[0] == 'r') ? 0 : FE_FAN_DEFAULT_DESIGN);
+  }
+  return d;
 }
 
 static size_t tile_smem_bytes(int dim, int max_degree) {
@@ -655,11 +674,15 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
   const int grid = grid_for(p->n_owned, kTile);
   // variant 3 = fan walk (4-byte records when the plan could build them), 4 = fan walk on the 8-byte records
   bool r4 = p->fan_compact_ok && variant != 4;
+  const bool rw = fan_design() == 0;
   size_t smem = tile_smem_bytes(dim, p->max_degree);
   const size_t smem_limit = 200 * 1024;
-  if (r4 && fan_smem_bytes(dim, p->max_degree, p->fan_tile_max, true) > smem_limit) r4 = false;
-  const size_t smem_fan = fan_smem_bytes(dim, p->max_degree, p->fan_tile_max, r4);
-  const int rec_cap = fan_rec_cap(p->fan_tile_max, r4);
+  auto fan_bytes = [&](bool four) {
+    return rw ? rw_smem_bytes(dim, p->max_degree, p->fan_tile_max, four) : fan_smem_bytes(dim, p->max_degree, p->fan_tile_max, four);
+  };
+  if (r4 && fan_bytes(true) > smem_limit) r4 = false;
+  const size_t smem_fan = fan_bytes(r4);
+  const int rec_cap = rw ? rw_rec_cap(p->fan_tile_max, r4) : fan_rec_cap(p->fan_tile_max, r4);
   if (variant == 0) variant = (p->fan_ok && smem_fan <= smem_limit) ? 3 : ((smem <= smem_limit) ? 2 : 1);
   if (variant == 4) variant = 3;
   if (variant == 3) smem = smem_fan;
@@ -672,14 +695,25 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
 
 #define FE_FAN_LAUNCH(KC, R4, RECS)                                                                              \
   do {                                                                                                          \
-    int minb = FE_FAN_MINB;                                                                                     \
-    FE_CUDA(cudaFuncSetAttribute(k_assemble_fan<KC, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    FE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&minb, k_assemble_fan<KC, R4>, kFanThreads, smem));   \
-    if (minb < 1) minb = 1;                                                                                     \
-    const int fgrid = grid < minb * ctx->num_sms ? grid : minb * ctx->num_sms;                                  \
-    k_assemble_fan<KC, R4><<<fgrid, kFanThreads, smem, st>>>(p->n_owned, p->fan_ptr, RECS, p->fan_hdr,          \
-                                                             p->adj_ptr, xy, tab, vals, rec_cap,                \
-                                                             fan_warp_slot_bytes(dim, p->max_degree));          \
+    int minb = 1;                                                                                               \
+    if (rw) {                                                                                                   \
+      FE_CUDA(cudaFuncSetAttribute(k_assemble_fan_rw<KC, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      FE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&minb, k_assemble_fan_rw<KC, R4>, kRwThreads, smem)); \
+      if (minb < 1) minb = 1;                                                                                   \
+      const int fgrid = grid < minb * ctx->num_sms ? grid : minb * ctx->num_sms;                                \
+      k_assemble_fan_rw<KC, R4><<<fgrid, kRwThreads, smem, st>>>(p->n_owned, p->fan_ptr, RECS, p->fan_hdr,      \
+                                                                 p->adj_ptr, xy, tab, vals, rec_cap,            \
+                                                                 fan_warp_slot_bytes(dim, p->max_degree));      \
+    } else {                                                                                                    \
+      FE_CUDA(cudaFuncSetAttribute(k_assemble_fan<KC, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      FE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&minb, k_assemble_fan<KC, R4>, kFanThreads, smem)); \
+      if (minb < 1) minb = 1;                                                                                   \
+      const int cgrid = grid_for(p->n_owned, kFanThreads);                                                      \
+      const int fgrid = cgrid < minb * ctx->num_sms ? cgrid : minb * ctx->num_sms;                              \
+      k_assemble_fan<KC, R4><<<fgrid, kFanThreads, smem, st>>>(p->n_owned, p->fan_ptr, RECS, p->fan_hdr,        \
+                                                               p->adj_ptr, xy, tab, vals, rec_cap,              \
+                                                               fan_warp_slot_bytes(dim, p->max_degree));        \
+    }                                                                                                           \
   } while (0)
 #define FE_ASM_LAUNCH(KC)                                                                                       \
   do {                                                                                                          \

@@ -1,0 +1,206 @@
+// The register-walk form of the fan kernel (round 1's structure with round 2's arithmetic and record formats):
+// 2-stage TMA ring per warp, one 16-byte coordinate gather per step issued two steps ahead into three rotating
+// register sets, TMA bulk store of the sub-tile.  10 KB of shared memory per warp -> 20 warps per SM.
+// Included by assemble.cu (inside namespace fe) after FanOps / FanRec.
+#pragma once
+constexpr int kRwThreads = 128;
+constexpr int kRwWarps = 4;
+
+__host__ __device__ inline size_t rw_stage_bytes(int rec_cap, bool r4) {
+  return ((size_t)(r4 ? 3 : 2) * kFanPtrInts * sizeof(int32_t) + (size_t)rec_cap * (r4 ? 4 : 8) + 15) / 16 * 16;
+}
+__host__ __device__ inline size_t rw_warp_bytes(int rec_cap, int warp_slot_bytes, bool r4) {
+  return (32 + 2 * rw_stage_bytes(rec_cap, r4) + (size_t)warp_slot_bytes + 127) / 128 * 128;
+}
+
+template <int KC, bool R4>
+__global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_rw(
+    int32_t n_owned, const int32_t *__restrict__ fan_ptr, const typename FanRec<R4>::T *__restrict__ fan_rec,
+    const uint32_t *__restrict__ fan_hdr, const int32_t *__restrict__ adj_ptr, const double2 *__restrict__ coords,
+    const MatRow *__restrict__ tab, double *__restrict__ vals, int rec_cap, int warp_slot_bytes) {
+  using Ops = FanOps<KC>;
+  using Val = typename Ops::Val;
+  using Slot = typename Ops::Slot;
+  using RO = FanRec<R4>;
+  using Rec = typename RO::T;
+  constexpr int SPB = (KC == 2) ? 1 : 2;  // Slots per node-level block
+  constexpr int kPtrSlices = R4 ? 3 : 2;  // adj_ptr, fan_ptr (, fan_hdr)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wbase = smem_raw + (size_t)warp * rw_warp_bytes(rec_cap, warp_slot_bytes, R4);
+  uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
+  const size_t stage_bytes = rw_stage_bytes(rec_cap, R4);
+  int32_t *ep = reinterpret_cast<int32_t *>(wbase + 16);  // [2][2] record-range end points (LDGSTS)
+  unsigned char *stage0 = wbase + 32;
+  Slot *acc = reinterpret_cast<Slot *>(stage0 + 2 * stage_bytes);
+
+  const int n_chunks = (n_owned + kFanChunk - 1) / kFanChunk;
+  const int chunk_stride = gridDim.x * kRwWarps;
+  if (lane == 0) {
+    ptx::mbar_init(&full[0], 1);
+    ptx::mbar_init(&full[1], 1);
+    ptx::mbar_init_fence();
+  }
+  __syncwarp();
+
+  // ---- lane 0: the TMA loads of a chunk.  The end points of its record range are fetched one
+  //      chunk ahead with cp.async (global -> shared, no registers held across the compute loop).
+  auto request_endpoints = [&](int chunk, int slot) {
+    if (chunk < n_chunks) {
+      const int32_t n0 = chunk * kFanChunk;
+      ptx::cp_async4(ep + 2 * slot, fan_ptr + n0);
+      ptx::cp_async4(ep + 2 * slot + 1, fan_ptr + min(n0 + kFanChunk, n_owned));
+    }
+    ptx::cp_async_commit();
+  };
+  auto issue = [&](int chunk, int stage, int32_t r0, int32_t r1) {
+    const int32_t n0 = chunk * kFanChunk;
+    const int32_t base = r0 & ~(RO::kAlign - 1);  // 16-byte aligned start of the record copy
+    const uint32_t rec_bytes = (uint32_t)((r1 - base + RO::kAlign - 1) / RO::kAlign) * 16u;
+    unsigned char *st = stage0 + stage * stage_bytes;
+    ptx::mbar_expect_tx(&full[stage], (uint32_t)kPtrSlices * kFanPtrInts * 4u + rec_bytes);
+    ptx::bulk_load(st, adj_ptr + n0, kFanPtrInts * 4u, &full[stage]);
+    ptx::bulk_load(st + kFanPtrInts * 4, fan_ptr + n0, kFanPtrInts * 4u, &full[stage]);
+    if (R4) ptx::bulk_load(st + 2 * kFanPtrInts * 4, fan_hdr + n0, kFanPtrInts * 4u, &full[stage]);
+    if (rec_bytes) ptx::bulk_load(st + kPtrSlices * kFanPtrInts * 4, fan_rec + base, rec_bytes, &full[stage]);
+  };
+  int chunk = blockIdx.x * kRwWarps + warp;
+  if (lane == 0 && chunk < n_chunks) {
+    // chunks 0 and 1 of this warp: direct loads (start-up only); chunk 2's end points requested
+    for (int q = 0; q < 2; ++q) {
+      const int c = chunk + q * chunk_stride;
+      if (c < n_chunks) {
+        const int32_t n0 = c * kFanChunk;
+        issue(c, q, __ldg(fan_ptr + n0), __ldg(fan_ptr + min(n0 + kFanChunk, n_owned)));
+      }
+    }
+    request_endpoints(chunk + 2 * chunk_stride, 0);
+  }
+
+  // ---- per-thread state of the chunk about to be computed (filled by begin_chunk)
+  struct Item {
+    Rec rec;
+    double2 p;
+  };
+  Item ia, ib, ic;  // three rotating sets: current, previous, and the gather two steps ahead
+  ia.rec = ib.rec = ic.rec = Rec();
+  ia.p = ib.p = ic.p = make_double2(0.0, 0.0);
+  double2 ps = make_double2(0.0, 0.0);
+  const Rec *recs = nullptr;
+  Slot *my = acc;
+  int f = 0, fe = 0, deg = 0;
+  int32_t self = 0;
+  uint32_t hdr = 0;
+  auto fetch = [&](int i, Item &it) {
+    if (i < fe) {
+      it.rec = recs[i];
+      it.p = __ldg(coords + RO::nbr(it.rec, self, n_owned));
+    }
+  };
+  // Waits for the chunk's ring slot and puts the first gathers in flight.
+  auto begin_chunk = [&](int c, int jj) {
+    const int stage = jj & 1;
+    ptx::mbar_wait(&full[stage], (uint32_t)((jj >> 1) & 1));
+    const int32_t n0 = c * kFanChunk;
+    const int n_in = min(kFanChunk, n_owned - n0);
+    const unsigned char *st = stage0 + stage * stage_bytes;
+    const int32_t *a_sl = reinterpret_cast<const int32_t *>(st);
+    const int32_t *f_sl = a_sl + kFanPtrInts;
+    recs = reinterpret_cast<const Rec *>(st + kPtrSlices * kFanPtrInts * 4);
+    const int32_t base = f_sl[0] & ~(RO::kAlign - 1);
+    const int32_t out_lo = a_sl[0];
+    f = fe = deg = 0;
+    self = n0 + lane;
+    if (lane < n_in) {
+      ps = __ldg(coords + self);
+      f = f_sl[lane] - base;
+      fe = f_sl[lane + 1] - base;
+      deg = a_sl[lane + 1] - a_sl[lane];
+      my = acc + SPB * (a_sl[lane] - out_lo);
+      if (R4) hdr = reinterpret_cast<const uint32_t *>(f_sl + kFanPtrInts)[lane];
+    }
+    fetch(f, ia);
+    fetch(f + 1, ib);
+  };
+
+  int j = 0;  // ring position mod 4: stage = j & 1, barrier parity = (j >> 1) & 1
+  if (chunk < n_chunks) begin_chunk(chunk, 0);
+  for (; chunk < n_chunks; chunk += chunk_stride, j = (j + 1) & 3) {
+    const int stage = j & 1;
+    const int next = chunk + chunk_stride;
+
+    // ---- the fan walk of this thread's node (records + neighbour coordinates, 3 rotating sets)
+    const bool any = f < fe;
+    int kself = 0, cur_mat = RO::first_mat(hdr);
+    MatRow m = {0.0, 0.0, 0.0, 0.0};
+    if (R4 && any) m = tab[cur_mat];
+    Val diag = Ops::zero(), carry = Ops::zero();
+    auto process = [&](const Item &cur, const Item &prev) {
+      const Rec rc = cur.rec;
+      if (RO::seed(rc)) {  // a chain starts: its first neighbour, nothing carried
+        kself = RO::kself(rc, hdr);
+        carry = Ops::zero();
+        return;
+      }
+      if (RO::new_mat(rc, hdr, cur_mat)) m = tab[cur_mat];
+      const double2 e1 = make_double2(prev.p.x - ps.x, prev.p.y - ps.y);
+      const double2 e2 = make_double2(cur.p.x - ps.x, cur.p.y - ps.y);
+      Val cb;
+      Ops::step(e1, e2, m, carry, cb);  // carry: now the finished block towards the previous neighbour
+      Ops::store(my, deg, RO::k(prev.rec), carry);
+      Ops::diag_acc(diag, carry);
+      carry = cb;
+      if (RO::last(rc)) {
+        Ops::diag_acc(diag, cb);
+        if (RO::add_first(rc)) Ops::add(cb, Ops::load(my, deg, RO::k(rc)));
+        Ops::store(my, deg, RO::k(rc), cb);
+      }
+    };
+    while (true) {
+      if (f >= fe) break;
+      process(ia, ic);
+      fetch(f + 2, ic);
+      ++f;
+      if (f >= fe) break;
+      process(ib, ia);
+      fetch(f + 2, ia);
+      ++f;
+      if (f >= fe) break;
+      process(ic, ib);
+      fetch(f + 2, ib);
+      ++f;
+    }
+    if (any) Ops::store(my, deg, kself, diag);
+
+    // ---- the sub-tile is complete: the exact image of vals[dim^2 * out_lo ...)
+    ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy
+    __syncwarp();
+    int32_t out_lo, out_len;  // node-level block range of this chunk (slice still in the ring slot)
+    {
+      const int32_t *a_sl = reinterpret_cast<const int32_t *>(stage0 + stage * stage_bytes);
+      out_lo = a_sl[0];
+      out_len = a_sl[min(kFanChunk, n_owned - chunk * kFanChunk)] - out_lo;
+    }
+    if (KC == 2) {
+      // 1 DOF per node: the destination is only 8-byte aligned -> plain coalesced copy
+      const double *src = reinterpret_cast<const double *>(acc);
+      double *dst = vals + out_lo;
+      for (int q = lane; q < out_len; q += 32) dst[q] = src[q];
+    } else if (lane == 0 && out_len > 0) {
+      ptx::bulk_store(vals + 4 * (int64_t)out_lo, acc, (uint32_t)out_len * 32u);  // one TMA bulk store
+    }
+    if (lane == 0) {
+      // this warp is done with ring slot `stage`: refill it with the chunk after the next one
+      // (its end points were requested a whole chunk ago and sit in ep[stage])
+      const int nn = next + chunk_stride;
+      ptx::cp_async_wait_all();
+      if (nn < n_chunks) issue(nn, stage, ep[2 * stage], ep[2 * stage + 1]);
+      request_endpoints(nn + chunk_stride, stage ^ 1);
+    }
+    // first gathers of the next chunk go out before we wait for the store to drain the sub-tile
+    if (next < n_chunks) begin_chunk(next, (j + 1) & 3);
+    if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
+    __syncwarp();
+  }
+}
+
