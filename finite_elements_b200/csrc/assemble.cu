@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kTile) k_assemble_tile(int32_t n_owned, const 
 #endif
 
 struct FanFlags {
-  static constexpr uint32_t SEED = 1, ADD_CARRY = 2, HOLD_A = 4, LAST = 8, ADD_FIRST = 16;
+  static constexpr uint32_t SEED = 1, MULTI = 2, HOLD_A = 4, LAST = 8, ADD_FIRST = 16;
 };
 
 // 1 / d to ~1 ulp without the slow-path branch of the compiler's division: MUFU.RCP64H seed (>= 20 bits)
@@ -362,7 +362,7 @@ struct FanRec<false> {
   static __device__ __forceinline__ bool last(T r) { return (uint32_t)r.y & (FanFlags::LAST << 8); }
   static __device__ __forceinline__ bool add_first(T r) { return (uint32_t)r.y & (FanFlags::ADD_FIRST << 8); }
   static __device__ __forceinline__ int kself(T r, uint32_t /*hdr*/) { return (uint32_t)r.y >> 13; }
-  static __device__ __forceinline__ bool multi(T /*r*/) { return true; }  // (no flag in this format: general loop)
+  static __device__ __forceinline__ bool multi(T r) { return (uint32_t)r.y & (FanFlags::MULTI << 8); }
   static __device__ __forceinline__ int first_mat(uint32_t /*hdr*/) { return -1; }
   static __device__ __forceinline__ bool new_mat(T r, uint32_t /*hdr*/, int &cur) {
     const int mid = (uint32_t)r.y >> 13;
@@ -376,7 +376,7 @@ struct FanRec<true> {
   using T = uint32_t;
   static constexpr int kAlign = 4;
   static __device__ __forceinline__ int32_t nbr(T r, int32_t self, int32_t n_owned) {
-    return ((r & (FAN4_GHOST << 8)) ? n_owned : self) + ((int32_t)r >> 14);
+    return self + ((int32_t)r >> kFan4Shift);
   }
   static __device__ __forceinline__ uint32_t k(T r) { return r & 255; }
   static __device__ __forceinline__ bool seed(T r) { return r & (FAN4_SEED << 8); }

@@ -78,24 +78,20 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
   }
 
   // ---- per-thread state of the chunk about to be computed (filled by begin_chunk)
-  struct Item {
-    Rec rec;
-    double2 p;
-  };
-  Item ia, ib, ic;  // three rotating sets: current, previous, and the gather two steps ahead
-  ia.rec = ib.rec = ic.rec = Rec();
-  ia.p = ib.p = ic.p = make_double2(0.0, 0.0);
+  // Coordinates travel through five register sets: the fan's first neighbour, and two pairs (A, B) that
+  // alternate between "used by this trip" and "in flight for the next trip" (a trip = two fan steps).  Records are
+  // re-read from the ring stage where they are needed (an LDS is cheaper than a register held across a trip).
+  double2 p0 = make_double2(0.0, 0.0), pa1 = p0, pa2 = p0, pb1 = p0, pb2 = p0;
   double2 ps = make_double2(0.0, 0.0);
   const Rec *recs = nullptr;
   Slot *my = acc;
   int f = 0, fe = 0, deg = 0;
   int32_t self = 0;
   uint32_t hdr = 0;
-  auto fetch = [&](int i, Item &it) {
-    if (i < fe) {
-      it.rec = recs[i];
-      it.p = __ldg(coords + RO::nbr(it.rec, self, n_owned));
-    }
+  int cur_mat = -1, loaded_mat = -1;  // the material row in `m` survives from chunk to chunk
+  MatRow m = {0.0, 0.0, 0.0, 0.0};
+  auto fetch = [&](int i, double2 &p) {
+    if (i < fe) p = __ldg(coords + RO::nbr(recs[i], self, n_owned));
   };
   // Waits for the chunk's ring slot and puts the first gathers in flight.
   auto begin_chunk = [&](int c, int jj) {
@@ -119,8 +115,9 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
       my = acc + SPB * (a_sl[lane] - out_lo);
       if (R4) hdr = reinterpret_cast<const uint32_t *>(f_sl + kFanPtrInts)[lane];
     }
-    fetch(f, ia);
-    fetch(f + 1, ib);
+    fetch(f, p0);
+    fetch(f + 1, pa1);
+    fetch(f + 2, pa2);
   };
 
   int j = 0;  // ring position mod 4: stage = j & 1, barrier parity = (j >> 1) & 1
@@ -129,48 +126,85 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
     const int stage = j & 1;
     const int next = chunk + chunk_stride;
 
-    // ---- the fan walk of this thread's node (records + neighbour coordinates, 3 rotating sets)
-    const bool any = f < fe;
-    int kself = 0, cur_mat = RO::first_mat(hdr);
-    MatRow m = {0.0, 0.0, 0.0, 0.0};
-    if (R4 && any) m = tab[cur_mat];
-    Val diag = Ops::zero(), carry = Ops::zero();
-    auto process = [&](const Item &cur, const Item &prev) {
-      const Rec rc = cur.rec;
-      if (RO::seed(rc)) {  // a chain starts: its first neighbour, nothing carried
-        kself = RO::kself(rc, hdr);
-        carry = Ops::zero();
-        return;
+    // ---- the fan walk of this thread's node
+    if (f < fe) {
+      if (R4) cur_mat = RO::first_mat(hdr);
+      Val diag = Ops::zero(), X = Ops::zero(), Y;
+      const Rec r0 = recs[f];
+      int kself = RO::kself(r0, hdr);
+      double2 ea = make_double2(p0.x - ps.x, p0.y - ps.y);
+      // fan step of record i: element (self, neighbour of record i-1, neighbour of record i at `p`); cin arrives
+      // holding the previous element's share of the block towards the previous neighbour and is stored finished,
+      // cout = this element's share of the block towards this neighbour
+      auto step = [&](int i, const double2 p, const double2 eprev, double2 &ecur, Val &cin, Val &cout) {
+        const Rec rc = recs[i];
+        ecur = make_double2(p.x - ps.x, p.y - ps.y);
+        if (RO::new_mat(rc, hdr, cur_mat) || cur_mat != loaded_mat) {
+          m = tab[cur_mat];
+          loaded_mat = cur_mat;
+        }
+        Ops::step(eprev, ecur, m, cin, cout);
+        Ops::store(my, deg, RO::k(recs[i - 1]), cin);
+        Ops::diag_acc(diag, cin);
+      };
+      if (!RO::multi(r0)) {
+        // a single fan (all nodes but bow-ties and some boundary corners): records f+1 .. fe-1 are its steps and
+        // only the last one needs a flag test.  Two steps per trip; the pairs A and B swap roles every trip.
+        int i = f + 1;
+        double2 e1, e2;
+        while (true) {
+          if (i + 1 >= fe) break;
+          fetch(i + 2, pb1);
+          fetch(i + 3, pb2);
+          step(i, pa1, ea, e1, X, Y);
+          step(i + 1, pa2, e1, e2, Y, X);
+          ea = e2;
+          i += 2;
+          if (i + 1 >= fe) {
+            pa1 = pb1;
+            break;
+          }
+          fetch(i + 2, pa1);
+          fetch(i + 3, pa2);
+          step(i, pb1, ea, e1, X, Y);
+          step(i + 1, pb2, e1, e2, Y, X);
+          ea = e2;
+          i += 2;
+        }
+        if (i < fe) {  // an odd step left (its coordinate sits in pa1)
+          step(i, pa1, ea, e1, X, Y);
+          X = Y;
+        }
+        // X: the last element's block towards the last neighbour (a closed fan's first block waits in its slot)
+        if (fe - f > 1) {
+          const Rec rl = recs[fe - 1];
+          Ops::diag_acc(diag, X);
+          if (RO::add_first(rl)) Ops::add(X, Ops::load(my, deg, RO::k(rl)));
+          Ops::store(my, deg, RO::k(rl), X);
+        }
+      } else {
+        // general walk: several fans around the node
+        for (int i = f + 1; i < fe; ++i) {
+          const Rec rc = recs[i];
+          const double2 p = __ldg(coords + RO::nbr(rc, self, n_owned));
+          double2 e2 = make_double2(p.x - ps.x, p.y - ps.y);
+          if (RO::seed(rc)) {  // a chain starts: its first neighbour, nothing carried
+            kself = RO::kself(rc, hdr);
+            X = Ops::zero();
+          } else {
+            step(i, p, ea, e2, X, Y);
+            X = Y;
+            if (RO::last(rc)) {
+              Ops::diag_acc(diag, Y);
+              if (RO::add_first(rc)) Ops::add(Y, Ops::load(my, deg, RO::k(rc)));
+              Ops::store(my, deg, RO::k(rc), Y);
+            }
+          }
+          ea = e2;
+        }
       }
-      if (RO::new_mat(rc, hdr, cur_mat)) m = tab[cur_mat];
-      const double2 e1 = make_double2(prev.p.x - ps.x, prev.p.y - ps.y);
-      const double2 e2 = make_double2(cur.p.x - ps.x, cur.p.y - ps.y);
-      Val cb;
-      Ops::step(e1, e2, m, carry, cb);  // carry: now the finished block towards the previous neighbour
-      Ops::store(my, deg, RO::k(prev.rec), carry);
-      Ops::diag_acc(diag, carry);
-      carry = cb;
-      if (RO::last(rc)) {
-        Ops::diag_acc(diag, cb);
-        if (RO::add_first(rc)) Ops::add(cb, Ops::load(my, deg, RO::k(rc)));
-        Ops::store(my, deg, RO::k(rc), cb);
-      }
-    };
-    while (true) {
-      if (f >= fe) break;
-      process(ia, ic);
-      fetch(f + 2, ic);
-      ++f;
-      if (f >= fe) break;
-      process(ib, ia);
-      fetch(f + 2, ia);
-      ++f;
-      if (f >= fe) break;
-      process(ic, ib);
-      fetch(f + 2, ib);
-      ++f;
+      Ops::store(my, deg, kself, diag);
     }
-    if (any) Ops::store(my, deg, kself, diag);
 
     // ---- the sub-tile is complete: the exact image of vals[dim^2 * out_lo ...)
     ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy

@@ -39,7 +39,7 @@ struct PlanFlags {
 // ---------------------------------------------------------------------------------------
 constexpr int kFanMaxCorners = 32;
 constexpr int kFanMatBits = 19;
-enum : uint32_t { FAN_SEED = 1, FAN_ADD_CARRY = 2, FAN_HOLD_A = 4, FAN_LAST = 8, FAN_ADD_FIRST = 16 };
+enum : uint32_t { FAN_SEED = 1, FAN_MULTI = 2, FAN_HOLD_A = 4, FAN_LAST = 8, FAN_ADD_FIRST = 16 };
 
 __device__ __forceinline__ int row_position(const int32_t *row, int deg, int32_t target) {
   int lo = 0, hi = deg - 1;
@@ -76,9 +76,10 @@ __device__ int fan_walk(int32_t self, int nc, const int32_t *__restrict__ cs, co
     if (occurrences(va[i]) > 2 || occurrences(vb[i]) > 2) return -1;
   const uint32_t full = (nc == 32) ? 0xffffffffu : ((1u << nc) - 1u);
   uint32_t used = 0;
-  int nrec = 0;
+  int nrec = 0, chains = 0;
   const int k_self = EMIT ? row_position(row, deg, self) : 0;
   while (used != full) {
+    ++chains;
     int start = -1;
     int32_t sv = 0;
     for (int i = 0; i < nc && start < 0; ++i) {
@@ -119,7 +120,7 @@ __device__ int fan_walk(int32_t self, int nc, const int32_t *__restrict__ cs, co
       const bool last = jn < 0;
       if (last && closed && next != sv) return -1;
       if (EMIT) {
-        const uint32_t fl = (first ? 0u : FAN_ADD_CARRY) | ((first && closed) ? FAN_HOLD_A : 0u) |
+        const uint32_t fl = ((first && closed) ? FAN_HOLD_A : 0u) |
                             (last ? FAN_LAST : 0u) | ((last && closed) ? FAN_ADD_FIRST : 0u);
         const uint32_t mid = mat_id ? (uint32_t)mat_id[cs[j] >> 2] : 0u;
         out[nrec] = make_int2(next, (int)((uint32_t)row_position(row, deg, next) | (fl << 8) | (mid << 13)));
@@ -131,6 +132,7 @@ __device__ int fan_walk(int32_t self, int nc, const int32_t *__restrict__ cs, co
       j = jn;
     }
   }
+  if (EMIT && chains > 1) out[0].y |= (int)(FAN_MULTI << 8);  // several fans around this node: the kernels' general loop
   return nrec;
 }
 
@@ -301,11 +303,7 @@ __global__ void __launch_bounds__(128) k_fan_compact(int32_t n_owned, const int3
     const uint32_t k = y & 255, fl = (y >> 8) & 31, hi = y >> 13;
     uint32_t f4 = (fl & FAN_SEED ? FAN4_SEED : 0u) | (fl & FAN_LAST ? FAN4_LAST : 0u) |
                   (fl & FAN_ADD_FIRST ? FAN4_ADD_FIRST : 0u);
-    int32_t delta = r.x - n;
-    if (r.x >= n_owned) {  // ghost column (multi-GPU layout: owned first, ghosts after): index among the ghosts
-      f4 |= FAN4_GHOST;
-      delta = r.x - n_owned;
-    }
+    const int32_t delta = r.x - n;
     if (delta < -(1 << (kFan4FieldBits - 1)) || delta >= (1 << (kFan4FieldBits - 1))) *bad = 1;
     const uint32_t field = (uint32_t)delta & ((1u << kFan4FieldBits) - 1u);
     if (fl & FAN_SEED) {
@@ -322,9 +320,9 @@ __global__ void __launch_bounds__(128) k_fan_compact(int32_t n_owned, const int3
       }
       if (mid >= 4096) *bad = 1;
     }
-    rec4[f] = k | (f4 << 8) | (field << 14);
+    rec4[f] = k | (f4 << 8) | (field << kFan4Shift);
   }
-  if (n_seeds > 1) rec4[f0] |= FAN4_MULTI << 8;
+  if (n_seeds > 1) rec4[f0] |= FAN4_MULTI << 8;  // (= FAN_MULTI of the 8-byte record)
   hdr[n] = kself | ((uint32_t)(mat0 < 0 ? 0 : mat0) << 8) | ((uint32_t)(mat1 < 0 ? 0 : mat1) << 20);
 }
 

@@ -4,8 +4,8 @@
 #include "common.cuh"
 
 namespace fe {
-constexpr int kFan4FieldBits = 18;
-enum : uint32_t { FAN4_SEED = 1, FAN4_MATSW = 2, FAN4_ADD_FIRST = 4, FAN4_LAST = 8, FAN4_MULTI = 16, FAN4_GHOST = 32 };
+constexpr int kFan4FieldBits = 19, kFan4Shift = 32 - kFan4FieldBits;
+enum : uint32_t { FAN4_SEED = 1, FAN4_MATSW = 2, FAN4_ADD_FIRST = 4, FAN4_LAST = 8, FAN4_MULTI = 16 };
 constexpr int kTetStageNodes = 16;  // owned nodes per tile of the staged tetrahedral assembly (tet.cu)
 constexpr int kTile = 128;  // nodes (= threads) per CTA of the tiled assembly kernels
 }
@@ -39,10 +39,9 @@ struct fe_plan {
   int32_t *fan_ptr = nullptr;  // [n_owned + 1]
   int2 *fan_rec = nullptr;     // [n_fan]
   // the same records in 4 bytes (plan.cu: k_fan_compact) when the numbering is banded (|neighbour - node| <
-  // 2^17 for owned neighbours, fewer than 2^17 ghosts) and no node star holds more than two materials
-  // (ids < 4096): half the record traffic of the assembly kernel.
-  //   word        = k | FAN4_* flags << 8 | field << 14;  field (signed 18 bit) = neighbour - node, or with
-  //                 FAN4_GHOST neighbour - n_owned (its index among the ghost columns)
+  // 2^18, ghost columns included) and no node star holds more than two materials (ids < 4096): half the
+  // record traffic of the assembly kernel.
+  //   word        = k | FAN4_* flags << 8 | (neighbour - node) << 13   (signed 19-bit difference)
   //   fan_hdr[i]  = k_self | mat0 << 8 | mat1 << 20;  a node's walk starts on mat0 and FAN4_MATSW on a step
   //                 switches to the other material before the step is evaluated; FAN4_MULTI on a node's first
   //                 record: more than one fan around the node (the kernel's general loop)
