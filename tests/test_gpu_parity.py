@@ -265,8 +265,8 @@ def test_compact_fan_records_and_their_fallbacks():
             v3 = dm.assemble(kind, m, variant=3)
             assert np.array_equal(v3.cpu().numpy(), dm.assemble(kind, m, variant=4).cpu().numpy())
             assert_csr_values_close(dm.to_scipy(v3), no.assemble_k(kind, coords, conn, mat_id, m), 1e-12)
-    # a numbering that is not banded: neighbours further than 2^17 apart
-    coords, conn = no.structured_mesh(420, 400, jitter=0.1, seed=5)
+    # a numbering that is not banded: neighbours further than 2^18 apart
+    coords, conn = no.structured_mesh(720, 500, jitter=0.1, seed=5)   # 361 221 nodes: differences beyond 2^18
     perm = np.random.default_rng(7).permutation(len(coords))
     inv = np.empty_like(perm)
     inv[perm] = np.arange(len(perm))
