@@ -3,6 +3,9 @@
 // register sets, TMA bulk store of the sub-tile.  10 KB of shared memory per warp -> 20 warps per SM.
 // Included by assemble.cu (inside namespace fe) after FanOps / FanRec.
 #pragma once
+#ifndef FE_RW_EXP
+#define FE_RW_EXP 0
+#endif
 constexpr int kRwThreads = 128;
 constexpr int kRwWarps = 4;
 
@@ -115,9 +118,18 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
       my = acc + SPB * (a_sl[lane] - out_lo);
       if (R4) hdr = reinterpret_cast<const uint32_t *>(f_sl + kFanPtrInts)[lane];
     }
+#if FE_RW_EXP == 1
+    fetch(f + 1, pa1);
+    fetch(f + 2, pa2);
+    fetch(f, p0);
+#elif FE_RW_EXP == 2
+    fetch(f, p0);
+    fetch(f + 1, pa1);
+#else
     fetch(f, p0);
     fetch(f + 1, pa1);
     fetch(f + 2, pa2);
+#endif
   };
 
   int j = 0;  // ring position mod 4: stage = j & 1, barrier parity = (j >> 1) & 1
@@ -126,6 +138,7 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
     const int stage = j & 1;
     const int next = chunk + chunk_stride;
 
+#if FE_RW_EXP == 4
     // ---- the next chunk's first loads (own coordinate, first three neighbours) are on the critical path of its
     //      walk: if its ring stage has already landed, pull their lines into L1 now, a whole walk ahead
     //      (ncu r02 capture Q: 37 % of all stall samples sat on exactly those loads)
@@ -144,6 +157,7 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
       }
     }
 
+#endif
     // ---- the fan walk of this thread's node
     if (f < fe) {
       if (R4) cur_mat = RO::first_mat(hdr);
@@ -165,6 +179,9 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
         Ops::store(my, deg, RO::k(recs[i - 1]), cin);
         Ops::diag_acc(diag, cin);
       };
+#if FE_RW_EXP == 2
+      fetch(f + 2, pa2);
+#endif
       if (!RO::multi(r0)) {
         // a single fan (all nodes but bow-ties and some boundary corners): records f+1 .. fe-1 are its steps and
         // only the last one needs a flag test.  Two steps per trip; the pairs A and B swap roles every trip.
@@ -225,7 +242,9 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
     }
 
     // ---- the sub-tile is complete: the exact image of vals[dim^2 * out_lo ...)
+#if FE_RW_EXP != 3
     ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy
+#endif
     __syncwarp();
     int32_t out_lo, out_len;  // node-level block range of this chunk (slice still in the ring slot)
     {
@@ -238,9 +257,17 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
       const double *src = reinterpret_cast<const double *>(acc);
       double *dst = vals + out_lo;
       for (int q = lane; q < out_len; q += 32) dst[q] = src[q];
+#if FE_RW_EXP == 3
+    } else {
+      const double2 *src = reinterpret_cast<const double2 *>(acc);
+      double2 *dst = reinterpret_cast<double2 *>(vals + 4 * (int64_t)out_lo);
+      for (int q = lane; q < 2 * out_len; q += 32) dst[q] = src[q];
+    }
+#else
     } else if (lane == 0 && out_len > 0) {
       ptx::bulk_store(vals + 4 * (int64_t)out_lo, acc, (uint32_t)out_len * 32u);  // one TMA bulk store
     }
+#endif
     if (lane == 0) {
       // this warp is done with ring slot `stage`: refill it with the chunk after the next one
       // (its end points were requested a whole chunk ago and sit in ep[stage])
@@ -251,7 +278,9 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
     }
     // first gathers of the next chunk go out before we wait for the store to drain the sub-tile
     if (next < n_chunks) begin_chunk(next, (j + 1) & 3);
+#if FE_RW_EXP != 3
     if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
+#endif
     __syncwarp();
   }
 }
