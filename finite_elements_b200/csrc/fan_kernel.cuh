@@ -1,23 +1,43 @@
-// The register-walk form of the fan kernel (round 1's structure with round 2's arithmetic and record formats):
-// 2-stage TMA ring per warp, one 16-byte coordinate gather per step issued two steps ahead into three rotating
-// register sets, TMA bulk store of the sub-tile.  10 KB of shared memory per warp -> 20 warps per SM.
-// Included by assemble.cu (inside namespace fe) after FanOps / FanRec.
+// k_assemble_fan: the default numeric-assembly kernel (variant 3).  Included by assemble.cu inside namespace fe,
+// after FanOps (per-kind arithmetic of one fan step) and FanRec (the two record formats).
+//
+// Every WARP of the persistent grid is an independent software pipeline over 32-node chunks (chunk = global
+// warp id, + total warps, ...); warps never synchronise with each other.
+//  * Input ring per warp (2 stages, one mbarrier each): while chunk c is computed, lane 0 has already handed
+//    chunk c+1 to the TMA engine -- the pointer slices (adj_ptr, fan_ptr, fan_hdr: 36 words each) and the chunk's
+//    contiguous record range -- and the end points of chunk c+2's record range are travelling into shared memory
+//    by cp.async (no load is in flight into a register across the loop's back edge).
+//  * Walk: one thread per node.  A node's first record is the seed of its fan (its first neighbour); every further
+//    record is one element (self, previous neighbour, this neighbour).  A step gathers ONE 16-byte coordinate,
+//    adds the element's share to the block towards the previous neighbour -- which arrives in registers from the
+//    step before and is stored finished -- and keeps the share of the block towards this neighbour for the next
+//    step.  The diagonal block is never evaluated: it is minus the sum of the row's finished blocks (FanOps).
+//    Nodes with a single fan (all but bow-ties) run two steps per trip with no flag tests; the coordinates of the
+//    next trip are in flight in a second pair of registers while this trip computes.
+//  * Output: the warp's private sub-tile is the exact image of its 32 nodes' slice of `vals`; one thread hands it
+//    to the TMA engine as a single bulk store.
+// 10 KB of shared memory per warp at valence 7 -> 5 CTAs of 4 warps per SM, 96 registers.
+//
+// Measured alternatives (S16M plane stress, B200, profiles/r02_b_fan_kernel_search.md; round 1: 0.458 ms):
+//   this kernel, 4-byte records 0.42 ms; 8-byte records 0.45 ms; coalesced 128-bit copy-out instead of the bulk
+//   store 0.47 ms; neighbour coordinates through cp.async into shared memory a chunk ahead (no register
+//   gathers at all, 20 KB per warp, 10 warps per SM) 0.51 - 0.57 ms; 3-stage ring + first gathers a chunk ahead
+//   (13 KB per warp, 16 warps) 0.57 ms.  The kernel is bound by issue slots and dependent-instruction latency at
+//   20 warps per SM (ncu: 43 % issue-active, FP64 pipe 28 %, DRAM 2.29 GB in 0.41 ms), not by HBM: every design
+//   that traded warps for deeper prefetch lost.
 #pragma once
-#ifndef FE_RW_EXP
-#define FE_RW_EXP 0
-#endif
-constexpr int kRwThreads = 128;
-constexpr int kRwWarps = 4;
+constexpr int kFanThreads = 128;
+constexpr int kFanWarps = 4;
 
-__host__ __device__ inline size_t rw_stage_bytes(int rec_cap, bool r4) {
+__host__ __device__ inline size_t fan_stage_bytes(int rec_cap, bool r4) {
   return ((size_t)(r4 ? 3 : 2) * kFanPtrInts * sizeof(int32_t) + (size_t)rec_cap * (r4 ? 4 : 8) + 15) / 16 * 16;
 }
-__host__ __device__ inline size_t rw_warp_bytes(int rec_cap, int warp_slot_bytes, bool r4) {
-  return (32 + 2 * rw_stage_bytes(rec_cap, r4) + (size_t)warp_slot_bytes + 127) / 128 * 128;
+__host__ __device__ inline size_t fan_warp_bytes(int rec_cap, int warp_slot_bytes, bool r4) {
+  return (32 + 2 * fan_stage_bytes(rec_cap, r4) + (size_t)warp_slot_bytes + 127) / 128 * 128;
 }
 
 template <int KC, bool R4>
-__global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_rw(
+__global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan(
     int32_t n_owned, const int32_t *__restrict__ fan_ptr, const typename FanRec<R4>::T *__restrict__ fan_rec,
     const uint32_t *__restrict__ fan_hdr, const int32_t *__restrict__ adj_ptr, const double2 *__restrict__ coords,
     const MatRow *__restrict__ tab, double *__restrict__ vals, int rec_cap, int warp_slot_bytes) {
@@ -30,15 +50,15 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
   constexpr int kPtrSlices = R4 ? 3 : 2;  // adj_ptr, fan_ptr (, fan_hdr)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *wbase = smem_raw + (size_t)warp * rw_warp_bytes(rec_cap, warp_slot_bytes, R4);
+  unsigned char *wbase = smem_raw + (size_t)warp * fan_warp_bytes(rec_cap, warp_slot_bytes, R4);
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
-  const size_t stage_bytes = rw_stage_bytes(rec_cap, R4);
+  const size_t stage_bytes = fan_stage_bytes(rec_cap, R4);
   int32_t *ep = reinterpret_cast<int32_t *>(wbase + 16);  // [2][2] record-range end points (LDGSTS)
   unsigned char *stage0 = wbase + 32;
   Slot *acc = reinterpret_cast<Slot *>(stage0 + 2 * stage_bytes);
 
   const int n_chunks = (n_owned + kFanChunk - 1) / kFanChunk;
-  const int chunk_stride = gridDim.x * kRwWarps;
+  const int chunk_stride = gridDim.x * kFanWarps;
   if (lane == 0) {
     ptx::mbar_init(&full[0], 1);
     ptx::mbar_init(&full[1], 1);
@@ -67,7 +87,7 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
     if (R4) ptx::bulk_load(st + 2 * kFanPtrInts * 4, fan_hdr + n0, kFanPtrInts * 4u, &full[stage]);
     if (rec_bytes) ptx::bulk_load(st + kPtrSlices * kFanPtrInts * 4, fan_rec + base, rec_bytes, &full[stage]);
   };
-  int chunk = blockIdx.x * kRwWarps + warp;
+  int chunk = blockIdx.x * kFanWarps + warp;
   if (lane == 0 && chunk < n_chunks) {
     // chunks 0 and 1 of this warp: direct loads (start-up only); chunk 2's end points requested
     for (int q = 0; q < 2; ++q) {
@@ -118,18 +138,9 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
       my = acc + SPB * (a_sl[lane] - out_lo);
       if (R4) hdr = reinterpret_cast<const uint32_t *>(f_sl + kFanPtrInts)[lane];
     }
-#if FE_RW_EXP == 1
-    fetch(f + 1, pa1);
-    fetch(f + 2, pa2);
-    fetch(f, p0);
-#elif FE_RW_EXP == 2
-    fetch(f, p0);
-    fetch(f + 1, pa1);
-#else
     fetch(f, p0);
     fetch(f + 1, pa1);
     fetch(f + 2, pa2);
-#endif
   };
 
   int j = 0;  // ring position mod 4: stage = j & 1, barrier parity = (j >> 1) & 1
@@ -138,26 +149,6 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
     const int stage = j & 1;
     const int next = chunk + chunk_stride;
 
-#if FE_RW_EXP == 4
-    // ---- the next chunk's first loads (own coordinate, first three neighbours) are on the critical path of its
-    //      walk: if its ring stage has already landed, pull their lines into L1 now, a whole walk ahead
-    //      (ncu r02 capture Q: 37 % of all stall samples sat on exactly those loads)
-    if (next < n_chunks && ptx::mbar_test(&full[stage ^ 1], (uint32_t)((((j + 1) & 3) >> 1) & 1))) {
-      const int32_t n1 = next * kFanChunk;
-      if (lane < min(kFanChunk, n_owned - n1)) {
-        const unsigned char *sn = stage0 + (stage ^ 1) * stage_bytes;
-        const int32_t *fn = reinterpret_cast<const int32_t *>(sn) + kFanPtrInts;
-        const Rec *rn = reinterpret_cast<const Rec *>(sn + kPtrSlices * kFanPtrInts * 4);
-        const int32_t bn = fn[0] & ~(RO::kAlign - 1);
-        const int g0 = fn[lane] - bn, g1 = fn[lane + 1] - bn;
-        ptx::prefetch_l1(coords + n1 + lane);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-          if (g0 + q < g1) ptx::prefetch_l1(coords + RO::nbr(rn[g0 + q], n1 + lane, n_owned));
-      }
-    }
-
-#endif
     // ---- the fan walk of this thread's node
     if (f < fe) {
       if (R4) cur_mat = RO::first_mat(hdr);
@@ -179,9 +170,6 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
         Ops::store(my, deg, RO::k(recs[i - 1]), cin);
         Ops::diag_acc(diag, cin);
       };
-#if FE_RW_EXP == 2
-      fetch(f + 2, pa2);
-#endif
       if (!RO::multi(r0)) {
         // a single fan (all nodes but bow-ties and some boundary corners): records f+1 .. fe-1 are its steps and
         // only the last one needs a flag test.  Two steps per trip; the pairs A and B swap roles every trip.
@@ -242,9 +230,7 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
     }
 
     // ---- the sub-tile is complete: the exact image of vals[dim^2 * out_lo ...)
-#if FE_RW_EXP != 3
     ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy
-#endif
     __syncwarp();
     int32_t out_lo, out_len;  // node-level block range of this chunk (slice still in the ring slot)
     {
@@ -257,17 +243,10 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
       const double *src = reinterpret_cast<const double *>(acc);
       double *dst = vals + out_lo;
       for (int q = lane; q < out_len; q += 32) dst[q] = src[q];
-#if FE_RW_EXP == 3
-    } else {
-      const double2 *src = reinterpret_cast<const double2 *>(acc);
-      double2 *dst = reinterpret_cast<double2 *>(vals + 4 * (int64_t)out_lo);
-      for (int q = lane; q < 2 * out_len; q += 32) dst[q] = src[q];
-    }
-#else
     } else if (lane == 0 && out_len > 0) {
       ptx::bulk_store(vals + 4 * (int64_t)out_lo, acc, (uint32_t)out_len * 32u);  // one TMA bulk store
     }
-#endif
+
     if (lane == 0) {
       // this warp is done with ring slot `stage`: refill it with the chunk after the next one
       // (its end points were requested a whole chunk ago and sit in ep[stage])
@@ -278,9 +257,7 @@ __global__ void __launch_bounds__(kRwThreads, (KC == 2 ? 7 : 5)) k_assemble_fan_
     }
     // first gathers of the next chunk go out before we wait for the store to drain the sub-tile
     if (next < n_chunks) begin_chunk(next, (j + 1) & 3);
-#if FE_RW_EXP != 3
     if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
-#endif
     __syncwarp();
   }
 }
