@@ -26,6 +26,9 @@
 //   20 warps per SM (ncu: 43 % issue-active, FP64 pipe 28 %, DRAM 2.29 GB in 0.41 ms), not by HBM: every design
 //   that traded warps for deeper prefetch lost.
 #pragma once
+#ifndef FE_FAN_EP_LDG
+#define FE_FAN_EP_LDG 1  // 1: lane 0 loads the next refill's end points into registers at the top of a trip; 0: cp.async (round 1)
+#endif
 constexpr int kFanThreads = 128;
 constexpr int kFanWarps = 4;
 
@@ -97,7 +100,9 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
         issue(c, q, __ldg(fan_ptr + n0), __ldg(fan_ptr + min(n0 + kFanChunk, n_owned)));
       }
     }
+#if !FE_FAN_EP_LDG
     request_endpoints(chunk + 2 * chunk_stride, 0);
+#endif
   }
 
   // ---- per-thread state of the chunk about to be computed (filled by begin_chunk)
@@ -149,6 +154,17 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
     const int stage = j & 1;
     const int next = chunk + chunk_stride;
 
+#if FE_FAN_EP_LDG
+    // lane 0: end points of the record range this trip's refill will need; consumed after the walk, within the same
+    // trip (a cp.async group for them shares its scoreboard with other loads: ncu r02 capture Q, 17 - 21 % of the stall
+    // samples on an unrelated LDG of begin_chunk)
+    int32_t ep0 = 0, ep1 = 0;
+    if (lane == 0 && next + chunk_stride < n_chunks) {
+      const int32_t nr = (next + chunk_stride) * kFanChunk;
+      ep0 = __ldg(fan_ptr + nr);
+      ep1 = __ldg(fan_ptr + min(nr + kFanChunk, n_owned));
+    }
+#endif
     // ---- the fan walk of this thread's node
     if (f < fe) {
       if (R4) cur_mat = RO::first_mat(hdr);
@@ -251,9 +267,13 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
       // this warp is done with ring slot `stage`: refill it with the chunk after the next one
       // (its end points were requested a whole chunk ago and sit in ep[stage])
       const int nn = next + chunk_stride;
+#if FE_FAN_EP_LDG
+      if (nn < n_chunks) issue(nn, stage, ep0, ep1);
+#else
       ptx::cp_async_wait_all();
       if (nn < n_chunks) issue(nn, stage, ep[2 * stage], ep[2 * stage + 1]);
       request_endpoints(nn + chunk_stride, stage ^ 1);
+#endif
     }
     // first gathers of the next chunk go out before we wait for the store to drain the sub-tile
     if (next < n_chunks) begin_chunk(next, (j + 1) & 3);
