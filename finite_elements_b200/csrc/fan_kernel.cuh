@@ -26,6 +26,9 @@
 //   20 warps per SM (ncu: 43 % issue-active, FP64 pipe 28 %, DRAM 2.29 GB in 0.41 ms), not by HBM: every design
 //   that traded warps for deeper prefetch lost.
 #pragma once
+#ifndef FE_FAN_EARLY_BEGIN
+#define FE_FAN_EARLY_BEGIN 1  // next chunk's first loads before (1) or after (0) this chunk's store / refill sequence
+#endif
 #ifndef FE_FAN_EP_LDG
 #define FE_FAN_EP_LDG 1  // 1: lane 0 loads the next refill's end points into registers at the top of a trip; 0: cp.async (round 1)
 #endif
@@ -246,14 +249,19 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
     }
 
     // ---- the sub-tile is complete: the exact image of vals[dim^2 * out_lo ...)
-    ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy
-    __syncwarp();
     int32_t out_lo, out_len;  // node-level block range of this chunk (slice still in the ring slot)
     {
       const int32_t *a_sl = reinterpret_cast<const int32_t *>(stage0 + stage * stage_bytes);
       out_lo = a_sl[0];
       out_len = a_sl[min(kFanChunk, n_owned - chunk * kFanChunk)] - out_lo;
     }
+#if FE_FAN_EARLY_BEGIN
+    // the next chunk's first loads go out NOW: they travel while this chunk's store and the ring refill are issued
+    // (issued after those, their latency sat in front of every walk: ncu r02 capture V, 33 % of the stall samples)
+    if (next < n_chunks) begin_chunk(next, (j + 1) & 3);
+#endif
+    ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy
+    __syncwarp();
     if (KC == 2) {
       // 1 DOF per node: the destination is only 8-byte aligned -> plain coalesced copy
       const double *src = reinterpret_cast<const double *>(acc);
@@ -262,21 +270,22 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
     } else if (lane == 0 && out_len > 0) {
       ptx::bulk_store(vals + 4 * (int64_t)out_lo, acc, (uint32_t)out_len * 32u);  // one TMA bulk store
     }
-
     if (lane == 0) {
       // this warp is done with ring slot `stage`: refill it with the chunk after the next one
-      // (its end points were requested a whole chunk ago and sit in ep[stage])
       const int nn = next + chunk_stride;
 #if FE_FAN_EP_LDG
       if (nn < n_chunks) issue(nn, stage, ep0, ep1);
 #else
+      // (its end points were requested a whole chunk ago and sit in ep[stage])
       ptx::cp_async_wait_all();
       if (nn < n_chunks) issue(nn, stage, ep[2 * stage], ep[2 * stage + 1]);
       request_endpoints(nn + chunk_stride, stage ^ 1);
 #endif
     }
+#if !FE_FAN_EARLY_BEGIN
     // first gathers of the next chunk go out before we wait for the store to drain the sub-tile
     if (next < n_chunks) begin_chunk(next, (j + 1) & 3);
+#endif
     if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
     __syncwarp();
   }

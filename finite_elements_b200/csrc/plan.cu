@@ -935,7 +935,7 @@ int fe_tet_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_own
       TP_TRY(dev_alloc(&p->tile_erec, hst[0], &p->bytes));
       TP_TRY(dev_alloc(&p->tile_nodes, hst[1], &p->bytes));
       TP_TRY(dev_alloc(&p->contrib16, p->n_contrib + 8, &p->bytes));
-      TP_TRY(dev_alloc(&p->tet_kself, (int64_t)n_owned, &p->bytes));
+      TP_TRY(dev_alloc(&p->tet_kself, (int64_t)n_owned + 16, &p->bytes));  // +16: word-wise staging over-read
       k_tet_stage_tiles<true><<<p->n_tiles, 256, 0, st>>>(n_owned, conn, p->corner_ptr, p->corner_elem, p->adj_ptr, p->adj,
                                                          p->contrib_ptr, p->contrib, nullptr, nullptr, p->tile_eptr,
                                                          p->tile_nptr, p->tile_elist, p->tile_erec, p->tile_nodes,

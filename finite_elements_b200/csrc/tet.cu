@@ -667,6 +667,210 @@ __global__ void __launch_bounds__(kTetStageThreads, 4) k_tet_assemble_staged(
   for (int k = tid; k < 9 * na; k += kTetStageThreads) dst[k] = s_out[k];
 }
 
+// ---------------------------------------------------------------------------------------
+// Pipelined form of the staged kernel (default): persistent CTAs, the inputs of tile t+1 arrive by cp.async while
+// tile t is computed.  ncu on the one-tile-per-CTA form above (r02 capture N): 42 % of the stall samples in the
+// staging phase -- three dependent global round trips (descriptor -> slices and node list -> coordinates) with four
+// CTAs per SM to overlap them.  Here per trip
+//   top    : wait for the coordinates of tile t (requested during tile t-1), barrier; request the slices of tile t+1
+//            (node list, element records, contribution offsets / codes, k_self) and the descriptor of tile t+2
+//   phase A: the tile's elements, once each, from the staged coordinates
+//   middle : wait for those slices (the barrier that closes phase A publishes them); request the coordinates of
+//            tile t+1 through its node list
+//   phase B, diagonal, copy-out as above.
+// Two input buffers, three descriptors in flight; the arithmetic and the order of every sum are those of the form
+// above: bit-identical values.
+// ---------------------------------------------------------------------------------------
+struct TetPipeSmem {
+  size_t grad, out, in0, in_bytes, total;
+  // offsets inside one input buffer
+  size_t nodes, erec, elist, cptr, aptr, codes, kself, xyz;
+};
+__host__ __device__ inline TetPipeSmem tet_pipe_smem(int ne_max, int na_max, int nn_max, int nq_max) {
+  auto up16 = [](size_t b) { return (b + 15) / 16 * 16; };
+  TetPipeSmem s;
+  s.nodes = 0;
+  s.erec = s.nodes + up16((size_t)nn_max * 4);
+  s.elist = s.erec + up16((size_t)ne_max * 8);
+  s.cptr = s.elist + up16((size_t)ne_max * 4);
+  s.aptr = s.cptr + up16(((size_t)na_max + 1) * 4);
+  s.codes = s.aptr + up16(((size_t)kTetStageNodes + 1) * 4);
+  s.kself = s.codes + up16(((size_t)nq_max + 3) * 2);
+  s.xyz = s.kself + up16((size_t)kTetStageNodes + 4);
+  s.in_bytes = s.xyz + up16((size_t)nn_max * 24);
+  s.grad = 128;  // three descriptors (2 x int4 each) in front
+  s.out = s.grad + up16((size_t)ne_max * kTetGradStride * 8);
+  s.in0 = s.out + up16((size_t)na_max * 72);
+  s.total = s.in0 + 2 * s.in_bytes;
+  return s;
+}
+
+__device__ __forceinline__ void cp_async_b4(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_b8(void *dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_b16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <bool MASS>
+__global__ void __launch_bounds__(kTetStageThreads, 3) k_tet_assemble_pipe(
+    int32_t n_owned, int32_t n_tiles, const int32_t *__restrict__ adj_ptr, const int32_t *__restrict__ contrib_ptr,
+    const uint16_t *__restrict__ contrib16, const int4 *__restrict__ tile_desc, const int32_t *__restrict__ tile_elist,
+    const ushort4 *__restrict__ tile_erec, const int32_t *__restrict__ tile_nodes, const uint8_t *__restrict__ kself,
+    const double *__restrict__ coords, const int32_t *__restrict__ mat_id, const double *__restrict__ mat,
+    double *__restrict__ vals, int ne_max, int na_max, int nn_max, int nq_max) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const TetPipeSmem L = tet_pipe_smem(ne_max, na_max, nn_max, nq_max);
+  int4 *s_desc = reinterpret_cast<int4 *>(smem_raw);  // [3][2]
+  double *s_grad = reinterpret_cast<double *>(smem_raw + L.grad);
+  double *s_out = reinterpret_cast<double *>(smem_raw + L.out);
+  const int tid = threadIdx.x;
+  const int stride = gridDim.x;
+
+  auto in_buf = [&](int b) { return smem_raw + L.in0 + (size_t)b * L.in_bytes; };
+  // slices of a tile whose descriptor sits in s_desc[slot]: contiguous ranges, 4- and 8-byte cp.async
+  auto request_slices = [&](int tile, int slot, int b) {
+    const int4 d0 = s_desc[2 * slot], d1 = s_desc[2 * slot + 1];
+    const int32_t a0 = d0.x, eb = d0.z, nb = d1.x, q0 = d1.z;
+    const int na = d0.y, ne = d0.w, nn = d1.y, nq = d1.w;
+    unsigned char *in = in_buf(b);
+    const int32_t n0 = tile * kTetStageNodes;
+    const int nt = min(kTetStageNodes, n_owned - n0);
+    for (int k = tid; k < nn; k += kTetStageThreads) cp_async_b4(in + L.nodes + 4 * k, tile_nodes + nb + k);
+    for (int k = tid; k < ne; k += kTetStageThreads) cp_async_b8(in + L.erec + 8 * k, tile_erec + eb + k);
+    if (mat_id)
+      for (int k = tid; k < ne; k += kTetStageThreads) cp_async_b4(in + L.elist + 4 * k, tile_elist + eb + k);
+    for (int k = tid; k <= na; k += kTetStageThreads) cp_async_b4(in + L.cptr + 4 * k, contrib_ptr + a0 + k);
+    if (tid <= nt) cp_async_b4(in + L.aptr + 4 * tid, adj_ptr + n0 + tid);
+    // 16-bit codes: copied in 4-byte words from the word that holds code q0 (index shifted by q0 & 1 at use)
+    const int32_t qw = q0 >> 1;
+    const int nw = ((q0 & 1) + nq + 1) >> 1;
+    for (int k = tid; k < nw; k += kTetStageThreads)
+      cp_async_b4(in + L.codes + 4 * k, reinterpret_cast<const uint32_t *>(contrib16) + qw + k);
+    // k_self: bytes n0 .. n0 + nt (n0 is a multiple of 16: word aligned)
+    if (tid < (nt + 3) / 4) cp_async_b4(in + L.kself + 4 * tid, reinterpret_cast<const uint32_t *>(kself + n0) + tid);
+  };
+  auto request_coords = [&](int slot, int b) {
+    const int nn = s_desc[2 * slot + 1].y;
+    unsigned char *in = in_buf(b);
+    const int32_t *nodes = reinterpret_cast<const int32_t *>(in + L.nodes);
+    for (int k = tid; k < 3 * nn; k += kTetStageThreads) {
+      const int nd = k / 3;
+      cp_async_b8(in + L.xyz + 8 * k, coords + 3 * (int64_t)nodes[nd] + (k - 3 * nd));
+    }
+  };
+  auto request_desc = [&](int tile, int slot) {
+    if (tile < n_tiles && tid < 2) cp_async_b16(s_desc + 2 * slot + tid, tile_desc + 2 * tile + tid);
+  };
+
+  // ---- prologue: descriptors of the first two tiles, slices and coordinates of the first
+  int tile = blockIdx.x;
+  if (tile >= n_tiles) return;
+  request_desc(tile, 0);
+  request_desc(tile + stride, 1);
+  cp_async_commit_wait_all();
+  __syncthreads();
+  request_slices(tile, 0, 0);
+  cp_async_commit_wait_all();
+  __syncthreads();
+  request_coords(0, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  for (int it = 0; tile < n_tiles; tile += stride, ++it) {
+    const int b = it & 1, slot = it % 3, slot1 = (it + 1) % 3, slot2 = (it + 2) % 3;
+    const int next = tile + stride;
+    // ---- top: this tile's coordinates (and, first trip, everything else) have landed
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int4 d0 = s_desc[2 * slot], d1 = s_desc[2 * slot + 1];
+    const int32_t a0 = d0.x, q0 = d1.z;
+    const int na = d0.y, ne = d0.w;
+    const int32_t n0 = tile * kTetStageNodes;
+    const int nt = min(kTetStageNodes, n_owned - n0);
+    if (next < n_tiles) request_slices(next, slot1, b ^ 1);
+    request_desc(next + stride, slot2);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const unsigned char *in = in_buf(b);
+    const double *s_xyz = reinterpret_cast<const double *>(in + L.xyz);
+    const ushort4 *s_erec = reinterpret_cast<const ushort4 *>(in + L.erec);
+    const int32_t *s_elist = reinterpret_cast<const int32_t *>(in + L.elist);
+    const int32_t *s_cptr = reinterpret_cast<const int32_t *>(in + L.cptr);
+    const int32_t *s_aptr = reinterpret_cast<const int32_t *>(in + L.aptr);
+    const uint16_t *s_codes = reinterpret_cast<const uint16_t *>(in + L.codes) + (q0 & 1);
+    const uint8_t *s_kself = in + L.kself;
+    // ---- phase A: the tile's elements, once each
+    for (int le = tid; le < ne; le += kTetStageThreads) {
+      const ushort4 r = s_erec[le];
+      const double *p0 = s_xyz + 3 * r.x, *p1 = s_xyz + 3 * r.y, *p2 = s_xyz + 3 * r.z, *p3 = s_xyz + 3 * r.w;
+      const TetGeom t = tet_geom_xyz(p0[0], p0[1], p0[2], p1[0], p1[1], p1[2], p2[0], p2[1], p2[2], p3[0], p3[1], p3[2]);
+      const int mid = mat_id ? __ldg(mat_id + s_elist[le]) : 0;
+      const TetMat m = tet_material(MASS ? FE_MASS_TET : FE_ELAST_TET, mat, mid, t.vol);
+      const double sc = MASS ? 0.0 : sqrt(m.p1);
+      double *g = s_grad + kTetGradStride * le;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        g[3 * k] = sc * t.g[k][0];
+        g[3 * k + 1] = sc * t.g[k][1];
+        g[3 * k + 2] = sc * t.g[k][2];
+      }
+      g[12] = MASS ? m.p0 : (m.p1 != 0.0 ? m.p0 / m.p1 : 0.0);
+    }
+    // ---- middle: the next tile's slices have landed (requested a whole phase ago); its coordinates go out
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (next < n_tiles) request_coords(slot1, b ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // ---- phase B: one lane per block
+    const int nl = tid >> 4, lane = tid & 15;
+    int al = 0, deg = 0;
+    if (nl < nt) {
+      al = s_aptr[nl] - a0;
+      deg = s_aptr[nl + 1] - s_aptr[nl];
+    }
+    double *rows = s_out + 9 * al;
+    for (int k = lane; k < deg; k += 16) {
+      double acc[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+      const int qb = s_cptr[al + k + 1] - q0;
+      for (int q = s_cptr[al + k] - q0; q < qb; ++q) {
+        const uint32_t code = s_codes[q];
+        const double *ge = s_grad + kTetGradStride * (code >> 4);
+        const double *gi = ge + 3 * ((code >> 2) & 3), *gj = ge + 3 * (code & 3);
+        const D4 hi = {gi[0], gi[1], gi[2], ge[12]};
+        D4 hj = hi;
+        if (!MASS) hj = D4{gj[0], gj[1], gj[2], 0.0};
+        tet_pair_add<MASS>(hi, hj, acc);
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) rows[r * 3 * deg + 3 * k + t] = acc[3 * r + t];
+    }
+    __syncwarp();
+    if (lane < 9 && deg > 0) {  // diagonal block from the off-diagonal ones, slot order
+      const int ks = s_kself[nl];
+      const int r = lane / 3, t = lane - 3 * r;
+      const double *row = rows + r * 3 * deg + t;
+      double sum = 0.0;
+      for (int k = 0; k < deg; ++k)
+        if (k != ks) sum += row[3 * k];
+      rows[r * 3 * deg + 3 * ks + t] = (MASS ? (2.0 / 3.0) : -1.0) * sum;
+    }
+    __syncthreads();
+    // ---- store the image of vals[9 a0 .. 9 (a0 + na))
+    double *dst = vals + 9 * (int64_t)a0;
+    for (int k = tid; k < 9 * na; k += kTetStageThreads) dst[k] = s_out[k];
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 }  // namespace fe
 
 using namespace fe;
@@ -704,7 +908,7 @@ int fe_tet_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind, const
   FE_REQUIRE(kind == FE_ELAST_TET || kind == FE_MASS_TET, "fe_tet_assemble: kind %d is not a tetrahedral kind", kind);
   FE_REQUIRE(n_mat > 0, "fe_tet_assemble: bad sizes");
   FE_REQUIRE(((uintptr_t)conn & 15) == 0, "fe_tet_assemble: conn must be 16-byte aligned");
-  FE_REQUIRE(variant >= 0 && variant <= 5, "fe_tet_assemble: unknown variant %d", variant);
+  FE_REQUIRE(variant >= 0 && variant <= 6, "fe_tet_assemble: unknown variant %d", variant);
   if (p->n_owned == 0 || p->nnz == 0) return FE_OK;
   cudaStream_t st = as_stream(stream);
   const int max_degree = p->max_degree;
@@ -715,11 +919,32 @@ int fe_tet_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind, const
   if (variant == 2 && !fits)
     return fail(FE_ERR_UNSUPPORTED, "fe_tet_assemble: the tile variant needs %zu B of shared memory (valence %d)", smem, max_degree);
   const TetStageSmem sl = tet_stage_smem(p->tile_elems_max, p->tile_adj_max, p->tile_nodes_max, p->tile_contrib_max);
+  const TetPipeSmem pl = tet_pipe_smem(p->tile_elems_max, p->tile_adj_max, p->tile_nodes_max, p->tile_contrib_max);
   const bool stage_fits = p->tet_stage_ok && sl.total <= 200 * 1024;
-  if (variant == 5 && !stage_fits)
-    return fail(FE_ERR_UNSUPPORTED, "fe_tet_assemble: the staged variant needs tiles of <= 4095 elements within %d B of shared memory",
+  const bool pipe_fits = p->tet_stage_ok && pl.total <= 200 * 1024;
+  if ((variant == 5 && !stage_fits) || (variant == 6 && !pipe_fits))
+    return fail(FE_ERR_UNSUPPORTED, "fe_tet_assemble: the staged variants need tiles of <= 4095 elements within %d B of shared memory",
                 200 * 1024);
-  if (variant == 0) variant = stage_fits ? 5 : (!p->tet_degenerate ? 4 : (fits ? 2 : 1));
+  if (variant == 0) variant = pipe_fits ? 6 : (stage_fits ? 5 : (!p->tet_degenerate ? 4 : (fits ? 2 : 1)));
+  if (variant == 6) {
+#define FE_TET_PIPE(MASS)                                                                                            \
+  do {                                                                                                               \
+    int nb = 1;                                                                                                      \
+    FE_CUDA(cudaFuncSetAttribute(k_tet_assemble_pipe<MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total)); \
+    FE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tet_assemble_pipe<MASS>, kTetStageThreads, pl.total)); \
+    if (nb < 1) nb = 1;                                                                                              \
+    const int grid = p->n_tiles < nb * ctx->num_sms ? p->n_tiles : nb * ctx->num_sms;                                \
+    k_tet_assemble_pipe<MASS><<<grid, kTetStageThreads, pl.total, st>>>(                                              \
+        p->n_owned, p->n_tiles, p->adj_ptr, p->contrib_ptr, p->contrib16, p->tile_desc, p->tile_elist, p->tile_erec, \
+        p->tile_nodes, p->tet_kself, coords, mat_id, mat, vals, p->tile_elems_max, p->tile_adj_max,                  \
+        p->tile_nodes_max, p->tile_contrib_max);                                                                     \
+  } while (0)
+    if (kind == FE_MASS_TET)
+      FE_TET_PIPE(true);
+    else
+      FE_TET_PIPE(false);
+#undef FE_TET_PIPE
+  } else
   if (variant == 5) {
 #define FE_TET_STAGED(MASS)                                                                                          \
   do {                                                                                                               \

@@ -187,14 +187,15 @@ int fe_tet_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_own
                        int64_t n_elems, const int32_t *conn, fe_plan **out);
 /* Global matrix values of the tetrahedral mesh; replaces the k_matrix_data / m_matrix_data loops
  * (analysis.py:324-339, :357-365) + csr_matrix (:661) for 3 DOF per node.  Deterministic, no atomics.
- * variant 0 = automatic; 5 = staged tiles (default): one CTA per 16 consecutive nodes evaluates the elements
- * its rows touch once into shared memory and one lane per 3x3 block walks the plan's per-block element lists
- * there (needs elements with four distinct nodes, <= 4095 elements per tile and the tile within 200 KB of
- * shared memory); 4 = the same walk over a global gradient table written by a first pass (128 B per element
- * of ctx scratch; the fallback of 5); 3 = the same walk rebuilding the
+ * variant 0 = automatic; 6 = staged tiles, pipelined (default): per tile of 16 consecutive nodes a CTA evaluates
+ * the elements its rows touch once into shared memory and one lane per 3x3 block walks the plan's per-block
+ * element lists there, while the next tile's inputs arrive by cp.async (needs elements with four distinct
+ * nodes, <= 4095 elements per tile and the tile within 200 KB of shared memory); 5 = the same, one tile per
+ * CTA without the prefetch (bit-identical); 4 = the same walk over a global gradient table written by a first pass (128 B per element
+ * of ctx scratch; the fallback of 6 / 5); 3 = the same walk rebuilding the
  * geometry at every visit (no scratch); 1 = one thread per node accumulating in global memory, 2 = the
  * same through a shared-memory tile (1 and 2 are bit-identical to each other and add a block's elements
- * in ascending order; 3, 4 and 5 agree with them to rounding). */
+ * in ascending order; 3, 4, 5 and 6 agree with them to rounding). */
 int fe_tet_assemble(fe_ctx *ctx, void *stream, const fe_plan *plan, int kind, const double *coords,
                     const int32_t *conn, const int32_t *mat_id, const double *mat, int32_t n_mat,
                     double *vals, int32_t variant);

@@ -22,10 +22,10 @@ for v in (0, 4, 2, 1):
 dm1 = DeviceMesh(coords, conn, mid, dim=1)
 for v in (0, 4):
     dm1.assemble(KIND_MAGNETIC, np.array([[1.0, 0, 0, 0], [30.0, 0, 0, 0]]), variant=v)
-c3, t3 = mesh.structured_tet_mesh(9, 7, 5, h=0.5, jitter=0.15, seed=4)
+c3, t3 = mesh.structured_tet_mesh(19, 7, 5, h=0.5, jitter=0.15, seed=4)   # 960 nodes: 60 tiles, several per CTA
 d3 = DeviceMesh3D(c3, t3, (np.arange(len(t3)) % 2).astype(np.int32))
 m3 = np.array([[210e9, 0.25, 1.0, 7860.0], [70e9, 0.3, 1.0, 2700.0]])
-for v in (0, 5, 4, 3, 2, 1):
+for v in (0, 6, 5, 4, 3, 2, 1):
     d3.assemble(KIND_ELAST_TET, m3, variant=v)
     d3.assemble(KIND_MASS_TET, m3, variant=v)
 torch.cuda.synchronize()

@@ -166,10 +166,12 @@ def test_gpu_tet_element_and_global_matrices_vs_reference(name):
     # summation order and element labelling) agrees with them to rounding
     k1 = dm.assemble(KIND_ELAST_TET, fx.mat, variant=1)
     assert torch.equal(k1, dm.assemble(KIND_ELAST_TET, fx.mat, variant=2))
-    # default = staged tiles (5); 4 = the same walk over a global gradient table: same off-diagonal blocks bit for
-    # bit (same records, same order), the diagonal block is summed in another order
+    # default = staged tiles, pipelined (6) = one tile per CTA (5); 4 = the same walk over a global gradient table: same
+    # off-diagonal blocks bit for bit (same records, same order), the diagonal block is summed in another order
     k4 = dm.assemble(KIND_ELAST_TET, fx.mat, variant=4)
     assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, fx.mat, variant=5))
+    assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, fx.mat, variant=6))
+    assert torch.equal(dm.assemble(KIND_MASS_TET, fx.mat, variant=5), dm.assemble(KIND_MASS_TET, fx.mat, variant=6))
     assert float((kv - k4).abs().max()) <= 1e-14 * float(k4.abs().max())
     rp, ci = dm.csr_pattern()
     offdiag = (ci.long() // 3) != torch.repeat_interleave(torch.arange(dm.n_rows, device=ci.device) // 3,
@@ -264,7 +266,8 @@ def test_gpu_tet_mid_size_properties():
     k2 = dm.assemble(KIND_ELAST_TET, MAT2, variant=2)
     assert torch.equal(k2, dm.assemble(KIND_ELAST_TET, MAT2, variant=1))
     assert float((kv - k2).abs().max()) <= 1e-13 * float(k2.abs().max())
-    assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, MAT2, variant=5))        # the default is the staged variant
+    assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, MAT2, variant=6))        # the default is the pipelined staged variant
+    assert torch.equal(kv, dm.assemble(KIND_ELAST_TET, MAT2, variant=5))
     assert float((kv - dm.assemble(KIND_ELAST_TET, MAT2, variant=4)).abs().max()) <= 1e-14 * float(k2.abs().max())
     k = dm.to_scipy(kv)
     assert_csr_values_close(k, no.assemble_k(no.KIND_ELAST_TET, coords, conn, mid, MAT2), 1e-12)
