@@ -26,11 +26,8 @@
 //   20 warps per SM (ncu: 43 % issue-active, FP64 pipe 28 %, DRAM 2.29 GB in 0.41 ms), not by HBM: every design
 //   that traded warps for deeper prefetch lost.
 #pragma once
-#ifndef FE_FAN_EARLY_BEGIN
-#define FE_FAN_EARLY_BEGIN 1  // next chunk's first loads before (1) or after (0) this chunk's store / refill sequence
-#endif
-#ifndef FE_FAN_EP_LDG
-#define FE_FAN_EP_LDG 1  // 1: lane 0 loads the next refill's end points into registers at the top of a trip; 0: cp.async (round 1)
+#ifndef FE_FAN_L2PF
+#define FE_FAN_L2PF 1
 #endif
 constexpr int kFanThreads = 128;
 constexpr int kFanWarps = 4;
@@ -46,7 +43,8 @@ template <int KC, bool R4>
 __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan(
     int32_t n_owned, const int32_t *__restrict__ fan_ptr, const typename FanRec<R4>::T *__restrict__ fan_rec,
     const uint32_t *__restrict__ fan_hdr, const int32_t *__restrict__ adj_ptr, const double2 *__restrict__ coords,
-    const MatRow *__restrict__ tab, double *__restrict__ vals, int rec_cap, int warp_slot_bytes) {
+    const MatRow *__restrict__ tab, double *__restrict__ vals, int rec_cap, int warp_slot_bytes, int32_t n_nodes,
+    int32_t fwd_hint) {
   using Ops = FanOps<KC>;
   using Val = typename Ops::Val;
   using Slot = typename Ops::Slot;
@@ -54,6 +52,13 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
   using Rec = typename RO::T;
   constexpr int SPB = (KC == 2) ? 1 : 2;  // Slots per node-level block
   constexpr int kPtrSlices = R4 ? 3 : 2;  // adj_ptr, fan_ptr (, fan_hdr)
+  // Two scheduling choices, settled per instance by measurement (r02 captures V, W; ms at S16M, 4-byte records):
+  //   kEpLdg : lane 0 reads the refill's end points with plain loads at the top of a trip (consumed after the walk)
+  //            instead of a cp.async group one chunk earlier.        2 DOF: 0.417 -> 0.407; scalar: 0.243 -> 0.257
+  //   kEarly : the next chunk's first loads go out before this chunk's store / refill sequence instead of after it.
+  //            2 DOF (with kEpLdg): 0.407 -> 0.439 (12 B of spills); scalar (cp.async end points): 0.243 -> 0.231
+  //            2 DOF, 8-byte records (what a rank of a partition runs; no spills there): 0.418 -> 0.410
+  constexpr bool kEpLdg = KC != 2, kEarly = KC == 2 || !R4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *wbase = smem_raw + (size_t)warp * fan_warp_bytes(rec_cap, warp_slot_bytes, R4);
@@ -92,6 +97,14 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
     ptx::bulk_load(st + kFanPtrInts * 4, fan_ptr + n0, kFanPtrInts * 4u, &full[stage]);
     if (R4) ptx::bulk_load(st + 2 * kFanPtrInts * 4, fan_hdr + n0, kFanPtrInts * 4u, &full[stage]);
     if (rec_bytes) ptx::bulk_load(st + kPtrSlices * kFanPtrInts * 4, fan_rec + base, rec_bytes, &full[stage]);
+#if FE_FAN_L2PF
+    // the coordinates this chunk touches FIRST (banded numbering: the nodes fwd_hint ahead; everything nearer was
+    // gathered by earlier chunks) would otherwise come from DRAM in front of its walk: pull them into L2 now
+    if (fwd_hint > 0) {
+      const int32_t a = max(0, (n0 + fwd_hint - kFanChunk - 8) & ~7), b = min(n_nodes, n0 + fwd_hint + 8);
+      if (b > a) ptx::bulk_prefetch_l2(coords + a, (uint32_t)(b - a) * 16u & ~15u);
+    }
+#endif
   };
   int chunk = blockIdx.x * kFanWarps + warp;
   if (lane == 0 && chunk < n_chunks) {
@@ -103,9 +116,7 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
         issue(c, q, __ldg(fan_ptr + n0), __ldg(fan_ptr + min(n0 + kFanChunk, n_owned)));
       }
     }
-#if !FE_FAN_EP_LDG
-    request_endpoints(chunk + 2 * chunk_stride, 0);
-#endif
+    if (!kEpLdg) request_endpoints(chunk + 2 * chunk_stride, 0);
   }
 
   // ---- per-thread state of the chunk about to be computed (filled by begin_chunk)
@@ -157,17 +168,15 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
     const int stage = j & 1;
     const int next = chunk + chunk_stride;
 
-#if FE_FAN_EP_LDG
     // lane 0: end points of the record range this trip's refill will need; consumed after the walk, within the same
     // trip (a cp.async group for them shares its scoreboard with other loads: ncu r02 capture Q, 17 - 21 % of the stall
     // samples on an unrelated LDG of begin_chunk)
     int32_t ep0 = 0, ep1 = 0;
-    if (lane == 0 && next + chunk_stride < n_chunks) {
+    if (kEpLdg && lane == 0 && next + chunk_stride < n_chunks) {
       const int32_t nr = (next + chunk_stride) * kFanChunk;
       ep0 = __ldg(fan_ptr + nr);
       ep1 = __ldg(fan_ptr + min(nr + kFanChunk, n_owned));
     }
-#endif
     // ---- the fan walk of this thread's node
     if (f < fe) {
       if (R4) cur_mat = RO::first_mat(hdr);
@@ -255,11 +264,8 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
       out_lo = a_sl[0];
       out_len = a_sl[min(kFanChunk, n_owned - chunk * kFanChunk)] - out_lo;
     }
-#if FE_FAN_EARLY_BEGIN
-    // the next chunk's first loads go out NOW: they travel while this chunk's store and the ring refill are issued
-    // (issued after those, their latency sat in front of every walk: ncu r02 capture V, 33 % of the stall samples)
-    if (next < n_chunks) begin_chunk(next, (j + 1) & 3);
-#endif
+    // kEarly: the next chunk's first loads go out NOW and travel while this chunk's store and the ring refill are issued
+    if (kEarly && next < n_chunks) begin_chunk(next, (j + 1) & 3);
     ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy
     __syncwarp();
     if (KC == 2) {
@@ -273,19 +279,16 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
     if (lane == 0) {
       // this warp is done with ring slot `stage`: refill it with the chunk after the next one
       const int nn = next + chunk_stride;
-#if FE_FAN_EP_LDG
-      if (nn < n_chunks) issue(nn, stage, ep0, ep1);
-#else
-      // (its end points were requested a whole chunk ago and sit in ep[stage])
-      ptx::cp_async_wait_all();
-      if (nn < n_chunks) issue(nn, stage, ep[2 * stage], ep[2 * stage + 1]);
-      request_endpoints(nn + chunk_stride, stage ^ 1);
-#endif
+      if (kEpLdg) {
+        if (nn < n_chunks) issue(nn, stage, ep0, ep1);
+      } else {  // (the end points were requested a whole chunk ago and sit in ep[stage])
+        ptx::cp_async_wait_all();
+        if (nn < n_chunks) issue(nn, stage, ep[2 * stage], ep[2 * stage + 1]);
+        request_endpoints(nn + chunk_stride, stage ^ 1);
+      }
     }
-#if !FE_FAN_EARLY_BEGIN
     // first gathers of the next chunk go out before we wait for the store to drain the sub-tile
-    if (next < n_chunks) begin_chunk(next, (j + 1) & 3);
-#endif
+    if (!kEarly && next < n_chunks) begin_chunk(next, (j + 1) & 3);
     if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
     __syncwarp();
   }
