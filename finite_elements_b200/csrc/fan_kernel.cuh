@@ -26,9 +26,6 @@
 //   20 warps per SM (ncu: 43 % issue-active, FP64 pipe 28 %, DRAM 2.29 GB in 0.41 ms), not by HBM: every design
 //   that traded warps for deeper prefetch lost.
 #pragma once
-#ifndef FE_FAN_L2PF
-#define FE_FAN_L2PF 1
-#endif
 constexpr int kFanThreads = 128;
 constexpr int kFanWarps = 4;
 
@@ -43,8 +40,7 @@ template <int KC, bool R4>
 __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan(
     int32_t n_owned, const int32_t *__restrict__ fan_ptr, const typename FanRec<R4>::T *__restrict__ fan_rec,
     const uint32_t *__restrict__ fan_hdr, const int32_t *__restrict__ adj_ptr, const double2 *__restrict__ coords,
-    const MatRow *__restrict__ tab, double *__restrict__ vals, int rec_cap, int warp_slot_bytes, int32_t n_nodes,
-    int32_t fwd_hint) {
+    const MatRow *__restrict__ tab, double *__restrict__ vals, int rec_cap, int warp_slot_bytes) {
   using Ops = FanOps<KC>;
   using Val = typename Ops::Val;
   using Slot = typename Ops::Slot;
@@ -97,14 +93,6 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
     ptx::bulk_load(st + kFanPtrInts * 4, fan_ptr + n0, kFanPtrInts * 4u, &full[stage]);
     if (R4) ptx::bulk_load(st + 2 * kFanPtrInts * 4, fan_hdr + n0, kFanPtrInts * 4u, &full[stage]);
     if (rec_bytes) ptx::bulk_load(st + kPtrSlices * kFanPtrInts * 4, fan_rec + base, rec_bytes, &full[stage]);
-#if FE_FAN_L2PF
-    // the coordinates this chunk touches FIRST (banded numbering: the nodes fwd_hint ahead; everything nearer was
-    // gathered by earlier chunks) would otherwise come from DRAM in front of its walk: pull them into L2 now
-    if (fwd_hint > 0) {
-      const int32_t a = max(0, (n0 + fwd_hint - kFanChunk - 8) & ~7), b = min(n_nodes, n0 + fwd_hint + 8);
-      if (b > a) ptx::bulk_prefetch_l2(coords + a, (uint32_t)(b - a) * 16u & ~15u);
-    }
-#endif
   };
   int chunk = blockIdx.x * kFanWarps + warp;
   if (lane == 0 && chunk < n_chunks) {

@@ -54,9 +54,6 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, 
                "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
                : "memory");
 }
-__device__ __forceinline__ void bulk_prefetch_l2(const void *gmem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
                "l"(gmem_src)
