@@ -5,8 +5,8 @@
 // warp id, + total warps, ...); warps never synchronise with each other.
 //  * Input ring per warp (2 stages, one mbarrier each): while chunk c is computed, lane 0 has already handed
 //    chunk c+1 to the TMA engine -- the pointer slices (adj_ptr, fan_ptr, fan_hdr: 36 words each) and the chunk's
-//    contiguous record range -- and the end points of chunk c+2's record range are travelling into shared memory
-//    by cp.async (no load is in flight into a register across the loop's back edge).
+//    contiguous record range; the end points of the record range a refill needs are read by lane 0 at the top of
+//    the trip and consumed after the walk (scalar instance: by cp.async a chunk earlier; kEpLdg below).
 //  * Walk: one thread per node.  A node's first record is the seed of its fan (its first neighbour); every further
 //    record is one element (self, previous neighbour, this neighbour).  A step gathers ONE 16-byte coordinate,
 //    adds the element's share to the block towards the previous neighbour -- which arrives in registers from the
@@ -19,8 +19,8 @@
 // 10 KB of shared memory per warp at valence 7 -> 5 CTAs of 4 warps per SM, 96 registers.
 //
 // Measured alternatives (S16M plane stress, B200, profiles/r02_b_fan_kernel_search.md; round 1: 0.458 ms):
-//   this kernel, 4-byte records 0.42 ms; 8-byte records 0.45 ms; coalesced 128-bit copy-out instead of the bulk
-//   store 0.47 ms; neighbour coordinates through cp.async into shared memory a chunk ahead (no register
+//   this kernel, 4-byte records 0.406 ms; 8-byte records 0.410 ms; coalesced 128-bit copy-out instead of the bulk
+//   store 0.47 ms; TMA L2 prefetch of the coordinates a chunk touches first 0.49 ms; neighbour coordinates through cp.async into shared memory a chunk ahead (no register
 //   gathers at all, 20 KB per warp, 10 warps per SM) 0.51 - 0.57 ms; 3-stage ring + first gathers a chunk ahead
 //   (13 KB per warp, 16 warps) 0.57 ms.  The kernel is bound by issue slots and dependent-instruction latency at
 //   20 warps per SM (ncu: 43 % issue-active, FP64 pipe 28 %, DRAM 2.29 GB in 0.41 ms), not by HBM: every design
