@@ -283,6 +283,17 @@ template <bool DOT>
 static int launch_spmv(fe_ctx *ctx, cudaStream_t s, int lpr, int32_t n_rows, const int32_t *rowptr,
                        const int32_t *colidx, const double *vals, const double *x, double *y, double *partials,
                        PcgState *st, const StreamPlan *sp = nullptr, const HaloPlan *fused_halo = nullptr) {
+  if (sp && sp->on && sp->bs3) {  // persistent TMA-streamed kernel, 3x3 blocks (3 DOF per node)
+    if (fused_halo)
+      k_spmv_stream3<DOT, true><<<sp->grid, kStreamThreads, sp->smem, s>>>(
+          n_rows / 3, sp->cap, sp->bptr, sp->bidx, vals, x, y, partials, st, ctx->p2p_dev, (HaloDev *)ctx->p2p_halo.ptr,
+          fused_halo->send_idx);
+    else
+      k_spmv_stream3<DOT, false><<<sp->grid, kStreamThreads, sp->smem, s>>>(n_rows / 3, sp->cap, sp->bptr, sp->bidx, vals, x,
+                                                                           y, partials, st, nullptr, nullptr, nullptr);
+    FE_LAUNCH_CHECK(ctx);
+    return FE_OK;
+  }
   if (sp && sp->on && sp->scalar) {  // persistent TMA-streamed kernel, scalar CSR (1 DOF per node)
 #define FE_STREAM1(P)                                                                                                   \
   do {                                                                                                                  \
@@ -696,7 +707,7 @@ static int get_chunk_graph(PcgLaunch &L, int len, cudaGraphExec_t *out) {
                          (void *)(intptr_t)(len * 256 + (L.lpr & 31) + (L.sp.on ? 32 : 0) + (L.p2p ? 64 : 0) + (L.sp.scalar ? 128 : 0)),
                          (void *)(intptr_t)L.sp.cap, (void *)(intptr_t)L.sp.smem, (void *)(intptr_t)L.sp.grid,
                          (void *)L.sp.bptr, (void *)L.sp.bidx, (void *)(L.halo ? L.halo->send_idx : nullptr),
-                         (void *)(intptr_t)ctx->bp_built_token, (void *)(intptr_t)(L.vgrid * 8 + L.sp.passes)};
+                         (void *)(intptr_t)ctx->bp_built_token, (void *)(intptr_t)(L.vgrid * 16 + L.sp.passes + (L.sp.bs3 ? 8 : 0))};
   if (ctx->pcg_graph && memcmp(key, ctx->pcg_graph_key, sizeof(key)) == 0) {
     *out = (cudaGraphExec_t)ctx->pcg_graph;
     return FE_OK;
@@ -840,7 +851,7 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
   FE_REQUIRE(ctx && rowptr && colidx && vals && b && x && work, "pcg: NULL argument");
   FE_REQUIRE(n_rows >= 0 && n_cols >= n_rows, "pcg: bad sizes %d x %d", n_rows, n_cols);
   FE_REQUIRE(maxit >= 0, "pcg: negative iteration count");
-  FE_REQUIRE(block_dim == 1 || block_dim == 2, "pcg: block_dim must be 1 or 2");
+  FE_REQUIRE(block_dim >= 1 && block_dim <= 3, "pcg: block_dim must be 1, 2 or 3");
   FE_CUDA(cudaSetDevice(ctx->device));
   // The legacy / per-thread default streams cannot be captured into a CUDA graph: run the
   // solve on the ctx's own stream, ordered after the caller's stream.  The driver ends with a
@@ -931,7 +942,54 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
     }
   }
 
-  if (L.lpr != kBlock2 && n_rows > 0 && getenv("FE_B200_NO_STREAM") == nullptr &&
+  if (block_dim == 3 && n_rows > 0 && n_rows % 3 == 0 && h_rowptr_end % 9 == 0 && getenv("FE_B200_NO_STREAM") == nullptr &&
+      getenv("FE_B200_NO_BLOCK3") == nullptr && ((uintptr_t)vals & 15) == 0) {
+    // 3 DOF per node: node-level pattern (4 index bytes per 3x3 block) for k_spmv_stream3
+    const int32_t n_nodes = n_rows / 3;
+    const int64_t nnzb = h_rowptr_end / 9;
+    const size_t bptr_bytes = ((size_t)(n_nodes + 1 + 128) * 4 + 255) / 256 * 256;  // +128: tile slice over-read
+    const size_t bidx_bytes = ((size_t)(nnzb + 8) * 4 + 255) / 256 * 256;
+    if ((rc = ctx->scratch_c.reserve(bptr_bytes + bidx_bytes + 256))) return rc;
+    L.sp.bptr = (int32_t *)ctx->scratch_c.ptr;
+    L.sp.bidx = (int32_t *)((char *)ctx->scratch_c.ptr + bptr_bytes);
+    int *flags3 = (int *)((char *)ctx->scratch_c.ptr + bptr_bytes + bidx_bytes);  // [0] tile max, [1] bad
+    const bool cached = ctx->bp_token != 0 && ctx->bp_rowptr == rowptr && ctx->bp_colidx == colidx &&
+                        ctx->bp_built_token == ctx->bp_token && ctx->bp_built_rows == -3 - n_rows;
+    int h3[2] = {ctx->bp_max_deg, 0};
+    if (!cached) {
+      ctx->bp_built_token = 0;
+      FE_CUDA(cudaMemsetAsync(flags3, 0, 2 * sizeof(int), s));
+      k_block_pattern3<<<grid_for(((int64_t)n_nodes + 1) * 16, 256), 256, 0, s>>>(n_nodes, rowptr, colidx, L.sp.bptr, L.sp.bidx,
+                                                                                 flags3 + 1);
+      FE_LAUNCH_CHECK(ctx);
+      const int n_tiles = (n_nodes + kBlock3Tile - 1) / kBlock3Tile;
+      k_tile_max_entries<<<grid_for(n_tiles, 256), 256, 0, s>>>(n_nodes, kBlock3Tile, L.sp.bptr, flags3);
+      FE_LAUNCH_CHECK(ctx);
+      FE_CUDA(cudaMemcpyAsync(h3, flags3, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      FE_CUDA(cudaStreamSynchronize(s));
+      if (!h3[1] && ctx->bp_token != 0 && ctx->bp_rowptr == rowptr && ctx->bp_colidx == colidx) {
+        ctx->bp_built_token = ctx->bp_token;
+        ctx->bp_built_rows = -3 - n_rows;  // (3-DOF entry: distinct from the scalar (-2 - n) and the 2-DOF (n) ones)
+        ctx->bp_max_deg = h3[0];
+      }
+    }
+    const int cap = ((h3[0] > 0 ? h3[0] : 1) + 3) & ~3;
+    const size_t smem = stream3_smem_bytes(cap);
+    if (!h3[1] && smem <= 110 * 1024) {  // (a CSR that is not 3x3-blocked falls through to the scalar kernel)
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FE_CUDA(cudaFuncSetAttribute(k_spmv_stream3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      L.sp.on = true;
+      L.sp.bs3 = true;
+      L.sp.cap = cap;
+      L.sp.smem = smem;
+      const int n_tiles = (n_nodes + kBlock3Tile - 1) / kBlock3Tile;
+      L.sp.grid = n_tiles < 2 * ctx->num_sms ? n_tiles : 2 * ctx->num_sms;
+    }
+  }
+
+  if (!L.sp.on && L.lpr != kBlock2 && n_rows > 0 && getenv("FE_B200_NO_STREAM") == nullptr &&
       ((uintptr_t)vals & 15) == 0 && ((uintptr_t)colidx & 15) == 0 && ((uintptr_t)rowptr & 15) == 0) {
     // scalar CSR: the streamed kernel works on rowptr / colidx as they are; only the largest tile
     // (in entries) is needed to size the ring
@@ -1002,7 +1060,7 @@ int pcg_drive(fe_ctx *ctx, cudaStream_t s, int32_t n_rows, int32_t n_cols, const
   bool want_persist = L.dist && ctx->nranks >= 4;
   if (const char *e = getenv("FE_B200_PERSIST")) want_persist = atoi(e) != 0;
   if (getenv("FE_B200_NO_PERSIST")) want_persist = false;
-  if (want_persist && L.sp.on && !L.sp.scalar && aligned16 && (!L.dist || L.p2p))
+  if (want_persist && L.sp.on && !L.sp.scalar && !L.sp.bs3 && aligned16 && (!L.dist || L.p2p))
     return persist_solve(L, work, n_cols, rtol, maxit, fixed, iters_out, relres_out);
 
   if ((rc = L.true_residual_start())) return rc;

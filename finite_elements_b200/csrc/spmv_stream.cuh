@@ -396,6 +396,192 @@ __global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream1(
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// The streaming structure for 3 DOF per node (tetrahedra): node i owns rows 3i .. 3i+2, whose values are one
+// contiguous run of 9 * valence doubles (row r at offset r * 3 * valence), and whose columns are the triples
+// (3m, 3m+1, 3m+2) of its neighbour nodes m.  k_block_pattern3 extracts bptr[i] = rowptr[3i] / 9 and
+// bidx[b] = colidx[rowptr[3i] + 3j] / 3: 4 index bytes per 72-byte block instead of 36 -- the scalar streamed kernel
+// the tetrahedral PCG used before moves 12 nnz, this one 8.44 nnz.  A tile = 30 nodes (16 lanes per node, one
+// 3x3 block per lane: 9 LDS.64, one index, three gathers of x, 9 FMAs); value slices are 8-byte aligned only, so
+// the copies are aligned down / rounded up to 16 bytes and the last two tiles are copied with exact bounds, as in
+// k_spmv_stream1.  HBM bytes per call: 8 nnz + 4 nnz / 9 + 4 n / 3 (bptr) + 8 n (x) + 8 n (y).
+// ---------------------------------------------------------------------------------------
+constexpr int kBlock3Tile = 2 * kStreamConsumerWarps;           // 30 nodes per tile: two 16-lane groups per warp
+constexpr int kBlock3PtrInts = (kBlock3Tile + 1 + 3 + 3) & ~3;  // 36: the slice starts at the tile's first node rounded down to 4
+
+__global__ void __launch_bounds__(256) k_block_pattern3(int32_t n_nodes, const int32_t *__restrict__ rowptr,
+                                                       const int32_t *__restrict__ colidx, int32_t *__restrict__ bptr,
+                                                       int32_t *__restrict__ bidx, int *__restrict__ bad) {
+  const int64_t node = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 4;  // 16 lanes per node
+  const int lane = threadIdx.x & 15;
+  if (node > n_nodes) return;
+  if (node == n_nodes) {
+    if (lane == 0) bptr[n_nodes] = rowptr[3 * n_nodes] / 9;
+    return;
+  }
+  const int32_t s0 = rowptr[3 * node], s1 = rowptr[3 * node + 1], s3 = rowptr[3 * node + 3];
+  const int deg = (s3 - s0) / 9;
+  // the three rows of a node must have the same length and start on a block boundary
+  if (lane == 0) {
+    if (s0 % 9 != 0 || (s3 - s0) != 9 * deg || (s1 - s0) != 3 * deg || rowptr[3 * node + 2] - s1 != 3 * deg) *bad = 1;
+    bptr[node] = s0 / 9;
+  }
+  for (int j = lane; j < deg; j += 16) {
+    const int32_t c = colidx[s0 + 3 * j];
+    if (c % 3 != 0) *bad = 1;
+    bidx[s0 / 9 + j] = c / 3;
+  }
+}
+
+static size_t stream3_smem_bytes(int cap) {
+  const size_t ptr_bytes = (128 + (size_t)kStreamStages * kBlock3PtrInts * sizeof(int32_t) + 127) / 128 * 128;
+  return ptr_bytes + (size_t)kStreamStages * (9 * (size_t)cap + 2) * 8 + (size_t)kStreamStages * (cap + 8) * 4;
+}
+
+template <bool DOT, bool HALO>
+__global__ void __launch_bounds__(kStreamThreads, 2) k_spmv_stream3(
+    int32_t n_nodes, int cap /* blocks per stage */, const int32_t *__restrict__ bptr, const int32_t *__restrict__ bidx,
+    const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+    double *__restrict__ partials, PcgState *__restrict__ st, P2PDev *pp, HaloDev *hd,
+    const int32_t *__restrict__ send_idx) {
+  constexpr int T = kBlock3Tile, S = kStreamStages;
+  __shared__ double red[kStreamThreads / 32];
+  if (DOT && (st->converged | st->breakdown)) return;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *empty = full + S;
+  constexpr size_t kHdr = 128;
+  int32_t *ptr_s = reinterpret_cast<int32_t *>(smem + kHdr);
+  constexpr size_t ptr_bytes = (kHdr + (size_t)S * kBlock3PtrInts * sizeof(int32_t) + 127) / 128 * 128;
+  const size_t vstride = 9 * (size_t)cap + 2;                                             // doubles per stage
+  double *vals_s = reinterpret_cast<double *>(smem + ptr_bytes);
+  int32_t *idx_s = reinterpret_cast<int32_t *>(smem + ptr_bytes + (size_t)S * vstride * 8);  // S x (cap + 8) ints
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tiles = (n_nodes + T - 1) / T;
+  unsigned hseq = 0;
+  const uint4 *gcells = nullptr;
+  if (HALO) {
+    hseq = pp->halo_seq + 1;
+    gcells = pp->ghost[pp->rank] + (hseq & 1);
+    const int pushers = min((int)gridDim.x, 32);
+    if ((int)blockIdx.x < pushers)
+      halo_push(pp, hd, send_idx, x, hseq, blockIdx.x * kStreamThreads + tid, pushers * kStreamThreads);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], kStreamConsumerWarps);
+    }
+    ptx::mbar_init_fence();
+  }
+  __syncthreads();
+
+  double dot = 0.0;
+  if (warp == kStreamConsumerWarps) {
+    const int pl = tid & 31;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+      const int stage = j % S, use = j / S;
+      if (use > 0) {
+        if (pl == 0) ptx::mbar_wait(&empty[stage], (uint32_t)((use - 1) & 1));
+        __syncwarp();
+      }
+      const int32_t n0 = tile * T, n1 = min(n0 + T, n_nodes);
+      const int32_t b0 = __ldg(bptr + n0), b1 = __ldg(bptr + n1);
+      const int64_t e0 = 9 * (int64_t)b0, e1 = 9 * (int64_t)b1;  // value range of the tile
+      const int64_t av = e0 & ~(int64_t)1;
+      const int32_t ai = b0 & ~3;  // 16-byte aligned starts of the two slices
+      if (tile < n_tiles - 2) {
+        if (pl == 0) {
+          const uint32_t nv = ((uint32_t)(e1 - av) + 1u) & ~1u, ni = ((uint32_t)(b1 - ai) + 3u) & ~3u;
+          const bool any = b1 > b0;
+          ptx::mbar_expect_tx(&full[stage], kBlock3PtrInts * 4u + (any ? nv * 8u + ni * 4u : 0u));
+          ptx::bulk_load(ptr_s + stage * kBlock3PtrInts, bptr + (n0 & ~3), kBlock3PtrInts * 4u, &full[stage]);
+          if (any) {
+            ptx::bulk_load(vals_s + (size_t)stage * vstride, vals + av, nv * 8u, &full[stage]);
+            ptx::bulk_load(idx_s + (size_t)stage * (cap + 8), bidx + ai, ni * 4u, &full[stage]);
+          }
+        }
+      } else {
+        for (int i = pl; i <= n1 - n0; i += 32) ptr_s[stage * kBlock3PtrInts + (n0 & 3) + i] = __ldg(bptr + n0 + i);
+        for (int64_t i = pl; i < e1 - e0; i += 32) vals_s[(size_t)stage * vstride + (e0 - av) + i] = __ldg(vals + e0 + i);
+        for (int i = pl; i < b1 - b0; i += 32) idx_s[(size_t)stage * (cap + 8) + (b0 - ai) + i] = __ldg(bidx + b0 + i);
+        __syncwarp();
+        if (pl == 0) ptx::mbar_arrive(&full[stage]);
+      }
+    }
+  } else {
+    const int grp = tid >> 4, lane = tid & 15;  // 30 groups of 16 lanes
+    int j = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+      const int stage = j % S, use = j / S;
+      ptx::mbar_wait(&full[stage], (uint32_t)(use & 1));
+      const int32_t n0 = tile * T;
+      const int nn = min(T, n_nodes - n0);
+      const int32_t *ps = ptr_s + stage * kBlock3PtrInts + (n0 & 3);
+      const int32_t b0 = ps[0];
+      const double *vs = vals_s + (size_t)stage * vstride + ((9 * (int64_t)b0) & 1);
+      const int32_t *is = idx_s + (size_t)stage * (cap + 8) + (b0 - (b0 & ~3));
+      int32_t sb = 0, deg = 0;
+      if (grp < nn) {
+        sb = ps[grp] - b0;
+        deg = ps[grp + 1] - ps[grp];
+      }
+      const double *vn = vs + 9 * (size_t)sb;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      for (int k = lane; k < deg; k += 16) {
+        const int32_t c = is[sb + k];
+        double x0, x1, x2;
+        if (HALO && c >= n_nodes) {
+          const uint4 *gc = gcells + 2 * (size_t)(3 * (c - n_nodes));
+          x0 = ll_wait(gc, hseq);
+          x1 = ll_wait(gc + 2, hseq);
+          x2 = ll_wait(gc + 4, hseq);
+        } else {
+          const double *xp = x + 3 * (size_t)c;
+          x0 = __ldg(xp);
+          x1 = __ldg(xp + 1);
+          x2 = __ldg(xp + 2);
+        }
+        const double *r0 = vn + 3 * k, *r1 = r0 + 3 * deg, *r2 = r1 + 3 * deg;
+        a0 += r0[0] * x0 + r0[1] * x1 + r0[2] * x2;
+        a1 += r1[0] * x0 + r1[1] * x1 + r1[2] * x2;
+        a2 += r2[0] * x0 + r2[1] * x1 + r2[2] * x2;
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) ptx::mbar_arrive(&empty[stage]);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      }
+      if (lane == 0 && grp < nn) {
+        double *yp = y + 3 * (size_t)(n0 + grp);
+        yp[0] = a0;
+        yp[1] = a1;
+        yp[2] = a2;
+        if (DOT) {
+          const double *xs = x + 3 * (size_t)(n0 + grp);
+          dot += a0 * xs[0] + a1 * xs[1] + a2 * xs[2];
+        }
+      }
+    }
+  }
+  if (DOT) {
+    const double loc[1] = {dot};
+    publish_and_reduce<1, kStreamThreads>(loc, partials, st, 0, red);
+  }
+  if (HALO) {
+    __syncthreads();
+    if (tid == 0 && atomicAdd(&hd->ticket, 1u) == gridDim.x - 1) {
+      hd->ticket = 0;
+      pp->halo_seq = hseq;
+    }
+  }
+}
+
 // max over the tiles of the streamed scalar kernel of (entries in the tile): sizes its ring stages
 __global__ void __launch_bounds__(256) k_tile_max_entries(int32_t n_rows, int32_t tile, const int32_t *__restrict__ rowptr,
                                                          int *__restrict__ out) {
@@ -415,6 +601,7 @@ static size_t stream1_smem_bytes(int cap, int passes) {
 struct StreamPlan {
   bool on = false;
   bool scalar = false;  // k_spmv_stream1 (1 DOF per node) instead of the 2x2-block kernel
+  bool bs3 = false;     // k_spmv_stream3 (3 DOF per node)
   int passes = 4;       // k_spmv_stream1: rows per 8-lane group and tile (4, 2 or 1)
   int T = 0, cap = 0, grid = 0;
   size_t smem = 0;

@@ -102,8 +102,8 @@ class DeviceMesh:
     @property
     def block_dim(self):
         """What the solve entry points may assume about the CSR (fe_b200.h): 2 = rows come in
-        (2i, 2i+1) pairs sharing one column list of (2m, 2m+1) pairs; 1 = nothing."""
-        return self.dim if self.dim in (1, 2) else 1
+        (2i, 2i+1) pairs sharing one column list of (2m, 2m+1) pairs; 3 = triples likewise; 1 = nothing."""
+        return self.dim if self.dim in (1, 2, 3) else 1
 
     def _vouch_pattern(self):
         """fe_pcg_cache_pattern: the CSR tensors of csr_pattern() live as long as this object and

@@ -155,7 +155,9 @@ int fe_scatter_add(fe_ctx *ctx, void *stream, int32_t n, const int32_t *dof, con
  * fe_plan with dim == 2 (rows 2i and 2i+1 share one column list made of (2m, 2m+1) pairs;
  * fe_dirichlet_apply keeps that structure), which lets the SpMV read ONE column index per
  * 2x2 block and use 128-bit loads.  Passing 2 for a matrix without that structure is an error
- * the library cannot detect.
+ * the library cannot detect.  3 = the CSR was produced by fe_tet_plan_create (rows 3i .. 3i+2 share one
+ * column list of (3m, 3m+1, 3m+2) triples): the PCG's SpMV reads one column index per 3x3 block; this
+ * structure IS verified when the solver builds its node-level pattern (a CSR without it takes the scalar path).
  *
  * y = A x, CSR, sub-warp-per-row (block_dim 1) or 8-lanes-per-node (block_dim 2). */
 int fe_spmv(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,

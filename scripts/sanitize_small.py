@@ -28,5 +28,21 @@ m3 = np.array([[210e9, 0.25, 1.0, 7860.0], [70e9, 0.3, 1.0, 2700.0]])
 for v in (0, 6, 5, 4, 3, 2, 1):
     d3.assemble(KIND_ELAST_TET, m3, variant=v)
     d3.assemble(KIND_MASS_TET, m3, variant=v)
+# a few PCG iterations on the tetrahedral matrix: the 3x3-block streamed SpMV (k_block_pattern3, k_spmv_stream3)
+kv = d3.assemble(KIND_ELAST_TET, m3)
+n3 = d3.n_rows
+left = np.nonzero(c3[:, 0] == 0)[0]
+bc3 = (3 * left[:, None] + np.arange(3)[None, :]).reshape(-1)
+rhs3 = torch.ones(n3, dtype=torch.float64, device="cuda")
+d3.dirichlet(kv, rhs3, bc3, np.zeros(len(bc3)))
+x3 = torch.zeros(n3, dtype=torch.float64, device="cuda")
+d3.pcg_fixed(kv, rhs3, x3, 10, work=d3.pcg_workspace())
+# and on the 2-DOF matrix (k_spmv_stream)
+kk = dm.assemble(KIND_ELAST_PSTRESS, mat)
+bc2 = np.arange(0, 2 * 34, dtype=np.int64)
+rhs2 = torch.ones(dm.n_rows, dtype=torch.float64, device="cuda")
+dm.dirichlet(kk, rhs2, bc2, np.zeros(len(bc2)))
+x2 = torch.zeros(dm.n_rows, dtype=torch.float64, device="cuda")
+dm.pcg_fixed(kk, rhs2, x2, 10, work=dm.pcg_workspace())
 torch.cuda.synchronize()
 print("sanitize_small: done", float(k.abs().sum()), dm.fan_record_bytes)
