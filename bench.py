@@ -535,7 +535,7 @@ def run_modal(k, nx, ny, device):
     step_bytes = 12.0 * dm.nnz + 4.0 * n + 48.0 * block * n   # vals + colidx, rowptr, (d, r, z) read + (d', r, z) written
     peak, peak_kind = measured_peak_hbm()
     steps = info.iterations * max(info.get("cheb_degree", 1) - 1, 1)
-    return {"roofline": {"bound": "hbm", "kernel": "k_spmm<CPL,G,0,1> (fused Chebyshev step, fe_cheb_step)",
+    return {"roofline": {"bound": "hbm", "kernel": "k_spmm_b2<CPL,G,0,1> (fused Chebyshev step on 2x2 node blocks, fe_cheb_step)",
                          "achieved": step_bytes / t_step / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": step_bytes / t_step / 1e9 / peak, "peak_kind": peak_kind, "traffic": None,
                          "algorithmic_bytes_per_step": step_bytes, "ms_per_step": 1e3 * t_step, "block_columns": block,

@@ -49,8 +49,8 @@ SIGNATURES = {
     "fe_tet_elem_post": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "fe_tet_plan_create": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, C.POINTER(_vp)]),
     "fe_tet_assemble": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _i32, _vp, _i32]),
-    "fe_spmm_pair": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
-    "fe_cheb_step": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _i32]),
+    "fe_spmm_pair": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32]),
+    "fe_cheb_step": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f64, _f64, _i32, _i32]),
     "fe_csr_diagonal": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "fe_pcg_work_len": (_i64, [_i32, _i32]),
     "fe_pcg_cache_pattern": (C.c_int, [_vp, _vp, _vp, _i64]),

@@ -105,6 +105,108 @@ __global__ void __launch_bounds__(256) k_spmm(int32_t n_rows, int32_t m, const i
   }
 }
 
+// Node-blocked form for 2 DOF per node (block_dim == 2, the CSR of an fe_plan with dim == 2): G lanes own a NODE,
+// i.e. rows 2i and 2i+1, which share one column list of (2m, 2m+1) pairs.  Per 2x2 block a lane loads the column
+// index once, the four matrix values as two 16-byte broadcasts, and the two rows of X once for BOTH output rows --
+// the row-per-group kernel above fetched every row of X twice (ncu r01: the fused Chebyshev step at 0.52 of its
+// roofline, L1 wavefronts of the 96-byte row gathers).  Entries are added in the same order as above (k_r0 x_2m, then
+// k_r1 x_2m+1, block after block): bit-identical results.
+template <int CPL, int G, bool PAIR, int EPI>
+__global__ void __launch_bounds__(256) k_spmm_b2(int32_t n_nodes, int32_t m, const int32_t *__restrict__ rowptr,
+                                                const int32_t *__restrict__ colidx, const double *__restrict__ va,
+                                                const double *__restrict__ vb, const double *__restrict__ X,
+                                                double *__restrict__ YA, double *__restrict__ YB,
+                                                const double *__restrict__ dinv, double *__restrict__ r,
+                                                double *__restrict__ z, double c1, double c2) {
+  const int64_t node = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
+  const int lane = threadIdx.x % G;
+  if (node >= n_nodes) return;
+  const int32_t s0 = __ldg(rowptr + 2 * node), s1 = __ldg(rowptr + 2 * node + 1);
+  const int nb = (s1 - s0) >> 1;  // 2x2 blocks in the node's rows
+  for (int c0 = 0; c0 < m; c0 += G * CPL) {
+    const int col = c0 + lane * CPL;
+    if (col >= m) continue;  // m % CPL == 0: a lane is fully on or fully off
+    const double *xc = X + col;
+    double a0[CPL], a1[CPL], b0[CPL], b1[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) a0[q] = a1[q] = b0[q] = b1[q] = 0.0;
+    auto load_x = [&](int64_t row, double *x) {
+      const double *src = xc + row * m;
+      if (CPL == 4) {
+        const double2 lo = __ldg(reinterpret_cast<const double2 *>(src));
+        const double2 hi = __ldg(reinterpret_cast<const double2 *>(src) + 1);
+        x[0] = lo.x, x[1] = lo.y, x[2 % CPL] = hi.x, x[3 % CPL] = hi.y;
+      } else if (CPL == 2) {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(src));
+        x[0] = v.x, x[1 % CPL] = v.y;
+      } else {
+        x[0] = __ldg(src);
+      }
+    };
+    auto block = [&](int jb, int32_t c, const double *x0, const double *x1) {
+      // (rows start on multiples of 4 entries and hold pairs: the value pairs are 16-byte aligned)
+      const double2 k0 = __ldg(reinterpret_cast<const double2 *>(va + s0) + jb);
+      const double2 k1 = __ldg(reinterpret_cast<const double2 *>(va + s1) + jb);
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+        a0[q] = fma(k0.x, x0[q], a0[q]);
+        a0[q] = fma(k0.y, x1[q], a0[q]);
+        a1[q] = fma(k1.x, x0[q], a1[q]);
+        a1[q] = fma(k1.y, x1[q], a1[q]);
+      }
+      if (PAIR) {
+        const double2 m0 = __ldg(reinterpret_cast<const double2 *>(vb + s0) + jb);
+        const double2 m1 = __ldg(reinterpret_cast<const double2 *>(vb + s1) + jb);
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          b0[q] = fma(m0.x, x0[q], b0[q]);
+          b0[q] = fma(m0.y, x1[q], b0[q]);
+          b1[q] = fma(m1.x, x0[q], b1[q]);
+          b1[q] = fma(m1.y, x1[q], b1[q]);
+        }
+      }
+      (void)c;
+    };
+    int jb = 0;
+    for (; jb + 2 <= nb; jb += 2) {  // two blocks in flight
+      const int32_t ca = __ldg(colidx + s0 + 2 * jb), cb = __ldg(colidx + s0 + 2 * jb + 2);
+      double xa0[CPL], xa1[CPL], xb0[CPL], xb1[CPL];
+      load_x(ca, xa0);
+      load_x((int64_t)ca + 1, xa1);
+      load_x(cb, xb0);
+      load_x((int64_t)cb + 1, xb1);
+      block(jb, ca, xa0, xa1);
+      block(jb + 1, cb, xb0, xb1);
+    }
+    if (jb < nb) {
+      const int32_t ca = __ldg(colidx + s0 + 2 * jb);
+      double xa0[CPL], xa1[CPL];
+      load_x(ca, xa0);
+      load_x((int64_t)ca + 1, xa1);
+      block(jb, ca, xa0, xa1);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int64_t row = 2 * node + rr;
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+        const int64_t o = row * m + col + q;
+        const double ya = rr ? a1[q] : a0[q];
+        if (EPI == 0) {
+          YA[o] = ya;
+          if (PAIR) YB[o] = rr ? b1[q] : b0[q];
+        } else {
+          const double xr = __ldg(X + o);
+          const double rn = r[o] - ya;
+          z[o] += xr;
+          r[o] = rn;
+          YA[o] = c1 * xr + c2 * (__ldg(dinv + row) * rn);
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_csr_diag(int32_t n_rows, const int32_t *__restrict__ rowptr,
                                                  const int32_t *__restrict__ colidx,
                                                  const double *__restrict__ vals, double *__restrict__ diag) {
@@ -125,12 +227,17 @@ static void spmm_shape(int m, int *cpl, int *g) {
 template <bool PAIR, int EPI>
 static void spmm_launch(cudaStream_t s, int32_t n_rows, int32_t m, const int32_t *rowptr, const int32_t *colidx,
                         const double *va, const double *vb, const double *x, double *ya, double *yb,
-                        const double *dinv, double *r, double *z, double c1, double c2) {
+                        const double *dinv, double *r, double *z, double c1, double c2, bool block2) {
   int cpl, g;
   spmm_shape(m, &cpl, &g);
-  const int grid = grid_for((int64_t)n_rows * g, 256);
-#define FE_SPMM(CPL, G) \
-  k_spmm<CPL, G, PAIR, EPI><<<grid, 256, 0, s>>>(n_rows, m, rowptr, colidx, va, vb, x, ya, yb, dinv, r, z, c1, c2)
+  const int grid = grid_for((int64_t)(block2 ? n_rows / 2 : n_rows) * g, 256);
+#define FE_SPMM(CPL, G)                                                                                                  \
+  do {                                                                                                                   \
+    if (block2)                                                                                                          \
+      k_spmm_b2<CPL, G, PAIR, EPI><<<grid, 256, 0, s>>>(n_rows / 2, m, rowptr, colidx, va, vb, x, ya, yb, dinv, r, z, c1, c2); \
+    else                                                                                                                 \
+      k_spmm<CPL, G, PAIR, EPI><<<grid, 256, 0, s>>>(n_rows, m, rowptr, colidx, va, vb, x, ya, yb, dinv, r, z, c1, c2);   \
+  } while (0)
 #define FE_SPMM_G(CPL)                    \
   switch (g) {                            \
     case 1: FE_SPMM(CPL, 1); break;       \
@@ -158,32 +265,34 @@ using namespace fe;
 extern "C" {
 
 int fe_spmm_pair(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr, const int32_t *colidx,
-                 const double *vals_a, const double *vals_b, const double *x, double *y_a, double *y_b, int32_t m) {
+                 const double *vals_a, const double *vals_b, const double *x, double *y_a, double *y_b, int32_t m,
+                 int32_t block_dim) {
   FE_REQUIRE(ctx && rowptr && colidx && vals_a && x && y_a, "fe_spmm_pair: NULL argument");
   FE_REQUIRE((vals_b == nullptr) == (y_b == nullptr), "fe_spmm_pair: vals_b and y_b go together");
   FE_REQUIRE(m >= 1 && m <= 1024, "fe_spmm_pair: block width %d outside [1, 1024]", m);
   FE_REQUIRE(((uintptr_t)x & 15) == 0, "fe_spmm_pair: x must be 16-byte aligned");
   if (n_rows <= 0) return FE_OK;
   cudaStream_t s = as_stream(stream);
+  const bool b2 = block_dim == 2 && n_rows % 2 == 0 && ((uintptr_t)vals_a & 15) == 0 && ((uintptr_t)vals_b & 15) == 0;
   if (vals_b)
-    spmm_launch<true, 0>(s, n_rows, m, rowptr, colidx, vals_a, vals_b, x, y_a, y_b, nullptr, nullptr, nullptr, 0, 0);
+    spmm_launch<true, 0>(s, n_rows, m, rowptr, colidx, vals_a, vals_b, x, y_a, y_b, nullptr, nullptr, nullptr, 0, 0, b2);
   else
     spmm_launch<false, 0>(s, n_rows, m, rowptr, colidx, vals_a, nullptr, x, y_a, nullptr, nullptr, nullptr, nullptr, 0,
-                          0);
+                          0, b2);
   FE_LAUNCH_CHECK(ctx);
   return FE_OK;
 }
 
 int fe_cheb_step(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr, const int32_t *colidx,
                  const double *vals, const double *dinv, const double *d_in, double *d_out, double *r, double *z,
-                 double c1, double c2, int32_t m) {
+                 double c1, double c2, int32_t m, int32_t block_dim) {
   FE_REQUIRE(ctx && rowptr && colidx && vals && dinv && d_in && d_out && r && z, "fe_cheb_step: NULL argument");
   FE_REQUIRE(d_in != d_out, "fe_cheb_step: d_out must not alias d_in (rows are still gathering from it)");
   FE_REQUIRE(m >= 1 && m <= 1024, "fe_cheb_step: block width %d outside [1, 1024]", m);
   FE_REQUIRE(((uintptr_t)d_in & 15) == 0, "fe_cheb_step: d_in must be 16-byte aligned");
   if (n_rows <= 0) return FE_OK;
   spmm_launch<false, 1>(as_stream(stream), n_rows, m, rowptr, colidx, vals, nullptr, d_in, d_out, nullptr, dinv, r, z,
-                        c1, c2);
+                        c1, c2, block_dim == 2 && n_rows % 2 == 0 && ((uintptr_t)vals & 15) == 0);
   FE_LAUNCH_CHECK(ctx);
   return FE_OK;
 }

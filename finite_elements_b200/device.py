@@ -232,7 +232,7 @@ class DeviceMesh:
             yb = out_b if out_b is not None else torch.empty(self.n_rows, m, dtype=torch.float64, device=x.device)
         with torch.cuda.device(self.ctx.device):
             check(lib.fe_spmm_pair(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals_a),
-                                   _ptr(vals_b), _ptr(x), _ptr(ya), _ptr(yb), m))
+                                   _ptr(vals_b), _ptr(x), _ptr(ya), _ptr(yb), m, self.block_dim))
         return ya, yb
 
     def cheb_step(self, vals, dinv, d_in, d_out, r, z, c1, c2):
@@ -244,7 +244,7 @@ class DeviceMesh:
         with torch.cuda.device(self.ctx.device):
             check(lib.fe_cheb_step(self.ctx.handle, _stream(), self.n_rows, _ptr(rowptr), _ptr(colidx), _ptr(vals),
                                    _ptr(dinv), _ptr(d_in), _ptr(d_out), _ptr(r), _ptr(z), float(c1), float(c2),
-                                   int(d_in.shape[1])))
+                                   int(d_in.shape[1]), self.block_dim))
 
     def csr_diagonal(self, vals):
         rowptr, colidx = self.csr_pattern()

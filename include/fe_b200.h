@@ -206,17 +206,19 @@ int fe_tet_assemble(fe_ctx *ctx, void *stream, const fe_plan *plan, int kind, co
  * The reference gives K and M to scipy.sparse.linalg.eigsh (:779-782), whose Lanczos loop
  * multiplies one vector at a time; the LOBPCG driver of the host layer works on blocks of m
  * vectors.  y_a = A x and (when vals_b / y_b are non-NULL) y_b = B x in one pass over the
- * pattern both matrices share.  x: double[n_cols][m] row-major, y_*: double[n_rows][m]. */
+ * pattern both matrices share.  x: double[n_cols][m] row-major, y_*: double[n_rows][m].
+ * block_dim as in the solve entry points below: 2 lets a group of lanes own both rows of a node and fetch every
+ * row of x once for the two of them (bit-identical results); 1 (or 3) = row by row. */
 int fe_spmm_pair(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
                  const int32_t *colidx, const double *vals_a, const double *vals_b,
-                 const double *x, double *y_a, double *y_b, int32_t m);
+                 const double *x, double *y_a, double *y_b, int32_t m, int32_t block_dim);
 /* One step of the Chebyshev iteration that preconditions the block eigensolver, fused into the
  * block product (all of it is row-local once y = A d_in is known):
  *   z += d_in;  r -= A d_in;  d_out = c1 d_in + c2 diag(dinv) r          (blocks are [n][m])
  * d_out must not alias d_in. */
 int fe_cheb_step(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
                  const int32_t *colidx, const double *vals, const double *dinv, const double *d_in,
-                 double *d_out, double *r, double *z, double c1, double c2, int32_t m);
+                 double *d_out, double *r, double *z, double c1, double c2, int32_t m, int32_t block_dim);
 /* diag[i] = A[i][i] (0 if the entry is not stored): the Jacobi preconditioner of the block solver */
 int fe_csr_diagonal(fe_ctx *ctx, void *stream, int32_t n_rows, const int32_t *rowptr,
                     const int32_t *colidx, const double *vals, double *diag);
