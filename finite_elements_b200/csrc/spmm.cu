@@ -19,6 +19,17 @@
 
 namespace fe {
 
+// 256-bit global accesses (one sector per lane and instruction; two 128-bit halves count the sector twice in L1)
+__device__ __forceinline__ void ld4_nc(const double *p, double *x) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld4(const double *p, double *x) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st4(double *p, const double *x) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
+}
+
 // CPL columns per lane (1, 2 or 4: one 8-, 16- or 32-byte load of X per matrix entry), G lanes per
 // row.  EPI selects what happens to y = A x in the epilogue:
 //   0  Y_A = y (and Y_B = B x when PAIR)
@@ -117,7 +128,7 @@ __global__ void __launch_bounds__(256) k_spmm_b2(int32_t n_nodes, int32_t m, con
                                                 const double *__restrict__ vb, const double *__restrict__ X,
                                                 double *__restrict__ YA, double *__restrict__ YB,
                                                 const double *__restrict__ dinv, double *__restrict__ r,
-                                                double *__restrict__ z, double c1, double c2) {
+                                                double *__restrict__ z, double c1, double c2, bool vec32) {
   const int64_t node = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
   const int lane = threadIdx.x % G;
   if (node >= n_nodes) return;
@@ -132,7 +143,9 @@ __global__ void __launch_bounds__(256) k_spmm_b2(int32_t n_nodes, int32_t m, con
     for (int q = 0; q < CPL; ++q) a0[q] = a1[q] = b0[q] = b1[q] = 0.0;
     auto load_x = [&](int64_t row, double *x) {
       const double *src = xc + row * m;
-      if (CPL == 4) {
+      if (CPL == 4 && vec32) {
+        ld4_nc(src, x);
+      } else if (CPL == 4) {
         const double2 lo = __ldg(reinterpret_cast<const double2 *>(src));
         const double2 hi = __ldg(reinterpret_cast<const double2 *>(src) + 1);
         x[0] = lo.x, x[1] = lo.y, x[2 % CPL] = hi.x, x[3 % CPL] = hi.y;
@@ -188,19 +201,42 @@ __global__ void __launch_bounds__(256) k_spmm_b2(int32_t n_nodes, int32_t m, con
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       const int64_t row = 2 * node + rr;
-#pragma unroll
-      for (int q = 0; q < CPL; ++q) {
-        const int64_t o = row * m + col + q;
-        const double ya = rr ? a1[q] : a0[q];
+      const int64_t o0 = row * m + col;
+      const double *ya = rr ? a1 : a0;
+      if (CPL == 4 && vec32) {  // whole 32-byte pieces: one access per array instead of four
         if (EPI == 0) {
-          YA[o] = ya;
-          if (PAIR) YB[o] = rr ? b1[q] : b0[q];
+          st4(YA + o0, ya);
+          if (PAIR) st4(YB + o0, rr ? b1 : b0);
         } else {
-          const double xr = __ldg(X + o);
-          const double rn = r[o] - ya;
-          z[o] += xr;
-          r[o] = rn;
-          YA[o] = c1 * xr + c2 * (__ldg(dinv + row) * rn);
+          double xr[4], rv[4], zv[4], out[4];
+          ld4_nc(X + o0, xr);
+          ld4(r + o0, rv);
+          ld4(z + o0, zv);
+          const double di = __ldg(dinv + row);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            rv[q] -= ya[q];
+            zv[q] += xr[q];
+            out[q] = c1 * xr[q] + c2 * (di * rv[q]);
+          }
+          st4(z + o0, zv);
+          st4(r + o0, rv);
+          st4(YA + o0, out);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+          const int64_t o = o0 + q;
+          if (EPI == 0) {
+            YA[o] = ya[q];
+            if (PAIR) YB[o] = rr ? b1[q] : b0[q];
+          } else {
+            const double xr = __ldg(X + o);
+            const double rn = r[o] - ya[q];
+            z[o] += xr;
+            r[o] = rn;
+            YA[o] = c1 * xr + c2 * (__ldg(dinv + row) * rn);
+          }
         }
       }
     }
@@ -231,10 +267,13 @@ static void spmm_launch(cudaStream_t s, int32_t n_rows, int32_t m, const int32_t
   int cpl, g;
   spmm_shape(m, &cpl, &g);
   const int grid = grid_for((int64_t)(block2 ? n_rows / 2 : n_rows) * g, 256);
+  // 256-bit accesses need 32-byte aligned blocks (row pitch 8 m bytes with m % 4 == 0 keeps every piece aligned)
+  const bool vec32 = m % 4 == 0 && (((uintptr_t)x | (uintptr_t)ya | (uintptr_t)yb | (uintptr_t)r | (uintptr_t)z) & 31) == 0;
 #define FE_SPMM(CPL, G)                                                                                                  \
   do {                                                                                                                   \
     if (block2)                                                                                                          \
-      k_spmm_b2<CPL, G, PAIR, EPI><<<grid, 256, 0, s>>>(n_rows / 2, m, rowptr, colidx, va, vb, x, ya, yb, dinv, r, z, c1, c2); \
+      k_spmm_b2<CPL, G, PAIR, EPI><<<grid, 256, 0, s>>>(n_rows / 2, m, rowptr, colidx, va, vb, x, ya, yb, dinv, r, z, c1, c2, \
+                                                        vec32);                                                          \
     else                                                                                                                 \
       k_spmm<CPL, G, PAIR, EPI><<<grid, 256, 0, s>>>(n_rows, m, rowptr, colidx, va, vb, x, ya, yb, dinv, r, z, c1, c2);   \
   } while (0)
