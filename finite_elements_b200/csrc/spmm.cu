@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) k_spmm(int32_t n_rows, int32_t m, const i
                                              const double *__restrict__ vb, const double *__restrict__ X,
                                              double *__restrict__ YA, double *__restrict__ YB,
                                              const double *__restrict__ dinv, double *__restrict__ r,
-                                             double *__restrict__ z, double c1, double c2) {
+                                             double *__restrict__ z, double c1, double c2, bool vec32) {
   const int64_t row = ((int64_t)blockIdx.x * 256 + threadIdx.x) / G;
   const int lane = threadIdx.x % G;
   if (row >= n_rows) return;
@@ -56,7 +56,9 @@ __global__ void __launch_bounds__(256) k_spmm(int32_t n_rows, int32_t m, const i
     for (int q = 0; q < CPL; ++q) accA[q] = accB[q] = 0.0;
     auto load_x = [&](int32_t c, double *x) {
       const double *src = xc + (int64_t)c * m;
-      if (CPL == 4) {
+      if (CPL == 4 && vec32) {
+        ld4_nc(src, x);
+      } else if (CPL == 4) {
         const double2 lo = __ldg(reinterpret_cast<const double2 *>(src));
         const double2 hi = __ldg(reinterpret_cast<const double2 *>(src) + 1);
         x[0] = lo.x, x[1] = lo.y, x[2 % CPL] = hi.x, x[3 % CPL] = hi.y;
@@ -275,7 +277,8 @@ static void spmm_launch(cudaStream_t s, int32_t n_rows, int32_t m, const int32_t
       k_spmm_b2<CPL, G, PAIR, EPI><<<grid, 256, 0, s>>>(n_rows / 2, m, rowptr, colidx, va, vb, x, ya, yb, dinv, r, z, c1, c2, \
                                                         vec32);                                                          \
     else                                                                                                                 \
-      k_spmm<CPL, G, PAIR, EPI><<<grid, 256, 0, s>>>(n_rows, m, rowptr, colidx, va, vb, x, ya, yb, dinv, r, z, c1, c2);   \
+      k_spmm<CPL, G, PAIR, EPI><<<grid, 256, 0, s>>>(n_rows, m, rowptr, colidx, va, vb, x, ya, yb, dinv, r, z, c1, c2,    \
+                                                     vec32);                                                             \
   } while (0)
 #define FE_SPMM_G(CPL)                    \
   switch (g) {                            \
