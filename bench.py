@@ -111,26 +111,25 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)
         self.proc.terminate()
-        rows = list(self.rows)
-        inside = [r for t, r in rows if t0 is not None and t0 <= t <= t1]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
+        for t, r in list(self.rows):  # keep the rows that parse (a line can arrive truncated when the sampler is killed)
+            try:
+                rows.append((t, float(r[0]), float(r[1]),
+                             {nm for k, nm in enumerate(names) if r[3 + k].lower().startswith("active")}))
+            except Exception:  # noqa: BLE001
+                pass
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
         where = "inside timed region"
         if not inside and rows and t0 is not None:
             mid = 0.5 * (t0 + t1)
-            inside = [r for _, r in sorted(rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
             where = "nearest to timed region"
         elif t0 is None:
-            inside = [r for _, r in rows]
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in inside:
-            try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for k, nm in enumerate(names):
-                    if r[3 + k].lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:  # noqa: BLE001
-                pass
+            inside = rows
+        sm = [r[1] for r in inside]
+        mx = inside[-1][2] if inside else None
+        reasons = set().union(*[r[3] for r in inside]) if inside else set()
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm), "where": where}
 

@@ -498,3 +498,48 @@ def test_magnetic_properties_at_s1m():
     true = float(torch.linalg.norm(rhs - dm.spmv(vals, u)) / torch.linalg.norm(rhs))
     assert relres <= 1e-6 and abs(true - relres) <= 1e-3 * relres, (iters, relres, true)
     assert float(u[right.long()].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dofs", [1, 2, 3])
+def test_streamed_spmv_kernels_vs_scipy_cg(dofs):
+    """The PCG's SpMV is a different kernel per DOF count (k_spmv_stream1 / k_spmv_stream / k_spmv_stream3: TMA-streamed
+    tiles, one column index per entry / 2x2 block / 3x3 block).  Three iterations of fe_pcg_fixed from x = 0 must
+    reproduce the same three Jacobi-PCG iterations done with scipy on the matrix copied to the host."""
+    import torch
+    from oracle import numpy_oracle as no
+    from finite_elements_b200.device import DeviceMesh, DeviceMesh3D, KIND_MAGNETIC, KIND_ELAST_PSTRESS, KIND_ELAST_TET
+    rng = np.random.default_rng(11)
+    if dofs == 3:
+        coords, conn = no.structured_tet_mesh(13, 9, 7, h=0.3, jitter=0.15, seed=2)
+        dm = DeviceMesh3D(coords, conn, None)
+        vals = dm.assemble(KIND_ELAST_TET, np.array([[2.0e3, 0.3, 1.0, 1.0]]))
+        fixed = np.nonzero(coords[:, 0] == 0)[0]
+    else:
+        coords, conn = no.structured_mesh(97, 61, jitter=0.2, seed=4)
+        dm = DeviceMesh(coords, conn, None, dim=dofs)
+        mat = np.array([[1.0e3, 0.3, 1.0, 1.0]]) if dofs == 2 else np.array([[2.0, 0, 0, 0]])
+        vals = dm.assemble(KIND_ELAST_PSTRESS if dofs == 2 else KIND_MAGNETIC, mat)
+        fixed = np.nonzero(coords[:, 0] == 0)[0]
+    n = dm.n_rows
+    bc = (dofs * fixed[:, None] + np.arange(dofs)[None, :]).reshape(-1)
+    b = torch.as_tensor(rng.standard_normal(n)).cuda()
+    dm.dirichlet(vals, b, bc, np.zeros(len(bc)))
+    a = dm.to_scipy(vals)
+    bh = b.cpu().numpy()
+    dinv = 1.0 / a.diagonal()
+    x, r = np.zeros(n), bh.copy()
+    z = dinv * r
+    p, rz = z.copy(), r @ z
+    for _ in range(3):                                   # textbook PCG, the recurrence solve.cu implements
+        q = a @ p
+        alpha = rz / (p @ q)
+        x += alpha * p
+        r -= alpha * q
+        z = dinv * r
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    xd = torch.zeros(n, dtype=torch.float64, device="cuda")
+    dm.pcg_fixed(vals, b, xd, 3)
+    err = np.abs(xd.cpu().numpy() - x).max() / np.abs(x).max()
+    assert err <= 1e-12, err
