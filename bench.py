@@ -539,7 +539,7 @@ def run_modal(k, nx, ny, device):
                          "frac": step_bytes / t_step / 1e9 / peak, "peak_kind": peak_kind, "traffic": None,
                          "algorithmic_bytes_per_step": step_bytes, "ms_per_step": 1e3 * t_step, "block_columns": block,
                          "steps_in_solve": steps, "share_of_solve": steps * t_step / t if t > 0 else None},
-            "cheb_degree": info.get("cheb_degree"),
+            "cheb_degree": info.get("cheb_degree"), "prof": info.get("prof"),
             "workload": f"lowest {k} modes, {nx}x{ny}-cell plane-stress mesh ({2 * nx * ny} triangles, "
                         f"{dm.n_rows} DOF), free-free", "seconds": t, "iterations": info.iterations,
             "block_products": info.products, "converged": info.converged,
