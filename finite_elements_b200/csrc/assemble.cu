@@ -360,13 +360,10 @@ struct FanRec<true> {
 
 #include "fan_kernel.cuh"
 
-static int fan_warp_slot_bytes(int dim, int max_degree, int npl) { return dim * dim * max_degree * kFanChunk * npl * 8; }
-// (fan_tile_max is the record count of the fullest 32-node chunk; a chunk of npl * 32 nodes is npl such chunks)
-static int fan_rec_cap(int fan_tile_max, bool r4, int npl) {
-  return r4 ? ((npl * fan_tile_max + 7) & ~3) : ((npl * fan_tile_max + 3) & ~1);
-}
-static size_t fan_smem_bytes(int dim, int max_degree, int fan_tile_max, bool r4, int npl) {
-  return kFanWarps * fan_warp_bytes(fan_rec_cap(fan_tile_max, r4, npl), fan_warp_slot_bytes(dim, max_degree, npl), r4, npl);
+static int fan_warp_slot_bytes(int dim, int max_degree) { return dim * dim * max_degree * kFanChunk * 8; }
+static int fan_rec_cap(int fan_tile_max, bool r4) { return r4 ? ((fan_tile_max + 7) & ~3) : ((fan_tile_max + 3) & ~1); }
+static size_t fan_smem_bytes(int dim, int max_degree, int fan_tile_max, bool r4) {
+  return kFanWarps * fan_warp_bytes(fan_rec_cap(fan_tile_max, r4), fan_warp_slot_bytes(dim, max_degree), r4);
 }
 static size_t tile_smem_bytes(int dim, int max_degree) {
   return ((kTile + 1) * sizeof(int32_t) + 15) / 16 * 16 + (size_t)dim * dim * max_degree * (kTile + 1) * sizeof(double);
@@ -395,10 +392,9 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
   bool r4 = p->fan_compact_ok && variant != 4;
   size_t smem = tile_smem_bytes(dim, p->max_degree);
   const size_t smem_limit = 200 * 1024;
-  const int npl = fan_npl(kind == FE_MAGNETIC ? 2 : 0);
-  if (r4 && fan_smem_bytes(dim, p->max_degree, p->fan_tile_max, true, npl) > smem_limit) r4 = false;
-  const size_t smem_fan = fan_smem_bytes(dim, p->max_degree, p->fan_tile_max, r4, npl);
-  const int rec_cap = fan_rec_cap(p->fan_tile_max, r4, npl);
+  if (r4 && fan_smem_bytes(dim, p->max_degree, p->fan_tile_max, true) > smem_limit) r4 = false;
+  const size_t smem_fan = fan_smem_bytes(dim, p->max_degree, p->fan_tile_max, r4);
+  const int rec_cap = fan_rec_cap(p->fan_tile_max, r4);
   if (variant == 0) variant = (p->fan_ok && smem_fan <= smem_limit) ? 3 : ((smem <= smem_limit) ? 2 : 1);
   if (variant == 4) variant = 3;
   if (variant == 3) smem = smem_fan;
@@ -415,11 +411,10 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
     FE_CUDA(cudaFuncSetAttribute(k_assemble_fan<KC, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     FE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&minb, k_assemble_fan<KC, R4>, kFanThreads, smem));   \
     if (minb < 1) minb = 1;                                                                                     \
-    const int cgrid = grid_for(p->n_owned, kFanThreads * npl);                                                  \
-    const int fgrid = cgrid < minb * ctx->num_sms ? cgrid : minb * ctx->num_sms;                                \
+    const int fgrid = grid < minb * ctx->num_sms ? grid : minb * ctx->num_sms;                                  \
     k_assemble_fan<KC, R4><<<fgrid, kFanThreads, smem, st>>>(p->n_owned, p->fan_ptr, RECS, p->fan_hdr,          \
                                                              p->adj_ptr, xy, tab, vals, rec_cap,                \
-                                                             fan_warp_slot_bytes(dim, p->max_degree, npl));     \
+                                                             fan_warp_slot_bytes(dim, p->max_degree));          \
   } while (0)
 #define FE_ASM_LAUNCH(KC)                                                                                       \
   do {                                                                                                          \

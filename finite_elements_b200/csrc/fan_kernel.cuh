@@ -29,16 +29,12 @@
 constexpr int kFanThreads = 128;
 constexpr int kFanWarps = 4;
 
-// npl = nodes per lane: a chunk holds 32 * npl consecutive nodes (1 for the 2-DOF kinds; 2 for the scalar kind, whose
-// per-chunk fixed work -- ring refill, barrier, store -- was half of its instructions at 32 nodes, ncu r02 capture AD)
-__host__ __device__ constexpr int fan_ptr_ints(int npl) { return (kFanChunk * npl + 1 + 3) & ~3; }
-__host__ __device__ inline size_t fan_stage_bytes(int rec_cap, bool r4, int npl) {
-  return ((size_t)(r4 ? 3 : 2) * fan_ptr_ints(npl) * sizeof(int32_t) + (size_t)rec_cap * (r4 ? 4 : 8) + 15) / 16 * 16;
+__host__ __device__ inline size_t fan_stage_bytes(int rec_cap, bool r4) {
+  return ((size_t)(r4 ? 3 : 2) * kFanPtrInts * sizeof(int32_t) + (size_t)rec_cap * (r4 ? 4 : 8) + 15) / 16 * 16;
 }
-__host__ __device__ inline size_t fan_warp_bytes(int rec_cap, int warp_slot_bytes, bool r4, int npl) {
-  return (32 + 2 * fan_stage_bytes(rec_cap, r4, npl) + (size_t)warp_slot_bytes + 127) / 128 * 128;
+__host__ __device__ inline size_t fan_warp_bytes(int rec_cap, int warp_slot_bytes, bool r4) {
+  return (32 + 2 * fan_stage_bytes(rec_cap, r4) + (size_t)warp_slot_bytes + 127) / 128 * 128;
 }
-__host__ __device__ constexpr int fan_npl(int kc) { return kc == 2 ? 2 : 1; }
 
 template <int KC, bool R4>
 __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan(
@@ -52,7 +48,6 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
   using Rec = typename RO::T;
   constexpr int SPB = (KC == 2) ? 1 : 2;  // Slots per node-level block
   constexpr int kPtrSlices = R4 ? 3 : 2;  // adj_ptr, fan_ptr (, fan_hdr)
-  constexpr int NPL = fan_npl(KC), CH = kFanChunk * NPL, PI = fan_ptr_ints(NPL);  // nodes per lane / chunk, slice length
   // Two scheduling choices, settled per instance by measurement (r02 captures V, W; ms at S16M, 4-byte records):
   //   kEpLdg : lane 0 reads the refill's end points with plain loads at the top of a trip (consumed after the walk)
   //            instead of a cp.async group one chunk earlier.        2 DOF: 0.417 -> 0.407; scalar: 0.243 -> 0.257
@@ -62,14 +57,14 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
   constexpr bool kEpLdg = KC != 2, kEarly = KC == 2 || !R4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *wbase = smem_raw + (size_t)warp * fan_warp_bytes(rec_cap, warp_slot_bytes, R4, NPL);
+  unsigned char *wbase = smem_raw + (size_t)warp * fan_warp_bytes(rec_cap, warp_slot_bytes, R4);
   uint64_t *full = reinterpret_cast<uint64_t *>(wbase);
-  const size_t stage_bytes = fan_stage_bytes(rec_cap, R4, NPL);
+  const size_t stage_bytes = fan_stage_bytes(rec_cap, R4);
   int32_t *ep = reinterpret_cast<int32_t *>(wbase + 16);  // [2][2] record-range end points (LDGSTS)
   unsigned char *stage0 = wbase + 32;
   Slot *acc = reinterpret_cast<Slot *>(stage0 + 2 * stage_bytes);
 
-  const int n_chunks = (n_owned + CH - 1) / CH;
+  const int n_chunks = (n_owned + kFanChunk - 1) / kFanChunk;
   const int chunk_stride = gridDim.x * kFanWarps;
   if (lane == 0) {
     ptx::mbar_init(&full[0], 1);
@@ -82,22 +77,22 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
   //      chunk ahead with cp.async (global -> shared, no registers held across the compute loop).
   auto request_endpoints = [&](int chunk, int slot) {
     if (chunk < n_chunks) {
-      const int32_t n0 = chunk * CH;
+      const int32_t n0 = chunk * kFanChunk;
       ptx::cp_async4(ep + 2 * slot, fan_ptr + n0);
-      ptx::cp_async4(ep + 2 * slot + 1, fan_ptr + min(n0 + CH, n_owned));
+      ptx::cp_async4(ep + 2 * slot + 1, fan_ptr + min(n0 + kFanChunk, n_owned));
     }
     ptx::cp_async_commit();
   };
   auto issue = [&](int chunk, int stage, int32_t r0, int32_t r1) {
-    const int32_t n0 = chunk * CH;
+    const int32_t n0 = chunk * kFanChunk;
     const int32_t base = r0 & ~(RO::kAlign - 1);  // 16-byte aligned start of the record copy
     const uint32_t rec_bytes = (uint32_t)((r1 - base + RO::kAlign - 1) / RO::kAlign) * 16u;
     unsigned char *st = stage0 + stage * stage_bytes;
-    ptx::mbar_expect_tx(&full[stage], (uint32_t)kPtrSlices * PI * 4u + rec_bytes);
-    ptx::bulk_load(st, adj_ptr + n0, PI * 4u, &full[stage]);
-    ptx::bulk_load(st + PI * 4, fan_ptr + n0, PI * 4u, &full[stage]);
-    if (R4) ptx::bulk_load(st + 2 * PI * 4, fan_hdr + n0, PI * 4u, &full[stage]);
-    if (rec_bytes) ptx::bulk_load(st + kPtrSlices * PI * 4, fan_rec + base, rec_bytes, &full[stage]);
+    ptx::mbar_expect_tx(&full[stage], (uint32_t)kPtrSlices * kFanPtrInts * 4u + rec_bytes);
+    ptx::bulk_load(st, adj_ptr + n0, kFanPtrInts * 4u, &full[stage]);
+    ptx::bulk_load(st + kFanPtrInts * 4, fan_ptr + n0, kFanPtrInts * 4u, &full[stage]);
+    if (R4) ptx::bulk_load(st + 2 * kFanPtrInts * 4, fan_hdr + n0, kFanPtrInts * 4u, &full[stage]);
+    if (rec_bytes) ptx::bulk_load(st + kPtrSlices * kFanPtrInts * 4, fan_rec + base, rec_bytes, &full[stage]);
   };
   int chunk = blockIdx.x * kFanWarps + warp;
   if (lane == 0 && chunk < n_chunks) {
@@ -105,8 +100,8 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
     for (int q = 0; q < 2; ++q) {
       const int c = chunk + q * chunk_stride;
       if (c < n_chunks) {
-        const int32_t n0 = c * CH;
-        issue(c, q, __ldg(fan_ptr + n0), __ldg(fan_ptr + min(n0 + CH, n_owned)));
+        const int32_t n0 = c * kFanChunk;
+        issue(c, q, __ldg(fan_ptr + n0), __ldg(fan_ptr + min(n0 + kFanChunk, n_owned)));
       }
     }
     if (!kEpLdg) request_endpoints(chunk + 2 * chunk_stride, 0);
@@ -128,28 +123,27 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
   auto fetch = [&](int i, double2 &p) {
     if (i < fe) p = __ldg(coords + RO::nbr(recs[i], self, n_owned));
   };
-  // Waits for the chunk's ring slot (first sub-walk only) and puts the first gathers of the lane's h-th node in flight.
-  auto begin_chunk = [&](int c, int jj, int h) {
+  // Waits for the chunk's ring slot and puts the first gathers in flight.
+  auto begin_chunk = [&](int c, int jj) {
     const int stage = jj & 1;
-    if (h == 0) ptx::mbar_wait(&full[stage], (uint32_t)((jj >> 1) & 1));
-    const int32_t n0 = c * CH;
-    const int n_in = min(CH, n_owned - n0);
-    const int li = h * kFanChunk + lane;  // this lane's node within the chunk
+    ptx::mbar_wait(&full[stage], (uint32_t)((jj >> 1) & 1));
+    const int32_t n0 = c * kFanChunk;
+    const int n_in = min(kFanChunk, n_owned - n0);
     const unsigned char *st = stage0 + stage * stage_bytes;
     const int32_t *a_sl = reinterpret_cast<const int32_t *>(st);
-    const int32_t *f_sl = a_sl + PI;
-    recs = reinterpret_cast<const Rec *>(st + kPtrSlices * PI * 4);
+    const int32_t *f_sl = a_sl + kFanPtrInts;
+    recs = reinterpret_cast<const Rec *>(st + kPtrSlices * kFanPtrInts * 4);
     const int32_t base = f_sl[0] & ~(RO::kAlign - 1);
     const int32_t out_lo = a_sl[0];
     f = fe = deg = 0;
-    self = n0 + li;
-    if (li < n_in) {
+    self = n0 + lane;
+    if (lane < n_in) {
       ps = __ldg(coords + self);
-      f = f_sl[li] - base;
-      fe = f_sl[li + 1] - base;
-      deg = a_sl[li + 1] - a_sl[li];
-      my = acc + SPB * (a_sl[li] - out_lo);
-      if (R4) hdr = reinterpret_cast<const uint32_t *>(f_sl + PI)[li];
+      f = f_sl[lane] - base;
+      fe = f_sl[lane + 1] - base;
+      deg = a_sl[lane + 1] - a_sl[lane];
+      my = acc + SPB * (a_sl[lane] - out_lo);
+      if (R4) hdr = reinterpret_cast<const uint32_t *>(f_sl + kFanPtrInts)[lane];
     }
     fetch(f, p0);
     fetch(f + 1, pa1);
@@ -157,7 +151,7 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
   };
 
   int j = 0;  // ring position mod 4: stage = j & 1, barrier parity = (j >> 1) & 1
-  if (chunk < n_chunks) begin_chunk(chunk, 0, 0);
+  if (chunk < n_chunks) begin_chunk(chunk, 0);
   for (; chunk < n_chunks; chunk += chunk_stride, j = (j + 1) & 3) {
     const int stage = j & 1;
     const int next = chunk + chunk_stride;
@@ -167,13 +161,11 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
     // samples on an unrelated LDG of begin_chunk)
     int32_t ep0 = 0, ep1 = 0;
     if (kEpLdg && lane == 0 && next + chunk_stride < n_chunks) {
-      const int32_t nr = (next + chunk_stride) * CH;
+      const int32_t nr = (next + chunk_stride) * kFanChunk;
       ep0 = __ldg(fan_ptr + nr);
-      ep1 = __ldg(fan_ptr + min(nr + CH, n_owned));
+      ep1 = __ldg(fan_ptr + min(nr + kFanChunk, n_owned));
     }
-    // ---- the fan walk(s) of this thread's node(s)
-#pragma unroll
-    for (int h = 0; h < NPL; ++h) {
+    // ---- the fan walk of this thread's node
     if (f < fe) {
       if (R4) cur_mat = RO::first_mat(hdr);
       Val diag = Ops::zero(), X = Ops::zero(), Y;
@@ -252,18 +244,16 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
       }
       Ops::store(my, deg, kself, diag);
     }
-    if (h + 1 < NPL) begin_chunk(chunk, j, h + 1);  // the lane's next node of this chunk (same ring stage)
-    }
 
     // ---- the sub-tile is complete: the exact image of vals[dim^2 * out_lo ...)
     int32_t out_lo, out_len;  // node-level block range of this chunk (slice still in the ring slot)
     {
       const int32_t *a_sl = reinterpret_cast<const int32_t *>(stage0 + stage * stage_bytes);
       out_lo = a_sl[0];
-      out_len = a_sl[min(CH, n_owned - chunk * CH)] - out_lo;
+      out_len = a_sl[min(kFanChunk, n_owned - chunk * kFanChunk)] - out_lo;
     }
     // kEarly: the next chunk's first loads go out NOW and travel while this chunk's store and the ring refill are issued
-    if (kEarly && next < n_chunks) begin_chunk(next, (j + 1) & 3, 0);
+    if (kEarly && next < n_chunks) begin_chunk(next, (j + 1) & 3);
     ptx::fence_async_smem();  // generic smem accesses of this chunk ordered before the async proxy
     __syncwarp();
     if (KC == 2) {
@@ -286,7 +276,7 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
       }
     }
     // first gathers of the next chunk go out before we wait for the store to drain the sub-tile
-    if (!kEarly && next < n_chunks) begin_chunk(next, (j + 1) & 3, 0);
+    if (!kEarly && next < n_chunks) begin_chunk(next, (j + 1) & 3);
     if (KC != 2 && lane == 0) ptx::bulk_store_wait_read();
     __syncwarp();
   }
