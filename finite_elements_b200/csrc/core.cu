@@ -336,7 +336,7 @@ int fe_ctx_destroy(fe_ctx *ctx) {
   if (ctx->pcg_graph) cudaGraphExecDestroy((cudaGraphExec_t)ctx->pcg_graph);
   if (ctx->work_stream) cudaStreamDestroy((cudaStream_t)ctx->work_stream);
   if (ctx->work_event) cudaEventDestroy((cudaEvent_t)ctx->work_event);
-  extern void fe_dist_teardown(fe_ctx *);
+  extern __attribute__((visibility("hidden"))) void fe_dist_teardown(fe_ctx *);
   fe_dist_teardown(ctx);
   delete ctx;
   return FE_OK;

@@ -259,7 +259,7 @@ int fe_dist_p2p_import(fe_ctx *ctx, const void *handles) {
   return FE_OK;
 }
 
-void fe_dist_teardown(fe_ctx *ctx) {
+__attribute__((visibility("hidden"))) void fe_dist_teardown(fe_ctx *ctx) {  // library-internal (fe_ctx_destroy), not part of the ABI
   if (ctx) {
     for (int r = 0; r < kMaxRanks; ++r)
       if (ctx->p2p_peer[r] && ctx->p2p_peer[r] != ctx->p2p_buf) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
