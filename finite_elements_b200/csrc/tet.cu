@@ -10,16 +10,16 @@
 // (i, j) of V B^T D B is  V [ lam g_i g_j^T + mu g_j g_i^T + mu (g_i . g_j) I ]  -- evaluated in
 // registers, the 6x12 B is never formed.
 //
-// First version of the 3D path: the symbolic phase (corner lists, node adjacency) is prepared by
-// the host layer with device-side sorts; the numeric phase below is the analogue of the 2D
-// "variant 1 / 2" kernels -- one thread owns a node's three CSR rows, visits its incident elements
-// in ascending element order and accumulates the (node, neighbour) blocks, in global memory
-// (k_tet_assemble) or in a shared-memory tile streamed out with coalesced stores
-// (k_tet_assemble_tile, default): no atomics, the summation order is fixed, two runs -- and the two
-// kernels -- are bit-identical.  Measured on B200 (1.33 M tetrahedra): 2.90 ms -> 1.23 ms (tile) -> 0.94 ms
-// (tile + relabelling, tet_row).  Both are
-// latency-bound (serial corner loop, dependent corner -> conn -> coords loads, 3 CTAs of 64 threads
-// per SM): the fan-ordered, TMA-pipelined treatment the triangles got is the next step.
+// The symbolic phase is fe_tet_plan_create (plan.cu).  Numeric assembly, deterministic in every variant (no atomics,
+// fixed summation order; two runs are bit-identical):
+//   6  k_tet_assemble_pipe    (default) persistent CTAs, tiles of 16 nodes staged in shared memory, next tile's inputs
+//                             by cp.async; one lane per 3x3 block
+//   5  k_tet_assemble_staged  the same, one tile per CTA, no prefetch (bit-identical to 6)
+//   4  k_tet_gradient_table + k_tet_assemble_table   per-element records in a global table, one lane per block
+//   3  k_tet_assemble_slots   one lane per block, geometry rebuilt at every visit
+//   2  k_tet_assemble_tile / 1  k_tet_assemble   round 1: one thread owns a node's three rows and visits its
+//                             incident elements in ascending order (shared-memory tile / global accumulation)
+// Measured on B200 (1.33 M tetrahedra): 2.90 ms (1) -> 1.23 / 0.94 ms (2) -> 0.36 (3) -> 0.30 (4) -> 0.235 (5) -> 0.225 ms (6).
 #include "common.cuh"
 #include "elem.cuh"
 #include "plan.cuh"
