@@ -414,8 +414,7 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
     const int fgrid = grid < minb * ctx->num_sms ? grid : minb * ctx->num_sms;                                  \
     k_assemble_fan<KC, R4><<<fgrid, kFanThreads, smem, st>>>(p->n_owned, p->fan_ptr, RECS, p->fan_hdr,          \
                                                              p->adj_ptr, xy, tab, vals, rec_cap,                \
-                                                             fan_warp_slot_bytes(dim, p->max_degree), p->n_nodes, \
-                                                             p->fan_fwd_max);                                   \
+                                                             fan_warp_slot_bytes(dim, p->max_degree));          \
   } while (0)
 #define FE_ASM_LAUNCH(KC)                                                                                       \
   do {                                                                                                          \

@@ -26,9 +26,6 @@
 //   20 warps per SM (ncu: 43 % issue-active, FP64 pipe 28 %, DRAM 2.29 GB in 0.41 ms), not by HBM: every design
 //   that traded warps for deeper prefetch lost.
 #pragma once
-#ifndef FE_FAN_PF
-#define FE_FAN_PF 2
-#endif
 constexpr int kFanThreads = 128;
 constexpr int kFanWarps = 4;
 
@@ -43,8 +40,7 @@ template <int KC, bool R4>
 __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan(
     int32_t n_owned, const int32_t *__restrict__ fan_ptr, const typename FanRec<R4>::T *__restrict__ fan_rec,
     const uint32_t *__restrict__ fan_hdr, const int32_t *__restrict__ adj_ptr, const double2 *__restrict__ coords,
-    const MatRow *__restrict__ tab, double *__restrict__ vals, int rec_cap, int warp_slot_bytes, int32_t n_nodes,
-    int32_t fwd_hint) {
+    const MatRow *__restrict__ tab, double *__restrict__ vals, int rec_cap, int warp_slot_bytes) {
   using Ops = FanOps<KC>;
   using Val = typename Ops::Val;
   using Slot = typename Ops::Slot;
@@ -169,16 +165,6 @@ __global__ void __launch_bounds__(kFanThreads, (KC == 2 ? 7 : 5)) k_assemble_fan
       ep0 = __ldg(fan_ptr + nr);
       ep1 = __ldg(fan_ptr + min(nr + kFanChunk, n_owned));
     }
-#if FE_FAN_PF
-    // The coordinates a chunk touches FIRST (banded numbering: the nodes fwd_hint ahead of it; everything nearer was
-    // gathered by earlier chunks and sits in L2) come from DRAM, and two of them are among the loads that open its
-    // walk.  One prefetch.global.L2 per lane pulls the line this lane's node of the chunk FE_FAN_PF trips ahead
-    // will need -- independent of the ring, harmless when the hint is wrong.
-    if (fwd_hint > 0) {
-      const int64_t t = (int64_t)(chunk + FE_FAN_PF * chunk_stride) * kFanChunk + lane + fwd_hint;
-      if (t < n_nodes) ptx::prefetch_l2(coords + t);
-    }
-#endif
     // ---- the fan walk of this thread's node
     if (f < fe) {
       if (R4) cur_mat = RO::first_mat(hdr);

@@ -291,12 +291,10 @@ __global__ void k_fan_tile_max(int32_t n_owned, const int32_t *__restrict__ fan_
 // 8-byte fan records -> 4-byte words + one header word per node (layout in plan.cuh).  One thread per node.
 __global__ void __launch_bounds__(128) k_fan_compact(int32_t n_owned, const int32_t *__restrict__ fan_ptr,
                                                     const int2 *__restrict__ rec, uint32_t *__restrict__ rec4,
-                                                    uint32_t *__restrict__ hdr, int *__restrict__ bad,
-                                                    int *__restrict__ fwd_max) {
+                                                    uint32_t *__restrict__ hdr, int *__restrict__ bad) {
   const int32_t n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_owned) return;
   const int32_t f0 = fan_ptr[n], f1 = fan_ptr[n + 1];
-  int32_t fwd = 0;
   uint32_t kself = 0;
   int mat0 = -1, mat1 = -1, cur = -1, n_seeds = 0;
   for (int32_t f = f0; f < f1; ++f) {
@@ -306,7 +304,6 @@ __global__ void __launch_bounds__(128) k_fan_compact(int32_t n_owned, const int3
     uint32_t f4 = (fl & FAN_SEED ? FAN4_SEED : 0u) | (fl & FAN_LAST ? FAN4_LAST : 0u) |
                   (fl & FAN_ADD_FIRST ? FAN4_ADD_FIRST : 0u);
     const int32_t delta = r.x - n;
-    fwd = max(fwd, delta);
     if (delta < -(1 << (kFan4FieldBits - 1)) || delta >= (1 << (kFan4FieldBits - 1))) *bad = 1;
     const uint32_t field = (uint32_t)delta & ((1u << kFan4FieldBits) - 1u);
     if (fl & FAN_SEED) {
@@ -326,7 +323,6 @@ __global__ void __launch_bounds__(128) k_fan_compact(int32_t n_owned, const int3
     rec4[f] = k | (f4 << 8) | (field << kFan4Shift);
   }
   if (n_seeds > 1) rec4[f0] |= FAN4_MULTI << 8;  // (= FAN_MULTI of the 8-byte record)
-  if (fwd > *reinterpret_cast<volatile int *>(fwd_max)) atomicMax(fwd_max, fwd);
   hdr[n] = kself | ((uint32_t)(mat0 < 0 ? 0 : mat0) << 8) | ((uint32_t)(mat1 < 0 ? 0 : mat1) << 20);
 }
 
@@ -511,14 +507,12 @@ int fe_plan_create(fe_ctx *ctx, void *stream, int32_t n_nodes, int32_t n_owned, 
     PLAN_TRY(dev_alloc(&p->fan_rec4, p->n_fan + 8, &p->bytes));  // +8: 16-byte staging over-read
     PLAN_TRY(dev_alloc(&p->fan_hdr, (int64_t)n_owned + 136, &p->bytes));  // +136: slice over-read
     PLAN_CUDA(cudaMemsetAsync(&flags->bad_node, 0, sizeof(int), st));
-    PLAN_CUDA(cudaMemsetAsync(&flags->too_dense, 0, sizeof(int), st));  // reused: largest forward neighbour difference
     k_fan_compact<<<grid_for(n_owned, 128), 128, 0, st>>>(n_owned, p->fan_ptr, p->fan_rec, p->fan_rec4, p->fan_hdr,
-                                                         &flags->bad_node, &flags->too_dense);
+                                                         &flags->bad_node);
     PLAN_LAUNCHED();
     PLAN_CUDA(cudaMemcpyAsync(&hflags, flags, sizeof(PlanFlags), cudaMemcpyDeviceToHost, st));
     PLAN_CUDA(cudaStreamSynchronize(st));
     p->fan_compact_ok = hflags.bad_node == 0;
-    p->fan_fwd_max = hflags.too_dense;
   }
 
 done:

@@ -46,7 +46,6 @@ struct fe_plan {
   //                 switches to the other material before the step is evaluated; FAN4_MULTI on a node's first
   //                 record: more than one fan around the node (the kernel's general loop)
   bool fan_compact_ok = false;
-  int32_t fan_fwd_max = 0;  // largest (neighbour - node): the coordinates a chunk touches first lie that far ahead
   uint32_t *fan_rec4 = nullptr;  // [n_fan]
   uint32_t *fan_hdr = nullptr;   // [n_owned]
   // linear tetrahedra (npe == 4, dim == 3; fe_tet_plan_create): per OFF-DIAGONAL block (node i, slot k) the
