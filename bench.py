@@ -67,8 +67,8 @@ def measured_peak_hbm():
         return 6650.0, "fallback"
 
 
-def _gpu_spin(torch, cycles=200_000):
-    """~0.1 ms of device-side spinning (torch.cuda._sleep); skipped if this torch build lacks it."""
+def _gpu_spin(torch, cycles=600_000):
+    """~0.3 ms of device-side spinning (torch.cuda._sleep); skipped if this torch build lacks it."""
     spin = getattr(torch.cuda, "_sleep", None)
     if spin is not None:
         spin(cycles)
@@ -353,7 +353,7 @@ def run_gpu(args):
 
     def step(timers=None):
         a0, a1, p0, p1 = ev(), ev(), ev(), ev()
-        # the previous step ended with a host synchronisation: keep the GPU busy for ~0.1 ms so the
+        # the previous step ended with a host synchronisation: keep the GPU busy for ~0.3 ms so the
         # launches below are queued before it gets to them (the events then bracket device time,
         # not the CPU's launch latency)
         _gpu_spin(torch)

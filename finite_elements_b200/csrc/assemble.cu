@@ -407,11 +407,19 @@ extern "C" int fe_assemble(fe_ctx *ctx, void *stream, const fe_plan *p, int kind
 
 #define FE_FAN_LAUNCH(KC, R4, RECS)                                                                              \
   do {                                                                                                          \
-    int minb = 1;  /* persistent grid: as many CTAs as are resident */                                          \
-    FE_CUDA(cudaFuncSetAttribute(k_assemble_fan<KC, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    FE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&minb, k_assemble_fan<KC, R4>, kFanThreads, smem));   \
-    if (minb < 1) minb = 1;                                                                                     \
-    const int fgrid = grid < minb * ctx->num_sms ? grid : minb * ctx->num_sms;                                  \
+    /* persistent grid: as many CTAs as are resident.  The attribute / occupancy calls cost the CPU ~20 us:    */ \
+    /* remembered per instance and shared-memory size                                                          */ \
+    static thread_local size_t cached_smem = ~(size_t)0;                                                        \
+    static thread_local int cached_minb = 1, cached_dev = -1;                                                   \
+    if (cached_smem != smem || cached_dev != ctx->device) {                                                     \
+      int minb = 1;                                                                                             \
+      FE_CUDA(cudaFuncSetAttribute(k_assemble_fan<KC, R4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      FE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&minb, k_assemble_fan<KC, R4>, kFanThreads, smem)); \
+      cached_minb = minb < 1 ? 1 : minb;                                                                        \
+      cached_smem = smem;                                                                                       \
+      cached_dev = ctx->device;                                                                                 \
+    }                                                                                                           \
+    const int fgrid = grid < cached_minb * ctx->num_sms ? grid : cached_minb * ctx->num_sms;                    \
     k_assemble_fan<KC, R4><<<fgrid, kFanThreads, smem, st>>>(p->n_owned, p->fan_ptr, RECS, p->fan_hdr,          \
                                                              p->adj_ptr, xy, tab, vals, rec_cap,                \
                                                              fan_warp_slot_bytes(dim, p->max_degree));          \

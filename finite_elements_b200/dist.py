@@ -218,7 +218,7 @@ class DistributedMesh:
         return x, iters.value, relres.value
 
 
-def _gpu_spin(torch_mod, cycles=200_000):
+def _gpu_spin(torch_mod, cycles=600_000):
     spin = getattr(torch_mod.cuda, "_sleep", None)
     if spin is not None:
         spin(cycles)
@@ -311,7 +311,7 @@ def bench_distributed(args, metric, mat, measured_peak_hbm, ClockSampler, asm_by
 
     def step(timers=None):
         a0, a1, p0, p1 = ev(), ev(), ev(), ev()
-        # the previous step ended with a host synchronisation: keep the GPU busy for ~0.1 ms so the
+        # the previous step ended with a host synchronisation: keep the GPU busy for ~0.3 ms so the
         # launches below are queued before it gets to them (the events then bracket device time,
         # not the CPU's launch latency)
         _gpu_spin(torch)
